@@ -1,0 +1,469 @@
+// api.cu -- the C-ABI of include/flyby_b200.h: context lifetime, host/device
+// buffer staging and call ordering.  All compute is in the kernels of
+// prep.cu / lbvh.cu / views.cu / trace.cu / label.cu.
+#include <new>
+
+#include "ctx.h"
+
+namespace fb {
+int label_point_features(flyby_ctx*, const int32_t*, int64_t, const float*, int, float, float*);
+int label_backproject(flyby_ctx*, const int32_t*, const int32_t*, int64_t, int, int32_t*);
+int label_backproject_soft(flyby_ctx*, const int32_t*, const float*, int64_t, int, int64_t*);
+int label_argmax(flyby_ctx*, const int32_t*, int64_t, int, int32_t, int32_t*);
+int label_cells_to_points(flyby_ctx*, const int32_t*, int32_t, int32_t*);
+int nccl_unique_id(flyby_ctx*, uint8_t*);
+int nccl_init(flyby_ctx*, const uint8_t*, int, int);
+void nccl_destroy(flyby_ctx*);
+int nccl_votes_allreduce(flyby_ctx*, int32_t*, int64_t, int);
+const double* prep_centre_scale(flyby_ctx* c);
+
+// input: device pointers are used in place, host pointers are copied to `stage`
+template <class T>
+static int stage_in(flyby_ctx* c, DevBuf& stage, const T* src, size_t count, const T** out) {
+  if (!src || count == 0) { *out = src; return FLYBY_OK; }
+  if (is_device_ptr(src)) { *out = src; return FLYBY_OK; }
+  FB_CUDA(c, stage.reserve(count * sizeof(T)));
+  FB_CUDA(c, cudaMemcpyAsync(stage.p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  *out = stage.as<T>();
+  return FLYBY_OK;
+}
+
+// output: device pointers are written in place; host pointers get a device
+// twin that finish() copies back
+template <class T>
+struct StageOut {
+  T* user = nullptr;
+  T* dev = nullptr;
+  size_t count = 0;
+  bool host = false;
+  int begin(flyby_ctx* c, DevBuf& stage, T* dst, size_t n) {
+    user = dst; count = n; dev = dst; host = false;
+    if (!dst || n == 0) return FLYBY_OK;
+    if (!is_device_ptr(dst)) {
+      host = true;
+      FB_CUDA(c, stage.reserve(n * sizeof(T)));
+      dev = stage.as<T>();
+    }
+    return FLYBY_OK;
+  }
+  int finish(flyby_ctx* c, bool* need_sync) {
+    if (host && user && count) {
+      FB_CUDA(c, cudaMemcpyAsync(user, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+      *need_sync = true;
+    }
+    return FLYBY_OK;
+  }
+};
+
+static int sync_if(flyby_ctx* c, bool need) {
+  if (need) FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FLYBY_OK;
+}
+
+__global__ void check_tris_kernel(const int32_t* __restrict__ tris, int64_t n, int64_t V, int32_t* bad) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && (tris[i] < 0 || tris[i] >= V)) atomicAdd(bad, 1);
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+#define CHECK_CTX(c) \
+  if (!(c)) return FLYBY_ERR_INVALID; \
+  { cudaError_t _e = cudaSetDevice((c)->device); \
+    if (_e != cudaSuccess) return fail((c), FLYBY_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); }
+
+extern "C" {
+
+int flyby_abi_version(void) { return FLYBY_ABI_VERSION; }
+
+int flyby_create(int device, void* stream, flyby_ctx** out) {
+  if (!out) return FLYBY_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return FLYBY_ERR_CUDA;  // no CUDA device: there is no CPU path
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return FLYBY_ERR_CUDA;
+  flyby_ctx* c = new (std::nothrow) flyby_ctx();
+  if (!c) return FLYBY_ERR_INVALID;
+  c->device = device;
+  memset(&c->norm, 0, sizeof c->norm);
+  memset(&c->stats, 0, sizeof c->stats);
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+    c->own_stream = true;
+  }
+  for (int i = 0; i < 8; i++)
+    if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (c->counters.reserve(8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+  *out = c;
+  return FLYBY_OK;
+}
+
+void flyby_destroy(flyby_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  nccl_destroy(c);
+  MeshDev& m = c->mesh;
+  DevBuf* bufs[] = {&m.raw_verts, &m.tris, &m.verts, &m.normals, &m.face_n, &m.adj_start, &m.adj_cur, &m.adj,
+                    &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.leaf_box,
+                    &m.node_box, &m.knode, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid,
+                    &c->view_pts, &c->views, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
+                    &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->counters};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < 8; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* flyby_last_error(const flyby_ctx* c) { return c ? c->err : "null context"; }
+
+int flyby_synchronize(flyby_ctx* c) {
+  CHECK_CTX(c);
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FLYBY_OK;
+}
+
+int flyby_set_mesh(flyby_ctx* c, const float* verts, int64_t V, const int32_t* tris, int64_t T,
+                   const flyby_norm_opts* opts) {
+  CHECK_CTX(c);
+  if (!verts || V <= 0 || T < 0 || (T > 0 && !tris)) return fail(c, FLYBY_ERR_INVALID, "set_mesh: empty or null mesh");
+  if (V >= (int64_t)1 << 31 || T >= (int64_t)1 << 30) return fail(c, FLYBY_ERR_INVALID, "set_mesh: mesh too large");
+  MeshDev& m = c->mesh;
+  m.has_mesh = false;
+  m.built = false;
+  if (opts) c->norm = *opts; else memset(&c->norm, 0, sizeof c->norm);
+  FB_CUDA(c, m.raw_verts.reserve(sizeof(float) * 3 * (size_t)V));
+  FB_CUDA(c, m.tris.reserve(sizeof(int32_t) * 3 * (size_t)(T > 0 ? T : 1)));
+  FB_CUDA(c, cudaMemcpyAsync(m.raw_verts.p, verts, sizeof(float) * 3 * (size_t)V, cudaMemcpyDefault, c->stream));
+  if (T > 0)
+    FB_CUDA(c, cudaMemcpyAsync(m.tris.p, tris, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyDefault, c->stream));
+  m.V = V;
+  m.T = T;
+  m.has_mesh = true;
+  return FLYBY_OK;
+}
+
+int flyby_build(flyby_ctx* c) {
+  CHECK_CTX(c);
+  MeshDev& m = c->mesh;
+  if (!m.has_mesh) return fail(c, FLYBY_ERR_INVALID, "build: call flyby_set_mesh first");
+  // index validation first: an out-of-range index must never reach a gather
+  int32_t* bad = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 7);
+  FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
+  if (m.T > 0) {
+    check_tris_kernel<<<(unsigned)cdiv(3 * m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), 3 * m.T, m.V, bad);
+    FB_LAUNCH_CHECK(c);
+  }
+  int32_t nbad = 0;
+  FB_CUDA(c, cudaMemcpyAsync(&nbad, bad, 4, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (nbad) return fail(c, FLYBY_ERR_INVALID, "build: %d triangle indices outside [0, n_verts)", nbad);
+  int rc = prep_run(c);
+  if (rc) return rc;
+  rc = lbvh_run(c);
+  if (rc) return rc;
+  m.built = true;
+  return FLYBY_OK;
+}
+
+int flyby_get_mesh(flyby_ctx* c, float* unit_verts, float* normals, double* centre_scale) {
+  CHECK_CTX(c);
+  MeshDev& m = c->mesh;
+  if (!m.built) return fail(c, FLYBY_ERR_INVALID, "get_mesh: mesh not built");
+  if (unit_verts)
+    FB_CUDA(c, cudaMemcpyAsync(unit_verts, m.verts.p, sizeof(float) * 3 * (size_t)m.V, cudaMemcpyDefault, c->stream));
+  if (normals)  // device layout is float4 per point
+    FB_CUDA(c, cudaMemcpy2DAsync(normals, 12, m.normals.p, 16, 12, (size_t)m.V, cudaMemcpyDefault, c->stream));
+  if (centre_scale)
+    FB_CUDA(c, cudaMemcpyAsync(centre_scale, prep_centre_scale(c), 4 * sizeof(double), cudaMemcpyDefault, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FLYBY_OK;
+}
+
+int flyby_get_bvh(flyby_ctx* c, int64_t* n_nodes, int32_t* n_top, void* nodes_out, int32_t* slot_cell_ids) {
+  CHECK_CTX(c);
+  MeshDev& m = c->mesh;
+  if (!m.built) return fail(c, FLYBY_ERR_INVALID, "get_bvh: mesh not built");
+  if (n_nodes) *n_nodes = m.n_nodes;
+  if (n_top) {
+    *n_top = 0;
+    if (m.n_top_dev) FB_CUDA(c, cudaMemcpyAsync(n_top, m.n_top_dev, 4, cudaMemcpyDefault, c->stream));
+  }
+  if (nodes_out && m.n_nodes > 0)
+    FB_CUDA(c, cudaMemcpyAsync(nodes_out, m.nodes.p, sizeof(Node) * (size_t)m.n_nodes, cudaMemcpyDefault, c->stream));
+  if (slot_cell_ids && m.T > 0)  // 4th word of every int4 id record
+    FB_CUDA(c, cudaMemcpy2DAsync(slot_cell_ids, 4, reinterpret_cast<char*>(m.tvid.p) + 12, 16, 4, (size_t)m.T,
+                                 cudaMemcpyDefault, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FLYBY_OK;
+}
+
+int flyby_views_icosahedron(flyby_ctx* c, int L, double radius, int dedupe) {
+  CHECK_CTX(c);
+  return views_icosahedron(c, L, radius, dedupe);
+}
+
+int flyby_views_spiral(flyby_ctx* c, int n, double turns, double radius) {
+  CHECK_CTX(c);
+  return views_spiral(c, n, turns, radius);
+}
+
+int flyby_views_custom(flyby_ctx* c, const float* pts, int n, double radius) {
+  CHECK_CTX(c);
+  if (!pts || n < 1) return fail(c, FLYBY_ERR_INVALID, "views_custom: no points");
+  FB_CUDA(c, c->view_pts.reserve(sizeof(float) * 3 * (size_t)n));
+  FB_CUDA(c, cudaMemcpyAsync(c->view_pts.p, pts, sizeof(float) * 3 * (size_t)n, cudaMemcpyDefault, c->stream));
+  if (!is_device_ptr(pts)) FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_views = n;
+  c->radius = radius;
+  return FLYBY_OK;
+}
+
+int flyby_num_views(flyby_ctx* c, int* n) {
+  if (!c || !n) return FLYBY_ERR_INVALID;
+  *n = c->n_views;
+  return FLYBY_OK;
+}
+
+int flyby_get_views(flyby_ctx* c, float* out) {
+  CHECK_CTX(c);
+  if (!out || c->n_views <= 0) return fail(c, FLYBY_ERR_INVALID, "get_views: no viewpoints");
+  FB_CUDA(c, cudaMemcpyAsync(out, c->view_pts.p, sizeof(float) * 3 * (size_t)c->n_views, cudaMemcpyDefault, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FLYBY_OK;
+}
+
+static int check_render_args(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, bool need_mesh) {
+  if (!o) return fail(c, FLYBY_ERR_INVALID, "render: null options");
+  if (need_mesh && !c->mesh.built) return fail(c, FLYBY_ERR_INVALID, "render: mesh not built");
+  if (c->n_views <= 0) return fail(c, FLYBY_ERR_INVALID, "render: no viewpoints set");
+  if (vb < 0 || ve > c->n_views || vb >= ve) return fail(c, FLYBY_ERR_INVALID, "render: bad view range [%d,%d)", vb, ve);
+  if (res < 1 || res > 16384) return fail(c, FLYBY_ERR_INVALID, "render: bad resolution %d", res);
+  return FLYBY_OK;
+}
+
+int flyby_generate_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double* rays_out) {
+  CHECK_CTX(c);
+  int rc = check_render_args(c, vb, ve, res, o, false);
+  if (rc) return rc;
+  if (!rays_out) return fail(c, FLYBY_ERR_INVALID, "generate_rays: null output");
+  rc = views_setup(c, o);
+  if (rc) return rc;
+  StageOut<double> so;
+  rc = so.begin(c, c->stage_out0, rays_out, (size_t)(ve - vb) * res * res * 6);
+  if (rc) return rc;
+  rc = trace_rays(c, vb, ve, res, o, so.dev);
+  if (rc) return rc;
+  bool need = false;
+  rc = so.finish(c, &need);
+  if (rc) return rc;
+  return sync_if(c, need);
+}
+
+int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* out_features,
+                 int32_t* out_cell_ids, double* out_t) {
+  CHECK_CTX(c);
+  int rc = check_render_args(c, vb, ve, res, o, true);
+  if (rc) return rc;
+  const size_t n_pix = (size_t)(ve - vb) * res * res;
+  const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  rc = views_setup(c, o);
+  if (rc) return rc;
+  StageOut<float> sf;
+  StageOut<int32_t> si;
+  StageOut<double> st;
+  if ((rc = sf.begin(c, c->stage_feat, out_features, n_pix * channels))) return rc;
+  if ((rc = si.begin(c, c->stage_ids, out_cell_ids, n_pix))) return rc;
+  if ((rc = st.begin(c, c->stage_t, out_t, n_pix))) return rc;
+  rc = trace_render(c, vb, ve, res, o, sf.dev, si.dev, st.dev);
+  if (rc) return rc;
+  bool need = false;
+  if ((rc = sf.finish(c, &need))) return rc;
+  if ((rc = si.finish(c, &need))) return rc;
+  if ((rc = st.finish(c, &need))) return rc;
+  return sync_if(c, need);
+}
+
+int flyby_cast(flyby_ctx* c, const double* rays, int64_t n, int32_t* out_ids, double* out_t, double* out_w) {
+  CHECK_CTX(c);
+  if (!c->mesh.built) return fail(c, FLYBY_ERR_INVALID, "cast: mesh not built");
+  if (n < 0 || (n > 0 && !rays)) return fail(c, FLYBY_ERR_INVALID, "cast: bad arguments");
+  const double* drays;
+  int rc = stage_in(c, c->stage_in0, rays, (size_t)n * 6, &drays);
+  if (rc) return rc;
+  StageOut<int32_t> si;
+  StageOut<double> st, sw;
+  if ((rc = si.begin(c, c->stage_ids, out_ids, (size_t)n))) return rc;
+  if ((rc = st.begin(c, c->stage_t, out_t, (size_t)n))) return rc;
+  if ((rc = sw.begin(c, c->stage_out0, out_w, (size_t)n * 3))) return rc;
+  rc = trace_cast(c, drays, n, si.dev, st.dev, sw.dev);
+  if (rc) return rc;
+  bool need = !is_device_ptr(rays);
+  if ((rc = si.finish(c, &need))) return rc;
+  if ((rc = st.finish(c, &need))) return rc;
+  if ((rc = sw.finish(c, &need))) return rc;
+  return sync_if(c, need);
+}
+
+int flyby_point_features(flyby_ctx* c, const int32_t* cell_ids, int64_t n_pix, const float* feats, int F,
+                         float zero, int mode, float* out) {
+  CHECK_CTX(c);
+  if (!c->mesh.has_mesh) return fail(c, FLYBY_ERR_INVALID, "point_features: no mesh");
+  if (mode != 0) return fail(c, FLYBY_ERR_UNSUPPORTED, "point_features: only mode 0 (vertex 0 of the hit cell)");
+  if (!cell_ids || !feats || !out || F < 1 || n_pix < 0) return fail(c, FLYBY_ERR_INVALID, "point_features: bad arguments");
+  const int32_t* dids;
+  const float* dfeats;
+  int rc;
+  if ((rc = stage_in(c, c->stage_in0, cell_ids, (size_t)n_pix, &dids))) return rc;
+  if ((rc = stage_in(c, c->stage_in1, feats, (size_t)c->mesh.V * F, &dfeats))) return rc;
+  StageOut<float> so;
+  if ((rc = so.begin(c, c->stage_out0, out, (size_t)n_pix * F))) return rc;
+  if ((rc = label_point_features(c, dids, n_pix, dfeats, F, zero, so.dev))) return rc;
+  bool need = !is_device_ptr(cell_ids) || !is_device_ptr(feats);
+  if ((rc = so.finish(c, &need))) return rc;
+  return sync_if(c, need);
+}
+
+int flyby_backproject(flyby_ctx* c, const int32_t* cell_ids, const int32_t* labels, int64_t n_pix, int K,
+                      int32_t* votes) {
+  CHECK_CTX(c);
+  if (!c->mesh.has_mesh) return fail(c, FLYBY_ERR_INVALID, "backproject: no mesh");
+  if (!cell_ids || !labels || !votes || K < 1 || n_pix < 0) return fail(c, FLYBY_ERR_INVALID, "backproject: bad arguments");
+  const int32_t *dids, *dlab;
+  int rc;
+  if ((rc = stage_in(c, c->stage_in0, cell_ids, (size_t)n_pix, &dids))) return rc;
+  if ((rc = stage_in(c, c->stage_in1, labels, (size_t)n_pix, &dlab))) return rc;
+  const size_t nv = (size_t)c->mesh.T * K;
+  int32_t* dvotes = votes;
+  bool host_votes = !is_device_ptr(votes);
+  if (host_votes) {
+    FB_CUDA(c, c->stage_out0.reserve(nv * 4 + 4));
+    dvotes = c->stage_out0.as<int32_t>();
+    FB_CUDA(c, cudaMemcpyAsync(dvotes, votes, nv * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  if ((rc = label_backproject(c, dids, dlab, n_pix, K, dvotes))) return rc;
+  bool need = !is_device_ptr(cell_ids) || !is_device_ptr(labels);
+  if (host_votes) {
+    FB_CUDA(c, cudaMemcpyAsync(votes, dvotes, nv * 4, cudaMemcpyDeviceToHost, c->stream));
+    need = true;
+  }
+  return sync_if(c, need);
+}
+
+int flyby_backproject_soft(flyby_ctx* c, const int32_t* cell_ids, const float* probs, int64_t n_pix, int K,
+                           int64_t* votes_fx) {
+  CHECK_CTX(c);
+  if (!c->mesh.has_mesh) return fail(c, FLYBY_ERR_INVALID, "backproject_soft: no mesh");
+  if (!cell_ids || !probs || !votes_fx || K < 1 || n_pix < 0) return fail(c, FLYBY_ERR_INVALID, "backproject_soft: bad arguments");
+  const int32_t* dids;
+  const float* dprobs;
+  int rc;
+  if ((rc = stage_in(c, c->stage_in0, cell_ids, (size_t)n_pix, &dids))) return rc;
+  if ((rc = stage_in(c, c->stage_in1, probs, (size_t)n_pix * K, &dprobs))) return rc;
+  const size_t nv = (size_t)c->mesh.T * K;
+  int64_t* dvotes = votes_fx;
+  bool host_votes = !is_device_ptr(votes_fx);
+  if (host_votes) {
+    FB_CUDA(c, c->stage_out0.reserve(nv * 8 + 8));
+    dvotes = c->stage_out0.as<int64_t>();
+    FB_CUDA(c, cudaMemcpyAsync(dvotes, votes_fx, nv * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  if ((rc = label_backproject_soft(c, dids, dprobs, n_pix, K, dvotes))) return rc;
+  bool need = !is_device_ptr(cell_ids) || !is_device_ptr(probs);
+  if (host_votes) {
+    FB_CUDA(c, cudaMemcpyAsync(votes_fx, dvotes, nv * 8, cudaMemcpyDeviceToHost, c->stream));
+    need = true;
+  }
+  return sync_if(c, need);
+}
+
+int flyby_votes_argmax(flyby_ctx* c, const int32_t* votes, int64_t n_cells, int K, int32_t dflt, int32_t* out) {
+  CHECK_CTX(c);
+  if (!votes || !out || K < 1 || n_cells < 0) return fail(c, FLYBY_ERR_INVALID, "votes_argmax: bad arguments");
+  const int32_t* dv;
+  int rc;
+  if ((rc = stage_in(c, c->stage_in0, votes, (size_t)n_cells * K, &dv))) return rc;
+  StageOut<int32_t> so;
+  if ((rc = so.begin(c, c->stage_out0, out, (size_t)n_cells))) return rc;
+  if ((rc = label_argmax(c, dv, n_cells, K, dflt, so.dev))) return rc;
+  bool need = !is_device_ptr(votes);
+  if ((rc = so.finish(c, &need))) return rc;
+  return sync_if(c, need);
+}
+
+int flyby_cells_to_points(flyby_ctx* c, const int32_t* cell_labels, int32_t dflt, int32_t* out) {
+  CHECK_CTX(c);
+  if (!c->mesh.has_mesh) return fail(c, FLYBY_ERR_INVALID, "cells_to_points: no mesh");
+  if (!cell_labels || !out) return fail(c, FLYBY_ERR_INVALID, "cells_to_points: bad arguments");
+  const int32_t* dl;
+  int rc;
+  if ((rc = stage_in(c, c->stage_in0, cell_labels, (size_t)c->mesh.T, &dl))) return rc;
+  StageOut<int32_t> so;
+  if ((rc = so.begin(c, c->stage_out0, out, (size_t)c->mesh.V))) return rc;
+  if ((rc = label_cells_to_points(c, dl, dflt, so.dev))) return rc;
+  bool need = !is_device_ptr(cell_labels);
+  if ((rc = so.finish(c, &need))) return rc;
+  return sync_if(c, need);
+}
+
+int flyby_nccl_unique_id(flyby_ctx* c, uint8_t id_out[128]) {
+  CHECK_CTX(c);
+  return nccl_unique_id(c, id_out);
+}
+int flyby_nccl_init(flyby_ctx* c, const uint8_t id[128], int rank, int world) {
+  CHECK_CTX(c);
+  return nccl_init(c, id, rank, world);
+}
+int flyby_votes_allreduce(flyby_ctx* c, int32_t* votes, int64_t n, int root) {
+  CHECK_CTX(c);
+  if (!is_device_ptr(votes)) return fail(c, FLYBY_ERR_INVALID, "votes_allreduce: votes must be device memory");
+  return nccl_votes_allreduce(c, votes, n, root);
+}
+
+int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {
+  CHECK_CTX(c);
+  if (!out) return FLYBY_ERR_INVALID;
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  flyby_stats s = c->stats;
+  auto el = [&](int a, int b) -> float {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return ms;
+  };
+  if (c->mesh.built) {
+    s.ms_normalise = el(0, 1);
+    s.ms_normals = el(1, 2);
+    if (c->mesh.T > 0) { s.ms_sort = el(2, 3); s.ms_tree = el(3, 4); }
+  }
+  s.ms_render = el(5, 6);
+  unsigned long long h[8] = {0};
+  FB_CUDA(c, cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+  s.nodes_visited = (int64_t)h[1];
+  s.tris_tested = (int64_t)h[2];
+  s.n_hits = (int64_t)h[3];
+  *out = s;
+  return FLYBY_OK;
+}
+
+int flyby_set_count_work(flyby_ctx* c, int enable) {
+  if (!c) return FLYBY_ERR_INVALID;
+  c->count_work = enable ? 1 : 0;
+  return FLYBY_OK;
+}
+
+int flyby_launch_count(flyby_ctx* c, int64_t* n) {
+  if (!c || !n) return FLYBY_ERR_INVALID;
+  *n = c->launches;
+  return FLYBY_OK;
+}
+
+}  // extern "C"

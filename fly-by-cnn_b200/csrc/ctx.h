@@ -1,0 +1,147 @@
+// ctx.h -- internal context of libflyby_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/flyby_b200.h"
+#include "flyby_core.cuh"
+
+namespace fb {
+
+// grow-only device allocation
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct MeshDev {
+  int64_t V = 0, T = 0;
+  DevBuf raw_verts;   // float [V,3] as given
+  DevBuf tris;        // int32 [T,3] original order
+  DevBuf verts;       // float [V,3] unit surface
+  DevBuf normals;     // float4 [V] point normals (w unused)
+  DevBuf face_n;      // float [T,3] unit face normals (float32, as vtkPolyDataNormals stores them)
+  DevBuf adj_start;   // int32 [V+1] CSR of incident cells
+  DevBuf adj_cur;     // int32 [V]
+  DevBuf adj;         // int32 [3T]
+  DevBuf reduce;      // small: bbox / centre / scale scratch
+  // LBVH
+  DevBuf codes, codes_alt, idx, idx_alt;  // uint32 [T] radix sort ping-pong
+  DevBuf hist;                            // uint32 [256 * nblocks]
+  DevBuf scan_tmp;                        // scan block totals
+  DevBuf leaf_box;                        // float [T,6] boxes of sorted slots
+  DevBuf node_box;                        // float [T-1,6] internal boxes (Karras numbering)
+  DevBuf knode;                           // int32 [T-1,4] child0, child1, parent, flag (Karras numbering)
+  DevBuf remap;                           // int32 [T-1] Karras index -> final index
+  DevBuf topflag;                         // int32 [T-1]
+  DevBuf nodes;                           // Node [max(T-1,1)] final layout, top-of-tree first
+  DevBuf tv0, tv1, tv2;                   // float4 [T] sorted vertices; tv0.w = cell id bits
+  DevBuf tvid;                            // int4 [T] sorted (pid0, pid1, pid2, cell id)
+  int32_t n_nodes = 0;
+  int32_t* n_top_dev = nullptr;  // device word: nodes in the breadth-first top block
+  double centre_scale[4] = {0, 0, 0, 1};
+  bool has_mesh = false, built = false;
+};
+
+}  // namespace fb
+
+struct flyby_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  char err[512] = {0};
+  flyby_norm_opts norm;
+  fb::MeshDev mesh;
+  // viewpoints
+  fb::DevBuf view_pts;  // float [n,3]
+  fb::DevBuf views;     // fb::View [n]
+  int n_views = 0;
+  double radius = 0;
+  // staging for host-side buffers
+  fb::DevBuf stage_feat, stage_ids, stage_t, stage_in0, stage_in1, stage_out0, stage_misc;
+  fb::DevBuf counters;  // uint64 [8]: tile counter, work counters
+  // stats
+  cudaEvent_t ev[8] = {nullptr};
+  flyby_stats stats;
+  int count_work = 0;
+  int64_t launches = 0;
+  int sm_count = 148;
+  // NCCL (nccl_glue.cu)
+  void* nccl_comm = nullptr;
+  int nccl_rank = 0, nccl_world = 1;
+};
+
+namespace fb {
+
+inline int fail(flyby_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof c->err, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define FB_CUDA(ctx, expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fb::fail((ctx), FLYBY_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr,        \
+                      cudaGetErrorString(_e));                                                 \
+  } while (0)
+
+#define FB_LAUNCH_CHECK(ctx)                                                                   \
+  do {                                                                                         \
+    (ctx)->launches++;                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return fb::fail((ctx), FLYBY_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,    \
+                      cudaGetErrorString(_e));                                                 \
+  } while (0)
+
+inline bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// stage launchers (each file implements its own)
+int prep_run(flyby_ctx* c);                       // prep.cu: unit surf + normals
+int lbvh_run(flyby_ctx* c);                       // lbvh.cu: sort + tree + layout
+int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp);  // lbvh.cu
+int views_setup(flyby_ctx* c, const flyby_render_opts* o);                      // trace.cu
+int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
+                 int32_t* ids, double* tt);                                     // trace.cu
+int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double* rays);
+int trace_cast(flyby_ctx* c, const double* rays, int64_t n, int32_t* ids, double* tt, double* w);
+int views_icosahedron(flyby_ctx* c, int L, double radius, int dedupe);          // views.cu
+int views_spiral(flyby_ctx* c, int n, double turns, double radius);             // views.cu
+
+}  // namespace fb

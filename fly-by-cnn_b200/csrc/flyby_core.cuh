@@ -1,0 +1,381 @@
+// flyby_core.cuh -- per-element device logic of the fly-by path.
+//
+// Everything here is __host__ __device__ so that tests/hostsim can compile the
+// very same traversal / intersection / tree-construction code with g++ and
+// debug it without a GPU.  The product only ever runs it inside the CUDA
+// kernels of this directory; there is no CPU execution path in the library.
+//
+// Arithmetic contract (DESIGN.md "Exactness"):
+//  * everything that decides WHICH cell a ray hits, and the values written to
+//    the output tensor, is IEEE double with explicitly rounded operations
+//    (no FMA contraction) in a fixed evaluation order;
+//  * the BVH traversal around it is float32 and CONSERVATIVE: it may visit a
+//    box the exact ray misses, it never skips a box the exact hit lies in.
+#pragma once
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#if !defined(__CUDACC__)
+struct float4 { float x, y, z, w; };  // host simulator build only
+#endif
+
+#if defined(__CUDACC__)
+#define FB_HD __host__ __device__ __forceinline__
+#else
+#define FB_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define FB_MUL(a, b) __dmul_rn((a), (b))
+#define FB_ADD(a, b) __dadd_rn((a), (b))
+#define FB_SUB(a, b) __dsub_rn((a), (b))
+#define FB_DIV(a, b) __ddiv_rn((a), (b))
+#define FB_SQRT(a) __dsqrt_rn((a))
+#define FB_FADD(a, b) __fadd_rn((a), (b))
+#define FB_FMUL(a, b) __fmul_rn((a), (b))
+#define FB_F2F_RU(a) __double2float_ru((a))
+#else  // host build: compile with -ffp-contract=off
+#define FB_MUL(a, b) ((a) * (b))
+#define FB_ADD(a, b) ((a) + (b))
+#define FB_SUB(a, b) ((a) - (b))
+#define FB_DIV(a, b) ((a) / (b))
+#define FB_SQRT(a) sqrt((a))
+#define FB_FADD(a, b) ((float)(a) + (float)(b))
+#define FB_FMUL(a, b) ((float)(a) * (float)(b))
+static inline float fb_f2f_ru(double a) {
+  float f = (float)a;
+  return ((double)f < a) ? nextafterf(f, INFINITY) : f;
+}
+#define FB_F2F_RU(a) fb_f2f_ru((a))
+#endif
+
+namespace fb {
+
+// ---------------------------------------------------------------- vectors
+FB_HD double dot3(const double* a, const double* b) {
+  return FB_ADD(FB_ADD(FB_MUL(a[0], b[0]), FB_MUL(a[1], b[1])), FB_MUL(a[2], b[2]));
+}
+FB_HD void cross3(const double* a, const double* b, double* c) {
+  c[0] = FB_SUB(FB_MUL(a[1], b[2]), FB_MUL(a[2], b[1]));
+  c[1] = FB_SUB(FB_MUL(a[2], b[0]), FB_MUL(a[0], b[2]));
+  c[2] = FB_SUB(FB_MUL(a[0], b[1]), FB_MUL(a[1], b[0]));
+}
+FB_HD double norm3(const double* a) { return FB_SQRT(dot3(a, a)); }
+
+// ---------------------------------------------------------------- views
+// One record per viewpoint; rebuilt by view_setup_kernel for every render
+// call because it depends on plane_scale / plane_spacing.
+// Reference: src/app/fly_by_features.cxx:652-702 (basis and vtkPlaneSource
+// corner points) and :742-748 (segment from each plane point).
+struct View {
+  double sp[3], n[3], x[3], y[3];
+  double origin[3], v1[3], v2[3];  // plane Origin, Point1-Origin, Point2-Origin
+  double delta[3];                 // sp - sp*spacing
+  double dir[3];                   // end - origin = -(n*R)*2
+  float dirf[3], invf[3];          // float32 direction and its reciprocal (traversal only)
+  float slack;                     // box inflation covering float32 ray rounding
+  float tslack;                    // slack in units of the segment parameter
+};
+
+FB_HD void view_setup(const float* spf, double radius, double plane_scale, double spacing, View* v) {
+  for (int k = 0; k < 3; k++) v->sp[k] = (double)spf[k];
+  double len = norm3(v->sp);
+  for (int k = 0; k < 3; k++) v->n[k] = FB_DIV(v->sp[k], len);
+  bool north = fabs(v->n[0]) <= 1e-8 && fabs(v->n[1]) <= 1e-8 && fabs(FB_SUB(v->n[2], 1.0)) <= 1e-8;
+  bool south = fabs(v->n[0]) <= 1e-8 && fabs(v->n[1]) <= 1e-8 && fabs(FB_ADD(v->n[2], 1.0)) <= 1e-8;
+  if (north) {
+    v->x[0] = 1; v->x[1] = 0; v->x[2] = 0; v->y[0] = 0; v->y[1] = 1; v->y[2] = 0;
+  } else if (south) {
+    v->x[0] = -1; v->x[1] = 0; v->x[2] = 0; v->y[0] = 0; v->y[1] = -1; v->y[2] = 0;
+  } else {
+    double up[3] = {0.0, 0.0, 1.0}, c[3];
+    cross3(v->n, up, c);
+    double l = norm3(c);
+    for (int k = 0; k < 3; k++) v->x[k] = FB_DIV(c[k], l);
+    cross3(v->n, v->x, c);
+    l = norm3(c);
+    for (int k = 0; k < 3; k++) v->y[k] = FB_DIV(c[k], l);
+  }
+  double amax = 1.0;
+  for (int k = 0; k < 3; k++) {
+    double hx = FB_MUL(FB_MUL(v->x[k], 0.5), plane_scale);
+    double hy = FB_MUL(FB_MUL(v->y[k], 0.5), plane_scale);
+    v->origin[k] = FB_SUB(FB_SUB(v->sp[k], hx), hy);
+    double p1 = FB_ADD(v->origin[k], FB_MUL(v->x[k], plane_scale));
+    double p2 = FB_ADD(v->origin[k], FB_MUL(v->y[k], plane_scale));
+    v->v1[k] = FB_SUB(p1, v->origin[k]);
+    v->v2[k] = FB_SUB(p2, v->origin[k]);
+    v->delta[k] = FB_SUB(v->sp[k], FB_MUL(v->sp[k], spacing));
+    v->dir[k] = -FB_MUL(FB_MUL(v->n[k], radius), 2.0);
+    v->dirf[k] = (float)v->dir[k];
+    v->invf[k] = 1.0f / v->dirf[k];
+    // largest coordinate any ray of this view can take (origin or end)
+    double reach = fabs(v->sp[k]) * fabs(spacing) + fabs(v->delta[k]) + fabs(plane_scale * spacing) +
+                   fabs(v->dir[k]);
+    if (reach > amax) amax = reach;
+  }
+  // float32 rounding of origin/direction moves a ray by < 4 ulp(amax); 64 ulp of slack
+  v->slack = (float)(amax * 64.0 * 5.9604644775390625e-08);
+  double dl = norm3(v->dir);
+  v->tslack = (float)(dl > 0.0 ? 4.0 * (double)v->slack / dl : 0.0);
+}
+
+// origin of ray (i, j) of a res x res plane; i is the fast axis (vtkPlaneSource
+// with resolution res-1, points stored as float32)
+FB_HD void view_ray(const View& v, int res, int i, int j, double spacing, double* o) {
+  double tc0 = (res > 1) ? FB_DIV((double)i, (double)(res - 1)) : 0.0;
+  double tc1 = (res > 1) ? FB_DIV((double)j, (double)(res - 1)) : 0.0;
+  for (int k = 0; k < 3; k++) {
+    float pf = (float)FB_ADD(FB_ADD(v.origin[k], FB_MUL(tc0, v.v1[k])), FB_MUL(tc1, v.v2[k]));
+    o[k] = FB_ADD(FB_MUL((double)pf, spacing), v.delta[k]);
+  }
+}
+
+// ---------------------------------------------------------------- exact test
+// vtkTriangle::IntersectWithLine -> vtkPlane::IntersectWithLine ->
+// vtkTriangle::EvaluatePosition, restated (reference call site
+// src/app/fly_by_features.cxx:750-758,778).  P* are float32 vertices.
+// Returns true on hit and fills t; x and w are filled when the plane is hit.
+FB_HD bool tri_exact(const double* o, const double* d, const float* P0, const float* P1,
+                     const float* P2, double t_limit, double* t_out, double* x, double* w) {
+  double pt1[3] = {(double)P1[0], (double)P1[1], (double)P1[2]};
+  double pt2[3] = {(double)P2[0], (double)P2[1], (double)P2[2]};
+  double pt3[3] = {(double)P0[0], (double)P0[1], (double)P0[2]};
+  double a[3] = {FB_SUB(pt3[0], pt2[0]), FB_SUB(pt3[1], pt2[1]), FB_SUB(pt3[2], pt2[2])};
+  double b[3] = {FB_SUB(pt1[0], pt2[0]), FB_SUB(pt1[1], pt2[1]), FB_SUB(pt1[2], pt2[2])};
+  double n[3];
+  cross3(a, b, n);
+  if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) return false;
+  double num = FB_SUB(dot3(n, pt1), dot3(n, o));
+  double den = dot3(n, d);
+  double fabsden = den < 0.0 ? -den : den;
+  double fabstol = num < 0.0 ? FB_MUL(-num, 1.0e-06) : FB_MUL(num, 1.0e-06);
+  if (fabsden <= fabstol) return false;
+  double t = FB_DIV(num, den);
+  if (!(t >= 0.0 && t <= 1.0)) return false;
+  if (t > t_limit) return false;  // cannot beat the current nearest hit
+  for (int k = 0; k < 3; k++) x[k] = FB_ADD(o[k], FB_MUL(t, d[k]));
+  double xo[3] = {FB_SUB(x[0], pt1[0]), FB_SUB(x[1], pt1[1]), FB_SUB(x[2], pt1[2])};
+  double tp = dot3(n, xo), n2 = dot3(n, n);
+  double cp[3];
+  for (int k = 0; k < 3; k++)
+    cp[k] = (n2 != 0.0) ? FB_SUB(x[k], FB_DIV(FB_MUL(tp, n[k]), n2)) : x[k];
+  int idx = 0;
+  double maxc = 0.0;
+  for (int k = 0; k < 3; k++) {
+    double f = n[k] < 0 ? -n[k] : n[k];
+    if (f > maxc) { maxc = f; idx = k; }
+  }
+  int ia = (idx == 0) ? 1 : 0, ib = (idx == 2) ? 1 : 2;
+  double r0 = FB_SUB(cp[ia], pt3[ia]), r1 = FB_SUB(cp[ib], pt3[ib]);
+  double c10 = FB_SUB(pt1[ia], pt3[ia]), c11 = FB_SUB(pt1[ib], pt3[ib]);
+  double c20 = FB_SUB(pt2[ia], pt3[ia]), c21 = FB_SUB(pt2[ib], pt3[ib]);
+  double det = FB_SUB(FB_MUL(c10, c21), FB_MUL(c20, c11));
+  if (det == 0.0) return false;
+  double pc0 = FB_DIV(FB_SUB(FB_MUL(r0, c21), FB_MUL(c20, r1)), det);
+  double pc1 = FB_DIV(FB_SUB(FB_MUL(c10, r1), FB_MUL(r0, c11)), det);
+  w[0] = FB_SUB(1.0, FB_ADD(pc0, pc1));
+  w[1] = pc0;
+  w[2] = pc1;
+  if (w[0] >= 0.0 && w[0] <= 1.0 && w[1] >= 0.0 && w[1] <= 1.0 && w[2] >= 0.0 && w[2] <= 1.0) {
+    *t_out = t;
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------- LBVH
+// 64-byte node: the two child boxes live in the parent so one fetch decides
+// both descents.  Words (DESIGN.md "Data layout"):
+//   f[0..5]  child0 lo xyz, hi xyz      f[6..11] child1 lo xyz, hi xyz
+//   i[12] child0  i[13] child1   (>= 0 internal node index, < 0 leaf: ~slot)
+//   i[14] parent (-1 for the root)    i[15] sibling (same encoding as a child)
+struct __attribute__((aligned(16))) Node {
+  float box[12];
+  int32_t c0, c1, parent, sibling;
+};
+
+FB_HD uint32_t expand10(uint32_t v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+// 30-bit Morton code of a point in [0,1]^3 (x is the most significant axis)
+FB_HD uint32_t morton30(float x, float y, float z) {
+  x = fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f);
+  y = fminf(fmaxf(y * 1024.0f, 0.0f), 1023.0f);
+  z = fminf(fmaxf(z * 1024.0f, 0.0f), 1023.0f);
+  return (expand10((uint32_t)x) << 2) | (expand10((uint32_t)y) << 1) | expand10((uint32_t)z);
+}
+
+FB_HD int clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)v);
+#else
+  return v ? __builtin_clz(v) : 32;
+#endif
+}
+// common-prefix length of sorted keys i and j (-1 when j is out of range);
+// equal codes fall back to the position, so every key is distinct.
+FB_HD int lcp(const uint32_t* codes, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint32_t a = codes[i], b = codes[j];
+  if (a != b) return clz32(a ^ b);
+  return 32 + clz32((uint32_t)i ^ (uint32_t)j);
+}
+// Karras 2012: range and split of internal node i over n sorted keys (n >= 2).
+FB_HD void karras_node(const uint32_t* codes, int n, int i, int* first, int* last, int* split) {
+  int d = (lcp(codes, n, i, i + 1) - lcp(codes, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = lcp(codes, n, i, i - d);
+  int lmax = 2;
+  while (lcp(codes, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (lcp(codes, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = lcp(codes, n, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (lcp(codes, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  *split = i + s * d + (d < 0 ? -1 : 0);
+  *first = d > 0 ? i : j;
+  *last = d > 0 ? j : i;
+}
+
+// ---------------------------------------------------------------- traversal
+struct Hit {
+  double t;
+  int32_t slot;  // Morton-sorted triangle slot, -1 = miss
+  int32_t cell;  // original cell id
+};
+
+// Conservative float32 slab test of one child box against a segment.
+FB_HD bool slab(const float* b, const float* o, const float* inv, float slack, float tcull,
+                float* tnear) {
+  float t0x = (b[0] - slack - o[0]) * inv[0], t1x = (b[3] + slack - o[0]) * inv[0];
+  float t0y = (b[1] - slack - o[1]) * inv[1], t1y = (b[4] + slack - o[1]) * inv[1];
+  float t0z = (b[2] - slack - o[2]) * inv[2], t1z = (b[5] + slack - o[2]) * inv[2];
+  // fminf/fmaxf drop NaNs (0 * inf), which keeps an axis-parallel ray inside its slab
+  float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+  float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tcull));
+  *tnear = tn;
+  return tn <= tf;
+}
+
+// Stackless traversal: a 64-bit trail holds one "far sibling still pending" bit
+// per level, parent / sibling links walk back up.  Depth <= 62 is guaranteed by
+// the 30+32-bit key length of the LBVH.  NodeFetch: node(i) -> Node by value,
+// parent(i), sibling(i) -> links of node i.
+// Tie-break: smallest t, then lowest original cell id.
+template <class NodeFetch, class Counter>
+FB_HD Hit traverse(const NodeFetch& fetch, const float4* __restrict__ tv0,
+                   const float4* __restrict__ tv1, const float4* __restrict__ tv2, const double* o,
+                   const double* d, const float* dirf, const float* invf, float slack, float tslack,
+                   Counter& cnt) {
+  (void)dirf;
+  Hit best;
+  best.t = DBL_MAX;
+  best.slot = -1;
+  best.cell = 0x7fffffff;
+  float of[3] = {(float)o[0], (float)o[1], (float)o[2]};
+  float tcull = 1.0f + tslack;
+  uint64_t trail = 1;
+  int node = 0;
+  for (;;) {
+    const Node N = fetch.node(node);
+    cnt.node();
+    float tn0, tn1;
+    bool h0 = slab(N.box, of, invf, slack, tcull, &tn0);
+    bool h1 = slab(N.box + 6, of, invf, slack, tcull, &tn1);
+    int c0 = N.c0, c1 = N.c1;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      bool h = side ? h1 : h0;
+      int c = side ? c1 : c0;
+      if (h && c < 0) {
+        int slot = ~c;
+        float4 a = tv0[slot], b = tv1[slot], e = tv2[slot];
+        cnt.tri();
+        float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+        double t, x[3], w[3];
+        if (tri_exact(o, d, P0, P1, P2, best.t, &t, x, w)) {
+#if defined(__CUDA_ARCH__)
+          int cell = __float_as_int(a.w);
+#else
+          int cell;
+          memcpy(&cell, &a.w, 4);
+#endif
+          if (t < best.t || (t == best.t && cell < best.cell)) {
+            best.t = t;
+            best.slot = slot;
+            best.cell = cell;
+            tcull = fminf(tcull, FB_F2F_RU(t) + tslack);
+          }
+        }
+      }
+    }
+    h0 = h0 && c0 >= 0 && tn0 <= tcull;
+    h1 = h1 && c1 >= 0 && tn1 <= tcull;
+    if (h0 || h1) {
+      bool both = h0 && h1;
+      node = both ? (tn1 < tn0 ? c1 : c0) : (h0 ? c0 : c1);
+      trail = (trail << 1) | (both ? 1u : 0u);
+      continue;
+    }
+    // climb until a level with a pending sibling (or the sentinel)
+    for (;;) {
+      if (trail & 1) break;
+      trail >>= 1;
+      node = fetch.parent(node);
+    }
+    if (trail == 1) break;
+    trail ^= 1;
+    node = fetch.sibling(node);
+  }
+  if (best.slot < 0) best.cell = -1;
+  return best;
+}
+
+struct NoCount {
+  FB_HD void node() {}
+  FB_HD void tri() {}
+};
+
+// ---------------------------------------------------------------- shading
+// src/app/fly_by_features.cxx:766-807 (barycentric normal, z, pixel) and
+// src/py/fly_by_features.py:124-150 (use_z / split_z channel assembly).
+FB_HD void shade(const double* o, const double* x, const double* w, const float* n0,
+                 const float* n1, const float* n2, int use_z, int split_z, int enc, double zscale,
+                 float* px) {
+  double nn[3];
+  for (int k = 0; k < 3; k++) {
+    double s = FB_ADD(0.0, FB_MUL((double)n0[k], w[0]));
+    s = FB_ADD(s, FB_MUL((double)n1[k], w[1]));
+    nn[k] = FB_ADD(s, FB_MUL((double)n2[k], w[2]));
+  }
+  double dd[3] = {FB_SUB(o[0], x[0]), FB_SUB(o[1], x[1]), FB_SUB(o[2], x[2])};
+  double z = FB_MUL(norm3(dd), zscale);
+  double e[3];
+  for (int k = 0; k < 3; k++) {
+    if (enc == 2) e[k] = nn[k];
+    else if (enc == 1) e[k] = FB_MUL(FB_ADD(FB_MUL(nn[k], 0.5), 0.5), 255.0);
+    else e[k] = FB_ADD(FB_MUL(nn[k], 0.5), 0.5);
+  }
+  if (!use_z) {
+    for (int k = 0; k < 3; k++) px[k] = (float)e[k];
+  } else if (split_z) {
+    for (int k = 0; k < 3; k++) px[k] = (float)e[k];
+    px[3] = (float)z;
+  } else {
+    for (int k = 0; k < 3; k++) px[k] = (float)FB_MUL(e[k], z);
+  }
+}
+
+}  // namespace fb

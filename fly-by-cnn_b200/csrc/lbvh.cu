@@ -1,0 +1,450 @@
+// lbvh.cu -- GPU LBVH build: Morton codes, hand-written LSD radix sort (no CUB),
+// Karras radix-tree topology, bottom-up AABB refit, top-of-tree-first node
+// layout and the Morton-ordered SoA triangle arrays.
+//
+// Replaces vtkCellLocator::BuildLocator (reference
+// src/app/fly_by_features.cxx:484-486, src/py/predict.py:70-72).
+//
+// Every kernel is an HBM/L2-bound integer pass over T keys or T-1 nodes.
+// Bytes per triangle over the whole build: codes 4 passes x
+// (8 B read for the histogram + 8 B read + 8 B write for the scatter) = 96 B,
+// tree 64 B node + 48 B SoA vertices + 16 B ids written once.
+#include "ctx.h"
+
+namespace fb {
+
+const float* prep_unit_box(flyby_ctx* c);
+
+// ============================================================ exclusive scan
+// 256 threads x 8 items per block; recursion on the block totals.
+#define SCAN_ITEMS 8
+#define SCAN_TILE (256 * SCAN_ITEMS)
+
+__global__ void __launch_bounds__(256) scan_tile_kernel(uint32_t* data, int64_t n, uint32_t* block_sums) {
+  __shared__ uint32_t warp_tot[8];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? data[base + k] : 0u;
+    sum += v[k];
+  }
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++)
+    if (w < warp) woff += warp_tot[w];
+  uint32_t run = woff + incl - sum;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) data[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 255 && block_sums) block_sums[blockIdx.x] = woff + incl;
+}
+
+__global__ void scan_add_kernel(uint32_t* data, int64_t n, const uint32_t* __restrict__ block_offs) {
+  int64_t i = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x;
+  uint32_t off = block_offs[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++, i += 256)
+    if (i < n) data[i] += off;
+}
+
+static int scan_rec(flyby_ctx* c, uint32_t* data, int64_t n, uint32_t* tmp) {
+  int64_t nb = cdiv(n, SCAN_TILE);
+  scan_tile_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(data, n, nb > 1 ? tmp : nullptr);
+  FB_LAUNCH_CHECK(c);
+  if (nb > 1) {
+    int rc = scan_rec(c, tmp, nb, tmp + nb);
+    if (rc) return rc;
+    scan_add_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(data, n, tmp);
+    FB_LAUNCH_CHECK(c);
+  }
+  return FLYBY_OK;
+}
+
+int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp) {
+  if (n <= 0) return FLYBY_OK;
+  // total temp over all recursion levels < n/2048 + n/2048^2 + ... + 8
+  size_t need = 0;
+  for (int64_t m = cdiv(n, SCAN_TILE); m > 1; m = cdiv(m, SCAN_TILE)) need += (size_t)m;
+  need += 16;
+  FB_CUDA(c, tmp.reserve(need * sizeof(uint32_t)));
+  return scan_rec(c, data, n, tmp.as<uint32_t>());
+}
+
+// ============================================================ Morton codes
+__global__ void morton_kernel(const float* __restrict__ v, const int32_t* __restrict__ tris, int64_t T,
+                              const float* __restrict__ ubox, uint32_t* __restrict__ codes,
+                              uint32_t* __restrict__ idx) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  int i0 = tris[3 * c], i1 = tris[3 * c + 1], i2 = tris[3 * c + 2];
+  float q[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float a = v[3 * (int64_t)i0 + k], b = v[3 * (int64_t)i1 + k], e = v[3 * (int64_t)i2 + k];
+    float mn = fminf(a, fminf(b, e)), mx = fmaxf(a, fmaxf(b, e));
+    float ext = ubox[3 + k] - ubox[k];
+    q[k] = ext > 0.f ? (0.5f * (mn + mx) - ubox[k]) / ext : 0.5f;
+  }
+  codes[c] = morton30(q[0], q[1], q[2]);
+  idx[c] = (uint32_t)c;
+}
+
+// ============================================================ radix sort
+// Stable LSD sort of (code, index) pairs, 8 bits per pass.  Per pass:
+//   radix_hist_kernel   per-block digit histogram -> hist[digit][block]
+//   exclusive scan      over the digit-major table = global base per (digit, block)
+//   radix_scatter_kernel stable ranking inside the block with warp match votes
+#define RS_THREADS 256
+#define RS_ITEMS 8
+#define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 keys per block, 256 per warp
+
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist,
+                  int nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    int64_t i = base + k * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n,
+                     int shift, const uint32_t* __restrict__ hist_scanned, int nblocks,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  // per-warp digit counts, turned into per-warp bases, then used as running cursors
+  __shared__ uint32_t cnt[8][256];
+  __shared__ uint32_t gbase[256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 8 * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+  gbase[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+  __syncthreads();
+  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (RS_TILE / 8);
+  uint32_t k[RS_ITEMS], v[RS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    int64_t i = wbase + r * 32 + lane;
+    bool ok = i < n;
+    k[r] = ok ? keys[i] : 0u;
+    v[r] = ok ? vals[i] : 0u;
+    if (ok) atomicAdd(&cnt[warp][(k[r] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  // exclusive prefix over warps for each digit (thread d owns digit d)
+  {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      uint32_t t = cnt[w][threadIdx.x];
+      cnt[w][threadIdx.x] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    int64_t i = wbase + r * 32 + lane;
+    bool ok = i < n;
+    uint32_t d = (k[r] >> shift) & 255u;
+    uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : (0x100u | (uint32_t)lane));
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t pos = 0;
+    if (ok) pos = gbase[d] + cnt[warp][d] + rank;
+    __syncwarp();
+    if (ok && rank == 0) cnt[warp][d] += __popc(peers);
+    __syncwarp();
+    if (ok) {
+      keys_out[pos] = k[r];
+      vals_out[pos] = v[r];
+    }
+  }
+}
+
+// ============================================================ tree
+// sorted slot -> SoA vertices, ids and leaf boxes
+__global__ void reorder_kernel(const float* __restrict__ v, const int32_t* __restrict__ tris, int64_t T,
+                               const uint32_t* __restrict__ idx, float4* __restrict__ tv0,
+                               float4* __restrict__ tv1, float4* __restrict__ tv2,
+                               int4* __restrict__ tvid, float* __restrict__ leaf_box) {
+  int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= T) return;
+  int cell = (int)idx[s];
+  int i0 = tris[3 * (int64_t)cell], i1 = tris[3 * (int64_t)cell + 1], i2 = tris[3 * (int64_t)cell + 2];
+  float p0[3], p1[3], p2[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    p0[k] = v[3 * (int64_t)i0 + k];
+    p1[k] = v[3 * (int64_t)i1 + k];
+    p2[k] = v[3 * (int64_t)i2 + k];
+    leaf_box[6 * s + k] = fminf(p0[k], fminf(p1[k], p2[k]));
+    leaf_box[6 * s + 3 + k] = fmaxf(p0[k], fmaxf(p1[k], p2[k]));
+  }
+  tv0[s] = make_float4(p0[0], p0[1], p0[2], __int_as_float(cell));
+  tv1[s] = make_float4(p1[0], p1[1], p1[2], 0.f);
+  tv2[s] = make_float4(p2[0], p2[1], p2[2], 0.f);
+  tvid[s] = make_int4(i0, i1, i2, cell);
+}
+
+// knode[i] = (child0, child1, parent, arrival flag); leaf children are ~slot
+__global__ void karras_kernel(const uint32_t* __restrict__ codes, int n, int4* __restrict__ knode,
+                              int32_t* __restrict__ leaf_parent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int first, last, split;
+  karras_node(codes, n, i, &first, &last, &split);
+  int c0 = (split == first) ? ~split : split;
+  int c1 = (split + 1 == last) ? ~(split + 1) : split + 1;
+  knode[i].x = c0;
+  knode[i].y = c1;
+  knode[i].w = 0;
+  if (i == 0) knode[0].z = -1;
+  if (c0 >= 0) knode[c0].z = i; else leaf_parent[~c0] = i;
+  if (c1 >= 0) knode[c1].z = i; else leaf_parent[~c1] = i;
+}
+
+// bottom-up: the second thread to reach a node merges its children's boxes
+__global__ void refit_kernel(int n, int4* knode, const int32_t* __restrict__ leaf_parent,
+                             const float* __restrict__ leaf_box, float* node_box) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int node = leaf_parent[s];
+  while (node >= 0) {
+    __threadfence();
+    if (atomicAdd(&knode[node].w, 1) == 0) return;  // first arrival leaves
+    __threadfence();
+    int c0 = __ldcg(&knode[node].x), c1 = __ldcg(&knode[node].y);
+    const float* b0 = c0 < 0 ? leaf_box + 6 * (int64_t)(~c0) : node_box + 6 * (int64_t)c0;
+    const float* b1 = c1 < 0 ? leaf_box + 6 * (int64_t)(~c1) : node_box + 6 * (int64_t)c1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      __stcg(&node_box[6 * (int64_t)node + k], fminf(__ldcg(b0 + k), __ldcg(b1 + k)));
+      __stcg(&node_box[6 * (int64_t)node + 3 + k], fmaxf(__ldcg(b0 + 3 + k), __ldcg(b1 + 3 + k)));
+    }
+    node = __ldcg(&knode[node].z);
+  }
+}
+
+// breadth-first prefix of the tree (at most ntop_max nodes) -> remap[karras] = rank
+// One block of 1024 threads; every level is appended with a block-wide scan so
+// the order is deterministic.
+__global__ void __launch_bounds__(1024)
+top_bfs_kernel(const int4* __restrict__ knode, int n_internal, int ntop_max, int32_t* remap,
+               int32_t* topflag, int32_t* n_top_out) {
+  __shared__ int32_t order[1024];
+  __shared__ int32_t warp_tot[32];
+  __shared__ int head_s, count_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { order[0] = 0; head_s = 0; count_s = 1; }
+  __syncthreads();
+  for (;;) {
+    int head = head_s, count = count_s;
+    if (head >= count || count >= ntop_max) break;
+    int item = head + tid;
+    int c0 = -1, c1 = -1, k = 0;
+    if (item < count) {
+      int4 kn = knode[order[item]];
+      if (kn.x >= 0) { c0 = kn.x; k++; }
+      if (kn.y >= 0) { c1 = kn.y; k++; }
+    }
+    int incl = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int w = 0; w < 32; w++) {
+      if (w < warp) woff += warp_tot[w];
+      total += warp_tot[w];
+    }
+    int pos = count + woff + incl - k;
+    if (c0 >= 0) { if (pos < ntop_max) order[pos] = c0; pos++; }
+    if (c1 >= 0) { if (pos < ntop_max) order[pos] = c1; }
+    __syncthreads();
+    if (tid == 0) {
+      head_s = count;
+      int nc = count + total;
+      count_s = nc < ntop_max ? nc : ntop_max;
+    }
+    __syncthreads();
+  }
+  int count = count_s;
+  if (count > n_internal) count = n_internal;
+  for (int i = tid; i < count; i += blockDim.x) {
+    remap[order[i]] = i;
+    topflag[order[i]] = 0;  // 0 = top (not counted by the non-top scan)
+  }
+  if (tid == 0) *n_top_out = count;
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, int64_t n, uint32_t v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// final index of a Karras node: top nodes keep their BFS rank, the rest follow
+// in Karras order (which keeps subtrees contiguous)
+__device__ __forceinline__ int final_index(int k, const int32_t* remap, const uint32_t* nontop_scan,
+                                           const int32_t* nontop_flag, int n_top) {
+  return nontop_flag[k] ? n_top + (int)nontop_scan[k] : remap[k];
+}
+
+__global__ void layout_kernel(int n_internal, const int4* __restrict__ knode,
+                              const float* __restrict__ leaf_box, const float* __restrict__ node_box,
+                              const int32_t* __restrict__ remap, const uint32_t* __restrict__ nontop_scan,
+                              const int32_t* __restrict__ nontop_flag, const int32_t* __restrict__ n_top_p,
+                              Node* __restrict__ nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal) return;
+  const int n_top = *n_top_p;
+  int4 kn = knode[i];
+  Node out;
+  const float* b0 = kn.x < 0 ? leaf_box + 6 * (int64_t)(~kn.x) : node_box + 6 * (int64_t)kn.x;
+  const float* b1 = kn.y < 0 ? leaf_box + 6 * (int64_t)(~kn.y) : node_box + 6 * (int64_t)kn.y;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    out.box[k] = b0[k];
+    out.box[6 + k] = b1[k];
+  }
+  out.c0 = kn.x < 0 ? kn.x : final_index(kn.x, remap, nontop_scan, nontop_flag, n_top);
+  out.c1 = kn.y < 0 ? kn.y : final_index(kn.y, remap, nontop_scan, nontop_flag, n_top);
+  int sib = -1;
+  if (kn.z >= 0) {
+    int4 pn = knode[kn.z];
+    int s = (pn.x == i) ? pn.y : pn.x;
+    sib = s < 0 ? s : final_index(s, remap, nontop_scan, nontop_flag, n_top);
+    out.parent = final_index(kn.z, remap, nontop_scan, nontop_flag, n_top);
+  } else {
+    out.parent = -1;
+  }
+  out.sibling = sib;
+  nodes[final_index(i, remap, nontop_scan, nontop_flag, n_top)] = out;
+}
+
+// a mesh with a single triangle: one node with the leaf as both children (the
+// duplicate test of the same cell cannot change the result)
+__global__ void single_leaf_kernel(const float* __restrict__ leaf_box, Node* nodes) {
+  if (threadIdx.x != 0) return;
+  Node out;
+  for (int k = 0; k < 6; k++) { out.box[k] = leaf_box[k]; out.box[6 + k] = leaf_box[k]; }
+  out.c0 = ~0;
+  out.c1 = ~0;
+  out.parent = -1;
+  out.sibling = -1;
+  nodes[0] = out;
+}
+
+// ============================================================ driver
+#define FB_NTOP_MAX 1024
+
+int lbvh_run(flyby_ctx* c) {
+  MeshDev& m = c->mesh;
+  cudaStream_t st = c->stream;
+  const int64_t T = m.T;
+  m.n_nodes = 0;
+  m.n_top_dev = nullptr;
+  if (T == 0) return FLYBY_OK;
+  const int nblocks = (int)cdiv(T, RS_TILE);
+  const size_t Tz = (size_t)T;
+  FB_CUDA(c, m.codes.reserve(4 * Tz));
+  FB_CUDA(c, m.codes_alt.reserve(4 * Tz));
+  FB_CUDA(c, m.idx.reserve(4 * Tz));
+  FB_CUDA(c, m.idx_alt.reserve(4 * Tz));
+  FB_CUDA(c, m.hist.reserve(4 * 256 * (size_t)nblocks));
+  FB_CUDA(c, m.leaf_box.reserve(24 * Tz));
+  FB_CUDA(c, m.node_box.reserve(24 * Tz));
+  FB_CUDA(c, m.knode.reserve(16 * Tz));
+  FB_CUDA(c, m.remap.reserve(4 * Tz + 64));
+  FB_CUDA(c, m.topflag.reserve(4 * Tz + 64));
+  FB_CUDA(c, m.nodes.reserve(sizeof(Node) * Tz));
+  FB_CUDA(c, m.tv0.reserve(16 * Tz));
+  FB_CUDA(c, m.tv1.reserve(16 * Tz));
+  FB_CUDA(c, m.tv2.reserve(16 * Tz));
+  FB_CUDA(c, m.tvid.reserve(16 * Tz));
+
+  const unsigned gT = (unsigned)cdiv(T, 256);
+  morton_kernel<<<gT, 256, 0, st>>>(m.verts.as<float>(), m.tris.as<int32_t>(), T, prep_unit_box(c),
+                                    m.codes.as<uint32_t>(), m.idx.as<uint32_t>());
+  FB_LAUNCH_CHECK(c);
+  uint32_t *k0 = m.codes.as<uint32_t>(), *k1 = m.codes_alt.as<uint32_t>();
+  uint32_t *v0 = m.idx.as<uint32_t>(), *v1 = m.idx_alt.as<uint32_t>();
+  for (int pass = 0; pass < 4; pass++) {
+    int shift = 8 * pass;
+    radix_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, T, shift, m.hist.as<uint32_t>(), nblocks);
+    FB_LAUNCH_CHECK(c);
+    int rc = exclusive_scan_u32(c, m.hist.as<uint32_t>(), 256 * (int64_t)nblocks, m.scan_tmp);
+    if (rc) return rc;
+    radix_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, v0, T, shift, m.hist.as<uint32_t>(),
+                                                         nblocks, k1, v1);
+    FB_LAUNCH_CHECK(c);
+    uint32_t* t = k0; k0 = k1; k1 = t;
+    t = v0; v0 = v1; v1 = t;
+  }
+  // after 4 passes the sorted data is back in codes / idx
+  FB_CUDA(c, cudaEventRecord(c->ev[3], st));
+
+  reorder_kernel<<<gT, 256, 0, st>>>(m.verts.as<float>(), m.tris.as<int32_t>(), T, v0,
+                                     m.tv0.as<float4>(), m.tv1.as<float4>(), m.tv2.as<float4>(),
+                                     m.tvid.as<int4>(), m.leaf_box.as<float>());
+  FB_LAUNCH_CHECK(c);
+  if (T == 1) {
+    single_leaf_kernel<<<1, 32, 0, st>>>(m.leaf_box.as<float>(), m.nodes.as<Node>());
+    FB_LAUNCH_CHECK(c);
+    fill_u32_kernel<<<1, 32, 0, st>>>(m.remap.as<uint32_t>(), 1, 1u);
+    FB_LAUNCH_CHECK(c);
+    m.n_nodes = 1;
+    m.n_top_dev = m.remap.as<int32_t>();
+    FB_CUDA(c, cudaEventRecord(c->ev[4], st));
+    return FLYBY_OK;
+  }
+  const int n = (int)T, ni = n - 1;
+  int32_t* leaf_parent = m.idx_alt.as<int32_t>();  // sort scratch is free again
+  karras_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(k0, n, m.knode.as<int4>(), leaf_parent);
+  FB_LAUNCH_CHECK(c);
+  refit_kernel<<<gT, 256, 0, st>>>(n, m.knode.as<int4>(), leaf_parent, m.leaf_box.as<float>(),
+                                   m.node_box.as<float>());
+  FB_LAUNCH_CHECK(c);
+  // top-of-tree first: flag = 1 for every node, the BFS clears it for the top set
+  int32_t* n_top_dev = m.remap.as<int32_t>() + ni;  // one spare word behind the table
+  fill_u32_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(m.topflag.as<uint32_t>(), ni, 1u);
+  FB_LAUNCH_CHECK(c);
+  top_bfs_kernel<<<1, 1024, 0, st>>>(m.knode.as<int4>(), ni, FB_NTOP_MAX, m.remap.as<int32_t>(),
+                                     m.topflag.as<int32_t>(), n_top_dev);
+  FB_LAUNCH_CHECK(c);
+  // scan of the non-top flags (kept separately: the layout needs flag and rank)
+  uint32_t* nontop_scan = m.codes_alt.as<uint32_t>();
+  FB_CUDA(c, cudaMemcpyAsync(nontop_scan, m.topflag.p, 4 * (size_t)ni, cudaMemcpyDeviceToDevice, st));
+  int rc = exclusive_scan_u32(c, nontop_scan, ni, m.scan_tmp);
+  if (rc) return rc;
+  layout_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(
+      ni, m.knode.as<int4>(), m.leaf_box.as<float>(), m.node_box.as<float>(), m.remap.as<int32_t>(),
+      nontop_scan, m.topflag.as<int32_t>(), n_top_dev, m.nodes.as<Node>());
+  FB_LAUNCH_CHECK(c);
+  FB_CUDA(c, cudaEventRecord(c->ev[4], st));
+  m.n_nodes = ni;
+  m.n_top_dev = n_top_dev;
+  return FLYBY_OK;
+}
+
+}  // namespace fb

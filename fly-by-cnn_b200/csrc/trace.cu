@@ -1,0 +1,450 @@
+// trace.cu -- view setup, ray generation, LBVH traversal, shading and tensor write.
+//
+// Replaces the hot loops of the reference's ray-cast engine
+// (src/app/fly_by_features.cxx:652-852: per view, per plane point,
+// vtkCellLocator::IntersectWithLine + barycentric normal + depth) and the
+// channel assembly of FlyByGenerator.getFlyBy (src/py/fly_by_features.py:124-150).
+//
+// render_kernel is a persistent kernel: one CTA slot per SM x occupancy, each
+// warp pulls 8x4-pixel tiles from a global counter.  Rays that miss the mesh
+// bounds are written as background at once; the survivors are compacted into a
+// per-warp queue with warp votes so that every traversal runs 32 live rays.
+// The top of the LBVH (breadth-first prefix, <= 1024 nodes = 64 KB) is staged in
+// shared memory with one bulk async copy (cp.async.bulk + mbarrier).
+// Traversal is stackless (flyby_core.cuh); the triangle decision and the output
+// values are exact double arithmetic.
+//
+// Roofline: algorithmic bytes per ray = 4*C + 4 (+8 with t); the
+// kernel is bound by L1/L2 node-fetch latency, not HBM.
+#include "ctx.h"
+
+namespace fb {
+
+const float* prep_unit_box(flyby_ctx* c);
+
+// ---------------------------------------------------------------- view setup
+__global__ void view_setup_kernel(const float* __restrict__ pts, int n, double radius, double plane_scale,
+                                  double spacing, View* __restrict__ views) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  View v;
+  float sp[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  view_setup(sp, radius, plane_scale, spacing, &v);
+  views[i] = v;
+}
+
+int views_setup(flyby_ctx* c, const flyby_render_opts* o) {
+  if (c->n_views <= 0) return fail(c, FLYBY_ERR_INVALID, "no viewpoints set");
+  FB_CUDA(c, c->views.reserve(sizeof(View) * (size_t)c->n_views));
+  view_setup_kernel<<<(unsigned)cdiv(c->n_views, 64), 64, 0, c->stream>>>(
+      c->view_pts.as<float>(), c->n_views, c->radius, o->plane_scale, o->plane_spacing, c->views.as<View>());
+  FB_LAUNCH_CHECK(c);
+  return FLYBY_OK;
+}
+
+// ---------------------------------------------------------------- ray dump (parity of a5)
+__global__ void rays_kernel(const View* __restrict__ views, int view_begin, int n_views, int res,
+                            double spacing, double* __restrict__ out) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t per = (int64_t)res * res;
+  if (p >= per * n_views) return;
+  int v = (int)(p / per);
+  int pix = (int)(p % per);
+  const View& vw = views[view_begin + v];
+  double o[3];
+  view_ray(vw, res, pix % res, pix / res, spacing, o);
+  double* r = out + 6 * p;
+  for (int k = 0; k < 3; k++) {
+    r[k] = o[k];
+    r[3 + k] = FB_ADD(o[k], vw.dir[k]);
+  }
+}
+
+int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double* rays) {
+  int64_t n = (int64_t)(ve - vb) * res * res;
+  rays_kernel<<<(unsigned)cdiv(n, 256), 256, 0, c->stream>>>(c->views.as<View>(), vb, ve - vb, res,
+                                                             o->plane_spacing, rays);
+  FB_LAUNCH_CHECK(c);
+  return FLYBY_OK;
+}
+
+// ---------------------------------------------------------------- node fetch
+struct GlobalFetch {
+  const Node* gl;
+  __device__ __forceinline__ Node node(int i) const {
+    const float4* p = reinterpret_cast<const float4*>(gl + i);
+    Node n;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    n.box[0] = a.x; n.box[1] = a.y; n.box[2] = a.z; n.box[3] = a.w;
+    n.box[4] = b.x; n.box[5] = b.y; n.box[6] = b.z; n.box[7] = b.w;
+    n.box[8] = c.x; n.box[9] = c.y; n.box[10] = c.z; n.box[11] = c.w;
+    n.c0 = __float_as_int(d.x); n.c1 = __float_as_int(d.y);
+    n.parent = __float_as_int(d.z); n.sibling = __float_as_int(d.w);
+    return n;
+  }
+  __device__ __forceinline__ int parent(int i) const { return __ldg(&gl[i].parent); }
+  __device__ __forceinline__ int sibling(int i) const { return __ldg(&gl[i].sibling); }
+};
+
+// top-of-tree in shared memory, the rest through the read-only path
+struct TopFetch {
+  const Node* gl;
+  const Node* sm;
+  int ntop;
+  __device__ __forceinline__ Node node(int i) const {
+    Node n;
+    float4 a, b, c, d;
+    if (i < ntop) {
+      const float4* p = reinterpret_cast<const float4*>(sm + i);
+      a = p[0]; b = p[1]; c = p[2]; d = p[3];
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(gl + i);
+      a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); d = __ldg(p + 3);
+    }
+    n.box[0] = a.x; n.box[1] = a.y; n.box[2] = a.z; n.box[3] = a.w;
+    n.box[4] = b.x; n.box[5] = b.y; n.box[6] = b.z; n.box[7] = b.w;
+    n.box[8] = c.x; n.box[9] = c.y; n.box[10] = c.z; n.box[11] = c.w;
+    n.c0 = __float_as_int(d.x); n.c1 = __float_as_int(d.y);
+    n.parent = __float_as_int(d.z); n.sibling = __float_as_int(d.w);
+    return n;
+  }
+  __device__ __forceinline__ int parent(int i) const {
+    return i < ntop ? sm[i].parent : __ldg(&gl[i].parent);
+  }
+  __device__ __forceinline__ int sibling(int i) const {
+    return i < ntop ? sm[i].sibling : __ldg(&gl[i].sibling);
+  }
+};
+
+struct WorkCount {
+  unsigned int nodes = 0, tris = 0;
+  __device__ __forceinline__ void node() { nodes++; }
+  __device__ __forceinline__ void tri() { tris++; }
+};
+
+// ---------------------------------------------------------------- render
+struct RenderParams {
+  const Node* nodes;
+  const int32_t* n_top_dev;
+  const float4 *tv0, *tv1, *tv2;
+  const int4* tvid;
+  const float4* normals;
+  const View* views;
+  const float* ubox;
+  int view_begin, n_views, res;
+  int use_z, split_z, enc, channels;
+  double zscale, spacing;
+  float* feat;
+  int32_t* ids;
+  double* tt;
+  unsigned long long* counters;  // [0] tile counter, [1] nodes, [2] tris, [3] hits
+  int tiles_x, tiles_y;          // padded tile grid (x even, y multiple of 4)
+  long long n_tiles;
+  int top_cap;                   // nodes that fit in the dynamic shared memory
+};
+
+#define RK_THREADS 256
+#define RK_WARPS (RK_THREADS / 32)
+#define RK_QCAP 64
+
+__device__ __forceinline__ void write_pixel(const RenderParams& p, int64_t pix, const float* px, int cell,
+                                            double t) {
+  if (p.feat) {
+    if (p.channels == 4) {
+      __stcs(reinterpret_cast<float4*>(p.feat) + pix, make_float4(px[0], px[1], px[2], px[3]));
+    } else {
+      float* o = p.feat + pix * 3;
+      __stcs(o, px[0]);
+      __stcs(o + 1, px[1]);
+      __stcs(o + 2, px[2]);
+    }
+  }
+  if (p.ids) __stcs(p.ids + pix, cell);
+  if (p.tt) __stcs(p.tt + pix, t);
+}
+
+// conservative float32 test of a ray against the mesh bounds (same maths as the
+// node test, so a ray rejected here would also be rejected at the root)
+__device__ __forceinline__ bool hits_bounds(const float* ubox, const double* o, const View& vw) {
+  float of[3] = {(float)o[0], (float)o[1], (float)o[2]};
+  float tn;
+  return slab(ubox, of, vw.invf, vw.slack, 1.0f + vw.tslack, &tn);
+}
+
+template <bool USE_TOP, bool COUNT>
+__global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Node* top = reinterpret_cast<Node*>(smem_raw);
+  uint32_t* queues = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.top_cap * sizeof(Node));
+  __shared__ float s_ubox[6];
+  __shared__ __align__(8) unsigned long long s_bar;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int ntop = 0;
+  if (USE_TOP) {
+    ntop = *p.n_top_dev;
+    if (ntop > p.top_cap) ntop = p.top_cap;
+  }
+  if (threadIdx.x < 6) s_ubox[threadIdx.x] = p.ubox[threadIdx.x];
+
+  if (USE_TOP && ntop > 0) {
+    // one bulk async copy (TMA engine, UBLKCP) of the top-of-tree block
+    const uint32_t bytes = (uint32_t)ntop * (uint32_t)sizeof(Node);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(top);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+          "l"(p.nodes), "r"(bytes), "r"(bar)
+          : "memory");
+    }
+    // everybody waits for phase 0
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, q;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(0u)
+          : "memory");
+    }
+  } else {
+    __syncthreads();
+  }
+
+  uint32_t* q = queues + warp * RK_QCAP;
+  int qn = 0;
+  bool tiles_left = true;
+  const int res = p.res;
+  const int64_t per_view = (int64_t)res * res;
+  const long long tiles_per_view = (long long)p.tiles_x * p.tiles_y;
+  const int groups_x = p.tiles_x >> 1;
+  WorkCount wc;
+  unsigned int n_hits = 0;
+
+  for (;;) {
+    // ---- refill the queue until a full warp of live rays is available
+    while (qn < 32 && tiles_left) {
+      long long tile = 0;
+      if (lane == 0) tile = (long long)atomicAdd(p.counters, 1ull);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= p.n_tiles) {
+        tiles_left = false;
+        break;
+      }
+      int v = (int)(tile / tiles_per_view);
+      int tl = (int)(tile % tiles_per_view);
+      // 8 consecutive tiles form a 16x16-pixel block (2 tiles wide, 4 high)
+      int g = tl >> 3, r = tl & 7;
+      int tx = (g % groups_x) * 2 + (r & 1);
+      int ty = (g / groups_x) * 4 + (r >> 1);
+      int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+      bool valid = px < res && py < res;
+      bool live = false;
+      uint32_t pid = 0;
+      if (valid) {
+        const View& vw = p.views[p.view_begin + v];
+        double o[3];
+        view_ray(vw, res, px, py, p.spacing, o);
+        live = hits_bounds(s_ubox, o, vw);
+        pid = (uint32_t)((int64_t)v * per_view + (int64_t)py * res + px);
+        if (!live) {
+          float zero[4] = {0.f, 0.f, 0.f, 0.f};
+          write_pixel(p, (int64_t)pid, zero, -1, -1.0);
+        }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, live);
+      if (live) q[qn + __popc(m & ((1u << lane) - 1u))] = pid;
+      qn += __popc(m);
+      __syncwarp();
+    }
+    if (qn == 0) break;
+    // ---- take the oldest 32 (or the remainder once the tiles ran out)
+    const int take = qn < 32 ? qn : 32;
+    const bool active = lane < take;
+    uint32_t pid = active ? q[lane] : 0u;
+    __syncwarp();
+    {
+      uint32_t moved = (lane + 32 < qn) ? q[lane + 32] : 0u;
+      __syncwarp();
+      if (lane + 32 < qn) q[lane] = moved;
+      __syncwarp();
+    }
+    qn -= take;
+
+    if (active) {
+      int v = (int)(pid / (uint32_t)per_view);
+      int pix = (int)(pid % (uint32_t)per_view);
+      const View& vw = p.views[p.view_begin + v];
+      double o[3];
+      view_ray(vw, res, pix % res, pix / res, p.spacing, o);
+      double d[3] = {vw.dir[0], vw.dir[1], vw.dir[2]};
+      float invf[3] = {vw.invf[0], vw.invf[1], vw.invf[2]};
+      Hit h;
+      if (USE_TOP) {
+        TopFetch f{p.nodes, top, ntop};
+        if (COUNT) h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, wc);
+        else { NoCount nc; h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, nc); }
+      } else {
+        GlobalFetch f{p.nodes};
+        if (COUNT) h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, wc);
+        else { NoCount nc; h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, nc); }
+      }
+      float px[4] = {0.f, 0.f, 0.f, 0.f};
+      double t = -1.0;
+      if (h.slot >= 0) {
+        n_hits++;
+        float4 a = p.tv0[h.slot], b = p.tv1[h.slot], e = p.tv2[h.slot];
+        float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+        double x[3], w[3];
+        tri_exact(o, d, P0, P1, P2, DBL_MAX, &t, x, w);
+        if (p.feat) {
+          int4 vid = p.tvid[h.slot];
+          float4 n0 = __ldg(p.normals + vid.x), n1 = __ldg(p.normals + vid.y), n2 = __ldg(p.normals + vid.z);
+          float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
+          shade(o, x, w, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px);
+        }
+      }
+      write_pixel(p, (int64_t)pid, px, h.cell, t);
+    }
+    __syncwarp();
+  }
+  if (COUNT) {
+    atomicAdd(p.counters + 1, (unsigned long long)wc.nodes);
+    atomicAdd(p.counters + 2, (unsigned long long)wc.tris);
+  }
+  // hit count: one atomic per warp
+  for (int o2 = 16; o2 > 0; o2 >>= 1) n_hits += __shfl_xor_sync(0xffffffffu, n_hits, o2);
+  if (lane == 0 && n_hits) atomicAdd(p.counters + 3, (unsigned long long)n_hits);
+}
+
+__global__ void fill_miss_kernel(float* feat, int32_t* ids, double* tt, int64_t n_pix, int channels) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  if (feat) for (int k = 0; k < channels; k++) feat[i * channels + k] = 0.f;
+  if (ids) ids[i] = -1;
+  if (tt) tt[i] = -1.0;
+}
+
+static int g_use_top = 1;  // FLYBY_NO_SMEM_TOP=1 disables the shared-memory top (A/B measurements)
+
+int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
+                 int32_t* ids, double* tt) {
+  MeshDev& m = c->mesh;
+  cudaStream_t st = c->stream;
+  const int nv = ve - vb;
+  const int64_t n_pix = (int64_t)nv * res * res;
+  if (n_pix >= (int64_t)1 << 32) return fail(c, FLYBY_ERR_INVALID, "more than 2^32 rays in one render call");
+  const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  FB_CUDA(c, cudaEventRecord(c->ev[5], st));
+  if (m.T == 0) {
+    fill_miss_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(feat, ids, tt, n_pix, channels);
+    FB_LAUNCH_CHECK(c);
+    FB_CUDA(c, cudaEventRecord(c->ev[6], st));
+    return FLYBY_OK;
+  }
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("FLYBY_NO_SMEM_TOP");
+    if (e && e[0] == '1') g_use_top = 0;
+    env_read = true;
+  }
+  RenderParams p;
+  p.nodes = m.nodes.as<Node>();
+  p.n_top_dev = m.n_top_dev;
+  p.tv0 = m.tv0.as<float4>(); p.tv1 = m.tv1.as<float4>(); p.tv2 = m.tv2.as<float4>();
+  p.tvid = m.tvid.as<int4>();
+  p.normals = m.normals.as<float4>();
+  p.views = c->views.as<View>();
+  p.ubox = prep_unit_box(c);
+  p.view_begin = vb; p.n_views = nv; p.res = res;
+  p.use_z = o->use_z; p.split_z = o->split_z; p.enc = o->normal_encoding; p.channels = channels;
+  p.zscale = o->z_scale; p.spacing = o->plane_spacing;
+  p.feat = feat; p.ids = ids; p.tt = tt;
+  p.counters = c->counters.as<unsigned long long>();
+  int tx = (int)cdiv(res, 8), ty = (int)cdiv(res, 4);
+  p.tiles_x = (tx + 1) & ~1;
+  p.tiles_y = (ty + 3) & ~3;
+  p.n_tiles = (long long)p.tiles_x * p.tiles_y * nv;
+  p.top_cap = g_use_top ? 1024 : 0;
+  FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), st));
+  const size_t smem = (size_t)p.top_cap * sizeof(Node) + RK_WARPS * RK_QCAP * sizeof(uint32_t);
+  auto launch = [&](auto kern) -> int {
+    FB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    FB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RK_THREADS, smem));
+    if (occ < 1) occ = 1;
+    long long want = cdiv(p.n_tiles, RK_WARPS);
+    long long grid = (long long)c->sm_count * occ;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, RK_THREADS, smem, st>>>(p);
+    FB_LAUNCH_CHECK(c);
+    return FLYBY_OK;
+  };
+  int rc;
+  if (g_use_top) rc = c->count_work ? launch(render_kernel<true, true>) : launch(render_kernel<true, false>);
+  else rc = c->count_work ? launch(render_kernel<false, true>) : launch(render_kernel<false, false>);
+  if (rc) return rc;
+  FB_CUDA(c, cudaEventRecord(c->ev[6], st));
+  c->stats.n_rays = n_pix;
+  return FLYBY_OK;
+}
+
+// ---------------------------------------------------------------- generic segments
+// vtkCellLocator::IntersectWithLine for caller-supplied segments (predict.py:128)
+__global__ void cast_kernel(const Node* __restrict__ nodes, const float4* __restrict__ tv0,
+                            const float4* __restrict__ tv1, const float4* __restrict__ tv2, int has_tris,
+                            const double* __restrict__ rays, int64_t n, int32_t* ids, double* tt, double* ww) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double o[3] = {rays[6 * r], rays[6 * r + 1], rays[6 * r + 2]};
+  double d[3] = {FB_SUB(rays[6 * r + 3], o[0]), FB_SUB(rays[6 * r + 4], o[1]), FB_SUB(rays[6 * r + 5], o[2])};
+  Hit h;
+  h.slot = -1; h.cell = -1; h.t = DBL_MAX;
+  double w[3] = {0, 0, 0}, t = -1.0;
+  if (has_tris) {
+    float dirf[3], invf[3];
+    double amax = 1.0;
+    for (int k = 0; k < 3; k++) {
+      dirf[k] = (float)d[k];
+      invf[k] = 1.0f / dirf[k];
+      double reach = fabs(o[k]) + fabs(d[k]);
+      amax = reach > amax ? reach : amax;
+    }
+    float slack = (float)(amax * 64.0 * 5.9604644775390625e-08);
+    double dl = norm3(d);
+    float tslack = (float)(dl > 0.0 ? 4.0 * (double)slack / dl : 0.0);
+    GlobalFetch f{nodes};
+    NoCount nc;
+    h = traverse(f, tv0, tv1, tv2, o, d, dirf, invf, slack, tslack, nc);
+    if (h.slot >= 0) {
+      float4 a = tv0[h.slot], b = tv1[h.slot], e = tv2[h.slot];
+      float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+      double x[3];
+      tri_exact(o, d, P0, P1, P2, DBL_MAX, &t, x, w);
+    }
+  }
+  if (ids) ids[r] = h.cell;
+  if (tt) tt[r] = t;
+  if (ww) for (int k = 0; k < 3; k++) ww[3 * r + k] = w[k];
+}
+
+int trace_cast(flyby_ctx* c, const double* rays, int64_t n, int32_t* ids, double* tt, double* w) {
+  MeshDev& m = c->mesh;
+  if (n <= 0) return FLYBY_OK;
+  cast_kernel<<<(unsigned)cdiv(n, 128), 128, 0, c->stream>>>(
+      m.nodes.as<Node>(), m.tv0.as<float4>(), m.tv1.as<float4>(), m.tv2.as<float4>(), m.T > 0 ? 1 : 0,
+      rays, n, ids, tt, w);
+  FB_LAUNCH_CHECK(c);
+  return FLYBY_OK;
+}
+
+}  // namespace fb

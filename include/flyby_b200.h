@@ -1,0 +1,185 @@
+/*
+ * flyby_b200.h -- C-ABI of the B200-native fly-by feature extractor.
+ *
+ * The reference (DCBIA-OrthoLab/Fly-by-CNN) has no FFI layer: the path sits
+ * behind the Python class FlyByGenerator / CLI of src/py/fly_by_features.py and
+ * the C++ tool src/app/fly_by_features.cxx.  Each entry point below names the
+ * reference code it replaces (paths relative to the reference repo).  The
+ * Python host in fly-by-cnn_b200/flyby_b200/ binds these with ctypes and keeps
+ * the reference's class / function / CLI names on top.
+ *
+ * Conventions
+ *  - plain C types only; every call returns a flyby_status (0 = ok) and stores
+ *    a message retrievable with flyby_last_error(); nothing throws.
+ *  - a context is bound to one CUDA device and one stream; calls on one
+ *    context are not thread-safe, different contexts are independent.
+ *  - every buffer argument may be HOST or DEVICE memory (detected with
+ *    cudaPointerGetAttributes).  Device buffers are used in place and the call
+ *    returns without synchronising (work is ordered on the context stream);
+ *    host buffers are staged through context-owned device scratch and the call
+ *    returns after the copy back completed.
+ *  - there is no CPU implementation behind this API: without a CUDA device
+ *    flyby_create fails with FLYBY_ERR_CUDA.
+ */
+#ifndef FLYBY_B200_H
+#define FLYBY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLYBY_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FLYBY_API __attribute__((visibility("default")))
+#else
+#define FLYBY_API
+#endif
+
+typedef enum {
+  FLYBY_OK = 0,
+  FLYBY_ERR_INVALID = 1, /* bad argument / call order */
+  FLYBY_ERR_CUDA = 2,    /* CUDA runtime error (message has the detail) */
+  FLYBY_ERR_NCCL = 3,    /* NCCL missing or failed */
+  FLYBY_ERR_UNSUPPORTED = 4
+} flyby_status;
+
+typedef struct flyby_ctx flyby_ctx;
+
+/* Mesh normalisation: src/py/utils.py:249-290 (ScaleSurf/GetUnitSurf) and
+ * src/app/fly_by_features.cxx:393-450. */
+typedef struct {
+  int32_t centre_mode;   /* 0 bbox mid (utils.py:263-265), 1 centre of mass (cxx:397-403) */
+  int32_t scale_mode;    /* 0 1/|bbox_max-centre| (utils.py:281), 1 1/max|p-centre| (cxx:429-435) */
+  int32_t has_translate; /* use translate[] as the centre (--translate, utils.py:271) */
+  int32_t has_scale;     /* use scale_factor (--scale_factor, utils.py:279) */
+  double translate[3];
+  double scale_factor;
+  int32_t skip;          /* 1 = mesh is already normalised, use the points as given */
+  int32_t reserved;
+} flyby_norm_opts;
+
+/* Render options: src/py/fly_by_features.py:124-150 (channel assembly) and
+ * src/app/fly_by_features.xml:62-76 (planeSpacing, planeScaleFactor). */
+typedef struct {
+  int32_t use_z;           /* --use_z */
+  int32_t split_z;         /* --split_z */
+  int32_t normal_encoding; /* 0 n*0.5+0.5 (cxx:802-804), 1 *255 (8-bit raster range), 2 signed n (--rescale_features) */
+  int32_t reserved;
+  double plane_scale;      /* planeScaleFactor, default 1.0 */
+  double plane_spacing;    /* planeSpacing, default 1.0 */
+  double z_scale;          /* depth multiplier (1/z_far when rescaling), default 1.0 */
+} flyby_render_opts;
+
+/* Per-stage device timings of the last build/render on this context (ms, CUDA
+ * events on the context stream) and traversal counters (when enabled). */
+typedef struct {
+  float ms_normalise, ms_normals, ms_sort, ms_tree, ms_render;
+  int32_t reserved;
+  int64_t n_rays, n_hits;
+  int64_t nodes_visited, tris_tested; /* filled only by flyby_render with count_work=1 */
+} flyby_stats;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* device >= 0; stream = cudaStream_t (NULL = a stream owned by the context). */
+FLYBY_API int flyby_create(int device, void* stream, flyby_ctx** out);
+FLYBY_API void flyby_destroy(flyby_ctx* ctx);
+FLYBY_API const char* flyby_last_error(const flyby_ctx* ctx);
+FLYBY_API int flyby_abi_version(void);
+FLYBY_API int flyby_synchronize(flyby_ctx* ctx);
+
+/* ---- mesh: ReadSurf output -> unit surface -> normals -> LBVH ----------- */
+/* Replaces GetUnitSurf (utils.py:341) + ComputeNormals (utils.py:493-501) +
+ * vtkCellLocator::BuildLocator (fly_by_features.cxx:484-486).
+ * verts float32 [V,3], tris int32 [T,3].  flyby_build runs: normalise ->
+ * point normals -> Morton codes -> radix sort -> LBVH topology -> AABB refit
+ * -> SoA triangle reorder.  All on the GPU. */
+FLYBY_API int flyby_set_mesh(flyby_ctx* ctx, const float* verts, int64_t n_verts, const int32_t* tris,
+                   int64_t n_tris, const flyby_norm_opts* opts);
+FLYBY_API int flyby_build(flyby_ctx* ctx);
+/* Read back what the build produced (parity checks): unit-surf points [V,3],
+ * point normals [V,3], centre_scale[4] = centre xyz + scale.  Any may be NULL. */
+FLYBY_API int flyby_get_mesh(flyby_ctx* ctx, float* unit_verts, float* normals, double* centre_scale);
+/* LBVH introspection for tests: nodes_out [n_nodes,16] 32-bit words (layout in
+ * DESIGN.md), slot_cell_ids [T] = original cell id of each Morton-sorted slot. */
+FLYBY_API int flyby_get_bvh(flyby_ctx* ctx, int64_t* n_nodes, int32_t* n_top, void* nodes_out,
+                  int32_t* slot_cell_ids);
+
+/* ---- viewpoints -------------------------------------------------------- */
+/* CreateIcosahedron (utils.py:36-50 + LinearSubdivisionFilter.py:42-67 +
+ * normalize_points utils.py:22-31).  dedupe: 0 exact lattice (10 L^2 + 2),
+ * 1 float32-equality emulation of the reference's point locator. */
+FLYBY_API int flyby_views_icosahedron(flyby_ctx* ctx, int subdivision, double radius, int dedupe);
+/* CreateSpiral (utils.py:52-89; fly_by_features.cxx:214-251). */
+FLYBY_API int flyby_views_spiral(flyby_ctx* ctx, int n_samples, double turns, double radius);
+/* getFlyBy(sphere_points=...) (fly_by_features.py:63-70): float32 [n,3]. */
+FLYBY_API int flyby_views_custom(flyby_ctx* ctx, const float* points, int n_views, double radius);
+FLYBY_API int flyby_num_views(flyby_ctx* ctx, int* n_views);
+FLYBY_API int flyby_get_views(flyby_ctx* ctx, float* points_out /* [n,3] */);
+
+/* ---- ray generation (fly_by_features.cxx:652-702,742-748) --------------- */
+/* Writes the segments the render kernel casts: rays_out float64
+ * [view_end-view_begin, res, res, 6] = origin xyz, end xyz (i fastest). */
+FLYBY_API int flyby_generate_rays(flyby_ctx* ctx, int view_begin, int view_end, int res,
+                        const flyby_render_opts* opts, double* rays_out);
+
+/* ---- the hot path: FlyByGenerator.getFlyBy (fly_by_features.py:63-154) on
+ * the ray-cast engine of fly_by_features.cxx:742-807 ------------------------
+ * out_features float32 [view_end-view_begin, res, res, C], C = 4 when
+ * use_z && split_z else 3; out_cell_ids int32 [.., res, res] (-1 = miss);
+ * out_t float64 [.., res, res] hit parameter (-1 = miss).  Any may be NULL.
+ * Tie-break: smallest t, then lowest cell id. */
+FLYBY_API int flyby_render(flyby_ctx* ctx, int view_begin, int view_end, int res,
+                 const flyby_render_opts* opts, float* out_features, int32_t* out_cell_ids,
+                 double* out_t);
+/* Cast caller-supplied segments (rays float64 [n,6]); same outputs per ray
+ * plus barycentric weights w [n,3].  vtkCellLocator::IntersectWithLine
+ * (fly_by_features.cxx:758, predict.py:128). */
+FLYBY_API int flyby_cast(flyby_ctx* ctx, const double* rays, int64_t n_rays, int32_t* out_cell_ids,
+               double* out_t, double* out_w);
+
+/* ---- point features through the id map (utils.py:604-684) --------------- */
+/* mode 0: value at the hit cell's vertex 0 (reference ExtractPointFeatures).
+ * feats float32 [V,F]; out float32 [n_pix,F]; miss -> zero. */
+FLYBY_API int flyby_point_features(flyby_ctx* ctx, const int32_t* cell_ids, int64_t n_pix, const float* feats,
+                         int n_feat, float zero, int mode, float* out);
+
+/* ---- universal-labeling back-projection --------------------------------- */
+/* dental_model_seg.py:192-199, predict_v3.py:59-80, predict.py:154-169.
+ * votes int32 [n_cells,K] is ACCUMULATED into (caller zeroes it). */
+FLYBY_API int flyby_backproject(flyby_ctx* ctx, const int32_t* cell_ids, const int32_t* labels,
+                      int64_t n_pix, int n_classes, int32_t* votes);
+/* Soft votes: probs float32 [n_pix,K] accumulated as round(p * 2^20) into
+ * int64 votes_fx [n_cells,K] (integer atomics -> order independent). */
+FLYBY_API int flyby_backproject_soft(flyby_ctx* ctx, const int32_t* cell_ids, const float* probs,
+                           int64_t n_pix, int n_classes, int64_t* votes_fx);
+/* numpy argmax (lowest label wins ties); cells with no vote get dflt. */
+FLYBY_API int flyby_votes_argmax(flyby_ctx* ctx, const int32_t* votes, int64_t n_cells, int n_classes,
+                       int32_t dflt, int32_t* labels_out);
+/* cell label -> the cell's vertex 0, highest cell id wins
+ * (dental_model_seg.py:208-211). */
+FLYBY_API int flyby_cells_to_points(flyby_ctx* ctx, const int32_t* cell_labels, int32_t dflt,
+                          int32_t* point_labels_out /* [V] */);
+
+/* ---- the one collective: sum of label votes over ranks ------------------ */
+/* NCCL is loaded at run time (the libnccl.so.2 torch ships).  Rank 0 calls
+ * flyby_nccl_unique_id, the host shares the 128 bytes, every rank calls
+ * flyby_nccl_init; flyby_votes_allreduce then runs ncclAllReduce(sum) on the
+ * context stream right behind the scatter kernel (no host sync). */
+FLYBY_API int flyby_nccl_unique_id(flyby_ctx* ctx, uint8_t id_out[128]);
+FLYBY_API int flyby_nccl_init(flyby_ctx* ctx, const uint8_t id[128], int rank, int world);
+FLYBY_API int flyby_votes_allreduce(flyby_ctx* ctx, int32_t* votes, int64_t n, int root /* -1 = all */);
+
+/* ---- measurement -------------------------------------------------------- */
+FLYBY_API int flyby_get_stats(flyby_ctx* ctx, flyby_stats* out);
+/* 1: the next flyby_render also counts nodes visited / triangles tested. */
+FLYBY_API int flyby_set_count_work(flyby_ctx* ctx, int enable);
+/* number of kernels this context has launched since creation */
+FLYBY_API int flyby_launch_count(flyby_ctx* ctx, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLYBY_B200_H */

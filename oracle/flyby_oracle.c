@@ -1,0 +1,665 @@
+/*
+ * flyby_oracle.c -- CPU restatement of Fly-by-CNN's ray-cast fly-by feature path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under fly-by-cnn_b200/ (the product) may
+ * include, link or call this file.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs use it, as the checker.
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in VTK (vtk==9.2.2,
+ * reference src/py/challenge-teeth/flyby.yml:93; C++ tool built on VTK-9.0.1,
+ * src/app/README.md:22), which is not vendored under /root/reference and is
+ * not installable here.  The reference ships no golden vectors or tests for
+ * this path.  The VTK calls are therefore restated from VTK 9's published
+ * algorithms (vtkTriangle::IntersectWithLine, vtkPlane::IntersectWithLine,
+ * vtkTriangle::EvaluatePosition, vtkPlaneSource, vtkPolyDataNormals,
+ * vtkPlatonicSolidSource, vtkCellLocator) and anchored on the reference's own
+ * call sites, cited per function below (paths relative to /root/reference).
+ *
+ * Arithmetic: double on float32 inputs, exactly as VTK sees float vtkPoints.
+ * Build with -ffp-contract=off so no FMA contraction changes a result.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ */
+/* small helpers                                                       */
+/* ------------------------------------------------------------------ */
+static double dot3(const double a[3], const double b[3]) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+static void cross3(const double a[3], const double b[3], double c[3]) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+static double norm3(const double a[3]) { return sqrt(dot3(a, a)); }
+
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ */
+/* O1  unit surface                                                    */
+/*   src/py/utils.py:249-290 (ScaleSurf, canonical)                    */
+/*   src/app/fly_by_features.cxx:393-450 (centre-of-mass / magnitude)  */
+/* ------------------------------------------------------------------ */
+/* centre_mode: 0 = bbox mid (utils.py:263-265), 1 = centre of mass (cxx:397-403)
+ * scale_mode : 0 = 1/|bbox_max - centre| (utils.py:281), 1 = 1/max|p - centre| (cxx:429-435)
+ * has_translate / has_scale: caller overrides (utils.py:271,279; --translate, --scale_factor)
+ * out = float32((double(p) - centre) * scale); centre_scale_out[4] = centre xyz, scale. */
+ORC_API void orc_unit_surf(const float* verts, int64_t V, int centre_mode, int scale_mode,
+                           int has_translate, const double* translate, int has_scale,
+                           double scale_factor, float* out, double* centre_scale_out) {
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  double sum[3] = {0, 0, 0};
+  for (int64_t i = 0; i < V; i++)
+    for (int k = 0; k < 3; k++) {
+      double p = verts[3 * i + k];
+      if (p < lo[k]) lo[k] = p;
+      if (p > hi[k]) hi[k] = p;
+      sum[k] += p;
+    }
+  double c[3];
+  for (int k = 0; k < 3; k++) {
+    if (has_translate) c[k] = translate[k];
+    else if (centre_mode == 1) c[k] = sum[k] / (double)V;
+    else c[k] = (lo[k] + hi[k]) / 2.0;
+  }
+  double s;
+  if (has_scale) s = scale_factor;
+  else if (scale_mode == 1) {
+    double m = 0;
+    for (int64_t i = 0; i < V; i++) {
+      double d[3] = {verts[3 * i] - c[0], verts[3 * i + 1] - c[1], verts[3 * i + 2] - c[2]};
+      double n = norm3(d);
+      if (n > m) m = n;
+    }
+    s = 1.0 / m;
+  } else {
+    double d[3] = {hi[0] - c[0], hi[1] - c[1], hi[2] - c[2]};
+    s = 1.0 / norm3(d);
+  }
+  for (int64_t i = 0; i < V; i++)
+    for (int k = 0; k < 3; k++) out[3 * i + k] = (float)(((double)verts[3 * i + k] - c[k]) * s);
+  if (centre_scale_out) {
+    centre_scale_out[0] = c[0]; centre_scale_out[1] = c[1];
+    centre_scale_out[2] = c[2]; centre_scale_out[3] = s;
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* O2  point normals (vtkPolyDataNormals, splitting off)               */
+/*   src/py/utils.py:493-501 ; src/app/fly_by_features.cxx:472-478     */
+/* VTK: unit polygon normal (vtkTriangle::ComputeNormal: a=p2-p1,      */
+/* b=p0-p1, n=a x b, /|n|) stored float32; point normal = float32 sum  */
+/* over incident cells in ascending cell id, then /sqrt(|sum|^2).      */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_point_normals(const float* verts, int64_t V, const int32_t* tris, int64_t T,
+                               float* out) {
+  memset(out, 0, sizeof(float) * 3 * (size_t)V);
+  for (int64_t c = 0; c < T; c++) {
+    const float* p0 = verts + 3 * (int64_t)tris[3 * c];
+    const float* p1 = verts + 3 * (int64_t)tris[3 * c + 1];
+    const float* p2 = verts + 3 * (int64_t)tris[3 * c + 2];
+    double a[3], b[3], n[3];
+    for (int k = 0; k < 3; k++) {
+      a[k] = (double)p2[k] - (double)p1[k];
+      b[k] = (double)p0[k] - (double)p1[k];
+    }
+    cross3(a, b, n);
+    double len = norm3(n);
+    float fn[3] = {0.f, 0.f, 0.f};
+    if (len != 0.0)
+      for (int k = 0; k < 3; k++) fn[k] = (float)(n[k] / len);
+    for (int j = 0; j < 3; j++) {
+      float* o = out + 3 * (int64_t)tris[3 * c + j];
+      for (int k = 0; k < 3; k++) o[k] = o[k] + fn[k];
+    }
+  }
+  for (int64_t i = 0; i < V; i++) {
+    float* o = out + 3 * i;
+    float s0 = o[0] * o[0], s1 = o[1] * o[1], s2 = o[2] * o[2];
+    float ss = (s0 + s1) + s2;
+    double len = sqrt((double)ss);
+    if (len != 0.0)
+      for (int k = 0; k < 3; k++) o[k] = (float)((double)o[k] / len);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* O3  icosahedron-subdivision viewpoints                              */
+/*   src/py/utils.py:36-50 (CreateIcosahedron)                         */
+/*   src/py/LinearSubdivisionFilter.py:42-67 (lattice order, de-dup)   */
+/*   src/py/utils.py:22-31 (normalize_points)                          */
+/* vtkPlatonicSolidSource tables restated from VTK 9 (un-vendored).    */
+/* ------------------------------------------------------------------ */
+static const double ICO_PTS[12][3] = {
+    {0.0, 0.0, -1.0},           {0.0, 0.894427, -0.447214},      {0.850651, 0.276393, -0.447214},
+    {0.525731, -0.723607, -0.447214}, {-0.525731, -0.723607, -0.447214}, {-0.850651, 0.276393, -0.447214},
+    {0.0, -0.894427, 0.447214}, {0.850651, -0.276393, 0.447214}, {0.525731, 0.723607, 0.447214},
+    {-0.525731, 0.723607, 0.447214}, {-0.850651, -0.276393, 0.447214}, {0.0, 0.0, 1.0}};
+static const int ICO_FACES[20][3] = {
+    {0, 5, 4},  {0, 4, 3},  {0, 3, 2},  {0, 2, 1},   {0, 1, 5},  {5, 1, 9},  {5, 9, 10},
+    {5, 10, 4}, {4, 10, 6}, {4, 6, 3},  {3, 6, 7},   {3, 7, 2},  {2, 7, 8},  {2, 8, 1},
+    {1, 8, 9},  {9, 8, 11}, {9, 11, 10}, {10, 11, 6}, {6, 11, 7}, {7, 11, 8}};
+/* uniform solid scale applied by vtkPlatonicSolidSource before float storage
+ * (recalled constant, medium confidence; irrelevant after normalize_points
+ * except for the last float32 bit of a viewpoint) */
+#define ICO_SOLID_SCALE (1.0 / 0.58285)
+
+/* dedupe: 0 = exact integer lattice (canonical, 10 L^2 + 2 points),
+ *         1 = float32 exact-equality emulation of
+ *             vtkIncrementalOctreePointLocator (LinearSubdivisionFilter.py:64-66).
+ * out must hold 20*(L+1)*(L+2)/2 * 3 floats.  Returns the number of viewpoints. */
+ORC_API int orc_icosahedron(int L, double radius, int dedupe, float* out) {
+  if (L < 1) return -1;
+  float base[12][3];
+  for (int i = 0; i < 12; i++)
+    for (int k = 0; k < 3; k++) base[i][k] = (float)(ICO_PTS[i][k] * ICO_SOLID_SCALE);
+  int cap = 20 * (L + 1) * (L + 2) / 2;
+  float* pts = (float*)malloc(sizeof(float) * 3 * (size_t)cap);
+  /* lattice key: sorted (vertex, weight) pairs with non-zero weight */
+  int64_t* keys = (int64_t*)malloc(sizeof(int64_t) * 3 * (size_t)cap);
+  int n = 0;
+  for (int f = 0; f < 20; f++) {
+    const int* fv = ICO_FACES[f];
+    double p1[3], p2[3], p3[3], d12[3], d13[3];
+    for (int k = 0; k < 3; k++) {
+      p1[k] = base[fv[0]][k]; p2[k] = base[fv[1]][k]; p3[k] = base[fv[2]][k];
+      d12[k] = (p2[k] - p1[k]) / (double)L;
+      d13[k] = (p3[k] - p1[k]) / (double)L;
+    }
+    for (int s13 = 0; s13 <= L; s13++)
+      for (int s12 = 0; s12 <= L - s13; s12++) {
+        float q[3];
+        for (int k = 0; k < 3; k++) q[k] = (float)((p1[k] + s12 * d12[k]) + s13 * d13[k]);
+        int found = -1;
+        if (dedupe == 1) {
+          for (int j = 0; j < n && found < 0; j++)
+            if (pts[3 * j] == q[0] && pts[3 * j + 1] == q[1] && pts[3 * j + 2] == q[2]) found = j;
+        } else {
+          int w[3] = {L - s12 - s13, s12, s13};
+          int64_t key[3] = {-1, -1, -1};
+          int m = 0;
+          for (int a = 0; a < 3; a++)
+            if (w[a] > 0) key[m++] = (int64_t)fv[a] * 100000 + w[a];
+          /* sort the up-to-3 entries */
+          for (int a = 0; a < m; a++)
+            for (int b = a + 1; b < m; b++)
+              if (key[b] < key[a]) { int64_t t = key[a]; key[a] = key[b]; key[b] = t; }
+          /* interior points (3 non-zero weights) are unique to the face */
+          if (m == 3) { key[0] += (int64_t)(f + 1) * 100000000000LL; }
+          for (int j = 0; j < n && found < 0; j++)
+            if (keys[3 * j] == key[0] && keys[3 * j + 1] == key[1] && keys[3 * j + 2] == key[2]) found = j;
+          if (found < 0) { keys[3 * n] = key[0]; keys[3 * n + 1] = key[1]; keys[3 * n + 2] = key[2]; }
+        }
+        if (found < 0) {
+          pts[3 * n] = q[0]; pts[3 * n + 1] = q[1]; pts[3 * n + 2] = q[2];
+          n++;
+        }
+      }
+  }
+  /* normalize_points: p / |p| * radius, stored float32 (utils.py:22-31) */
+  for (int i = 0; i < n; i++) {
+    double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    double nn = norm3(p);
+    for (int k = 0; k < 3; k++) out[3 * i + k] = (float)(p[k] / nn * radius);
+  }
+  free(pts); free(keys);
+  return n;
+}
+
+/* ------------------------------------------------------------------ */
+/* O4  spherical spiral  src/py/utils.py:52-89 ; cxx:214-251           */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_spiral(int N, double turns, double radius, float* out) {
+  double c = 2.0 * turns;
+  for (int i = 0; i < N; i++) {
+    double angle = ((double)i * M_PI) / (double)N;
+    out[3 * i + 0] = (float)(radius * sin(angle) * cos(c * angle));
+    out[3 * i + 1] = (float)(radius * sin(angle) * sin(c * angle));
+    out[3 * i + 2] = (float)(radius * cos(angle));
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* O5  view-plane basis and rays                                       */
+/*   src/app/fly_by_features.cxx:652-702 (basis, vtkPlaneSource)       */
+/*   src/app/fly_by_features.cxx:742-748 (segment per plane point)     */
+/*   python twin src/py/predict.py:88-126                              */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  double sp[3], n[3], x[3], y[3];
+  double origin[3], v1[3], v2[3]; /* vtkPlaneSource Origin, Point1-Origin, Point2-Origin */
+  double delta[3];                /* sp - sp*spacing */
+  double dir[3];                  /* end - origin = -(n*R)*2 */
+} orc_view;
+
+static void view_setup(const float spf[3], double radius, double plane_scale, double spacing,
+                       orc_view* v) {
+  for (int k = 0; k < 3; k++) v->sp[k] = spf[k];
+  double len = norm3(v->sp);
+  for (int k = 0; k < 3; k++) v->n[k] = v->sp[k] / len;
+  int north = fabs(v->n[0]) <= 1e-8 && fabs(v->n[1]) <= 1e-8 && fabs(v->n[2] - 1.0) <= 1e-8;
+  int south = fabs(v->n[0]) <= 1e-8 && fabs(v->n[1]) <= 1e-8 && fabs(v->n[2] + 1.0) <= 1e-8;
+  if (north) {
+    v->x[0] = 1; v->x[1] = 0; v->x[2] = 0; v->y[0] = 0; v->y[1] = 1; v->y[2] = 0;
+  } else if (south) {
+    v->x[0] = -1; v->x[1] = 0; v->x[2] = 0; v->y[0] = 0; v->y[1] = -1; v->y[2] = 0;
+  } else {
+    double up[3] = {0, 0, 1}, c[3];
+    cross3(v->n, up, c);
+    double l = norm3(c);
+    for (int k = 0; k < 3; k++) v->x[k] = c[k] / l;
+    cross3(v->n, v->x, c);
+    l = norm3(c);
+    for (int k = 0; k < 3; k++) v->y[k] = c[k] / l;
+  }
+  for (int k = 0; k < 3; k++) {
+    double hx = v->x[k] * 0.5 * plane_scale, hy = v->y[k] * 0.5 * plane_scale;
+    v->origin[k] = (v->sp[k] - hx) - hy;
+    double p1 = v->origin[k] + v->x[k] * plane_scale;
+    double p2 = v->origin[k] + v->y[k] * plane_scale;
+    v->v1[k] = p1 - v->origin[k];
+    v->v2[k] = p2 - v->origin[k];
+    v->delta[k] = v->sp[k] - v->sp[k] * spacing;
+    v->dir[k] = -((v->n[k] * radius) * 2.0);
+  }
+}
+
+/* ray (i fastest, j slowest; vtkPlaneSource with resolution res-1) */
+static void view_ray(const orc_view* v, int res, int i, int j, double spacing, double o[3]) {
+  double tc0 = (res > 1) ? (double)i / (double)(res - 1) : 0.0;
+  double tc1 = (res > 1) ? (double)j / (double)(res - 1) : 0.0;
+  for (int k = 0; k < 3; k++) {
+    float pf = (float)((v->origin[k] + tc0 * v->v1[k]) + tc1 * v->v2[k]); /* float vtkPoints */
+    o[k] = (double)pf * spacing + v->delta[k];
+  }
+}
+
+/* rays_out[res*res][6] = origin xyz, end xyz ; basis_out[9] = n, x, y */
+ORC_API void orc_view_rays(const float* sp, double radius, double plane_scale, double spacing,
+                           int res, double* rays_out, double* basis_out) {
+  orc_view v;
+  view_setup(sp, radius, plane_scale, spacing, &v);
+  if (basis_out)
+    for (int k = 0; k < 3; k++) {
+      basis_out[k] = v.n[k]; basis_out[3 + k] = v.x[k]; basis_out[6 + k] = v.y[k];
+    }
+  if (rays_out)
+    for (int j = 0; j < res; j++)
+      for (int i = 0; i < res; i++) {
+        double o[3];
+        view_ray(&v, res, i, j, spacing, o);
+        double* r = rays_out + 6 * ((size_t)j * res + i);
+        for (int k = 0; k < 3; k++) { r[k] = o[k]; r[3 + k] = o[k] + v.dir[k]; }
+      }
+}
+
+/* ------------------------------------------------------------------ */
+/* O6  segment / triangle test, VTK semantics                          */
+/*   call site src/app/fly_by_features.cxx:750-758 (tol 1e-10)         */
+/*   vtkTriangle::IntersectWithLine -> vtkPlane::IntersectWithLine ->  */
+/*   vtkTriangle::EvaluatePosition (inclusive [0,1] weights).          */
+/*   The |dist| <= tol dilation branch (tol = 1e-10) is not restated.  */
+/* Returns 1 on hit and fills t, x[3], w[3].                           */
+/* ------------------------------------------------------------------ */
+static int tri_hit(const double o[3], const double d[3], const float* P0, const float* P1,
+                   const float* P2, double* t_out, double x[3], double w[3]) {
+  double pt1[3] = {P1[0], P1[1], P1[2]}, pt2[3] = {P2[0], P2[1], P2[2]}, pt3[3] = {P0[0], P0[1], P0[2]};
+  /* ComputeNormalDirection(pt1, pt2, pt3): a = pt3 - pt2, b = pt1 - pt2, n = a x b */
+  double a[3] = {pt3[0] - pt2[0], pt3[1] - pt2[1], pt3[2] - pt2[2]};
+  double b[3] = {pt1[0] - pt2[0], pt1[1] - pt2[1], pt1[2] - pt2[2]};
+  double n[3];
+  cross3(a, b, n);
+  if (n[0] == 0.0 && n[1] == 0.0 && n[2] == 0.0) return 0; /* degenerate: treated as miss */
+  /* vtkPlane::IntersectWithLine(p1, p2, n, pt1, t, x), VTK_PLANE_TOL = 1e-6 */
+  double num = dot3(n, pt1) - (n[0] * o[0] + n[1] * o[1] + n[2] * o[2]);
+  double den = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
+  double fabsden = den < 0.0 ? -den : den;
+  double fabstol = num < 0.0 ? -num * 1.0e-06 : num * 1.0e-06;
+  if (fabsden <= fabstol) return 0;
+  double t = num / den;
+  for (int k = 0; k < 3; k++) x[k] = o[k] + t * d[k];
+  if (!(t >= 0.0 && t <= 1.0)) return 0;
+  /* EvaluatePosition(x): project onto the plane (vtkPlane::GeneralizedProjectPoint) */
+  double xo[3] = {x[0] - pt1[0], x[1] - pt1[1], x[2] - pt1[2]};
+  double tp = dot3(n, xo), n2 = dot3(n, n);
+  double cp[3];
+  for (int k = 0; k < 3; k++) cp[k] = (n2 != 0.0) ? x[k] - tp * n[k] / n2 : x[k];
+  /* drop the dominant axis of n (first max wins) */
+  int idx = 0;
+  double maxc = 0.0;
+  for (int k = 0; k < 3; k++) {
+    double f = n[k] < 0 ? -n[k] : n[k];
+    if (f > maxc) { maxc = f; idx = k; }
+  }
+  int ia = (idx == 0) ? 1 : 0, ib = (idx == 2) ? 1 : 2;
+  double rhs[2] = {cp[ia] - pt3[ia], cp[ib] - pt3[ib]};
+  double c1[2] = {pt1[ia] - pt3[ia], pt1[ib] - pt3[ib]};
+  double c2[2] = {pt2[ia] - pt3[ia], pt2[ib] - pt3[ib]};
+  double det = c1[0] * c2[1] - c2[0] * c1[1];
+  if (det == 0.0) return 0;
+  double pc0 = (rhs[0] * c2[1] - c2[0] * rhs[1]) / det;
+  double pc1 = (c1[0] * rhs[1] - rhs[0] * c1[1]) / det;
+  w[0] = 1 - (pc0 + pc1); w[1] = pc0; w[2] = pc1;
+  if (w[0] >= 0.0 && w[0] <= 1.0 && w[1] >= 0.0 && w[1] <= 1.0 && w[2] >= 0.0 && w[2] <= 1.0) {
+    *t_out = t;
+    return 1;
+  }
+  return 0;
+}
+
+ORC_API int orc_tri_intersect(const double* o, const double* e, const float* p0, const float* p1,
+                              const float* p2, double* t, double* x, double* w) {
+  double d[3] = {e[0] - o[0], e[1] - o[1], e[2] - o[2]};
+  return tri_hit(o, d, p0, p1, p2, t, x, w);
+}
+
+/* nearest hit by exhaustive search: min t, ties -> lowest cell id (strict <
+ * while scanning ascending ids == vtkCellLocator "first found wins") */
+static int cast_brute(const double o[3], const double d[3], const float* verts,
+                      const int32_t* tris, int64_t T, double* t, double x[3], double w[3]) {
+  int best = -1;
+  double bt = DBL_MAX;
+  for (int64_t c = 0; c < T; c++) {
+    double tt, xx[3], ww[3];
+    if (tri_hit(o, d, verts + 3 * (int64_t)tris[3 * c], verts + 3 * (int64_t)tris[3 * c + 1],
+                verts + 3 * (int64_t)tris[3 * c + 2], &tt, xx, ww) && tt < bt) {
+      bt = tt; best = (int)c;
+      memcpy(x, xx, sizeof xx); memcpy(w, ww, sizeof ww);
+    }
+  }
+  *t = bt;
+  return best;
+}
+
+/* ------------------------------------------------------------------ */
+/* vtkCellLocator-like uniform bucket grid (a6/a7)                     */
+/*   src/app/fly_by_features.cxx:484-486 (BuildLocator)                */
+/*   VTK defaults: 25 cells/bucket, MaxLevel 8, Automatic ->           */
+/*   level = ceil(log8(T/25)), 2^level divisions per axis.             */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int nd;              /* divisions per axis */
+  double lo[3], h[3];  /* grid origin and bucket size */
+  int64_t* start;      /* nd^3 + 1 */
+  int32_t* items;      /* cell ids, ascending within a bucket */
+  const float* verts;
+  const int32_t* tris;
+  int64_t T;
+} orc_grid;
+
+ORC_API void orc_grid_free(orc_grid* g) {
+  if (!g) return;
+  free(g->start); free(g->items); free(g);
+}
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* divisions <= 0 -> VTK automatic rule */
+ORC_API orc_grid* orc_grid_build(const float* verts, int64_t V, const int32_t* tris, int64_t T,
+                                 int divisions) {
+  orc_grid* g = (orc_grid*)calloc(1, sizeof(orc_grid));
+  g->verts = verts; g->tris = tris; g->T = T;
+  if (divisions <= 0) {
+    int level = (int)ceil(log((double)T / 25.0) / log(8.0));
+    if (level < 0) level = 0;
+    if (level > 8) level = 8;
+    divisions = 1 << level;
+  }
+  g->nd = divisions;
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (int64_t i = 0; i < V; i++)
+    for (int k = 0; k < 3; k++) {
+      double p = verts[3 * i + k];
+      if (p < lo[k]) lo[k] = p;
+      if (p > hi[k]) hi[k] = p;
+    }
+  for (int k = 0; k < 3; k++) {
+    double pad = (hi[k] - lo[k]) * 1e-6 + 1e-9;
+    g->lo[k] = lo[k] - pad;
+    g->h[k] = ((hi[k] + pad) - g->lo[k]) / g->nd;
+  }
+  int nd = g->nd;
+  int64_t nb = (int64_t)nd * nd * nd;
+  g->start = (int64_t*)calloc((size_t)nb + 1, sizeof(int64_t));
+  for (int pass = 0; pass < 2; pass++) {
+    int64_t* fill = NULL;
+    if (pass == 1) {
+      int64_t acc = 0;
+      for (int64_t b = 0; b < nb; b++) { int64_t c = g->start[b]; g->start[b] = acc; acc += c; }
+      g->start[nb] = acc;
+      g->items = (int32_t*)malloc(sizeof(int32_t) * (size_t)(acc > 0 ? acc : 1));
+      fill = (int64_t*)malloc(sizeof(int64_t) * (size_t)nb);
+      memcpy(fill, g->start, sizeof(int64_t) * (size_t)nb);
+    }
+    for (int64_t c = 0; c < T; c++) {
+      int r0[3], r1[3];
+      for (int k = 0; k < 3; k++) {
+        double a = verts[3 * (int64_t)tris[3 * c] + k], b = verts[3 * (int64_t)tris[3 * c + 1] + k],
+               e = verts[3 * (int64_t)tris[3 * c + 2] + k];
+        double mn = fmin(a, fmin(b, e)), mx = fmax(a, fmax(b, e));
+        /* one-ulp-ish slack so a hit point on a bucket face is never lost */
+        r0[k] = clampi((int)floor((mn - g->lo[k]) / g->h[k] - 1e-7), 0, nd - 1);
+        r1[k] = clampi((int)floor((mx - g->lo[k]) / g->h[k] + 1e-7), 0, nd - 1);
+      }
+      for (int z = r0[2]; z <= r1[2]; z++)
+        for (int y = r0[1]; y <= r1[1]; y++)
+          for (int xx = r0[0]; xx <= r1[0]; xx++) {
+            int64_t b = ((int64_t)z * nd + y) * nd + xx;
+            if (pass == 0) g->start[b]++;
+            else g->items[fill[b]++] = (int32_t)c;
+          }
+    }
+    free(fill);
+  }
+  return g;
+}
+
+/* Walk buckets front to back (3-D DDA), test every cell listed in a bucket,
+ * keep lexicographic min (t, cell id); stop once the best t lies before the
+ * exit of the current bucket.  Equals cast_brute on every ray (tested). */
+static int cast_grid(const orc_grid* g, const double o[3], const double d[3], double* t,
+                     double x[3], double w[3]) {
+  int nd = g->nd;
+  /* clip [0,1] against the grid box */
+  double t0 = 0.0, t1 = 1.0;
+  for (int k = 0; k < 3; k++) {
+    double lo = g->lo[k], hi = g->lo[k] + g->h[k] * nd;
+    if (d[k] == 0.0) {
+      if (o[k] < lo || o[k] > hi) { *t = DBL_MAX; return -1; }
+    } else {
+      double ta = (lo - o[k]) / d[k], tb = (hi - o[k]) / d[k];
+      if (ta > tb) { double s = ta; ta = tb; tb = s; }
+      if (ta > t0) t0 = ta;
+      if (tb < t1) t1 = tb;
+    }
+  }
+  if (t0 > t1) { *t = DBL_MAX; return -1; }
+  int c[3], step[3];
+  double tnext[3], tdelta[3];
+  for (int k = 0; k < 3; k++) {
+    double p = o[k] + t0 * d[k];
+    c[k] = clampi((int)floor((p - g->lo[k]) / g->h[k]), 0, nd - 1);
+    if (d[k] > 0) {
+      step[k] = 1;
+      tnext[k] = (g->lo[k] + (c[k] + 1) * g->h[k] - o[k]) / d[k];
+      tdelta[k] = g->h[k] / d[k];
+    } else if (d[k] < 0) {
+      step[k] = -1;
+      tnext[k] = (g->lo[k] + c[k] * g->h[k] - o[k]) / d[k];
+      tdelta[k] = -g->h[k] / d[k];
+    } else {
+      step[k] = 0; tnext[k] = DBL_MAX; tdelta[k] = DBL_MAX;
+    }
+  }
+  int best = -1;
+  double bt = DBL_MAX;
+  for (;;) {
+    int64_t b = ((int64_t)c[2] * nd + c[1]) * nd + c[0];
+    for (int64_t q = g->start[b]; q < g->start[b + 1]; q++) {
+      int32_t cid = g->items[q];
+      double tt, xx[3], ww[3];
+      if (tri_hit(o, d, g->verts + 3 * (int64_t)g->tris[3 * cid],
+                  g->verts + 3 * (int64_t)g->tris[3 * cid + 1],
+                  g->verts + 3 * (int64_t)g->tris[3 * cid + 2], &tt, xx, ww)) {
+        if (tt < bt || (tt == bt && cid < best)) {
+          bt = tt; best = cid;
+          memcpy(x, xx, sizeof xx); memcpy(w, ww, sizeof ww);
+        }
+      }
+    }
+    int ax = (tnext[0] <= tnext[1]) ? ((tnext[0] <= tnext[2]) ? 0 : 2) : ((tnext[1] <= tnext[2]) ? 1 : 2);
+    double texit = tnext[ax];
+    /* a hit strictly inside the walked span is final (small slack for the face) */
+    if (best >= 0 && bt < texit - 1e-9) break;
+    if (texit > t1 + 1e-9) break;
+    c[ax] += step[ax];
+    if (c[ax] < 0 || c[ax] >= nd) break;
+    tnext[ax] += tdelta[ax];
+  }
+  *t = bt;
+  return best;
+}
+
+/* Generic segment casting: rays[n][6] (origin, end).  grid may be NULL -> brute force. */
+ORC_API void orc_cast(const orc_grid* g, const float* verts, const int32_t* tris, int64_t T,
+                      const double* rays, int64_t n, int32_t* ids, double* t_out, double* x_out,
+                      double* w_out) {
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t r = 0; r < n; r++) {
+    const double* o = rays + 6 * r;
+    double d[3] = {o[3] - o[0], o[4] - o[1], o[5] - o[2]};
+    double t, x[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+    int id = g ? cast_grid(g, o, d, &t, x, w) : cast_brute(o, d, verts, tris, T, &t, x, w);
+    ids[r] = id;
+    if (t_out) t_out[r] = id >= 0 ? t : -1.0;
+    if (x_out) for (int k = 0; k < 3; k++) x_out[3 * r + k] = x[k];
+    if (w_out) for (int k = 0; k < 3; k++) w_out[3 * r + k] = w[k];
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* O7 + O8  shading and channel assembly                               */
+/*   src/app/fly_by_features.cxx:766-807 (bary normal, z, pixel)       */
+/*   src/py/fly_by_features.py:124-150 (use_z / split_z / rescale)     */
+/* normal_encoding: 0 unit01 (n*0.5+0.5), 1 byte255 ((n*0.5+0.5)*255), */
+/*                  2 signed (n; rescale_features)                     */
+/* Channels: use_z=0 -> 3 ; use_z=1,split_z=1 -> 4 ; use_z=1,split_z=0 */
+/* -> 3 (normals * depth, cxx:802-804).  zscale multiplies depth        */
+/* (1/z_far when rescaling, fly_by_features.py:138-146).  Miss -> 0.   */
+/* ------------------------------------------------------------------ */
+ORC_API int orc_channels(int use_z, int split_z) { return (use_z && split_z) ? 4 : 3; }
+
+static void shade(const double o[3], const double x[3], const double w[3], const float* normals,
+                  const int32_t* tri, int use_z, int split_z, int enc, double zscale, float* px) {
+  double nn[3] = {0, 0, 0};
+  for (int j = 0; j < 3; j++) {
+    const float* N = normals + 3 * (int64_t)tri[j];
+    for (int k = 0; k < 3; k++) nn[k] = nn[k] + (double)N[k] * w[j];
+  }
+  double dd[3] = {o[0] - x[0], o[1] - x[1], o[2] - x[2]};
+  double z = norm3(dd) * zscale;
+  double e[3];
+  for (int k = 0; k < 3; k++) {
+    if (enc == 2) e[k] = nn[k];
+    else if (enc == 1) e[k] = (nn[k] * 0.5 + 0.5) * 255.0;
+    else e[k] = nn[k] * 0.5 + 0.5;
+  }
+  if (!use_z) { for (int k = 0; k < 3; k++) px[k] = (float)e[k]; }
+  else if (split_z) { for (int k = 0; k < 3; k++) px[k] = (float)e[k]; px[3] = (float)z; }
+  else { for (int k = 0; k < 3; k++) px[k] = (float)(e[k] * z); }
+}
+
+/* Whole path for a set of viewpoints.  verts are the UNIT-SURF float32 points,
+ * normals the O2 point normals.  out_features [Vw,res,res,C], out_ids [Vw,res,res]
+ * (-1 miss), out_t optional [Vw,res,res] (-1 miss).  use_grid: 0 brute force,
+ * >0 bucket grid (divisions = grid_div, <=0 VTK automatic). */
+ORC_API void orc_render(const float* verts, int64_t V, const int32_t* tris, int64_t T,
+                        const float* normals, const float* views, int n_views, double radius,
+                        int res, double plane_scale, double spacing, int use_z, int split_z,
+                        int enc, double zscale, int use_grid, int grid_div, float* out_features,
+                        int32_t* out_ids, double* out_t) {
+  int C = orc_channels(use_z, split_z);
+  orc_grid* g = use_grid ? orc_grid_build(verts, V, tris, T, grid_div) : NULL;
+  for (int v = 0; v < n_views; v++) {
+    orc_view vw;
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = 0; p < (int64_t)res * res; p++) {
+      int i = (int)(p % res), j = (int)(p / res);
+      double o[3], t, x[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+      view_ray(&vw, res, i, j, spacing, o);
+      int id = g ? cast_grid(g, o, vw.dir, &t, x, w) : cast_brute(o, vw.dir, verts, tris, T, &t, x, w);
+      size_t pix = (size_t)v * res * res + (size_t)p;
+      if (out_ids) out_ids[pix] = id;
+      if (out_t) out_t[pix] = id >= 0 ? t : -1.0;
+      if (out_features) {
+        float* px = out_features + pix * C;
+        for (int k = 0; k < C; k++) px[k] = 0.f;
+        if (id >= 0) shade(o, x, w, normals, tris + 3 * (int64_t)id, use_z, split_z, enc, zscale, px);
+      }
+    }
+  }
+  orc_grid_free(g);
+}
+
+/* ------------------------------------------------------------------ */
+/* a10  point-feature lookup through the id map                        */
+/*   src/py/utils.py:604-621 (cell colour = id of the cell's vertex 0) */
+/*   src/py/utils.py:639-684 (ExtractPointFeatures; miss -> zero)      */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_point_features(const int32_t* cell_ids, int64_t n_pix, const int32_t* tris,
+                                const float* feats, int F, float zero, float* out) {
+  for (int64_t p = 0; p < n_pix; p++) {
+    int32_t c = cell_ids[p];
+    for (int k = 0; k < F; k++)
+      out[p * F + k] = (c >= 0) ? feats[(int64_t)tris[3 * (int64_t)c] * F + k] : zero;
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* O9  back-projection of per-pixel labels onto cells                  */
+/*   src/py/dental_model_seg.py:192-199 (per cell, through pix_to_face)*/
+/*   src/py/predict_v3.py:59-80 ; src/py/predict.py:154-169            */
+/* Miss pixels contribute nothing (deliberate fix of the -1 row bug).  */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_backproject(const int32_t* cell_ids, const int32_t* labels, int64_t n_pix, int K,
+                             int32_t* votes) {
+  for (int64_t p = 0; p < n_pix; p++) {
+    int32_t c = cell_ids[p], l = labels[p];
+    if (c >= 0 && l >= 0 && l < K) votes[(int64_t)c * K + l] += 1;
+  }
+}
+
+/* numpy argmax semantics (lowest label wins ties); no votes -> dflt
+ * (predict_v3.py:75-80, predict.py:164-169) */
+ORC_API void orc_votes_argmax(const int32_t* votes, int64_t T, int K, int32_t dflt, int32_t* out) {
+  for (int64_t c = 0; c < T; c++) {
+    int32_t best = 0, arg = -1;
+    for (int k = 0; k < K; k++)
+      if (votes[c * K + k] > best) { best = votes[c * K + k]; arg = k; }
+    out[c] = arg >= 0 ? arg : dflt;
+  }
+}
+
+/* cell label -> the cell's vertex 0, later cells overwrite earlier ones
+ * (src/py/dental_model_seg.py:208-211) */
+ORC_API void orc_cells_to_points(const int32_t* cell_labels, const int32_t* tris, int64_t T,
+                                 int64_t V, int32_t dflt, int32_t* out) {
+  for (int64_t i = 0; i < V; i++) out[i] = dflt;
+  for (int64_t c = 0; c < T; c++) out[tris[3 * c]] = cell_labels[c];
+}

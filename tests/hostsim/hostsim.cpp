@@ -1,0 +1,174 @@
+// hostsim.cpp -- TEST-ONLY host build of fly-by-cnn_b200/csrc/flyby_core.cuh.
+//
+// Compiles the very same per-element device logic (Morton codes, Karras
+// topology, conservative slab test, exact triangle test, stackless traversal,
+// shading) with g++ and drives it with serial loops, so that logic errors are
+// found on the CPU-only build box.  Never loaded by the product package.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../fly-by-cnn_b200/csrc/flyby_core.cuh"
+
+using namespace fb;
+
+struct SimFetch {
+  const Node* n;
+  Node node(int i) const { return n[i]; }
+  int parent(int i) const { return n[i].parent; }
+  int sibling(int i) const { return n[i].sibling; }
+};
+struct SimCount {
+  long long nodes = 0, tris = 0;
+  void node() { nodes++; }
+  void tri() { tris++; }
+};
+
+struct SimBvh {
+  std::vector<Node> nodes;
+  std::vector<float4> tv0, tv1, tv2;
+  std::vector<int32_t> vid;  // 4 per slot
+  int max_depth = 0;
+};
+
+static void box_of(const SimBvh& b, const std::vector<float>& leaf_box, const std::vector<float>& node_box,
+                   int child, float* out) {
+  const float* s = child < 0 ? &leaf_box[6 * (size_t)(~child)] : &node_box[6 * (size_t)child];
+  memcpy(out, s, 24);
+  (void)b;
+}
+
+static void build(const float* v, int64_t V, const int32_t* tris, int64_t T, SimBvh& b) {
+  float ubox[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int64_t i = 0; i < V; i++)
+    for (int k = 0; k < 3; k++) {
+      ubox[k] = fminf(ubox[k], v[3 * i + k]);
+      ubox[3 + k] = fmaxf(ubox[3 + k], v[3 * i + k]);
+    }
+  std::vector<uint32_t> codes(T), idx(T);
+  for (int64_t c = 0; c < T; c++) {
+    float q[3];
+    for (int k = 0; k < 3; k++) {
+      float a = v[3 * tris[3 * c] + k], bb = v[3 * tris[3 * c + 1] + k], e = v[3 * tris[3 * c + 2] + k];
+      float mn = fminf(a, fminf(bb, e)), mx = fmaxf(a, fmaxf(bb, e));
+      float ext = ubox[3 + k] - ubox[k];
+      q[k] = ext > 0.f ? (0.5f * (mn + mx) - ubox[k]) / ext : 0.5f;
+    }
+    codes[c] = morton30(q[0], q[1], q[2]);
+    idx[c] = (uint32_t)c;
+  }
+  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t c) { return codes[a] < codes[c]; });
+  std::vector<uint32_t> sc(T);
+  for (int64_t s = 0; s < T; s++) sc[s] = codes[idx[s]];
+  b.tv0.resize(T); b.tv1.resize(T); b.tv2.resize(T); b.vid.resize(4 * T);
+  std::vector<float> leaf_box(6 * T);
+  for (int64_t s = 0; s < T; s++) {
+    int cell = (int)idx[s];
+    const float* p0 = v + 3 * tris[3 * cell];
+    const float* p1 = v + 3 * tris[3 * cell + 1];
+    const float* p2 = v + 3 * tris[3 * cell + 2];
+    for (int k = 0; k < 3; k++) {
+      leaf_box[6 * s + k] = fminf(p0[k], fminf(p1[k], p2[k]));
+      leaf_box[6 * s + 3 + k] = fmaxf(p0[k], fmaxf(p1[k], p2[k]));
+    }
+    float w;
+    memcpy(&w, &cell, 4);
+    b.tv0[s] = {p0[0], p0[1], p0[2], w};
+    b.tv1[s] = {p1[0], p1[1], p1[2], 0.f};
+    b.tv2[s] = {p2[0], p2[1], p2[2], 0.f};
+    b.vid[4 * s] = tris[3 * cell]; b.vid[4 * s + 1] = tris[3 * cell + 1];
+    b.vid[4 * s + 2] = tris[3 * cell + 2]; b.vid[4 * s + 3] = cell;
+  }
+  int n = (int)T;
+  if (n == 1) {
+    Node nd;
+    for (int k = 0; k < 6; k++) { nd.box[k] = leaf_box[k]; nd.box[6 + k] = leaf_box[k]; }
+    nd.c0 = ~0; nd.c1 = ~0; nd.parent = -1; nd.sibling = -1;
+    b.nodes.assign(1, nd);
+    return;
+  }
+  int ni = n - 1;
+  std::vector<int> c0(ni), c1(ni), par(ni, -1);
+  for (int i = 0; i < ni; i++) {
+    int first, last, split;
+    karras_node(sc.data(), n, i, &first, &last, &split);
+    c0[i] = (split == first) ? ~split : split;
+    c1[i] = (split + 1 == last) ? ~(split + 1) : split + 1;
+    if (c0[i] >= 0) par[c0[i]] = i;
+    if (c1[i] >= 0) par[c1[i]] = i;
+  }
+  // boxes bottom-up: process nodes by decreasing depth (iterative post-order)
+  std::vector<float> node_box(6 * (size_t)ni);
+  std::vector<int> order, depth(ni, 0), stack{0};
+  while (!stack.empty()) {
+    int i = stack.back(); stack.pop_back();
+    order.push_back(i);
+    if (c0[i] >= 0) { depth[c0[i]] = depth[i] + 1; stack.push_back(c0[i]); }
+    if (c1[i] >= 0) { depth[c1[i]] = depth[i] + 1; stack.push_back(c1[i]); }
+    b.max_depth = std::max(b.max_depth, depth[i] + 1);
+  }
+  if ((int)order.size() != ni) { b.nodes.clear(); return; }  // topology error
+  for (int q = ni - 1; q >= 0; q--) {
+    int i = order[q];
+    float b0[6], b1[6];
+    box_of(b, leaf_box, node_box, c0[i], b0);
+    box_of(b, leaf_box, node_box, c1[i], b1);
+    for (int k = 0; k < 3; k++) {
+      node_box[6 * (size_t)i + k] = fminf(b0[k], b1[k]);
+      node_box[6 * (size_t)i + 3 + k] = fmaxf(b0[k + 3], b1[k + 3]);
+    }
+  }
+  b.nodes.resize(ni);
+  for (int i = 0; i < ni; i++) {
+    Node nd;
+    box_of(b, leaf_box, node_box, c0[i], nd.box);
+    box_of(b, leaf_box, node_box, c1[i], nd.box + 6);
+    nd.c0 = c0[i]; nd.c1 = c1[i]; nd.parent = par[i];
+    nd.sibling = -1;
+    if (par[i] >= 0) nd.sibling = (c0[par[i]] == i) ? c1[par[i]] : c0[par[i]];
+    b.nodes[i] = nd;
+  }
+}
+
+extern "C" __attribute__((visibility("default")))
+int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* normals,
+               const float* views, int n_views, double radius, int res, double plane_scale, double spacing,
+               int use_z, int split_z, int enc, double zscale, float* out_feat, int32_t* out_ids,
+               double* out_t, long long* work /* nodes, tris, max_depth */) {
+  SimBvh b;
+  build(verts, V, tris, T, b);
+  if (b.nodes.empty()) return 1;
+  int C = (use_z && split_z) ? 4 : 3;
+  SimCount cnt;
+  SimFetch f{b.nodes.data()};
+  for (int v = 0; v < n_views; v++) {
+    View vw;
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    for (int j = 0; j < res; j++)
+      for (int i = 0; i < res; i++) {
+        double o[3];
+        view_ray(vw, res, i, j, spacing, o);
+        Hit h = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o, vw.dir, vw.dirf, vw.invf, vw.slack,
+                         vw.tslack, cnt);
+        size_t pix = ((size_t)v * res + j) * res + i;
+        float px[4] = {0, 0, 0, 0};
+        double t = -1.0;
+        if (h.slot >= 0) {
+          float4 a = b.tv0[h.slot], bb = b.tv1[h.slot], e = b.tv2[h.slot];
+          float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
+          double x[3], w[3];
+          tri_exact(o, vw.dir, P0, P1, P2, DBL_MAX, &t, x, w);
+          const int32_t* vid = &b.vid[4 * (size_t)h.slot];
+          shade(o, x, w, normals + 3 * vid[0], normals + 3 * vid[1], normals + 3 * vid[2], use_z, split_z, enc,
+                zscale, px);
+        }
+        if (out_feat) memcpy(out_feat + pix * C, px, 4 * C);
+        if (out_ids) out_ids[pix] = h.cell;
+        if (out_t) out_t[pix] = t;
+      }
+  }
+  if (work) { work[0] = cnt.nodes; work[1] = cnt.tris; work[2] = b.max_depth; }
+  return 0;
+}
