@@ -1,0 +1,332 @@
+"""ctypes binding of libflyby_b200.so (include/flyby_b200.h).
+
+The library is the product: every compute call below runs hand-written sm_100a
+CUDA kernels.  There is no CPU fallback -- if the shared library is missing or
+no CUDA device is present, creating a :class:`Context` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libflyby_b200.so")
+ABI_VERSION = 1
+
+_lib = None
+
+
+class FlyByError(RuntimeError):
+    pass
+
+
+class NormOpts(C.Structure):
+    _fields_ = [("centre_mode", C.c_int32), ("scale_mode", C.c_int32), ("has_translate", C.c_int32),
+                ("has_scale", C.c_int32), ("translate", C.c_double * 3), ("scale_factor", C.c_double),
+                ("skip", C.c_int32), ("reserved", C.c_int32)]
+
+
+class RenderOpts(C.Structure):
+    _fields_ = [("use_z", C.c_int32), ("split_z", C.c_int32), ("normal_encoding", C.c_int32),
+                ("reserved", C.c_int32), ("plane_scale", C.c_double), ("plane_spacing", C.c_double),
+                ("z_scale", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_normalise", C.c_float), ("ms_normals", C.c_float), ("ms_sort", C.c_float),
+                ("ms_tree", C.c_float), ("ms_render", C.c_float), ("reserved", C.c_int32),
+                ("n_rays", C.c_int64), ("n_hits", C.c_int64), ("nodes_visited", C.c_int64),
+                ("tris_tested", C.c_int64)]
+
+
+# every symbol include/flyby_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "flyby_create", "flyby_destroy", "flyby_last_error", "flyby_abi_version", "flyby_synchronize",
+    "flyby_set_mesh", "flyby_build", "flyby_get_mesh", "flyby_get_bvh", "flyby_views_icosahedron",
+    "flyby_views_spiral", "flyby_views_custom", "flyby_num_views", "flyby_get_views",
+    "flyby_generate_rays", "flyby_render", "flyby_cast", "flyby_point_features", "flyby_backproject",
+    "flyby_backproject_soft", "flyby_votes_argmax", "flyby_cells_to_points", "flyby_nccl_unique_id",
+    "flyby_nccl_init", "flyby_votes_allreduce", "flyby_get_stats", "flyby_set_count_work",
+    "flyby_launch_count",
+]
+
+NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2}
+
+
+def load():
+    """Load the CUDA library; raises FlyByError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FlyByError(
+            "libflyby_b200.so is missing (%s). Build it with `python __graft_entry__.py` or "
+            "`make -C fly-by-cnn_b200`; there is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.flyby_last_error.restype = C.c_char_p
+    lib.flyby_last_error.argtypes = [C.c_void_p]
+    lib.flyby_destroy.restype = None
+    lib.flyby_destroy.argtypes = [C.c_void_p]
+    if lib.flyby_abi_version() != ABI_VERSION:
+        raise FlyByError("libflyby_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(x):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise FlyByError("array must be C-contiguous")
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):  # torch tensor (device or host)
+        if not x.is_contiguous():
+            raise FlyByError("tensor must be contiguous")
+        return C.c_void_p(x.data_ptr())
+    raise FlyByError("unsupported buffer type %r" % type(x))
+
+
+def _check_dtype(x, np_dtype, name):
+    if x is None or isinstance(x, int):
+        return
+    if isinstance(x, np.ndarray):
+        ok = x.dtype == np.dtype(np_dtype)
+    else:
+        ok = str(x.dtype).replace("torch.", "") == np.dtype(np_dtype).name
+    if not ok:
+        raise FlyByError("%s must have dtype %s, got %s" % (name, np.dtype(np_dtype).name, x.dtype))
+
+
+class Context:
+    """One GPU context = one device + one stream + the mesh/BVH/viewpoints it holds."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = load()
+        self._h = C.c_void_p()
+        rc = self._lib.flyby_create(C.c_int(int(device)), C.c_void_p(stream or 0), C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise FlyByError("flyby_create(device=%d) failed with status %d: a CUDA device is "
+                             "required, there is no CPU path" % (device, rc))
+        self.device = int(device)
+        self.n_verts = 0
+        self.n_tris = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.flyby_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.flyby_last_error(self._h)
+            raise FlyByError("flyby status %d: %s" % (rc, msg.decode() if msg else ""))
+
+    def synchronize(self):
+        self._ck(self._lib.flyby_synchronize(self._h))
+
+    # ---- mesh ---------------------------------------------------------------
+    def set_mesh(self, verts, tris, centre_mode=0, scale_mode=0, translate=None, scale_factor=None,
+                 skip_normalise=False):
+        _check_dtype(verts, np.float32, "verts")
+        _check_dtype(tris, np.int32, "tris")
+        V = int(verts.shape[0])
+        T = int(tris.shape[0])
+        o = NormOpts()
+        o.centre_mode, o.scale_mode = int(centre_mode), int(scale_mode)
+        if translate is not None:
+            o.has_translate = 1
+            for k in range(3):
+                o.translate[k] = float(translate[k])
+        if scale_factor is not None:
+            o.has_scale = 1
+            o.scale_factor = float(scale_factor)
+        o.skip = 1 if skip_normalise else 0
+        self._ck(self._lib.flyby_set_mesh(self._h, _ptr(verts), C.c_int64(V), _ptr(tris), C.c_int64(T),
+                                          C.byref(o)))
+        self.n_verts, self.n_tris = V, T
+
+    def build(self):
+        self._ck(self._lib.flyby_build(self._h))
+
+    def get_mesh(self):
+        """(unit_verts [V,3] f32, normals [V,3] f32, centre [3], scale) as numpy."""
+        uv = np.empty((self.n_verts, 3), np.float32)
+        nr = np.empty((self.n_verts, 3), np.float32)
+        cs = np.zeros(4, np.float64)
+        self._ck(self._lib.flyby_get_mesh(self._h, _ptr(uv), _ptr(nr), _ptr(cs)))
+        return uv, nr, cs[:3].copy(), float(cs[3])
+
+    def get_bvh(self):
+        """(nodes uint32 [n,16], n_top, slot_cell_ids [T]) -- introspection for tests."""
+        n_nodes = C.c_int64(0)
+        n_top = C.c_int32(0)
+        self._ck(self._lib.flyby_get_bvh(self._h, C.byref(n_nodes), C.byref(n_top), None, None))
+        nodes = np.empty((n_nodes.value, 16), np.uint32)
+        slots = np.empty(self.n_tris, np.int32)
+        self._ck(self._lib.flyby_get_bvh(self._h, C.byref(n_nodes), C.byref(n_top), _ptr(nodes), _ptr(slots)))
+        return nodes, int(n_top.value), slots
+
+    # ---- viewpoints ---------------------------------------------------------
+    def views_icosahedron(self, subdivision, radius, dedupe=0):
+        self._ck(self._lib.flyby_views_icosahedron(self._h, C.c_int(int(subdivision)), C.c_double(radius),
+                                                   C.c_int(int(dedupe))))
+        return self.num_views()
+
+    def views_spiral(self, n_samples, turns, radius):
+        self._ck(self._lib.flyby_views_spiral(self._h, C.c_int(int(n_samples)), C.c_double(float(turns)),
+                                              C.c_double(radius)))
+        return self.num_views()
+
+    def views_custom(self, points, radius):
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        self._ck(self._lib.flyby_views_custom(self._h, _ptr(pts), C.c_int(len(pts)), C.c_double(radius)))
+        return len(pts)
+
+    def num_views(self):
+        n = C.c_int(0)
+        self._ck(self._lib.flyby_num_views(self._h, C.byref(n)))
+        return n.value
+
+    def get_views(self):
+        out = np.empty((self.num_views(), 3), np.float32)
+        self._ck(self._lib.flyby_get_views(self._h, _ptr(out)))
+        return out
+
+    # ---- rendering ----------------------------------------------------------
+    @staticmethod
+    def render_opts(use_z=1, split_z=1, normal_encoding="unit01", plane_scale=1.0, plane_spacing=1.0,
+                    z_scale=1.0):
+        o = RenderOpts()
+        o.use_z, o.split_z = int(bool(use_z)), int(bool(split_z))
+        o.normal_encoding = NORMAL_ENCODINGS[normal_encoding] if isinstance(normal_encoding, str) \
+            else int(normal_encoding)
+        o.plane_scale, o.plane_spacing, o.z_scale = float(plane_scale), float(plane_spacing), float(z_scale)
+        return o
+
+    @staticmethod
+    def channels(opts):
+        return 4 if (opts.use_z and opts.split_z) else 3
+
+    def generate_rays(self, res, opts, view_begin=0, view_end=None):
+        ve = self.num_views() if view_end is None else view_end
+        out = np.empty((ve - view_begin, res, res, 6), np.float64)
+        self._ck(self._lib.flyby_generate_rays(self._h, C.c_int(view_begin), C.c_int(ve), C.c_int(res),
+                                               C.byref(opts), _ptr(out)))
+        return out
+
+    def render_into(self, res, opts, features=None, cell_ids=None, t=None, view_begin=0, view_end=None):
+        """Render into caller buffers (numpy = host staging + sync; torch cuda tensors = in place, async)."""
+        ve = self.num_views() if view_end is None else view_end
+        _check_dtype(features, np.float32, "features")
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        _check_dtype(t, np.float64, "t")
+        self._ck(self._lib.flyby_render(self._h, C.c_int(view_begin), C.c_int(ve), C.c_int(res), C.byref(opts),
+                                        _ptr(features), _ptr(cell_ids), _ptr(t)))
+
+    def render(self, res, opts, view_begin=0, view_end=None, want_t=False):
+        """Render to new numpy arrays: (features [n,res,res,C], cell_ids [n,res,res][, t])."""
+        ve = self.num_views() if view_end is None else view_end
+        n = ve - view_begin
+        feat = np.empty((n, res, res, self.channels(opts)), np.float32)
+        ids = np.empty((n, res, res), np.int32)
+        tt = np.empty((n, res, res), np.float64) if want_t else None
+        self.render_into(res, opts, feat, ids, tt, view_begin, ve)
+        return (feat, ids, tt) if want_t else (feat, ids)
+
+    def cast(self, rays):
+        r = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        n = len(r)
+        ids = np.empty(n, np.int32)
+        tt = np.empty(n, np.float64)
+        w = np.empty((n, 3), np.float64)
+        self._ck(self._lib.flyby_cast(self._h, _ptr(r), C.c_int64(n), _ptr(ids), _ptr(tt), _ptr(w)))
+        return ids, tt, w
+
+    # ---- features / labels --------------------------------------------------
+    def point_features(self, cell_ids, feats, zero=0.0, out=None):
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        _check_dtype(feats, np.float32, "feats")
+        n_pix = int(np.prod(cell_ids.shape))
+        F = int(feats.shape[1]) if len(feats.shape) > 1 else 1
+        if out is None:
+            out = np.empty(tuple(cell_ids.shape) + (F,), np.float32)
+        self._ck(self._lib.flyby_point_features(self._h, _ptr(cell_ids), C.c_int64(n_pix), _ptr(feats),
+                                                C.c_int(F), C.c_float(zero), C.c_int(0), _ptr(out)))
+        return out
+
+    def backproject(self, cell_ids, labels, n_classes, votes=None):
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        _check_dtype(labels, np.int32, "labels")
+        n_pix = int(np.prod(cell_ids.shape))
+        if votes is None:
+            votes = np.zeros((self.n_tris, n_classes), np.int32)
+        _check_dtype(votes, np.int32, "votes")
+        self._ck(self._lib.flyby_backproject(self._h, _ptr(cell_ids), _ptr(labels), C.c_int64(n_pix),
+                                             C.c_int(n_classes), _ptr(votes)))
+        return votes
+
+    def backproject_soft(self, cell_ids, probs, n_classes, votes_fx=None):
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        _check_dtype(probs, np.float32, "probs")
+        n_pix = int(np.prod(cell_ids.shape))
+        if votes_fx is None:
+            votes_fx = np.zeros((self.n_tris, n_classes), np.int64)
+        _check_dtype(votes_fx, np.int64, "votes_fx")
+        self._ck(self._lib.flyby_backproject_soft(self._h, _ptr(cell_ids), _ptr(probs), C.c_int64(n_pix),
+                                                  C.c_int(n_classes), _ptr(votes_fx)))
+        return votes_fx
+
+    def votes_argmax(self, votes, default=0, out=None):
+        _check_dtype(votes, np.int32, "votes")
+        n_cells, K = int(votes.shape[0]), int(votes.shape[1])
+        if out is None:
+            out = np.empty(n_cells, np.int32)
+        self._ck(self._lib.flyby_votes_argmax(self._h, _ptr(votes), C.c_int64(n_cells), C.c_int(K),
+                                              C.c_int32(default), _ptr(out)))
+        return out
+
+    def cells_to_points(self, cell_labels, default=0, out=None):
+        _check_dtype(cell_labels, np.int32, "cell_labels")
+        if out is None:
+            out = np.empty(self.n_verts, np.int32)
+        self._ck(self._lib.flyby_cells_to_points(self._h, _ptr(cell_labels), C.c_int32(default), _ptr(out)))
+        return out
+
+    # ---- collective ---------------------------------------------------------
+    def nccl_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._ck(self._lib.flyby_nccl_unique_id(self._h, buf))
+        return bytes(buf)
+
+    def nccl_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self._lib.flyby_nccl_init(self._h, buf, C.c_int(rank), C.c_int(world)))
+
+    def votes_allreduce(self, votes, root=-1):
+        n = int(np.prod(votes.shape))
+        self._ck(self._lib.flyby_votes_allreduce(self._h, _ptr(votes), C.c_int64(n), C.c_int(root)))
+
+    # ---- measurement --------------------------------------------------------
+    def stats(self):
+        s = Stats()
+        self._ck(self._lib.flyby_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_ if k != "reserved"}
+
+    def set_count_work(self, enable):
+        self._ck(self._lib.flyby_set_count_work(self._h, C.c_int(1 if enable else 0)))
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        self._ck(self._lib.flyby_launch_count(self._h, C.byref(n)))
+        return n.value

@@ -69,8 +69,16 @@ ORC_API void orc_unit_surf(const float* verts, int64_t V, int centre_mode, int s
       double p = verts[3 * i + k];
       if (p < lo[k]) lo[k] = p;
       if (p > hi[k]) hi[k] = p;
-      sum[k] += p;
     }
+  /* centre of mass: fixed summation order (1024-point chunks, then the chunk
+   * sums) so that a parallel implementation can reproduce it bit for bit */
+  for (int64_t b = 0; b < V; b += 1024) {
+    double cs[3] = {0, 0, 0};
+    int64_t e = b + 1024 < V ? b + 1024 : V;
+    for (int64_t i = b; i < e; i++)
+      for (int k = 0; k < 3; k++) cs[k] += (double)verts[3 * i + k];
+    for (int k = 0; k < 3; k++) sum[k] += cs[k];
+  }
   double c[3];
   for (int k = 0; k < 3; k++) {
     if (has_translate) c[k] = translate[k];

@@ -1,0 +1,323 @@
+"""GPU parity tests: every call goes through the C-ABI (flyby_b200._cabi) and is
+compared with the CPU oracle (oracle/flyby_oracle.c) on the same seeded inputs.
+
+Bar: hit cell ids bit-exact (tie-break smallest t, then lowest cell id; any
+disagreement is counted and fails); t / depth / normals within 1e-5 relative
+(they are in fact expected to be bit-equal, which is reported).
+"""
+import numpy as np
+import pytest
+
+from flyby_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _build(ctx, P, F, **kw):
+    ctx.set_mesh(P, F, **kw)
+    ctx.build()
+    return ctx.get_mesh()
+
+
+def _oracle_mesh(orc, P, F, **kw):
+    U, c, s = orc.unit_surf(P, **kw)
+    return U, orc.point_normals(U, F), c, s
+
+
+MESHES = {
+    "bumpy12": lambda: synth.bumpy_sphere(12, 0),
+    "bumpy40": lambda: synth.bumpy_sphere(40, 3),
+    "crown30": lambda: synth.dental_crown(30, 1),
+    "cube": lambda: synth.cube(),
+}
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+def test_unit_surf_and_normals(gpu_ctx, orc, name):
+    P, F = MESHES[name]()
+    uv, nrm, c, s = _build(gpu_ctx, P, F)
+    U, N, co, so = _oracle_mesh(orc, P, F)
+    assert np.array_equal(c, co) and s == so
+    assert np.array_equal(uv, U)
+    assert np.array_equal(nrm, N), "max diff %g" % np.abs(nrm - N).max()
+
+
+@pytest.mark.parametrize("kw", [dict(centre_mode=1), dict(scale_mode=1), dict(centre_mode=1, scale_mode=1),
+                                dict(translate=[1.0, -2.0, 0.5]), dict(scale_factor=0.03),
+                                dict(translate=[0.5, 0.25, -1.0], scale_factor=0.02)])
+def test_unit_surf_options(gpu_ctx, orc, kw):
+    P, F = synth.bumpy_sphere(20, 4)
+    uv, nrm, c, s = _build(gpu_ctx, P, F, **kw)
+    U, c2, s2 = orc.unit_surf(P, **kw)
+    assert np.allclose(c, c2, rtol=1e-14) and np.isclose(s, s2, rtol=1e-14)
+    assert np.array_equal(uv, U)
+
+
+def test_views_icosahedron(gpu_ctx, orc):
+    for L, n in [(1, 12), (2, 42), (3, 92), (4, 162), (5, 252), (10, 1002)]:
+        assert gpu_ctx.views_icosahedron(L, 2.75) == n
+        assert np.array_equal(gpu_ctx.get_views(), orc.icosahedron(L, 2.75))
+    # float32-equality emulation of the reference's point locator (hazard H1)
+    for L in (2, 3, 5):
+        n = gpu_ctx.views_icosahedron(L, 2.0, dedupe=1)
+        ref = orc.icosahedron(L, 2.0, dedupe=1)
+        assert n == len(ref) and np.array_equal(gpu_ctx.get_views(), ref)
+
+
+def test_views_spiral(gpu_ctx, orc):
+    for N, turns, R in [(64, 4, 4.0), (64, 4, 2.0), (17, 3, 1.5)]:
+        assert gpu_ctx.views_spiral(N, turns, R) == N
+        got, ref = gpu_ctx.get_views(), orc.spiral(N, turns, R)
+        # device sin/cos differ from libm by <= 1 ulp of double; after float32 storage at most 1 float ulp
+        assert np.all(np.abs(got - ref) <= np.spacing(np.abs(ref).astype(np.float32)) + 1e-30)
+        assert np.array_equal(got[0], np.array([0, 0, R], np.float32))
+
+
+@pytest.mark.parametrize("ps,spacing", [(1.0, 1.0), (2.0, 1.0), (1.0, 0.75)])
+def test_rays(gpu_ctx, orc, ps, spacing):
+    gpu_ctx.views_icosahedron(2, 2.0)
+    views = gpu_ctx.get_views()
+    opts = gpu_ctx.render_opts(plane_scale=ps, plane_spacing=spacing)
+    res = 33
+    rays = gpu_ctx.generate_rays(res, opts)
+    for v in range(len(views)):
+        ref, _ = orc.view_rays(views[v], 2.0, res, ps, spacing)
+        assert np.array_equal(rays[v].reshape(-1, 6), ref), "view %d" % v
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+def test_bvh_invariants(gpu_ctx, name):
+    P, F = MESHES[name]()
+    uv, _, _, _ = _build(gpu_ctx, P, F)
+    nodes, n_top, slots = gpu_ctx.get_bvh()
+    T = len(F)
+    assert len(nodes) == T - 1 and sorted(slots.tolist()) == list(range(T))
+    box = nodes[:, :12].view(np.float32)
+    link = nodes[:, 12:].view(np.int32)
+    tri = uv[F[slots]]  # [T,3,3] in slot order
+    leaf_lo, leaf_hi = tri.min(1), tri.max(1)
+    # every leaf referenced exactly once; every internal node except the root exactly once
+    ch = link[:, :2].reshape(-1)
+    assert sorted((~ch[ch < 0]).tolist()) == list(range(T))
+    assert sorted(ch[ch >= 0].tolist()) == list(range(1, T - 1))
+    assert link[0, 2] == -1
+    # boxes: compute node boxes bottom-up from the stored child boxes and compare
+    lo = np.minimum(box[:, 0:3], box[:, 6:9])
+    hi = np.maximum(box[:, 3:6], box[:, 9:12])
+    for side in (0, 1):
+        c = link[:, side]
+        b_lo, b_hi = box[:, 6 * side:6 * side + 3], box[:, 6 * side + 3:6 * side + 6]
+        isleaf = c < 0
+        assert np.array_equal(b_lo[isleaf], leaf_lo[~c[isleaf]]) and np.array_equal(b_hi[isleaf], leaf_hi[~c[isleaf]])
+        assert np.array_equal(b_lo[~isleaf], lo[c[~isleaf]]) and np.array_equal(b_hi[~isleaf], hi[c[~isleaf]])
+        # parent / sibling links
+        inner = c[~isleaf]
+        idx = np.nonzero(~isleaf)[0]
+        assert np.array_equal(link[inner, 2], idx)
+        assert np.array_equal(link[inner, 3], link[idx, 1 - side])
+    # top block is closed under "parent" (a breadth-first prefix)
+    assert 1 <= n_top <= min(1024, T - 1)
+    par = link[1:n_top, 2]
+    assert np.all(par < np.arange(1, n_top))
+
+
+CONFIGS = [
+    dict(use_z=1, split_z=1),
+    dict(use_z=1, split_z=0),
+    dict(use_z=0, split_z=0),
+    dict(use_z=1, split_z=1, normal_encoding="byte255"),
+    dict(use_z=1, split_z=1, normal_encoding="signed", z_scale=0.25),
+    dict(use_z=1, split_z=1, plane_scale=2.0),
+    dict(use_z=1, split_z=1, plane_spacing=0.8),
+]
+ENC = {"unit01": 0, "byte255": 1, "signed": 2}
+
+
+def _compare_render(ctx, orc, P, F, radius, res, cfg, views=None, grid_div=32):
+    uv, nrm, _, _ = _build(ctx, P, F)
+    if views is None:
+        views = ctx.get_views()
+    opts = ctx.render_opts(**cfg)
+    feat, ids, t = ctx.render(res, opts, want_t=True)
+    fo, io, to = orc.render(uv, F, nrm, views, radius, res, plane_scale=cfg.get("plane_scale", 1.0),
+                            spacing=cfg.get("plane_spacing", 1.0), use_z=cfg["use_z"], split_z=cfg["split_z"],
+                            normal_encoding=ENC[cfg.get("normal_encoding", "unit01")],
+                            zscale=cfg.get("z_scale", 1.0), grid=True, grid_div=grid_div, want_t=True)
+    mism = int((ids != io).sum())
+    assert mism == 0, "%d / %d hit cell ids differ (grazing-edge disagreements are not tolerated)" % (mism, ids.size)
+    hit = io >= 0
+    assert np.array_equal(t[~hit], to[~hit])
+    assert np.allclose(t[hit], to[hit], rtol=RTOL, atol=0)
+    assert np.allclose(feat, fo, rtol=RTOL, atol=1e-7)
+    return dict(rays=ids.size, hits=int(hit.sum()), t_bit_equal=bool(np.array_equal(t, to)),
+                feat_bit_equal=bool(np.array_equal(feat, fo)))
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+@pytest.mark.parametrize("name", ["bumpy12", "crown30"])
+def test_render_parity(gpu_ctx, orc, name, cfg):
+    P, F = MESHES[name]()
+    gpu_ctx.views_icosahedron(2, 2.0)
+    r = _compare_render(gpu_ctx, orc, P, F, 2.0, 96, cfg)
+    assert r["hits"] > 0 and r["t_bit_equal"] and r["feat_bit_equal"]
+
+
+def test_render_spiral_and_odd_resolution(gpu_ctx, orc):
+    P, F = synth.dental_crown(40, 2)
+    gpu_ctx.views_spiral(24, 4, 4.0)
+    for res in (1, 7, 61, 224):
+        r = _compare_render(gpu_ctx, orc, P, F, 4.0, res, dict(use_z=1, split_z=0))
+    assert r["hits"] > 0
+
+
+def test_render_view_ranges_concatenate(gpu_ctx, orc):
+    """Sharding by view (config 5): slabs of a view range equal the full render bit for bit."""
+    P, F = synth.bumpy_sphere(30, 7)
+    _build(gpu_ctx, P, F)
+    n = gpu_ctx.views_icosahedron(2, 2.0)
+    opts = gpu_ctx.render_opts()
+    full_f, full_i = gpu_ctx.render(64, opts)
+    parts = [gpu_ctx.render(64, opts, view_begin=a, view_end=b) for a, b in [(0, 5), (5, 6), (6, 30), (30, n)]]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), full_f)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), full_i)
+
+
+def test_cube_grazing_tie_break(gpu_ctx, orc):
+    """Rays exactly through shared edges / vertices of a cube: both adjacent cells are
+    inclusive hits; the documented tie-break (smallest t, then lowest cell id) decides."""
+    P, F = synth.cube()
+    uv, nrm, _, _ = _build(gpu_ctx, P, F, skip_normalise=True)
+    assert np.array_equal(uv, P)
+    g = np.linspace(-1.0, 1.0, 9)
+    rays = []
+    for axis in range(3):
+        a, b = [k for k in range(3) if k != axis]
+        for u in g:
+            for v in g:
+                o = np.zeros(3); e = np.zeros(3)
+                o[a] = e[a] = u; o[b] = e[b] = v
+                o[axis], e[axis] = 3.0, -3.0
+                rays.append(np.concatenate([o, e]))
+                rays.append(np.concatenate([e, o]))
+    rays = np.array(rays)
+    ids, t, w = gpu_ctx.cast(rays)
+    io, to, xo, wo = orc.cast(uv, F, rays, grid=False)
+    assert np.array_equal(ids, io) and np.all(ids >= 0)
+    assert np.array_equal(t, to) and np.array_equal(w, wo)
+    # a ray through the face diagonal is an inclusive hit of both triangles: lowest id wins
+    diag = [i for i in range(len(rays)) if (np.sort(np.abs(rays[i][:3]))[:2] == 0).all()]
+    assert len(diag) > 0
+
+
+def test_cast_random_segments(gpu_ctx, orc):
+    rng = np.random.default_rng(11)
+    P, F = synth.bumpy_sphere(16, 5)
+    uv, _, _, _ = _build(gpu_ctx, P, F)
+    n = 20000
+    a = rng.normal(size=(n, 3)); a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b = rng.normal(size=(n, 3)); b /= np.linalg.norm(b, axis=1, keepdims=True)
+    rays = np.concatenate([a * rng.uniform(0.0, 3.0, (n, 1)), b * rng.uniform(0.0, 3.0, (n, 1))], axis=1)
+    # axis-parallel and degenerate (zero-length) segments
+    rays[:500, 3] = rays[:500, 0]; rays[:500, 4] = rays[:500, 1]
+    rays[500:1000, 4] = rays[500:1000, 1]
+    rays[1000:1010, 3:] = rays[1000:1010, :3]
+    ids, t, w = gpu_ctx.cast(rays)
+    io, to, xo, wo = orc.cast(uv, F, rays, grid=False)
+    assert int((ids != io).sum()) == 0
+    assert np.array_equal(t, to)
+    hit = io >= 0
+    assert hit.sum() > 1000 and np.array_equal(w[hit], wo[hit])
+
+
+def test_single_triangle_and_empty(gpu_ctx, orc):
+    V = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], np.float32)
+    F = np.array([[0, 1, 2]], np.int32)
+    gpu_ctx.views_custom(np.array([[0, 0, 2.0], [0, 0, -2.0], [2.0, 0, 0]], np.float32), 2.0)
+    r = _compare_render(gpu_ctx, orc, V, F, 2.0, 32, dict(use_z=1, split_z=1, plane_scale=2.0),
+                        views=gpu_ctx.get_views())
+    assert r["hits"] > 0
+    # a mesh without cells renders all-miss
+    gpu_ctx.set_mesh(V, np.zeros((0, 3), np.int32))
+    gpu_ctx.build()
+    feat, ids = gpu_ctx.render(16, gpu_ctx.render_opts())
+    assert np.all(ids == -1) and np.all(feat == 0)
+
+
+def test_bad_indices_rejected(gpu_ctx):
+    from flyby_b200 import FlyByError
+    V = np.zeros((3, 3), np.float32)
+    gpu_ctx.set_mesh(V, np.array([[0, 1, 3]], np.int32))
+    with pytest.raises(FlyByError):
+        gpu_ctx.build()
+
+
+def test_point_features_and_backprojection(gpu_ctx, orc):
+    rng = np.random.default_rng(3)
+    P, F = synth.bumpy_sphere(24, 9)
+    uv, _, _, _ = _build(gpu_ctx, P, F)
+    gpu_ctx.views_icosahedron(2, 2.0)
+    _, ids = gpu_ctx.render(128, gpu_ctx.render_opts())
+    feats = rng.normal(size=(len(P), 3)).astype(np.float32)
+    out = gpu_ctx.point_features(ids, feats, zero=-7.0)
+    assert np.array_equal(out, orc.point_features(ids, F, feats, zero=-7.0))
+    coords = gpu_ctx.point_features(ids, uv, zero=0.0)  # --point_features coords
+    assert np.array_equal(coords, orc.point_features(ids, F, uv, zero=0.0))
+    K = 34
+    labels = rng.integers(0, K, size=ids.shape).astype(np.int32)
+    labels[0, :4, :4] = -1  # invalid labels are ignored
+    votes = gpu_ctx.backproject(ids, labels, K)
+    ref = orc.backproject(ids, labels, len(F), K)
+    assert np.array_equal(votes, ref) and votes.sum() > 0
+    # accumulation over two calls == one call (determinism of the integer atomics)
+    half = ids.shape[0] // 2
+    v2 = gpu_ctx.backproject(ids[:half], labels[:half], K)
+    v2 = gpu_ctx.backproject(ids[half:], labels[half:], K, votes=v2)
+    assert np.array_equal(v2, ref)
+    cell_labels = gpu_ctx.votes_argmax(votes, default=33)
+    assert np.array_equal(cell_labels, orc.votes_argmax(ref, default=33))
+    pts = gpu_ctx.cells_to_points(cell_labels, default=33)
+    assert np.array_equal(pts, orc.cells_to_points(cell_labels, F, len(P), default=33))
+    # soft votes: fixed point 2^-20
+    probs = rng.random(size=ids.shape + (4,)).astype(np.float32)
+    vfx = gpu_ctx.backproject_soft(ids, probs, 4)
+    ref_fx = np.zeros((len(F), 4), np.int64)
+    hit = ids >= 0
+    np.add.at(ref_fx, ids[hit], np.rint(probs[hit].astype(np.float32) * np.float32(1048576.0)).astype(np.int64))
+    assert np.array_equal(vfx, ref_fx)
+
+
+def test_torch_device_buffers(gpu_ctx, orc):
+    """Device-resident inputs and outputs (the zero-copy path bench.py times)."""
+    torch = pytest.importorskip("torch")
+    P, F = synth.bumpy_sphere(24, 2)
+    dev = torch.device("cuda:0")
+    tp, tf = torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)
+    gpu_ctx.set_mesh(tp, tf)
+    gpu_ctx.build()
+    n = gpu_ctx.views_icosahedron(1, 2.0)
+    opts = gpu_ctx.render_opts()
+    feat = torch.empty((n, 80, 80, 4), dtype=torch.float32, device=dev)
+    ids = torch.empty((n, 80, 80), dtype=torch.int32, device=dev)
+    gpu_ctx.render_into(80, opts, feat, ids)
+    gpu_ctx.synchronize()
+    f2, i2 = gpu_ctx.render(80, opts)
+    assert np.array_equal(ids.cpu().numpy(), i2) and np.array_equal(feat.cpu().numpy(), f2)
+    labels = (ids % 7).to(torch.int32)
+    votes = torch.zeros((len(F), 7), dtype=torch.int32, device=dev)
+    gpu_ctx.backproject(ids, labels, 7, votes=votes)
+    gpu_ctx.synchronize()
+    assert np.array_equal(votes.cpu().numpy(), orc.backproject(i2, labels.cpu().numpy(), len(F), 7))
+
+
+def test_config1_full_size(gpu_ctx, orc):
+    """BASELINE config 1 at full size: 100 820 triangles, icosahedron subdivision 2 (42 views),
+    resolution 512, radius 2, use_z 1, split_z 1 -- every one of the 11 M rays against the oracle."""
+    P, F = synth.bumpy_sphere(71, 0)
+    gpu_ctx.views_icosahedron(2, 2.0)
+    r = _compare_render(gpu_ctx, orc, P, F, 2.0, 512, dict(use_z=1, split_z=1), grid_div=64)
+    assert r["rays"] == 42 * 512 * 512 and r["hits"] > r["rays"] // 2
+    assert r["t_bit_equal"] and r["feat_bit_equal"]
+    st = gpu_ctx.stats()
+    assert st["n_hits"] == r["hits"]
