@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- views/s (and Mrays/s) of the fly-by hot path at resolution 512.
+
+Workload (BASELINE.json configs[2], the res-512 configuration the metric is
+quoted on, one GPU's share): synthetic 200 000-triangle closed surfaces,
+icosahedron subdivision 3 -> 92 views, resolution 512, radius 2, use_z 1,
+split_z 1 (C = 4).  One STEP = one mesh through the whole path: normalise to
+the unit sphere, point normals, LBVH build, 92 x 512 x 512 rays, feature + cell
+id tensors written.  Sharding is by mesh (weak scaling): every rank processes
+its own meshes, there is no data-path collective.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+value  : whole-job views/s with the mesh already resident in HBM.
+e2e    : same metric through the C-ABI with HOST buffers (pinned): H2D of the
+         mesh and D2H of the feature / id tensors inside the timed region.
+roofline: the render kernel against the measured HBM peak, algorithmic bytes
+          / CUDA-event duration of the kernel.
+cpu_baseline: the oracle's vtkCellLocator-style port timed on this box's host
+         cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "fly-by-cnn_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+LM = 100            # 20*LM^2 = 200 000 triangles
+SUBDIVISION = 3     # 92 views
+RES = 512
+RADIUS = 2.0
+PLANE_SCALE = 1.0   # reference default planeScaleFactor (fly_by_features.xml:76)
+MESH_POOL = 4       # distinct meshes per rank, cycled
+METRIC = "views/s at res 512 (fly-by feature extraction; Mrays/s = views/s * 0.262144)"
+
+
+def workload_config(n_views):
+    return {"workload": "BASELINE configs[2] share of one GPU: 200000-triangle synthetic surfaces, icosahedron "
+                        "subdivision 3 (%d views), resolution 512, radius 2, use_z 1, split_z 1, plane scale 1.0; "
+                        "one step = one mesh (unit-surf + normals + LBVH build + %d rays + tensor write)"
+                        % (n_views, n_views * RES * RES),
+            "triangles": 20 * LM * LM, "views": n_views, "resolution": RES, "channels": 4,
+            "sharding": "by mesh, no collective",
+            "l2": "explicit 256 MiB L2 flush between timed steps (outside the per-step events)"}
+
+
+def algorithmic_bytes(n_rays, C, T, V):
+    """DESIGN.md / SURVEY 8(d): compulsory traffic of one render launch."""
+    return n_rays * (4 * C + 4) + T * 36 + V * 12 + (2 * T - 1) * 32
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path: vtkCellLocator-style bucket grid (VTK default
+    bucket rule) + VTK segment/triangle test, restated in oracle/flyby_oracle.c (the reference itself
+    needs VTK 9 and cannot be built here), all host threads, on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from flyby_b200 import synth
+    P, F = synth.bumpy_sphere(LM, seed=0)
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    views = orc.icosahedron(SUBDIVISION, RADIUS)
+    sample_views = 2  # per step
+    cores = orc.num_threads()
+
+    def step(k):
+        sel = views[(k * sample_views) % len(views):][:sample_views]
+        t0 = time.perf_counter()
+        orc.render(U, F, N, sel, RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=0)
+        return time.perf_counter() - t0
+
+    for k in range(args.warmup):
+        step(k)
+    times = [step(args.warmup + k) for k in range(args.steps)]
+    sec_per_view = sum(times) / (args.steps * sample_views)
+    value = 1.0 / sec_per_view
+    sample = ("%d of %d views per step at res %d on the 200000-triangle mesh, vtkCellLocator default buckets, "
+              "OpenMP over rays; unit-surf/normals/grid build not timed" % (sample_views, len(views), RES))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(len(views)),
+            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mrays_per_s": value * RES * RES / 1e6, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample():
+    from oracle import oracle as orc
+    from flyby_b200 import synth
+    P, F = synth.bumpy_sphere(LM, seed=0)
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    views = orc.icosahedron(SUBDIVISION, RADIUS)
+    out = {}
+    for name, div, nv in (("vtk_buckets", 0, 4), ("tuned_grid64", 64, 8)):
+        orc.render(U, F, N, views[:1], RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=div)
+        t0 = time.perf_counter()
+        orc.render(U, F, N, views[1:1 + nv], RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=div)
+        out[name] = nv / (time.perf_counter() - t0)
+    return {"value": out["vtk_buckets"], "unit": "views/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": "4 views at res 512 of the bench mesh, oracle port of vtkCellLocator (VTK default bucket "
+                      "rule) + VTK triangle test, OpenMP over rays, ray loop only",
+            "tuned_grid64_views_per_s": out["tuned_grid64"]}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from flyby_b200 import _cabi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the fly-by path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # an explicit (non-default) stream: the context launches every kernel on it and
+    # the timing events are recorded on the same stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = _cabi.Context(local, stream=stream.cuda_stream)
+    assert stream.cuda_stream != 0
+    n_views = ctx.views_icosahedron(SUBDIVISION, RADIUS)
+    opts = ctx.render_opts(use_z=1, split_z=1, plane_scale=PLANE_SCALE)
+    C = 4
+    n_rays = n_views * RES * RES
+
+    meshes = [synth.bumpy_sphere(LM, seed=rank * MESH_POOL + k) for k in range(MESH_POOL)]
+    dev_meshes = [(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)) for P, F in meshes]
+    pin_meshes = [(torch.from_numpy(P).pin_memory(), torch.from_numpy(F).pin_memory()) for P, F in meshes]
+    feat = torch.empty((n_views, RES, RES, C), dtype=torch.float32, device=dev)
+    ids = torch.empty((n_views, RES, RES), dtype=torch.int32, device=dev)
+    feat_host = torch.empty((n_views, RES, RES, C), dtype=torch.float32).pin_memory()
+    ids_host = torch.empty((n_views, RES, RES), dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    T, V = len(meshes[0][1]), len(meshes[0][0])
+
+    def step_resident(k):
+        P, F = dev_meshes[k % MESH_POOL]
+        ctx.set_mesh(P, F)
+        ctx.build()
+        ctx.render_into(RES, opts, feat, ids)
+
+    def step_e2e(k):
+        P, F = pin_meshes[k % MESH_POOL]
+        ctx.set_mesh(P.numpy(), F.numpy())
+        ctx.build()
+        ctx.render_into(RES, opts, feat_host.numpy(), ids_host.numpy())  # D2H inside, returns after the copy
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup, collect_render=False):
+        for k in range(warmup):
+            step_fn(k)
+        barrier()
+        total_ms, render_ms = 0.0, 0.0
+        for k in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn(warmup + k)
+            e1.record(stream)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            if collect_render:
+                render_ms += ctx.stats()["ms_render"]
+        barrier()
+        return total_ms / steps, render_ms / steps
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms_step, ms_render = timed(step_resident, args.steps, args.warmup, collect_render=True)
+    launches = ctx.launch_count() - l0
+    st = ctx.stats()
+    ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 5)), 1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([ms_step, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step_max, ms_e2e_max = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        alg = algorithmic_bytes(n_rays, C, T, V)
+        achieved = alg / (ms_render * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "render_kernel_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        views_per_s = world * n_views / (ms_step_max * 1e-3)
+        e2e_views = world * n_views / (ms_e2e_max * 1e-3)
+        cpu = cpu_baseline_sample() if world == 1 else None
+        line = {"metric": METRIC, "value": views_per_s, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64 (hit decision, depth, normals) over f32 traversal",
+                "data": "synthetic", "config": workload_config(n_views),
+                "mrays_per_s": views_per_s * RES * RES / 1e6,
+                "render_kernel_ms": ms_render, "render_mrays_per_s": n_rays / (ms_render * 1e-3) / 1e6,
+                "build_ms": {k: st[k] for k in ("ms_normalise", "ms_normals", "ms_sort", "ms_tree")},
+                "hit_fraction": st["n_hits"] / max(1, st["n_rays"]),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "kernel": "render_kernel",
+                             "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                             "note": "BVH traversal is L1/L2-latency bound; HBM fraction is expected to be ~1%"},
+                "e2e": {"value": e2e_views, "unit": "views/s", "ms_per_step": ms_e2e_max,
+                        "h2d_bytes_per_step": V * 12 + T * 12, "d2h_bytes_per_step": n_rays * (4 * C + 4)},
+                "gpu_launches": launches, "clocks": sampler.summary()}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

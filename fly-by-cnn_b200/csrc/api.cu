@@ -126,10 +126,19 @@ void flyby_destroy(flyby_ctx* c) {
 
 const char* flyby_last_error(const flyby_ctx* c) { return c ? c->err : "null context"; }
 
+// counters[6] is raised by the render kernel's watchdog (a scheduling bug must
+// surface as an error, never as a hung device)
+static int check_watchdog(flyby_ctx* c) {
+  unsigned long long flag = 0;
+  FB_CUDA(c, cudaMemcpyAsync(&flag, c->counters.as<unsigned long long>() + 6, 8, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (flag) return fail(c, FLYBY_ERR_CUDA, "render watchdog tripped in %llu warps: results are incomplete", flag);
+  return FLYBY_OK;
+}
+
 int flyby_synchronize(flyby_ctx* c) {
   CHECK_CTX(c);
-  FB_CUDA(c, cudaStreamSynchronize(c->stream));
-  return FLYBY_OK;
+  return check_watchdog(c);
 }
 
 int flyby_set_mesh(flyby_ctx* c, const float* verts, int64_t V, const int32_t* tris, int64_t T,
@@ -290,7 +299,8 @@ int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if ((rc = sf.finish(c, &need))) return rc;
   if ((rc = si.finish(c, &need))) return rc;
   if ((rc = st.finish(c, &need))) return rc;
-  return sync_if(c, need);
+  if (need) return check_watchdog(c);
+  return FLYBY_OK;
 }
 
 int flyby_cast(flyby_ctx* c, const double* rays, int64_t n, int32_t* out_ids, double* out_t, double* out_w) {

@@ -158,19 +158,27 @@ FB_HD bool tri_exact(const double* o, const double* d, const float* P0, const fl
   for (int k = 0; k < 3; k++) x[k] = FB_ADD(o[k], FB_MUL(t, d[k]));
   double xo[3] = {FB_SUB(x[0], pt1[0]), FB_SUB(x[1], pt1[1]), FB_SUB(x[2], pt1[2])};
   double tp = dot3(n, xo), n2 = dot3(n, n);
-  double cp[3];
-  for (int k = 0; k < 3; k++)
-    cp[k] = (n2 != 0.0) ? FB_SUB(x[k], FB_DIV(FB_MUL(tp, n[k]), n2)) : x[k];
+  // drop the dominant axis of n (first max wins); only the two kept components
+  // of the projected point are needed, selected without indexed arrays
   int idx = 0;
   double maxc = 0.0;
-  for (int k = 0; k < 3; k++) {
-    double f = n[k] < 0 ? -n[k] : n[k];
-    if (f > maxc) { maxc = f; idx = k; }
+  {
+    double f0 = n[0] < 0 ? -n[0] : n[0], f1 = n[1] < 0 ? -n[1] : n[1], f2 = n[2] < 0 ? -n[2] : n[2];
+    if (f0 > maxc) { maxc = f0; idx = 0; }
+    if (f1 > maxc) { maxc = f1; idx = 1; }
+    if (f2 > maxc) { maxc = f2; idx = 2; }
   }
-  int ia = (idx == 0) ? 1 : 0, ib = (idx == 2) ? 1 : 2;
-  double r0 = FB_SUB(cp[ia], pt3[ia]), r1 = FB_SUB(cp[ib], pt3[ib]);
-  double c10 = FB_SUB(pt1[ia], pt3[ia]), c11 = FB_SUB(pt1[ib], pt3[ib]);
-  double c20 = FB_SUB(pt2[ia], pt3[ia]), c21 = FB_SUB(pt2[ib], pt3[ib]);
+  const bool a0 = (idx == 0), b2 = (idx == 2);  // kept axes: ia = a0 ? 1 : 0, ib = b2 ? 1 : 2
+  double xa = a0 ? x[1] : x[0], xb = b2 ? x[1] : x[2];
+  double na = a0 ? n[1] : n[0], nb = b2 ? n[1] : n[2];
+  double p1a = a0 ? pt1[1] : pt1[0], p1b = b2 ? pt1[1] : pt1[2];
+  double p2a = a0 ? pt2[1] : pt2[0], p2b = b2 ? pt2[1] : pt2[2];
+  double p3a = a0 ? pt3[1] : pt3[0], p3b = b2 ? pt3[1] : pt3[2];
+  double cpa = (n2 != 0.0) ? FB_SUB(xa, FB_DIV(FB_MUL(tp, na), n2)) : xa;
+  double cpb = (n2 != 0.0) ? FB_SUB(xb, FB_DIV(FB_MUL(tp, nb), n2)) : xb;
+  double r0 = FB_SUB(cpa, p3a), r1 = FB_SUB(cpb, p3b);
+  double c10 = FB_SUB(p1a, p3a), c11 = FB_SUB(p1b, p3b);
+  double c20 = FB_SUB(p2a, p3a), c21 = FB_SUB(p2b, p3b);
   double det = FB_SUB(FB_MUL(c10, c21), FB_MUL(c20, c11));
   if (det == 0.0) return false;
   double pc0 = FB_DIV(FB_SUB(FB_MUL(r0, c21), FB_MUL(c20, r1)), det);
@@ -269,6 +277,43 @@ FB_HD bool slab(const float* b, const float* o, const float* inv, float slack, f
   return tn <= tf;
 }
 
+// Per-ray constants of the fused-multiply-add slab test used by the packet
+// traversal: t = b * inv - o * inv, with the slack folded into the addends.
+// Directions are uniform per view, so the near / far plane of every axis is
+// known up front (neg[k] selects hi as the near plane).  |inv| is clamped so an
+// axis-parallel ray (d = 0) still culls boxes it lies outside of.
+struct SlabRay {
+  float inv[3];
+  float cn[3], cf[3];  // near: fma(b_near, inv, cn)   far: fma(b_far, inv, cf)
+};
+FB_HD float clamp_inv(float dirf) {
+  float a = fabsf(dirf);
+  float inv = a > 1e-30f ? 1.0f / a : 1e30f;
+  return dirf < 0.f ? -inv : inv;  // -0.0f counts as positive: the ray does not move on that axis
+}
+FB_HD void slab_ray_setup(const float* of, const float* inv, float slack, SlabRay* r) {
+  for (int k = 0; k < 3; k++) {
+    r->inv[k] = inv[k];
+    float oi = of[k] * inv[k];
+    float sk = slack * fabsf(inv[k]) * 1.0001f;
+    r->cn[k] = -oi - sk;
+    r->cf[k] = -oi + sk;
+  }
+}
+// b = {lo xyz, hi xyz}; neg* = direction component is negative (warp-uniform)
+FB_HD bool slab_fma(const float* b, const SlabRay& r, bool negx, bool negy, bool negz, float tcull,
+                    float* tnear) {
+  float nx = negx ? b[3] : b[0], fx = negx ? b[0] : b[3];
+  float ny = negy ? b[4] : b[1], fy = negy ? b[1] : b[4];
+  float nz = negz ? b[5] : b[2], fz = negz ? b[2] : b[5];
+  float tn = fmaxf(fmaxf(fmaf(nx, r.inv[0], r.cn[0]), fmaf(ny, r.inv[1], r.cn[1])),
+                   fmaxf(fmaf(nz, r.inv[2], r.cn[2]), 0.0f));
+  float tf = fminf(fminf(fmaf(fx, r.inv[0], r.cf[0]), fmaf(fy, r.inv[1], r.cf[1])),
+                   fminf(fmaf(fz, r.inv[2], r.cf[2]), tcull));
+  *tnear = tn;
+  return tn <= tf;
+}
+
 // Stackless traversal: a 64-bit trail holds one "far sibling still pending" bit
 // per level, parent / sibling links walk back up.  Depth <= 62 is guaranteed by
 // the 30+32-bit key length of the LBVH.  NodeFetch: node(i) -> Node by value,
@@ -341,6 +386,124 @@ FB_HD Hit traverse(const NodeFetch& fetch, const float4* __restrict__ tv0,
   }
   if (best.slot < 0) best.cell = -1;
   return best;
+}
+
+// ---------------------------------------------------------------- lane state machine
+// The render kernel drives 32 of these per warp and lets warp votes decide which
+// step runs next (trace.cu); tests/hostsim drives one at a time.  Same exact
+// decisions as traverse(); differences are purely in scheduling:
+//  * leaf tests are deferred (up to two pending slots) so that a warp can batch
+//    them and run the long double-precision test with many live lanes;
+//  * a 4-entry register stack remembers the most recent far siblings together
+//    with their entry distance, so most pops need no memory access and culled
+//    subtrees are skipped without being visited; older entries fall back to the
+//    parent / sibling links (the trail stays authoritative).
+struct Lane {
+  double o[3];
+  float of[3];
+  double best_t;
+  int32_t best_slot, best_cell;
+  float tcull;
+  uint64_t trail;
+  int32_t node;            // -1: traversal finished
+  int32_t s0, s1, s2, s3;  // short stack of pending far siblings (-1 = empty)
+  float f0, f1, f2, f3;    // their entry distances
+  int32_t p0, p1;          // pending leaf slots (-1 = none); p0 is filled first
+};
+
+FB_HD void lane_init(Lane& L, const double* o, float tslack) {
+  for (int k = 0; k < 3; k++) { L.o[k] = o[k]; L.of[k] = (float)o[k]; }
+  L.best_t = DBL_MAX;
+  L.best_slot = -1;
+  L.best_cell = 0x7fffffff;
+  L.tcull = 1.0f + tslack;
+  L.trail = 1;
+  L.node = 0;
+  L.s0 = L.s1 = L.s2 = L.s3 = -1;
+  L.f0 = L.f1 = L.f2 = L.f3 = 0.f;
+  L.p0 = L.p1 = -1;
+}
+
+FB_HD int ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
+
+// visit L.node (precondition: L.node >= 0 and no pending leaves)
+template <class NodeFetch, class Counter>
+FB_HD void lane_node_step(Lane& L, const NodeFetch& fetch, const float* invf, float slack, Counter& cnt) {
+  const Node N = fetch.node(L.node);
+  cnt.node();
+  float tn0, tn1;
+  bool h0 = slab(N.box, L.of, invf, slack, L.tcull, &tn0);
+  bool h1 = slab(N.box + 6, L.of, invf, slack, L.tcull, &tn1);
+  const int c0 = N.c0, c1 = N.c1;
+  if (h0 && c0 < 0) { L.p0 = ~c0; }
+  if (h1 && c1 < 0) { if (L.p0 < 0) L.p0 = ~c1; else L.p1 = ~c1; }
+  h0 = h0 && c0 >= 0;
+  h1 = h1 && c1 >= 0;
+  if (h0 || h1) {
+    const bool both = h0 && h1;
+    const bool swap = both && tn1 < tn0;
+    L.trail = (L.trail << 1) | (both ? 1u : 0u);
+    if (both) {
+      L.s3 = L.s2; L.s2 = L.s1; L.s1 = L.s0; L.s0 = swap ? c0 : c1;
+      L.f3 = L.f2; L.f2 = L.f1; L.f1 = L.f0; L.f0 = swap ? tn0 : tn1;
+    }
+    L.node = both ? (swap ? c1 : c0) : (h0 ? c0 : c1);
+    return;
+  }
+  // dead end: pop the nearest pending far sibling that is still within reach
+  int climbed = 0;
+  for (;;) {
+    int k = ctz64(L.trail);
+    L.trail >>= k;
+    climbed += k;
+    if (L.trail == 1) { L.node = -1; return; }
+    L.trail ^= 1;
+    int x = L.s0;
+    float fx = L.f0;
+    L.s0 = L.s1; L.s1 = L.s2; L.s2 = L.s3; L.s3 = -1;
+    L.f0 = L.f1; L.f1 = L.f2; L.f2 = L.f3;
+    if (x >= 0) {
+      if (fx <= L.tcull) { L.node = x; return; }
+      continue;  // culled by a hit found since it was pushed
+    }
+    // the entry was pushed out of the short stack: walk the links
+    int nd = L.node;
+    for (int i = 0; i < climbed; i++) nd = fetch.parent(nd);
+    L.node = fetch.sibling(nd);
+    return;
+  }
+}
+
+// test one pending leaf (precondition: L.p0 >= 0)
+template <class Counter>
+FB_HD void lane_leaf_step(Lane& L, const float4* __restrict__ tv0, const float4* __restrict__ tv1,
+                          const float4* __restrict__ tv2, const double* d, float tslack, Counter& cnt) {
+  int slot;
+  if (L.p1 >= 0) { slot = L.p1; L.p1 = -1; } else { slot = L.p0; L.p0 = -1; }
+  float4 a = tv0[slot], b = tv1[slot], e = tv2[slot];
+  cnt.tri();
+  float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+  double t, x[3], w[3];
+  if (tri_exact(L.o, d, P0, P1, P2, L.best_t, &t, x, w)) {
+#if defined(__CUDA_ARCH__)
+    int cell = __float_as_int(a.w);
+#else
+    int cell;
+    memcpy(&cell, &a.w, 4);
+#endif
+    if (t < L.best_t || (t == L.best_t && cell < L.best_cell)) {
+      L.best_t = t;
+      L.best_slot = slot;
+      L.best_cell = cell;
+      L.tcull = fminf(L.tcull, FB_F2F_RU(t) + tslack);
+    }
+  }
 }
 
 struct NoCount {

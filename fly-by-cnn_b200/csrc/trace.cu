@@ -145,7 +145,14 @@ struct RenderParams {
 
 #define RK_THREADS 256
 #define RK_WARPS (RK_THREADS / 32)
-#define RK_QCAP 64
+#define RK_QCAP 96
+#ifdef FLYBY_DEBUG
+#define RK_MAX_ITERS (1ull << 18)
+#else
+#define RK_MAX_ITERS (1ull << 26)
+#endif
+//  // ~60 steps per ray would allow a million rays per warp
+#define RK_RETIRE 12  // retire/refill once this many lanes are finished or idle
 
 __device__ __forceinline__ void write_pixel(const RenderParams& p, int64_t pix, const float* px, int cell,
                                             double t) {
@@ -171,6 +178,20 @@ __device__ __forceinline__ bool hits_bounds(const float* ubox, const double* o, 
   return slab(ubox, of, vw.invf, vw.slack, 1.0f + vw.tslack, &tn);
 }
 
+// Warp-cooperative packet traversal.  A warp owns a batch of up to 32 compacted
+// rays of ONE view (parallel rays from neighbouring pixels) and walks the LBVH as
+// a unit: node index and bit-trail are warp-uniform, every lane tests its own ray
+// against the two child boxes and warp votes decide where to go -- descend if ANY
+// lane hits, near child first by majority.  Control flow never diverges during
+// traversal, node fetches are broadcast loads, and climbing back through the
+// parent / sibling links costs one lane's worth of work instead of 32.  A small
+// per-warp ring in shared memory remembers recent far siblings so that most pops
+// need no link walk (the trail + links stay authoritative: stackless).
+// Each lane still decides its own hit exactly (double precision) and keeps its
+// own cull distance, so the result equals the per-ray traversal bit for bit.
+#define RK_RING 16
+#define RK_MAX_STEPS (1u << 24)  // node visits of one packet; a tree has < 2^31 nodes, a packet visits far fewer
+
 template <bool USE_TOP, bool COUNT>
 __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -178,8 +199,10 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
   uint32_t* queues = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.top_cap * sizeof(Node));
   __shared__ float s_ubox[6];
   __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int32_t s_ring[RK_WARPS][RK_RING];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   int ntop = 0;
   if (USE_TOP) {
     ntop = *p.n_top_dev;
@@ -204,7 +227,6 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
           "l"(p.nodes), "r"(bytes), "r"(bar)
           : "memory");
     }
-    // everybody waits for phase 0
     uint32_t done = 0;
     while (!done) {
       asm volatile(
@@ -220,107 +242,196 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
   }
 
   uint32_t* q = queues + warp * RK_QCAP;
-  int qn = 0;
-  bool tiles_left = true;
+  int32_t* ring = s_ring[warp];
+  int qn = 0;              // warp-uniform
+  bool tiles_left = true;  // warp-uniform
   const int res = p.res;
-  const int64_t per_view = (int64_t)res * res;
+  const uint32_t per_view = (uint32_t)res * (uint32_t)res;
   const long long tiles_per_view = (long long)p.tiles_x * p.tiles_y;
   const int groups_x = p.tiles_x >> 1;
-  WorkCount wc;
+  unsigned long long n_nodes = 0, n_tris = 0;
   unsigned int n_hits = 0;
+  TopFetch tf{p.nodes, top, ntop};
 
   for (;;) {
-    // ---- refill the queue until a full warp of live rays is available
+    // ---- refill the queue until a full warp of live rays is available (ray compaction by vote)
     while (qn < 32 && tiles_left) {
       long long tile = 0;
       if (lane == 0) tile = (long long)atomicAdd(p.counters, 1ull);
       tile = __shfl_sync(0xffffffffu, tile, 0);
-      if (tile >= p.n_tiles) {
-        tiles_left = false;
-        break;
-      }
-      int v = (int)(tile / tiles_per_view);
-      int tl = (int)(tile % tiles_per_view);
+      if (tile >= p.n_tiles) { tiles_left = false; break; }
+      const int v = (int)(tile / tiles_per_view);
+      const int tl = (int)(tile % tiles_per_view);
       // 8 consecutive tiles form a 16x16-pixel block (2 tiles wide, 4 high)
-      int g = tl >> 3, r = tl & 7;
-      int tx = (g % groups_x) * 2 + (r & 1);
-      int ty = (g / groups_x) * 4 + (r >> 1);
-      int px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
-      bool valid = px < res && py < res;
+      const int g = tl >> 3, r = tl & 7;
+      const int tx = (g % groups_x) * 2 + (r & 1);
+      const int ty = (g / groups_x) * 4 + (r >> 1);
+      const int px_ = tx * 8 + (lane & 7), py_ = ty * 4 + (lane >> 3);
+      const bool valid = px_ < res && py_ < res;
       bool live = false;
-      uint32_t pid = 0;
+      uint32_t npid = 0;
       if (valid) {
         const View& vw = p.views[p.view_begin + v];
         double o[3];
-        view_ray(vw, res, px, py, p.spacing, o);
+        view_ray(vw, res, px_, py_, p.spacing, o);
         live = hits_bounds(s_ubox, o, vw);
-        pid = (uint32_t)((int64_t)v * per_view + (int64_t)py * res + px);
+        npid = (uint32_t)v * per_view + (uint32_t)py_ * (uint32_t)res + (uint32_t)px_;
         if (!live) {
-          float zero[4] = {0.f, 0.f, 0.f, 0.f};
-          write_pixel(p, (int64_t)pid, zero, -1, -1.0);
+          const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+          write_pixel(p, (int64_t)npid, zero, -1, -1.0);
         }
       }
-      unsigned m = __ballot_sync(0xffffffffu, live);
-      if (live) q[qn + __popc(m & ((1u << lane) - 1u))] = pid;
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (live) q[qn + __popc(m & lt_mask)] = npid;
       qn += __popc(m);
       __syncwarp();
     }
     if (qn == 0) break;
-    // ---- take the oldest 32 (or the remainder once the tiles ran out)
-    const int take = qn < 32 ? qn : 32;
+    // ---- take the leading entries of one view (at most 32)
+    const int view = (int)(q[0] / per_view);
+    const int look = qn < 32 ? qn : 32;
+    const bool same = lane < look && (int)(q[lane] / per_view) == view;
+    const unsigned msame = __ballot_sync(0xffffffffu, same);
+    const int take = (msame == 0xffffffffu) ? 32 : __ffs(~msame) - 1;
     const bool active = lane < take;
-    uint32_t pid = active ? q[lane] : 0u;
+    const uint32_t pid = active ? q[lane] : 0u;
     __syncwarp();
     {
-      uint32_t moved = (lane + 32 < qn) ? q[lane + 32] : 0u;
+      uint32_t m0 = (lane + take < qn) ? q[lane + take] : 0u;
+      uint32_t m1 = (lane + 32 + take < qn) ? q[lane + 32 + take] : 0u;
       __syncwarp();
-      if (lane + 32 < qn) q[lane] = moved;
+      if (lane + take < qn) q[lane] = m0;
+      if (lane + 32 + take < qn) q[lane + 32] = m1;
       __syncwarp();
     }
     qn -= take;
 
-    if (active) {
-      int v = (int)(pid / (uint32_t)per_view);
-      int pix = (int)(pid % (uint32_t)per_view);
-      const View& vw = p.views[p.view_begin + v];
-      double o[3];
-      view_ray(vw, res, pix % res, pix / res, p.spacing, o);
-      double d[3] = {vw.dir[0], vw.dir[1], vw.dir[2]};
-      float invf[3] = {vw.invf[0], vw.invf[1], vw.invf[2]};
-      Hit h;
-      if (USE_TOP) {
-        TopFetch f{p.nodes, top, ntop};
-        if (COUNT) h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, wc);
-        else { NoCount nc; h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, nc); }
-      } else {
-        GlobalFetch f{p.nodes};
-        if (COUNT) h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, wc);
-        else { NoCount nc; h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, nc); }
+    // ---- per-lane ray, warp-uniform view constants
+    const View& vw = p.views[p.view_begin + view];
+    const double d[3] = {vw.dir[0], vw.dir[1], vw.dir[2]};
+    const float slack = vw.slack, tslack = vw.tslack;
+    const float dfx = vw.dirf[0], dfy = vw.dirf[1], dfz = vw.dirf[2];
+    const bool negx = dfx < 0.f, negy = dfy < 0.f, negz = dfz < 0.f;
+    double o[3] = {0.0, 0.0, 0.0};
+    SlabRay sr;
+    {
+      const uint32_t pix = pid % per_view;
+      if (active) view_ray(vw, res, (int)(pix % (uint32_t)res), (int)(pix / (uint32_t)res), p.spacing, o);
+      float of[3] = {(float)o[0], (float)o[1], (float)o[2]};
+      float inv[3] = {clamp_inv(dfx), clamp_inv(dfy), clamp_inv(dfz)};
+      slab_ray_setup(of, inv, slack, &sr);
+    }
+    double best_t = DBL_MAX;
+    int best_slot = -1, best_cell = 0x7fffffff;
+    float tcull = active ? 1.0f + tslack : -1.0f;  // an idle lane never hits a box
+
+    // ---- packet traversal (everything below the leaf tests is warp-uniform)
+    int node = 0;
+    unsigned long long trail = 1;
+    int ring_head = 0, ring_count = 0;
+    unsigned int steps = 0;
+    for (;;) {
+      if (++steps > RK_MAX_STEPS) {  // watchdog: a traversal bug must end as an error, not a hung GPU
+        if (lane == 0) atomicAdd(p.counters + 6, 1ull);
+        break;
       }
+      const Node N = tf.node(node);
+      float tn0, tn1;
+      const bool h0 = slab_fma(N.box, sr, negx, negy, negz, tcull, &tn0);
+      const bool h1 = slab_fma(N.box + 6, sr, negx, negy, negz, tcull, &tn1);
+      const unsigned m0 = __ballot_sync(0xffffffffu, h0);
+      const unsigned m1 = __ballot_sync(0xffffffffu, h1);
+      const int c0 = N.c0, c1 = N.c1;
+      if (COUNT) n_nodes += __popc(m0 | m1);
+      // leaves: every lane whose ray enters the leaf box runs the exact test
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        const unsigned m = side ? m1 : m0;
+        const int c = side ? c1 : c0;
+        if (m != 0u && c < 0) {
+          const int slot = ~c;
+          const float4 a = __ldg(p.tv0 + slot), b = __ldg(p.tv1 + slot), e = __ldg(p.tv2 + slot);
+          if (side ? h1 : h0) {
+            if (COUNT) n_tris++;
+            const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+            double t, x[3], w[3];
+            if (tri_exact(o, d, P0, P1, P2, best_t, &t, x, w)) {
+              const int cell = __float_as_int(a.w);
+              if (t < best_t || (t == best_t && cell < best_cell)) {
+                best_t = t;
+                best_slot = slot;
+                best_cell = cell;
+                tcull = fminf(tcull, FB_F2F_RU(t) + tslack);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // internal children still wanted by at least one lane (cull distances may have shrunk)
+      const bool w0 = h0 && c0 >= 0 && tn0 <= tcull;
+      const bool w1 = h1 && c1 >= 0 && tn1 <= tcull;
+      const unsigned d0 = __ballot_sync(0xffffffffu, w0);
+      const unsigned d1 = __ballot_sync(0xffffffffu, w1);
+      if (d0 != 0u || d1 != 0u) {
+        const bool both = d0 != 0u && d1 != 0u;
+        // near child first: majority of the lanes that want child 1 earlier (or only child 1)
+        const unsigned pref1 = __ballot_sync(0xffffffffu, w1 && (!w0 || tn1 < tn0));
+        const bool swap = both && 2 * __popc(pref1) > __popc(d0 | d1);
+        trail = (trail << 1) | (both ? 1ull : 0ull);
+        if (both) {
+          ring_head = (ring_head + 1) & (RK_RING - 1);
+          if (lane == 0) ring[ring_head] = swap ? c0 : c1;
+          ring_count = ring_count < RK_RING ? ring_count + 1 : RK_RING;
+        }
+        node = both ? (swap ? c1 : c0) : (d0 != 0u ? c0 : c1);
+        continue;
+      }
+      // dead end: climb to the nearest level with a pending far sibling
+      const int k = __ffsll((long long)trail) - 1;
+      trail >>= k;
+      if (trail == 1ull) break;
+      trail ^= 1ull;
+      if (ring_count > 0) {
+        __syncwarp();
+        node = ring[ring_head];
+        ring_head = (ring_head - 1) & (RK_RING - 1);
+        ring_count--;
+      } else {
+        int nd = node;
+        for (int i = 0; i < k; i++) nd = tf.parent(nd);
+        node = tf.sibling(nd);
+      }
+    }
+
+    // ---- shade + write
+    if (active) {
       float px[4] = {0.f, 0.f, 0.f, 0.f};
       double t = -1.0;
-      if (h.slot >= 0) {
+      if (best_slot >= 0) {
         n_hits++;
-        float4 a = p.tv0[h.slot], b = p.tv1[h.slot], e = p.tv2[h.slot];
-        float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+        const float4 a = p.tv0[best_slot], b = p.tv1[best_slot], e = p.tv2[best_slot];
+        const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
         double x[3], w[3];
         tri_exact(o, d, P0, P1, P2, DBL_MAX, &t, x, w);
         if (p.feat) {
-          int4 vid = p.tvid[h.slot];
-          float4 n0 = __ldg(p.normals + vid.x), n1 = __ldg(p.normals + vid.y), n2 = __ldg(p.normals + vid.z);
-          float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
+          const int4 vid = p.tvid[best_slot];
+          const float4 n0 = __ldg(p.normals + vid.x), n1 = __ldg(p.normals + vid.y), n2 = __ldg(p.normals + vid.z);
+          const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
           shade(o, x, w, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px);
         }
       }
-      write_pixel(p, (int64_t)pid, px, h.cell, t);
+      write_pixel(p, (int64_t)pid, px, best_slot >= 0 ? best_cell : -1, t);
     }
     __syncwarp();
   }
   if (COUNT) {
-    atomicAdd(p.counters + 1, (unsigned long long)wc.nodes);
-    atomicAdd(p.counters + 2, (unsigned long long)wc.tris);
+    for (int o2 = 16; o2 > 0; o2 >>= 1) n_tris += __shfl_xor_sync(0xffffffffu, n_tris, o2);
+    if (lane == 0) {
+      atomicAdd(p.counters + 1, n_nodes);
+      atomicAdd(p.counters + 2, n_tris);
+    }
   }
-  // hit count: one atomic per warp
   for (int o2 = 16; o2 > 0; o2 >>= 1) n_hits += __shfl_xor_sync(0xffffffffu, n_hits, o2);
   if (lane == 0 && n_hits) atomicAdd(p.counters + 3, (unsigned long long)n_hits);
 }

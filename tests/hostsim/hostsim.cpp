@@ -136,7 +136,7 @@ extern "C" __attribute__((visibility("default")))
 int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* normals,
                const float* views, int n_views, double radius, int res, double plane_scale, double spacing,
                int use_z, int split_z, int enc, double zscale, float* out_feat, int32_t* out_ids,
-               double* out_t, long long* work /* nodes, tris, max_depth */) {
+               double* out_t, long long* work /* nodes, tris, max_depth */, int mode /* 0 traverse(), 1 lane steps */) {
   SimBvh b;
   build(verts, V, tris, T, b);
   if (b.nodes.empty()) return 1;
@@ -150,8 +150,22 @@ int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, co
       for (int i = 0; i < res; i++) {
         double o[3];
         view_ray(vw, res, i, j, spacing, o);
-        Hit h = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o, vw.dir, vw.dirf, vw.invf, vw.slack,
-                         vw.tslack, cnt);
+        Hit h;
+        if (mode == 0) {
+          h = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o, vw.dir, vw.dirf, vw.invf, vw.slack,
+                       vw.tslack, cnt);
+        } else {
+          // the render kernel's per-lane state machine, one lane at a time; leaf tests are
+          // delayed as long as possible (mode 2) or run at once (mode 1) to cover both schedules
+          Lane L;
+          lane_init(L, o, vw.tslack);
+          while (L.node >= 0 || L.p0 >= 0) {
+            bool leaf_now = L.p0 >= 0 && (mode == 1 || L.node < 0 || L.p0 >= 0);
+            if (leaf_now) lane_leaf_step(L, b.tv0.data(), b.tv1.data(), b.tv2.data(), vw.dir, vw.tslack, cnt);
+            else lane_node_step(L, f, vw.invf, vw.slack, cnt);
+          }
+          h.t = L.best_t; h.slot = L.best_slot; h.cell = L.best_slot >= 0 ? L.best_cell : -1;
+        }
         size_t pix = ((size_t)v * res + j) * res + i;
         float px[4] = {0, 0, 0, 0};
         double t = -1.0;
@@ -167,6 +181,125 @@ int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, co
         if (out_feat) memcpy(out_feat + pix * C, px, 4 * C);
         if (out_ids) out_ids[pix] = h.cell;
         if (out_t) out_t[pix] = t;
+      }
+  }
+  if (work) { work[0] = cnt.nodes; work[1] = cnt.tris; work[2] = b.max_depth; }
+  return 0;
+}
+
+// ---- emulation of the render kernel's packet traversal (trace.cu): 32 lanes in
+// lockstep, ballots as loops.  Checks the vote / trail / ring / link logic and
+// the FMA slab test on the CPU.
+static void packet_trace(const SimBvh& b, const View& vw, const double (*o)[3], int n_active, int ring_cap,
+                         Hit* out, SimCount& cnt) {
+  const Node* nodes = b.nodes.data();
+  SlabRay sr[32];
+  double best_t[32]; int best_slot[32], best_cell[32]; float tcull[32];
+  bool negx = vw.dirf[0] < 0.f, negy = vw.dirf[1] < 0.f, negz = vw.dirf[2] < 0.f;
+  for (int l = 0; l < 32; l++) {
+    float of[3] = {0, 0, 0};
+    if (l < n_active) for (int k = 0; k < 3; k++) of[k] = (float)o[l][k];
+    float inv[3] = {clamp_inv(vw.dirf[0]), clamp_inv(vw.dirf[1]), clamp_inv(vw.dirf[2])};
+    slab_ray_setup(of, inv, vw.slack, &sr[l]);
+    best_t[l] = DBL_MAX; best_slot[l] = -1; best_cell[l] = 0x7fffffff;
+    tcull[l] = l < n_active ? 1.0f + vw.tslack : -1.0f;
+  }
+  int node = 0; uint64_t trail = 1;
+  std::vector<int> ring(ring_cap); int ring_head = 0, ring_count = 0;
+  for (;;) {
+    const Node N = nodes[node];
+    cnt.node();
+    bool h0[32], h1[32]; float tn0[32], tn1[32];
+    bool any0 = false, any1 = false;
+    for (int l = 0; l < 32; l++) {
+      h0[l] = slab_fma(N.box, sr[l], negx, negy, negz, tcull[l], &tn0[l]);
+      h1[l] = slab_fma(N.box + 6, sr[l], negx, negy, negz, tcull[l], &tn1[l]);
+      any0 |= h0[l]; any1 |= h1[l];
+    }
+    for (int side = 0; side < 2; side++) {
+      int c = side ? N.c1 : N.c0;
+      if ((side ? any1 : any0) && c < 0) {
+        int slot = ~c;
+        float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
+        float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
+        int cell; memcpy(&cell, &a.w, 4);
+        for (int l = 0; l < 32; l++) {
+          if (!(side ? h1[l] : h0[l])) continue;
+          cnt.tri();
+          double t, x[3], w[3];
+          if (tri_exact(o[l], vw.dir, P0, P1, P2, best_t[l], &t, x, w) &&
+              (t < best_t[l] || (t == best_t[l] && cell < best_cell[l]))) {
+            best_t[l] = t; best_slot[l] = slot; best_cell[l] = cell;
+            tcull[l] = fminf(tcull[l], FB_F2F_RU(t) + vw.tslack);
+          }
+        }
+      }
+    }
+    int nd0 = 0, nd1 = 0, npref1 = 0, nany = 0;
+    for (int l = 0; l < 32; l++) {
+      bool w0 = h0[l] && N.c0 >= 0 && tn0[l] <= tcull[l];
+      bool w1 = h1[l] && N.c1 >= 0 && tn1[l] <= tcull[l];
+      nd0 += w0; nd1 += w1; nany += (w0 || w1);
+      npref1 += (w1 && (!w0 || tn1[l] < tn0[l]));
+    }
+    if (nd0 || nd1) {
+      bool both = nd0 && nd1;
+      bool swap = both && 2 * npref1 > nany;
+      trail = (trail << 1) | (both ? 1ull : 0ull);
+      if (both) {
+        ring_head = (ring_head + 1) % ring_cap;
+        ring[ring_head] = swap ? N.c0 : N.c1;
+        ring_count = ring_count < ring_cap ? ring_count + 1 : ring_cap;
+      }
+      node = both ? (swap ? N.c1 : N.c0) : (nd0 ? N.c0 : N.c1);
+      continue;
+    }
+    int k = ctz64(trail);
+    trail >>= k;
+    if (trail == 1ull) break;
+    trail ^= 1ull;
+    if (ring_count > 0) {
+      node = ring[ring_head];
+      ring_head = (ring_head - 1 + ring_cap) % ring_cap;
+      ring_count--;
+    } else {
+      int nd = node;
+      for (int i = 0; i < k; i++) nd = nodes[nd].parent;
+      node = nodes[nd].sibling;
+    }
+  }
+  for (int l = 0; l < n_active; l++) {
+    out[l].t = best_t[l]; out[l].slot = best_slot[l]; out[l].cell = best_slot[l] >= 0 ? best_cell[l] : -1;
+  }
+}
+
+extern "C" __attribute__((visibility("default")))
+int sim_render_packet(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* views, int n_views,
+                      double radius, int res, double plane_scale, double spacing, int ring_cap, int32_t* out_ids,
+                      double* out_t, long long* work) {
+  SimBvh b;
+  build(verts, V, tris, T, b);
+  if (b.nodes.empty()) return 1;
+  SimCount cnt;
+  for (int v = 0; v < n_views; v++) {
+    View vw;
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    // 8x4 tiles like the kernel (no bounds compaction: partial tiles run with idle lanes)
+    for (int ty = 0; ty < (res + 3) / 4; ty++)
+      for (int tx = 0; tx < (res + 7) / 8; tx++) {
+        double o[32][3]; int pix[32]; int n = 0;
+        for (int l = 0; l < 32; l++) {
+          int px = tx * 8 + (l & 7), py = ty * 4 + (l >> 3);
+          if (px < res && py < res) { view_ray(vw, res, px, py, spacing, o[n]); pix[n] = py * res + px; n++; }
+        }
+        Hit h[32];
+        packet_trace(b, vw, o, n, ring_cap, h, cnt);
+        for (int l = 0; l < n; l++) {
+          size_t id = (size_t)v * res * res + pix[l];
+          double t = -1.0;
+          if (h[l].slot >= 0) t = h[l].t;
+          out_ids[id] = h[l].cell; out_t[id] = t;
+        }
       }
   }
   if (work) { work[0] = cnt.nodes; work[1] = cnt.tris; work[2] = b.max_depth; }
