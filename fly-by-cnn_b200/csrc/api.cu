@@ -6,7 +6,7 @@
 #include "ctx.h"
 
 namespace fb {
-int label_point_features(flyby_ctx*, const int32_t*, int64_t, const float*, int, float, float*);
+int label_point_features(flyby_ctx*, const int32_t*, int64_t, const float*, int, float, int, float*);
 int label_backproject(flyby_ctx*, const int32_t*, const int32_t*, int64_t, int, int32_t*);
 int label_backproject_soft(flyby_ctx*, const int32_t*, const float*, int64_t, int, int64_t*);
 int label_argmax(flyby_ctx*, const int32_t*, int64_t, int, int32_t, int32_t*);
@@ -100,6 +100,9 @@ int flyby_create(int device, void* stream, flyby_ctx** out) {
   }
   for (int i = 0; i < 8; i++)
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+  for (int i = 0; i < 16; i++)
+    if (cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (c->counters.reserve(8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
   *out = c;
@@ -120,6 +123,9 @@ void flyby_destroy(flyby_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 16; i++)
+    if (c->chunk_ev[i]) cudaEventDestroy(c->chunk_ev[i]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -283,7 +289,8 @@ int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   CHECK_CTX(c);
   int rc = check_render_args(c, vb, ve, res, o, true);
   if (rc) return rc;
-  const size_t n_pix = (size_t)(ve - vb) * res * res;
+  const size_t per_view = (size_t)res * res;
+  const size_t n_pix = (size_t)(ve - vb) * per_view;
   const int channels = (o->use_z && o->split_z) ? 4 : 3;
   rc = views_setup(c, o);
   if (rc) return rc;
@@ -293,17 +300,42 @@ int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if ((rc = sf.begin(c, c->stage_feat, out_features, n_pix * channels))) return rc;
   if ((rc = si.begin(c, c->stage_ids, out_cell_ids, n_pix))) return rc;
   if ((rc = st.begin(c, c->stage_t, out_t, n_pix))) return rc;
-  rc = trace_render(c, vb, ve, res, o, sf.dev, si.dev, st.dev);
-  if (rc) return rc;
-  bool need = false;
-  if ((rc = sf.finish(c, &need))) return rc;
-  if ((rc = si.finish(c, &need))) return rc;
-  if ((rc = st.finish(c, &need))) return rc;
-  if (need) return check_watchdog(c);
-  return FLYBY_OK;
+  const bool any_host = sf.host || si.host || st.host;
+  if (!any_host) return trace_render(c, vb, ve, res, o, sf.dev, si.dev, st.dev);
+
+  // Host outputs: render in view chunks and copy every finished chunk back on the copy
+  // stream while the next chunk renders (PCIe D2H overlaps the traversal).
+  const int nv = ve - vb;
+  int n_chunks = nv < 8 ? 1 : (nv + 11) / 12;
+  if (n_chunks > 16) n_chunks = 16;
+  // all kernels are queued first so that a pageable destination (synchronous copy) still overlaps
+  int bounds[17];
+  for (int k = 0; k <= n_chunks; k++) bounds[k] = vb + (int)((long long)nv * k / n_chunks);
+  for (int k = 0; k < n_chunks; k++) {
+    const size_t off = (size_t)(bounds[k] - vb) * per_view;
+    rc = trace_render(c, bounds[k], bounds[k + 1], res, o, sf.dev ? sf.dev + off * channels : nullptr,
+                      si.dev ? si.dev + off : nullptr, st.dev ? st.dev + off : nullptr, k == 0, k == n_chunks - 1);
+    if (rc) return rc;
+    FB_CUDA(c, cudaEventRecord(c->chunk_ev[k], c->stream));
+  }
+  for (int k = 0; k < n_chunks; k++) {
+    const size_t off = (size_t)(bounds[k] - vb) * per_view;
+    const size_t cnt = (size_t)(bounds[k + 1] - bounds[k]) * per_view;
+    FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[k], 0));
+    if (sf.host && sf.user)
+      FB_CUDA(c, cudaMemcpyAsync(sf.user + off * channels, sf.dev + off * channels, cnt * channels * sizeof(float),
+                                 cudaMemcpyDeviceToHost, c->copy_stream));
+    if (si.host && si.user)
+      FB_CUDA(c, cudaMemcpyAsync(si.user + off, si.dev + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (st.host && st.user)
+      FB_CUDA(c, cudaMemcpyAsync(st.user + off, st.dev + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  FB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  return check_watchdog(c);
 }
 
-int flyby_cast(flyby_ctx* c, const double* rays, int64_t n, int32_t* out_ids, double* out_t, double* out_w) {
+int flyby_cast(flyby_ctx* c, const double* rays, int64_t n, double tolerance, int32_t* out_ids, double* out_t,
+               double* out_w) {
   CHECK_CTX(c);
   if (!c->mesh.built) return fail(c, FLYBY_ERR_INVALID, "cast: mesh not built");
   if (n < 0 || (n > 0 && !rays)) return fail(c, FLYBY_ERR_INVALID, "cast: bad arguments");
@@ -315,7 +347,7 @@ int flyby_cast(flyby_ctx* c, const double* rays, int64_t n, int32_t* out_ids, do
   if ((rc = si.begin(c, c->stage_ids, out_ids, (size_t)n))) return rc;
   if ((rc = st.begin(c, c->stage_t, out_t, (size_t)n))) return rc;
   if ((rc = sw.begin(c, c->stage_out0, out_w, (size_t)n * 3))) return rc;
-  rc = trace_cast(c, drays, n, si.dev, st.dev, sw.dev);
+  rc = trace_cast(c, drays, n, tolerance, si.dev, st.dev, sw.dev);
   if (rc) return rc;
   bool need = !is_device_ptr(rays);
   if ((rc = si.finish(c, &need))) return rc;
@@ -328,7 +360,7 @@ int flyby_point_features(flyby_ctx* c, const int32_t* cell_ids, int64_t n_pix, c
                          float zero, int mode, float* out) {
   CHECK_CTX(c);
   if (!c->mesh.has_mesh) return fail(c, FLYBY_ERR_INVALID, "point_features: no mesh");
-  if (mode != 0) return fail(c, FLYBY_ERR_UNSUPPORTED, "point_features: only mode 0 (vertex 0 of the hit cell)");
+  if (mode != 0 && mode != 1) return fail(c, FLYBY_ERR_UNSUPPORTED, "point_features: mode must be 0 (cell ids) or 1 (point ids)");
   if (!cell_ids || !feats || !out || F < 1 || n_pix < 0) return fail(c, FLYBY_ERR_INVALID, "point_features: bad arguments");
   const int32_t* dids;
   const float* dfeats;
@@ -337,7 +369,7 @@ int flyby_point_features(flyby_ctx* c, const int32_t* cell_ids, int64_t n_pix, c
   if ((rc = stage_in(c, c->stage_in1, feats, (size_t)c->mesh.V * F, &dfeats))) return rc;
   StageOut<float> so;
   if ((rc = so.begin(c, c->stage_out0, out, (size_t)n_pix * F))) return rc;
-  if ((rc = label_point_features(c, dids, n_pix, dfeats, F, zero, so.dev))) return rc;
+  if ((rc = label_point_features(c, dids, n_pix, dfeats, F, zero, mode, so.dev))) return rc;
   bool need = !is_device_ptr(cell_ids) || !is_device_ptr(feats);
   if ((rc = so.finish(c, &need))) return rc;
   return sync_if(c, need);

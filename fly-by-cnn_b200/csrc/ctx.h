@@ -69,6 +69,8 @@ struct flyby_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished view chunks overlaps the next chunk's render
+  cudaEvent_t chunk_ev[16] = {nullptr};
   char err[512] = {0};
   flyby_norm_opts norm;
   fb::MeshDev mesh;
@@ -138,9 +140,9 @@ int lbvh_run(flyby_ctx* c);                       // lbvh.cu: sort + tree + layo
 int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp);  // lbvh.cu
 int views_setup(flyby_ctx* c, const flyby_render_opts* o);                      // trace.cu
 int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
-                 int32_t* ids, double* tt);                                     // trace.cu
+                 int32_t* ids, double* tt, bool first_chunk = true, bool last_chunk = true);                                     // trace.cu
 int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double* rays);
-int trace_cast(flyby_ctx* c, const double* rays, int64_t n, int32_t* ids, double* tt, double* w);
+int trace_cast(flyby_ctx* c, const double* rays, int64_t n, double tol, int32_t* ids, double* tt, double* w);
 int views_icosahedron(flyby_ctx* c, int L, double radius, int dedupe);          // views.cu
 int views_spiral(flyby_ctx* c, int n, double turns, double radius);             // views.cu
 

@@ -137,8 +137,54 @@ FB_HD void view_ray(const View& v, int res, int i, int j, double spacing, double
 // vtkTriangle::EvaluatePosition, restated (reference call site
 // src/app/fly_by_features.cxx:750-758,778).  P* are float32 vertices.
 // Returns true on hit and fills t; x and w are filled when the plane is hit.
+FB_HD double dist2pt(const double* a, const double* b) {
+  double d0 = FB_SUB(a[0], b[0]), d1 = FB_SUB(a[1], b[1]), d2 = FB_SUB(a[2], b[2]);
+  return FB_ADD(FB_ADD(FB_MUL(d0, d0), FB_MUL(d1, d1)), FB_MUL(d2, d2));
+}
+// vtkLine::DistanceToLine: squared distance from x to the segment p1-p2
+FB_HD double dist2seg(const double* x, const double* p1, const double* p2) {
+  double p21[3] = {FB_SUB(p2[0], p1[0]), FB_SUB(p2[1], p1[1]), FB_SUB(p2[2], p1[2])};
+  double num = FB_ADD(FB_ADD(FB_MUL(p21[0], FB_SUB(x[0], p1[0])), FB_MUL(p21[1], FB_SUB(x[1], p1[1]))),
+                      FB_MUL(p21[2], FB_SUB(x[2], p1[2])));
+  double denom = dot3(p21, p21);
+  double tolerance = FB_MUL(1.e-05, num);
+  if (tolerance < 0.0) tolerance = -tolerance;
+  if (denom < tolerance) return dist2pt(p1, x);
+  double t = FB_DIV(num, denom);
+  if (t < 0.0) return dist2pt(p1, x);
+  if (t > 1.0) return dist2pt(p2, x);
+  double c[3] = {FB_ADD(p1[0], FB_MUL(t, p21[0])), FB_ADD(p1[1], FB_MUL(t, p21[1])), FB_ADD(p1[2], FB_MUL(t, p21[2]))};
+  return dist2pt(c, x);
+}
+// vtkTriangle::EvaluatePosition for a point outside the triangle: squared distance
+// to the nearest edge / vertex, picked from the signs of the weights
+// (w[k] belongs to vertex k; pt1 = P1, pt2 = P2, pt3 = P0).  Rarely executed.
+FB_HD double outside_dist2(const double* x, const double* pt1, const double* pt2, const double* pt3,
+                           const double* w) {
+  double dp, d1, d2;
+  if (w[1] < 0.0 && w[2] < 0.0) {
+    dp = dist2pt(x, pt3); d1 = dist2seg(x, pt1, pt3); d2 = dist2seg(x, pt3, pt2);
+  } else if (w[2] < 0.0 && w[0] < 0.0) {
+    dp = dist2pt(x, pt1); d1 = dist2seg(x, pt1, pt3); d2 = dist2seg(x, pt1, pt2);
+  } else if (w[1] < 0.0 && w[0] < 0.0) {
+    dp = dist2pt(x, pt2); d1 = dist2seg(x, pt2, pt3); d2 = dist2seg(x, pt1, pt2);
+  } else if (w[0] < 0.0) {
+    return dist2seg(x, pt1, pt2);
+  } else if (w[1] < 0.0) {
+    return dist2seg(x, pt2, pt3);
+  } else if (w[2] < 0.0) {
+    return dist2seg(x, pt1, pt3);
+  } else {
+    return DBL_MAX;
+  }
+  double r = (dp < d1) ? dp : d1;
+  if (d2 < r) r = d2;
+  return r;
+}
+
+// tol2 = tol^2 of vtkCellLocator::IntersectWithLine (1e-10 in fly_by_features.cxx:750)
 FB_HD bool tri_exact(const double* o, const double* d, const float* P0, const float* P1,
-                     const float* P2, double t_limit, double* t_out, double* x, double* w) {
+                     const float* P2, double t_limit, double tol2, double* t_out, double* x, double* w) {
   double pt1[3] = {(double)P1[0], (double)P1[1], (double)P1[2]};
   double pt2[3] = {(double)P2[0], (double)P2[1], (double)P2[2]};
   double pt3[3] = {(double)P0[0], (double)P0[1], (double)P0[2]};
@@ -187,6 +233,33 @@ FB_HD bool tri_exact(const double* o, const double* d, const float* P0, const fl
   w[1] = pc0;
   w[2] = pc1;
   if (w[0] >= 0.0 && w[0] <= 1.0 && w[1] >= 0.0 && w[1] <= 1.0 && w[2] >= 0.0 && w[2] <= 1.0) {
+    *t_out = t;
+    return true;
+  }
+  // Outside.  vtkTriangle::IntersectWithLine still reports a hit when the squared
+  // distance from x to the triangle is <= tol^2 (this keeps a ray through a shared
+  // edge from falling between the two cells).  Cheap safe rejection first: a point
+  // with weight w_k < 0 lies |w_k| * height_k beyond the edge opposite vertex k,
+  // height_k = |n| / |edge_k|, so w_k^2 |n|^2 > 4 tol^2 |edge_k|^2 rules the slow
+  // path out (factor 4 covers the rounding of w, n and the edge).
+  {
+    const double lim = FB_MUL(4.0, tol2);
+    bool far = false;
+    if (w[0] < 0.0) {  // edge P1-P2
+      double e[3] = {FB_SUB(pt2[0], pt1[0]), FB_SUB(pt2[1], pt1[1]), FB_SUB(pt2[2], pt1[2])};
+      far = far || FB_MUL(FB_MUL(w[0], w[0]), n2) > FB_MUL(lim, dot3(e, e));
+    }
+    if (w[1] < 0.0) {  // edge P2-P0
+      double e[3] = {FB_SUB(pt3[0], pt2[0]), FB_SUB(pt3[1], pt2[1]), FB_SUB(pt3[2], pt2[2])};
+      far = far || FB_MUL(FB_MUL(w[1], w[1]), n2) > FB_MUL(lim, dot3(e, e));
+    }
+    if (w[2] < 0.0) {  // edge P0-P1
+      double e[3] = {FB_SUB(pt1[0], pt3[0]), FB_SUB(pt1[1], pt3[1]), FB_SUB(pt1[2], pt3[2])};
+      far = far || FB_MUL(FB_MUL(w[2], w[2]), n2) > FB_MUL(lim, dot3(e, e));
+    }
+    if (far) return false;
+  }
+  if (outside_dist2(x, pt1, pt2, pt3, w) <= tol2) {
     *t_out = t;
     return true;
   }
@@ -323,7 +396,7 @@ template <class NodeFetch, class Counter>
 FB_HD Hit traverse(const NodeFetch& fetch, const float4* __restrict__ tv0,
                    const float4* __restrict__ tv1, const float4* __restrict__ tv2, const double* o,
                    const double* d, const float* dirf, const float* invf, float slack, float tslack,
-                   Counter& cnt) {
+                   double tol2, Counter& cnt) {
   (void)dirf;
   Hit best;
   best.t = DBL_MAX;
@@ -350,7 +423,7 @@ FB_HD Hit traverse(const NodeFetch& fetch, const float4* __restrict__ tv0,
         cnt.tri();
         float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
         double t, x[3], w[3];
-        if (tri_exact(o, d, P0, P1, P2, best.t, &t, x, w)) {
+        if (tri_exact(o, d, P0, P1, P2, best.t, tol2, &t, x, w)) {
 #if defined(__CUDA_ARCH__)
           int cell = __float_as_int(a.w);
 #else
@@ -483,14 +556,15 @@ FB_HD void lane_node_step(Lane& L, const NodeFetch& fetch, const float* invf, fl
 // test one pending leaf (precondition: L.p0 >= 0)
 template <class Counter>
 FB_HD void lane_leaf_step(Lane& L, const float4* __restrict__ tv0, const float4* __restrict__ tv1,
-                          const float4* __restrict__ tv2, const double* d, float tslack, Counter& cnt) {
+                          const float4* __restrict__ tv2, const double* d, float tslack, double tol2,
+                          Counter& cnt) {
   int slot;
   if (L.p1 >= 0) { slot = L.p1; L.p1 = -1; } else { slot = L.p0; L.p0 = -1; }
   float4 a = tv0[slot], b = tv1[slot], e = tv2[slot];
   cnt.tri();
   float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
   double t, x[3], w[3];
-  if (tri_exact(L.o, d, P0, P1, P2, L.best_t, &t, x, w)) {
+  if (tri_exact(L.o, d, P0, P1, P2, L.best_t, tol2, &t, x, w)) {
 #if defined(__CUDA_ARCH__)
     int cell = __float_as_int(a.w);
 #else

@@ -15,15 +15,22 @@
 
 namespace fb {
 
+// mode 0: ids are hit CELL ids, the value is taken at the cell's vertex 0 (GetPointIdColors,
+//         utils.py:604-621, colours every cell with the id of its first point);
+// mode 1: ids are POINT ids already (decoded from an RGB id map, utils.py:644-662).
 __global__ void point_features_kernel(const int32_t* __restrict__ ids, int64_t n_pix,
-                                      const int32_t* __restrict__ tris, const float* __restrict__ feats,
-                                      int F, float zero, float* __restrict__ out) {
+                                      const int32_t* __restrict__ tris, int64_t n_cells, int64_t n_points,
+                                      const float* __restrict__ feats, int F, float zero, int mode,
+                                      float* __restrict__ out) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_pix * F) return;
   int64_t p = i / F;
   int k = (int)(i % F);
-  int32_t c = ids[p];
-  out[i] = c >= 0 ? feats[(int64_t)tris[3 * (int64_t)c] * F + k] : zero;
+  int64_t c = ids[p];
+  int64_t pt = -1;
+  if (mode == 0) { if (c >= 0 && c < n_cells) pt = tris[3 * c]; }
+  else if (c >= 0 && c < n_points) pt = c;
+  out[i] = pt >= 0 ? feats[pt * F + k] : zero;
 }
 
 // votes[cell, label] += 1.  Lanes of a warp that target the same counter are
@@ -83,10 +90,10 @@ __global__ void owner_label_kernel(const int32_t* __restrict__ owner, const int3
 }
 
 int label_point_features(flyby_ctx* c, const int32_t* ids, int64_t n_pix, const float* feats, int F,
-                         float zero, float* out) {
+                         float zero, int mode, float* out) {
   if (n_pix * F <= 0) return FLYBY_OK;
   point_features_kernel<<<(unsigned)cdiv(n_pix * F, 256), 256, 0, c->stream>>>(
-      ids, n_pix, c->mesh.tris.as<int32_t>(), feats, F, zero, out);
+      ids, n_pix, c->mesh.tris.as<int32_t>(), c->mesh.T, c->mesh.V, feats, F, zero, mode, out);
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;
 }

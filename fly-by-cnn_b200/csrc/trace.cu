@@ -134,6 +134,7 @@ struct RenderParams {
   int view_begin, n_views, res;
   int use_z, split_z, enc, channels;
   double zscale, spacing;
+  double tol2;  // tol^2 of IntersectWithLine
   float* feat;
   int32_t* ids;
   double* tt;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
             if (COUNT) n_tris++;
             const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
             double t, x[3], w[3];
-            if (tri_exact(o, d, P0, P1, P2, best_t, &t, x, w)) {
+            if (tri_exact(o, d, P0, P1, P2, best_t, p.tol2, &t, x, w)) {
               const int cell = __float_as_int(a.w);
               if (t < best_t || (t == best_t && cell < best_cell)) {
                 best_t = t;
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
         const float4 a = p.tv0[best_slot], b = p.tv1[best_slot], e = p.tv2[best_slot];
         const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
         double x[3], w[3];
-        tri_exact(o, d, P0, P1, P2, DBL_MAX, &t, x, w);
+        tri_exact(o, d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w);
         if (p.feat) {
           const int4 vid = p.tvid[best_slot];
           const float4 n0 = __ldg(p.normals + vid.x), n1 = __ldg(p.normals + vid.y), n2 = __ldg(p.normals + vid.z);
@@ -446,19 +447,26 @@ __global__ void fill_miss_kernel(float* feat, int32_t* ids, double* tt, int64_t 
 
 static int g_use_top = 1;  // FLYBY_NO_SMEM_TOP=1 disables the shared-memory top (A/B measurements)
 
+// first_chunk / last_chunk: a render call may be split into view chunks (api.cu overlaps the
+// copy-back of one chunk with the render of the next); stats and events span all chunks.
 int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
-                 int32_t* ids, double* tt) {
+                 int32_t* ids, double* tt, bool first_chunk, bool last_chunk) {
   MeshDev& m = c->mesh;
   cudaStream_t st = c->stream;
   const int nv = ve - vb;
   const int64_t n_pix = (int64_t)nv * res * res;
   if (n_pix >= (int64_t)1 << 32) return fail(c, FLYBY_ERR_INVALID, "more than 2^32 rays in one render call");
   const int channels = (o->use_z && o->split_z) ? 4 : 3;
-  FB_CUDA(c, cudaEventRecord(c->ev[5], st));
+  if (first_chunk) {
+    FB_CUDA(c, cudaEventRecord(c->ev[5], st));
+    FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 7 * sizeof(unsigned long long), st));
+    c->stats.n_rays = 0;
+  }
+  c->stats.n_rays += n_pix;
   if (m.T == 0) {
     fill_miss_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(feat, ids, tt, n_pix, channels);
     FB_LAUNCH_CHECK(c);
-    FB_CUDA(c, cudaEventRecord(c->ev[6], st));
+    if (last_chunk) FB_CUDA(c, cudaEventRecord(c->ev[6], st));
     return FLYBY_OK;
   }
   static bool env_read = false;
@@ -478,6 +486,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   p.view_begin = vb; p.n_views = nv; p.res = res;
   p.use_z = o->use_z; p.split_z = o->split_z; p.enc = o->normal_encoding; p.channels = channels;
   p.zscale = o->z_scale; p.spacing = o->plane_spacing;
+  p.tol2 = o->tolerance * o->tolerance;
   p.feat = feat; p.ids = ids; p.tt = tt;
   p.counters = c->counters.as<unsigned long long>();
   int tx = (int)cdiv(res, 8), ty = (int)cdiv(res, 4);
@@ -485,7 +494,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   p.tiles_y = (ty + 3) & ~3;
   p.n_tiles = (long long)p.tiles_x * p.tiles_y * nv;
   p.top_cap = g_use_top ? 1024 : 0;
-  FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), st));
+  FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), st));  // tile counter
   const size_t smem = (size_t)p.top_cap * sizeof(Node) + RK_WARPS * RK_QCAP * sizeof(uint32_t);
   auto launch = [&](auto kern) -> int {
     FB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -504,8 +513,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if (g_use_top) rc = c->count_work ? launch(render_kernel<true, true>) : launch(render_kernel<true, false>);
   else rc = c->count_work ? launch(render_kernel<false, true>) : launch(render_kernel<false, false>);
   if (rc) return rc;
-  FB_CUDA(c, cudaEventRecord(c->ev[6], st));
-  c->stats.n_rays = n_pix;
+  if (last_chunk) FB_CUDA(c, cudaEventRecord(c->ev[6], st));
   return FLYBY_OK;
 }
 
@@ -513,7 +521,8 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
 // vtkCellLocator::IntersectWithLine for caller-supplied segments (predict.py:128)
 __global__ void cast_kernel(const Node* __restrict__ nodes, const float4* __restrict__ tv0,
                             const float4* __restrict__ tv1, const float4* __restrict__ tv2, int has_tris,
-                            const double* __restrict__ rays, int64_t n, int32_t* ids, double* tt, double* ww) {
+                            const double* __restrict__ rays, int64_t n, double tol2, int32_t* ids, double* tt,
+                            double* ww) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n) return;
   double o[3] = {rays[6 * r], rays[6 * r + 1], rays[6 * r + 2]};
@@ -535,12 +544,12 @@ __global__ void cast_kernel(const Node* __restrict__ nodes, const float4* __rest
     float tslack = (float)(dl > 0.0 ? 4.0 * (double)slack / dl : 0.0);
     GlobalFetch f{nodes};
     NoCount nc;
-    h = traverse(f, tv0, tv1, tv2, o, d, dirf, invf, slack, tslack, nc);
+    h = traverse(f, tv0, tv1, tv2, o, d, dirf, invf, slack, tslack, tol2, nc);
     if (h.slot >= 0) {
       float4 a = tv0[h.slot], b = tv1[h.slot], e = tv2[h.slot];
       float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
       double x[3];
-      tri_exact(o, d, P0, P1, P2, DBL_MAX, &t, x, w);
+      tri_exact(o, d, P0, P1, P2, DBL_MAX, tol2, &t, x, w);
     }
   }
   if (ids) ids[r] = h.cell;
@@ -548,12 +557,12 @@ __global__ void cast_kernel(const Node* __restrict__ nodes, const float4* __rest
   if (ww) for (int k = 0; k < 3; k++) ww[3 * r + k] = w[k];
 }
 
-int trace_cast(flyby_ctx* c, const double* rays, int64_t n, int32_t* ids, double* tt, double* w) {
+int trace_cast(flyby_ctx* c, const double* rays, int64_t n, double tol, int32_t* ids, double* tt, double* w) {
   MeshDev& m = c->mesh;
   if (n <= 0) return FLYBY_OK;
   cast_kernel<<<(unsigned)cdiv(n, 128), 128, 0, c->stream>>>(
       m.nodes.as<Node>(), m.tv0.as<float4>(), m.tv1.as<float4>(), m.tv2.as<float4>(), m.T > 0 ? 1 : 0,
-      rays, n, ids, tt, w);
+      rays, n, tol * tol, ids, tt, w);
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;
 }

@@ -29,7 +29,7 @@ class NormOpts(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("use_z", C.c_int32), ("split_z", C.c_int32), ("normal_encoding", C.c_int32),
                 ("reserved", C.c_int32), ("plane_scale", C.c_double), ("plane_spacing", C.c_double),
-                ("z_scale", C.c_double)]
+                ("z_scale", C.c_double), ("tolerance", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -206,12 +206,13 @@ class Context:
     # ---- rendering ----------------------------------------------------------
     @staticmethod
     def render_opts(use_z=1, split_z=1, normal_encoding="unit01", plane_scale=1.0, plane_spacing=1.0,
-                    z_scale=1.0):
+                    z_scale=1.0, tolerance=1e-10):
         o = RenderOpts()
         o.use_z, o.split_z = int(bool(use_z)), int(bool(split_z))
         o.normal_encoding = NORMAL_ENCODINGS[normal_encoding] if isinstance(normal_encoding, str) \
             else int(normal_encoding)
         o.plane_scale, o.plane_spacing, o.z_scale = float(plane_scale), float(plane_spacing), float(z_scale)
+        o.tolerance = float(tolerance)
         return o
 
     @staticmethod
@@ -244,17 +245,17 @@ class Context:
         self.render_into(res, opts, feat, ids, tt, view_begin, ve)
         return (feat, ids, tt) if want_t else (feat, ids)
 
-    def cast(self, rays):
+    def cast(self, rays, tolerance=1e-10):
         r = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
         n = len(r)
         ids = np.empty(n, np.int32)
         tt = np.empty(n, np.float64)
         w = np.empty((n, 3), np.float64)
-        self._ck(self._lib.flyby_cast(self._h, _ptr(r), C.c_int64(n), _ptr(ids), _ptr(tt), _ptr(w)))
+        self._ck(self._lib.flyby_cast(self._h, _ptr(r), C.c_int64(n), C.c_double(tolerance), _ptr(ids), _ptr(tt), _ptr(w)))
         return ids, tt, w
 
     # ---- features / labels --------------------------------------------------
-    def point_features(self, cell_ids, feats, zero=0.0, out=None):
+    def point_features(self, cell_ids, feats, zero=0.0, out=None, mode=0):
         _check_dtype(cell_ids, np.int32, "cell_ids")
         _check_dtype(feats, np.float32, "feats")
         n_pix = int(np.prod(cell_ids.shape))
@@ -262,7 +263,7 @@ class Context:
         if out is None:
             out = np.empty(tuple(cell_ids.shape) + (F,), np.float32)
         self._ck(self._lib.flyby_point_features(self._h, _ptr(cell_ids), C.c_int64(n_pix), _ptr(feats),
-                                                C.c_int(F), C.c_float(zero), C.c_int(0), _ptr(out)))
+                                                C.c_int(F), C.c_float(zero), C.c_int(int(mode)), _ptr(out)))
         return out
 
     def backproject(self, cell_ids, labels, n_classes, votes=None):
@@ -312,6 +313,7 @@ class Context:
     def nccl_init(self, unique_id, rank, world):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._ck(self._lib.flyby_nccl_init(self._h, buf, C.c_int(rank), C.c_int(world)))
+        self._nccl_ready = True
 
     def votes_allreduce(self, votes, root=-1):
         n = int(np.prod(votes.shape))

@@ -1,0 +1,315 @@
+"""Drop-in for the reference's ``fly_by_features.py`` (reference src/py/fly_by_features.py).
+
+``FlyByGenerator`` keeps the reference's constructor and methods
+(src/py/fly_by_features.py:18-154) and ``main`` / the command line keep the
+reference's option surface (:156-493).  The renderer behind it is the CUDA ray
+caster of this repo (the engine of the reference's C++ tool with ``--useOctree``,
+src/app/fly_by_features.cxx:482-852): orthographic rays from the tangent plane at
+every viewpoint, nearest hit by LBVH traversal, barycentric normals and depth.
+
+Differences a caller can see (DESIGN.md "Deviations"):
+ * depth is the distance from the view plane along the ray (ray-cast engine), not
+   the perspective z-buffer of the OpenGL path; images are not flipped by a view-up;
+ * normals are float32, not 8-bit quantised; ``normal_encoding`` selects the value
+   range: "byte255" (default here, the range the Python reference produces),
+   "unit01" (the C++ tool's n*0.5+0.5) or "signed" (rescale_features);
+ * options that need an OpenGL window, a Keras model or fibre tubes are rejected.
+"""
+import argparse
+import glob
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import utils
+from ._cabi import Context
+from .utils import *  # noqa: F401,F403  (the reference re-exports utils through this module)
+
+
+class FlyByGenerator():
+    def __init__(self, sphere=None, resolution=224, visualize=False, use_z=False, split_z=False,
+                 rescale_features=False, normal_encoding=None, plane_scale=1.0, plane_spacing=1.0,
+                 z_far=None, device=0):
+        if visualize:
+            raise NotImplementedError("visualize needs an interactive VTK window; not available in flyby_b200")
+        self.sphere = sphere
+        self.visualize = False
+        self.resolution = int(resolution)
+        self.use_z = bool(use_z)
+        self.split_z = bool(split_z)
+        self.rescale_features = bool(rescale_features)
+        self.normal_encoding = normal_encoding or ("signed" if rescale_features else "byte255")
+        self.plane_scale = float(plane_scale)
+        self.plane_spacing = float(plane_spacing)
+        self.z_far = z_far
+        self.device = device
+        self.actors = []
+        self.ctx = Context(device)
+        self.last_cell_ids = None  # int32 [V, res, res] hit cell ids of the last getFlyBy (-1 = background)
+        self._built_for = None
+
+    # --- reference API ---------------------------------------------------------
+    def removeActor(self, actor):
+        self.actors = [a for a in self.actors if a is not actor]
+
+    def removeActors(self):
+        self.actors = []
+
+    def addActor(self, actor):
+        if actor is None:
+            return
+        if not isinstance(actor, utils.Actor):
+            raise TypeError("addActor expects GetNormalsActor / GetPointIdMapActor / GetCellIdMapActor output")
+        self.actors.append(actor)
+
+    def _mesh(self):
+        if not self.actors:
+            raise RuntimeError("getFlyBy: no actor added")
+        kinds = {a.kind for a in self.actors}
+        if len(kinds) != 1:
+            raise NotImplementedError("actors of different kinds cannot be rendered together")
+        if len(self.actors) == 1:
+            s = self.actors[0].surf
+            return s.points, s.polys, self.actors[0].kind
+        if "point_id" in kinds or "cell_id" in kinds:
+            raise NotImplementedError("id maps are defined for a single surface")
+        pts, tris, off = [], [], 0
+        for a in self.actors:  # several surfaces in one scene: nearest surface wins, as in a render
+            pts.append(a.surf.points)
+            tris.append(a.surf.polys + off)
+            off += len(a.surf.points)
+        return np.concatenate(pts), np.concatenate(tris), self.actors[0].kind
+
+    def getFlyBy(self, sphere_points=None, view_up_points=None, focal_points=None):
+        if view_up_points is not None or focal_points is not None:
+            raise NotImplementedError("the ray-cast engine looks at the origin with the sphere north as up "
+                                      "(src/app/fly_by_features.cxx:656-688); custom view-up / focal points "
+                                      "belong to the OpenGL camera path")
+        points, polys, kind = self._mesh()
+        ctx = self.ctx
+        # meshes handed to the generator are already normalised by GetUnitSurf (as in the reference);
+        # the LBVH build takes well under a millisecond, so it is simply redone per call
+        ctx.set_mesh(np.ascontiguousarray(points, np.float32), np.ascontiguousarray(polys, np.int32),
+                     skip_normalise=True)
+        ctx.build()
+        if sphere_points is None:
+            if self.sphere is None:
+                raise RuntimeError("getFlyBy: no viewpoints")
+            sphere_points = self.sphere.points
+            radius = self.sphere.radius
+        else:
+            sphere_points = np.asarray(sphere_points, dtype=np.float32).reshape(-1, 3)
+            radius = float(np.linalg.norm(sphere_points[0]))
+        print("number of points : ", len(sphere_points))
+        ctx.views_custom(sphere_points, radius)
+        res = self.resolution
+        if kind != "normals":
+            opts = ctx.render_opts(use_z=0, split_z=0, plane_scale=self.plane_scale, plane_spacing=self.plane_spacing)
+            ids = np.empty((len(sphere_points), res, res), np.int32)
+            ctx.render_into(res, opts, None, ids)
+            self.last_cell_ids = ids
+            if kind == "point_id":  # colour = id of the cell's first point (utils.py:604-621)
+                pid = np.where(ids >= 0, polys[np.maximum(ids, 0), 0], -1)
+                return utils.EncodeIdsRGB(pid)
+            return utils.EncodeIdsRGB(ids)
+        z_far = self.z_far if self.z_far is not None else radius + 1.0
+        z_scale = 1.0
+        if self.use_z and (self.rescale_features or not self.split_z):
+            z_scale = 1.0 / z_far  # fly_by_features.py:138-146
+        opts = ctx.render_opts(use_z=self.use_z, split_z=self.split_z, normal_encoding=self.normal_encoding,
+                               plane_scale=self.plane_scale, plane_spacing=self.plane_spacing, z_scale=z_scale)
+        feat, ids = ctx.render(res, opts)
+        self.last_cell_ids = ids
+        return feat
+
+
+def _find_surfaces(args):
+    """reference src/py/fly_by_features.py:158-213"""
+    filenames = []
+    if args.surf:
+        filenames.append({"surf": args.surf, "out": args.out})
+    else:
+        surf_filenames = []
+        replace_dir_name = ""
+        if args.dir:
+            replace_dir_name = args.dir
+            normpath = os.path.normpath("/".join([args.dir, '**', '*']))
+            for surf in glob.iglob(normpath, recursive=True):
+                if os.path.isfile(surf) and True in [ext in surf for ext in [".vtk", ".obj", ".stl", ".off"]]:
+                    surf_filenames.append(os.path.realpath(surf))
+            replace_dir_name = os.path.realpath(args.dir)
+        elif args.csv:
+            import pandas
+            replace_dir_name = args.csv_root_path
+            df = pandas.read_csv(args.csv)
+            for _, row in df.iterrows():
+                surf_filenames.append(row["surf"])
+        for surf in surf_filenames:
+            dir_filename = os.path.splitext(surf.replace(replace_dir_name, ''))[0] + ".nrrd"
+            out = os.path.normpath("/".join([args.out, dir_filename]))
+            if args.uuid:
+                import uuid
+                out = out.replace(".nrrd", "-" + str(uuid.uuid1()).split('-')[0] + ".nrrd")
+            if not os.path.exists(os.path.dirname(out)):
+                os.makedirs(os.path.dirname(out))
+            if args.ow or not os.path.exists(out):
+                filenames.append({"surf": surf, "out": out})
+    if args.n_rotations:
+        for fobj in filenames.copy():
+            for i in range(args.n_rotations):
+                out_name, out_ext = os.path.splitext(os.path.normpath(fobj["out"]))
+                rot = {"surf": fobj["surf"], "out": out_name + "_rot" + str(i) + out_ext, "rotate": True}
+                if args.ow or not os.path.exists(rot["out"]):
+                    filenames.append(rot)
+    return filenames
+
+
+def _write(out_np, path, concatenate, suffix=""):
+    """reference src/py/fly_by_features.py:404-424"""
+    if not concatenate:
+        if not os.path.exists(path):
+            os.makedirs(path)
+        for i in range(out_np.shape[0]):
+            name = os.path.join(path, str(i) + suffix + ".nrrd")
+            print("Writing:", name)
+            utils.WriteImage(utils.GetImage(out_np[i]), name)
+    else:
+        print("Writing:", path)
+        utils.WriteImage(utils.GetImage(out_np), path)
+
+
+def main(args):
+    for name in ("fiberBundle", "fiber", "property", "view_features", "model", "visualize"):
+        if getattr(args, name, None):
+            raise SystemExit("--%s is not supported by flyby_b200 (needs VTK tube filters / colour maps / Keras / "
+                             "an OpenGL window); see DESIGN.md" % name)
+    filenames = _find_surfaces(args)
+    device = getattr(args, "device", 0)
+    if args.subdivision:
+        sphere = utils.CreateIcosahedron(args.radius, args.subdivision, device=device)
+    else:
+        sphere = utils.CreateSpiral(args.radius, args.spiral, args.turns, device=device)
+    kw = dict(plane_scale=getattr(args, "plane_scale", 1.0), plane_spacing=getattr(args, "plane_spacing", 1.0),
+              normal_encoding=getattr(args, "normal_encoding", None), device=device)
+    flyby = FlyByGenerator(sphere, args.resolution, use_z=args.use_z, split_z=args.split_z,
+                           rescale_features=args.rescale_features, **kw)
+    flyby_features = None
+    if args.point_features or args.out_point_id:
+        flyby_features = FlyByGenerator(sphere, args.resolution, **kw)
+
+    for fobj in filenames:
+        if args.verbose:
+            print("Number of sphere points:", sphere.GetNumberOfPoints())
+            print("Reading:", fobj["surf"])
+        surf = utils.ReadSurf(fobj["surf"])
+        surf = utils.GetUnitSurf(surf, args.translate, args.scale_factor, device=device)
+        if args.random_rotation or fobj.get("rotate"):
+            surf, rotationAngle, rotationVector = utils.RandomRotation(surf)
+            if args.verbose:
+                print("angle:", rotationAngle, "vector:", rotationVector)
+            if args.save_rotation:
+                out_filename = os.path.splitext(fobj["out"])[0] + "_transform.npy"
+                print("Saving rotation:", out_filename)
+                np.save(out_filename, utils.GetTransform(rotationAngle, rotationVector).ravel())
+        flyby.addActor(utils.GetNormalsActor(surf))
+        out_np = flyby.getFlyBy()
+        if args.extract_components is not None:
+            out_np = out_np[:, :, :, args.extract_components[0]:args.extract_components[1]]
+            print(out_np.shape)
+        if flyby_features is not None:
+            flyby_features.addActor(utils.GetPointIdMapActor(surf))
+            out_point_ids_rgb_np = flyby_features.getFlyBy()
+            if args.out_point_id:
+                if not args.concatenate:
+                    _write(out_point_ids_rgb_np, fobj["out"], 0, "_point_id_map")
+                else:
+                    name = os.path.splitext(fobj["out"])
+                    _write(out_point_ids_rgb_np, name[0] + "_point_id_map" + name[1], 1)
+            if args.point_features:
+                for point_features_name in args.point_features:
+                    print("Extracting:", point_features_name)
+                    out_features_np = utils.ExtractPointFeatures(surf, out_point_ids_rgb_np, point_features_name,
+                                                                 args.zero, device=device)
+                    if args.point_features_concat:
+                        out_np = np.concatenate([out_np, out_features_np], axis=-1)
+                    elif not args.concatenate:
+                        _write(out_features_np, fobj["out"], 0, "_" + point_features_name)
+                    else:
+                        name = os.path.splitext(fobj["out"])
+                        _write(out_features_np, name[0] + "_" + point_features_name + name[1], 1)
+            flyby_features.removeActors()
+        _write(out_np, fobj["out"], args.concatenate)
+        flyby.removeActors()
+
+
+def build_parser():
+    """Option surface of reference src/py/fly_by_features.py:432-489 (same names, defaults and groups)."""
+    parser = argparse.ArgumentParser(description='Fly-by feature extraction on a B200 (drop-in for fly_by_features.py)',
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    input_group = parser.add_argument_group('Input parameters')
+    input_params = input_group.add_mutually_exclusive_group(required=True)
+    input_params.add_argument('--surf', type=str, help='Target surface/mesh')
+    input_params.add_argument('--dir', type=str, help='Input directory with 3D models')
+    input_params.add_argument('--csv', type=str, help='Input csv with column "surf"')
+    input_group.add_argument('--csv_root_path', type=str, help='CSV rooth path for replacement', default="")
+    input_group.add_argument('--model', type=str, help='(unsupported) directory with a saved Keras model', default=None)
+    input_group.add_argument('--random_rotation', type=bool, help='Apply a random rotation', default=False)
+    input_group.add_argument('--n_rotations', type=int, help='Number of additional random rotations', default=0)
+    input_group.add_argument('--scale_factor', type=float, help='Scale the surface by this vale', default=None)
+    input_group.add_argument('--bounds', type=float, nargs="+", help='(unused, as in the reference)', default=None)
+    input_group.add_argument('--translate', nargs="+", type=float, help='Center the surface at this point', default=None)
+    input_group.add_argument('--fiberBundle', type=bool, help='(unsupported) input is a fiber tract', default=False)
+    input_group.add_argument('--fiber', type=bool, help='(unsupported) input surface is a fiber', default=False)
+    input_group.add_argument('--nbFiber', type=int, help='(unsupported)', default=0.05)
+    input_group.add_argument('--subject', type=str, help='(unsupported)', default=None)
+
+    features_group = parser.add_argument_group('Shape features/property to extract')
+    features_group.add_argument('--extract_components', type=int, nargs='+', help='Which components to extract', default=None)
+    features_group.add_argument('--norm_shader', type=int, help='(unused, as in the reference)', default=1)
+    features_group.add_argument('--split_z', type=int, help='1 to split the z buffer as a separate channel. Otherwise, the normals are scaled by z buffer to create an rgb image.', default=0)
+    features_group.add_argument('--use_z', type=int, help='1 to use the z_buffer and compute the depth buffer (distance of the view plane to the shape at every location).', default=1)
+    features_group.add_argument('--rescale_features', type=int, help='1 to rescale features (Normals, Depth map) between 0 and 1', default=0)
+    features_group.add_argument('--property', type=str, help='(unsupported) input property file', default=None)
+    features_group.add_argument('--point_features', nargs='+', type=str, help='Name of array in point data to extract features. If name is coords or points, it extracts the x,y,z coordinates', default=None)
+    features_group.add_argument('--point_features_concat', type=int, help='Concatenate point features to the fly_by_features', default=0)
+    features_group.add_argument('--zero', type=float, help="Default zero value when extracting properties. This is used when there is no 'collision' with the surface", default=0)
+    features_group.add_argument('--view_features', type=str, help='(unsupported) name of array in point data to visualize', default=None)
+
+    sphere_params = parser.add_argument_group('Sampling parameters')
+    sphere_params_sampling = sphere_params.add_mutually_exclusive_group(required=True)
+    sphere_params_sampling.add_argument('--subdivision', type=int, help='Number of subdivisions for icosahedron')
+    sphere_params_sampling.add_argument('--spiral', type=int, help='Number of samples along the spherical spiral')
+    sphere_params.add_argument('--turns', type=int, default=4, help='Number of spiral turns')
+    sphere_params.add_argument('--resolution', type=int, help='Image resolution', default=256)
+    sphere_params.add_argument('--radius', type=float, help='Radius of the sphere for the view points', default=4)
+
+    training_orientation = parser.add_argument_group('training orientation')
+    training_orientation.add_argument('--save_rotation', type=int, help="save the orientation transform", default=0)
+
+    visu_params = parser.add_argument_group('Visualize')
+    visu_params.add_argument('--visualize', type=int, default=0, help='(unsupported) visualize the sampling')
+
+    output_params = parser.add_argument_group('Output parameters')
+    output_params.add_argument('--out', type=str, help='Output filename or directory', default="out.nrrd")
+    output_params.add_argument('--out_point_id', type=int, help='Output the point id map. Point ids are encoded in the rgb components', default=0)
+    output_params.add_argument('--uuid', type=bool, help='Use uuid to name the outputs', default=False)
+    output_params.add_argument('--ow', type=int, help='Overwrite outputs', default=1)
+    output_params.add_argument('--concatenate', type=int, help='0 for multiple output files, 1 for single output file', default=1)
+    output_params.add_argument('--verbose', type=int, help='Print messages', default=0)
+
+    # options of the reference's C++ tool (src/app/fly_by_features.xml:62-76) and of this implementation
+    engine = parser.add_argument_group('Ray-cast engine')
+    engine.add_argument('--plane_scale', type=float, default=1.0, help='planeScaleFactor: side length of the view plane')
+    engine.add_argument('--plane_spacing', type=float, default=1.0, help='planeSpacing')
+    engine.add_argument('--normal_encoding', type=str, default=None, choices=[None, 'byte255', 'unit01', 'signed'],
+                        help='value range of the normal channels (default byte255, signed with --rescale_features)')
+    engine.add_argument('--device', type=int, default=0, help='CUDA device')
+    return parser
+
+
+if __name__ == '__main__':
+    start_time = time.time()
+    main(build_parser().parse_args())
+    print("FlyBy time:", round((time.time() - start_time) * 1000.0), "ms", file=sys.stderr)

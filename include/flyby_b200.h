@@ -71,6 +71,8 @@ typedef struct {
   double plane_scale;      /* planeScaleFactor, default 1.0 */
   double plane_spacing;    /* planeSpacing, default 1.0 */
   double z_scale;          /* depth multiplier (1/z_far when rescaling), default 1.0 */
+  double tolerance;        /* tol of vtkCellLocator::IntersectWithLine: a point within tol of a cell counts as
+                              a hit (fly_by_features.cxx:750 uses 1e-10, predict.py:114 1e-8) */
 } flyby_render_opts;
 
 /* Per-stage device timings of the last build/render on this context (ms, CUDA
@@ -137,12 +139,14 @@ FLYBY_API int flyby_render(flyby_ctx* ctx, int view_begin, int view_end, int res
 /* Cast caller-supplied segments (rays float64 [n,6]); same outputs per ray
  * plus barycentric weights w [n,3].  vtkCellLocator::IntersectWithLine
  * (fly_by_features.cxx:758, predict.py:128). */
-FLYBY_API int flyby_cast(flyby_ctx* ctx, const double* rays, int64_t n_rays, int32_t* out_cell_ids,
-               double* out_t, double* out_w);
+FLYBY_API int flyby_cast(flyby_ctx* ctx, const double* rays, int64_t n_rays, double tolerance,
+               int32_t* out_cell_ids, double* out_t, double* out_w);
 
 /* ---- point features through the id map (utils.py:604-684) --------------- */
-/* mode 0: value at the hit cell's vertex 0 (reference ExtractPointFeatures).
- * feats float32 [V,F]; out float32 [n_pix,F]; miss -> zero. */
+/* mode 0: ids are hit cell ids, value at the cell's vertex 0 (GetPointIdColors
+ * utils.py:604-621 colours a cell with its first point's id); mode 1: ids are
+ * point ids already (decoded RGB id map, utils.py:644-662).
+ * feats float32 [V,F]; out float32 [n_pix,F]; miss / out of range -> zero. */
 FLYBY_API int flyby_point_features(flyby_ctx* ctx, const int32_t* cell_ids, int64_t n_pix, const float* feats,
                          int n_feat, float zero, int mode, float* out);
 

@@ -318,12 +318,57 @@ ORC_API void orc_view_rays(const float* sp, double radius, double plane_scale, d
 
 /* ------------------------------------------------------------------ */
 /* O6  segment / triangle test, VTK semantics                          */
-/*   call site src/app/fly_by_features.cxx:750-758 (tol 1e-10)         */
+/*   call site src/app/fly_by_features.cxx:750-758 (tol 1e-10),        */
+/*   src/py/predict.py:114-128 (tol 1e-8)                              */
 /*   vtkTriangle::IntersectWithLine -> vtkPlane::IntersectWithLine ->  */
-/*   vtkTriangle::EvaluatePosition (inclusive [0,1] weights).          */
-/*   The |dist| <= tol dilation branch (tol = 1e-10) is not restated.  */
+/*   vtkTriangle::EvaluatePosition (inclusive [0,1] weights); a point  */
+/*   outside the triangle still counts when its squared distance to    */
+/*   the triangle is <= tol^2 (this is what keeps a ray through a      */
+/*   shared edge from falling between the two cells).                  */
 /* Returns 1 on hit and fills t, x[3], w[3].                           */
 /* ------------------------------------------------------------------ */
+static double dist2pt(const double a[3], const double b[3]) {
+  double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+  return d0 * d0 + d1 * d1 + d2 * d2;
+}
+/* vtkLine::DistanceToLine: squared distance from x to the segment p1-p2 */
+static double dist2seg(const double x[3], const double p1[3], const double p2[3]) {
+  double p21[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  double num = p21[0] * (x[0] - p1[0]) + p21[1] * (x[1] - p1[1]) + p21[2] * (x[2] - p1[2]);
+  double denom = dot3(p21, p21);
+  double tolerance = 1.e-05 * num; /* VTK_TOL */
+  if (tolerance < 0.0) tolerance = -tolerance;
+  double t;
+  if (denom < tolerance) return dist2pt(p1, x); /* numerically bad: arbitrary end point */
+  if ((t = num / denom) < 0.0) return dist2pt(p1, x);
+  if (t > 1.0) return dist2pt(p2, x);
+  double c[3] = {p1[0] + t * p21[0], p1[1] + t * p21[1], p1[2] + t * p21[2]};
+  return dist2pt(c, x);
+}
+/* vtkTriangle::EvaluatePosition, point outside: squared distance to the nearest
+ * edge / vertex, chosen from the signs of the weights (w[k] belongs to vertex k;
+ * pt1 = P1, pt2 = P2, pt3 = P0) */
+static double outside_dist2(const double x[3], const double pt1[3], const double pt2[3],
+                            const double pt3[3], const double w[3]) {
+  double dp, d1, d2, r;
+  if (w[1] < 0.0 && w[2] < 0.0) {
+    dp = dist2pt(x, pt3); d1 = dist2seg(x, pt1, pt3); d2 = dist2seg(x, pt3, pt2);
+  } else if (w[2] < 0.0 && w[0] < 0.0) {
+    dp = dist2pt(x, pt1); d1 = dist2seg(x, pt1, pt3); d2 = dist2seg(x, pt1, pt2);
+  } else if (w[1] < 0.0 && w[0] < 0.0) {
+    dp = dist2pt(x, pt2); d1 = dist2seg(x, pt2, pt3); d2 = dist2seg(x, pt1, pt2);
+  } else if (w[0] < 0.0) return dist2seg(x, pt1, pt2);
+  else if (w[1] < 0.0) return dist2seg(x, pt2, pt3);
+  else if (w[2] < 0.0) return dist2seg(x, pt1, pt3);
+  else return DBL_MAX; /* no negative weight: VTK leaves dist2 unset; treated as far */
+  r = (dp < d1) ? dp : d1;
+  if (d2 < r) r = d2;
+  return r;
+}
+
+static double g_tol2 = 1.0e-20; /* tol^2, tol = 1e-10 (fly_by_features.cxx:750) */
+ORC_API void orc_set_tolerance(double tol) { g_tol2 = tol * tol; }
+
 static int tri_hit(const double o[3], const double d[3], const float* P0, const float* P1,
                    const float* P2, double* t_out, double x[3], double w[3]) {
   double pt1[3] = {P1[0], P1[1], P1[2]}, pt2[3] = {P2[0], P2[1], P2[2]}, pt3[3] = {P0[0], P0[1], P0[2]};
@@ -364,6 +409,11 @@ static int tri_hit(const double o[3], const double d[3], const float* P0, const 
   double pc1 = (c1[0] * rhs[1] - rhs[0] * c1[1]) / det;
   w[0] = 1 - (pc0 + pc1); w[1] = pc0; w[2] = pc1;
   if (w[0] >= 0.0 && w[0] <= 1.0 && w[1] >= 0.0 && w[1] <= 1.0 && w[2] >= 0.0 && w[2] <= 1.0) {
+    *t_out = t;
+    return 1;
+  }
+  /* outside: vtkTriangle::IntersectWithLine still reports a hit when dist2 <= tol^2 */
+  if (outside_dist2(x, pt1, pt2, pt3, w) <= g_tol2) {
     *t_out = t;
     return 1;
   }

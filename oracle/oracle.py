@@ -46,6 +46,11 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def set_tolerance(tol):
+    """tol of vtkCellLocator::IntersectWithLine (1e-10 in fly_by_features.cxx:750, 1e-8 in predict.py:114)."""
+    lib().orc_set_tolerance(C.c_double(tol))
+
+
 def num_threads():
     return lib().orc_num_threads()
 

@@ -153,7 +153,7 @@ int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, co
         Hit h;
         if (mode == 0) {
           h = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o, vw.dir, vw.dirf, vw.invf, vw.slack,
-                       vw.tslack, cnt);
+                       vw.tslack, 1e-20, cnt);
         } else {
           // the render kernel's per-lane state machine, one lane at a time; leaf tests are
           // delayed as long as possible (mode 2) or run at once (mode 1) to cover both schedules
@@ -161,7 +161,7 @@ int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, co
           lane_init(L, o, vw.tslack);
           while (L.node >= 0 || L.p0 >= 0) {
             bool leaf_now = L.p0 >= 0 && (mode == 1 || L.node < 0 || L.p0 >= 0);
-            if (leaf_now) lane_leaf_step(L, b.tv0.data(), b.tv1.data(), b.tv2.data(), vw.dir, vw.tslack, cnt);
+            if (leaf_now) lane_leaf_step(L, b.tv0.data(), b.tv1.data(), b.tv2.data(), vw.dir, vw.tslack, 1e-20, cnt);
             else lane_node_step(L, f, vw.invf, vw.slack, cnt);
           }
           h.t = L.best_t; h.slot = L.best_slot; h.cell = L.best_slot >= 0 ? L.best_cell : -1;
@@ -173,7 +173,7 @@ int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, co
           float4 a = b.tv0[h.slot], bb = b.tv1[h.slot], e = b.tv2[h.slot];
           float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
           double x[3], w[3];
-          tri_exact(o, vw.dir, P0, P1, P2, DBL_MAX, &t, x, w);
+          tri_exact(o, vw.dir, P0, P1, P2, DBL_MAX, 1e-20, &t, x, w);
           const int32_t* vid = &b.vid[4 * (size_t)h.slot];
           shade(o, x, w, normals + 3 * vid[0], normals + 3 * vid[1], normals + 3 * vid[2], use_z, split_z, enc,
                 zscale, px);
@@ -227,7 +227,7 @@ static void packet_trace(const SimBvh& b, const View& vw, const double (*o)[3], 
           if (!(side ? h1[l] : h0[l])) continue;
           cnt.tri();
           double t, x[3], w[3];
-          if (tri_exact(o[l], vw.dir, P0, P1, P2, best_t[l], &t, x, w) &&
+          if (tri_exact(o[l], vw.dir, P0, P1, P2, best_t[l], 1e-20, &t, x, w) &&
               (t < best_t[l] || (t == best_t[l] && cell < best_cell[l]))) {
             best_t[l] = t; best_slot[l] = slot; best_cell[l] = cell;
             tcull[l] = fminf(tcull[l], FB_F2F_RU(t) + vw.tslack);

@@ -1,0 +1,146 @@
+"""GPU tests of the reference-facing host layer: the fly_by_features command line, the
+FlyByGenerator class, the id-map / point-feature path and the labeling driver, each
+checked against the oracle."""
+import numpy as np
+import pytest
+
+from flyby_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fbf():
+    from flyby_b200 import fly_by_features
+    return fly_by_features
+
+
+def _mesh_file(tmp_path, P, F, **pd):
+    from flyby_b200 import readers
+    path = str(tmp_path / "surf.vtk")
+    readers.write_vtk(path, P, F, point_data=pd, binary=True)
+    return path
+
+
+def test_free_functions_match_oracle(fbf, orc):
+    P, F = synth.bumpy_sphere(16, 6)
+    surf = fbf.Surf(P, F)
+    unit, mean, scale = fbf.ScaleSurf(surf)
+    U, c, s = orc.unit_surf(P)
+    assert np.array_equal(unit.points, U) and np.array_equal(mean, c) and scale == s and unit.is_unit
+    assert np.array_equal(fbf.GetUnitSurf(surf, mean_arr=[1, 2, 3], scale_factor=0.05).points,
+                          orc.unit_surf(P, translate=[1, 2, 3], scale_factor=0.05)[0])
+    assert np.array_equal(fbf.ComputeNormals(unit).point_data["Normals"], orc.point_normals(U, F))
+    assert np.array_equal(fbf.CreateIcosahedron(2.75, 3).points, orc.icosahedron(3, 2.75))
+    sp = fbf.CreateSpiral(4, 64, 4)
+    assert sp.GetNumberOfPoints() == 64 and np.allclose(sp.points, orc.spiral(64, 4, 4.0), atol=1e-6)
+
+
+def test_cli_config1_small(fbf, orc, tmp_path):
+    """BASELINE config 1 option line at a reduced resolution, through main() to an NRRD file."""
+    from flyby_b200 import nrrd
+    P, F = synth.bumpy_sphere(20, 0)
+    surf = _mesh_file(tmp_path, P, F)
+    out = str(tmp_path / "out.nrrd")
+    args = fbf.build_parser().parse_args(("--surf %s --subdivision 2 --resolution 64 --radius 2 --use_z 1 --split_z 1 "
+                                          "--normal_encoding unit01 --out %s" % (surf, out)).split())
+    fbf.main(args)
+    img, hdr = nrrd.read(out)
+    assert img.shape == (42, 64, 64, 4) and hdr["sizes"] == "4 64 64 42"
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    ref, ids = orc.render(U, F, N, orc.icosahedron(2, 2.0), 2.0, 64, use_z=1, split_z=1, grid=True, grid_div=16)
+    assert np.allclose(img, ref, rtol=1e-5, atol=1e-7) and (ids >= 0).mean() > 0.5
+
+
+def test_cli_spiral_point_features_and_per_view_files(fbf, orc, tmp_path):
+    import os
+    from flyby_b200 import nrrd
+    P, F = synth.dental_crown(16, 1)
+    curv = np.linspace(-1, 1, len(P)).astype(np.float32)
+    surf = _mesh_file(tmp_path, P, F, Curv=curv)
+    outdir = str(tmp_path / "views")
+    args = fbf.build_parser().parse_args(("--surf %s --spiral 6 --turns 4 --resolution 40 --radius 4 --use_z 1 --split_z 0 "
+                                          "--point_features Curv coords --point_features_concat 1 --zero -5 "
+                                          "--concatenate 0 --out %s" % (surf, outdir)).split())
+    fbf.main(args)
+    files = sorted(os.listdir(outdir), key=lambda s: int(s.split(".")[0]))
+    assert files == ["%d.nrrd" % i for i in range(6)]
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    views = orc.spiral(6, 4, 4.0)
+    ref, ids = orc.render(U, F, N, views, 4.0, 40, use_z=1, split_z=0, normal_encoding=1, zscale=1.0 / 5.0, grid=False)
+    for i in range(6):
+        img, hdr = nrrd.read(os.path.join(outdir, files[i]))
+        assert img.shape == (40, 40, 7) and hdr["space dimension"] == "2"
+        assert np.allclose(img[..., :3], ref[i], rtol=1e-5, atol=1e-6)
+        v0 = F[np.maximum(ids[i], 0), 0]
+        hit = ids[i] >= 0
+        assert np.array_equal(img[..., 3][hit], curv[v0][hit]) and np.all(img[..., 3][~hit] == -5)
+        assert np.array_equal(img[..., 4:][hit], U[v0][hit]) and np.all(img[..., 4:][~hit] == -5)
+
+
+def test_flybygenerator_predict_v3_flow(fbf, orc):
+    """The call sequence of the reference's predict_v3.py:23-80 with a stand-in for the network."""
+    P, F = synth.bumpy_sphere(18, 3)
+    surf = fbf.Surf(P, F)
+    unit_surf = fbf.GetUnitSurf(surf)
+    sphere = fbf.CreateIcosahedron(radius=2.75, sl=2)
+    flyby = fbf.FlyByGenerator(sphere, resolution=48, visualize=False, use_z=True, split_z=True)
+    flyby.addActor(fbf.GetNormalsActor(unit_surf))
+    img_np = flyby.getFlyBy()
+    flyby.removeActors()
+    assert img_np.shape == (42, 48, 48, 4) and img_np.dtype == np.float32
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    ref, ids = orc.render(U, F, N, sphere.points, 2.75, 48, use_z=1, split_z=1, normal_encoding=1, grid=False)
+    assert np.allclose(img_np, ref, rtol=1e-5, atol=1e-5)       # byte255 range, like the Python reference
+    assert img_np[..., :3].max() <= 255.0 and img_np[..., :3].max() > 200
+    flyby_features = fbf.FlyByGenerator(sphere, 48, visualize=False)
+    flyby_features.addActor(fbf.GetPointIdMapActor(unit_surf))
+    rgb = flyby_features.getFlyBy()
+    assert rgb.dtype == np.uint8 and rgb.shape == (42, 48, 48, 3)
+    assert np.array_equal(flyby_features.last_cell_ids, ids)
+    point_ids = fbf.DecodeIdsRGB(rgb)                           # predict_v3.py:61-67
+    assert np.array_equal(point_ids, np.where(ids >= 0, F[np.maximum(ids, 0), 0], -1))
+    # per-point votes exactly as predict_v3.py:59-80, with miss pixels skipped
+    K = 4
+    pred = ((np.arange(ids.size).reshape(ids.shape) * 3) % K).astype(np.int32)
+    count = np.zeros((len(P), K))
+    np.add.at(count, (point_ids[point_ids >= 0], pred[point_ids >= 0]), 1)
+    feats = fbf.ExtractPointFeatures(unit_surf, rgb, "coords", zero=0)
+    assert np.array_equal(feats[ids >= 0], U[point_ids[ids >= 0]]) and np.all(feats[ids < 0] == 0)
+    with pytest.raises(NotImplementedError):
+        flyby.getFlyBy(view_up_points=np.zeros((42, 3)))
+
+
+def test_labeling_driver_single_process(orc):
+    """Config 4 in miniature: views -> a random-init torch network -> per-cell votes -> argmax."""
+    torch = pytest.importorskip("torch")
+    from flyby_b200 import _cabi, labeling
+    P, F = synth.dental_crown(20, 2)
+    ctx = _cabi.Context(0)
+    ctx.set_mesh(P, F)
+    ctx.build()
+    ctx.views_icosahedron(1, 2.0)
+    opts = ctx.render_opts(use_z=1, split_z=1)
+    torch.manual_seed(0)
+    K = 6
+    model = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, K, 1)).cuda()
+    cell_labels, votes = labeling.label_mesh_cells(ctx, model, K, 56, opts, default=33, batch_views=5)
+    feat, ids = ctx.render(56, opts)
+    with torch.no_grad():
+        logits = model(torch.from_numpy(feat).cuda().permute(0, 3, 1, 2).contiguous())
+    pred = logits.argmax(1).cpu().numpy().astype(np.int32)
+    ref = orc.backproject(ids, pred, len(F), K)
+    got = votes.cpu().numpy()
+    # cuDNN may pick different algorithms for different batch sizes: allow a handful of argmax flips
+    assert np.abs(got - ref).sum() <= 0.001 * ref.sum()
+    assert got.sum() == (ids >= 0).sum()
+    lab = cell_labels.cpu().numpy()
+    assert np.array_equal(lab, orc.votes_argmax(got, default=33))
+    voter = labeling.CellVoter(ctx, K, use_torch=False)
+    voter.add(ids, pred)
+    assert np.array_equal(voter.votes, ref)
+    assert np.array_equal(voter.point_labels(default=33), orc.cells_to_points(orc.votes_argmax(ref, 33), F, len(P), 33))
+    ctx.close()

@@ -1,0 +1,190 @@
+"""CPU tests of the host side: C-ABI surface, loud failure without a GPU, file formats,
+the id codec, rotations, and the reference's command-line option surface."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from flyby_b200 import _cabi, nrrd, readers, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE_FLAGS = {  # reference src/py/fly_by_features.py:432-489 -> default
+    "--surf": None, "--dir": None, "--csv": None, "--csv_root_path": "", "--model": None, "--random_rotation": False,
+    "--n_rotations": 0, "--scale_factor": None, "--bounds": None, "--translate": None, "--fiberBundle": False,
+    "--fiber": False, "--nbFiber": 0.05, "--subject": None, "--extract_components": None, "--norm_shader": 1,
+    "--split_z": 0, "--use_z": 1, "--rescale_features": 0, "--property": None, "--point_features": None,
+    "--point_features_concat": 0, "--zero": 0, "--view_features": None, "--subdivision": None, "--spiral": None,
+    "--turns": 4, "--resolution": 256, "--radius": 4, "--save_rotation": 0, "--visualize": 0, "--out": "out.nrrd",
+    "--out_point_id": 0, "--uuid": False, "--ow": 1, "--concatenate": 1, "--verbose": 0,
+}
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "flyby_b200.h")).read()
+    declared = re.findall(r"FLYBY_API\s+[\w\s\*]+?\b(flyby_\w+)\s*\(", header)
+    assert sorted(declared) == sorted(_cabi.SYMBOLS) and len(declared) == len(set(declared))
+    lib = _cabi.load()  # loads without a GPU; no compute call is made
+    for s in declared:
+        assert hasattr(lib, s), s
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (flyby_\w+)", out))
+    assert exported == set(declared)
+    assert lib.flyby_abi_version() == _cabi.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+    assert C.sizeof(_cabi.NormOpts) == 56 and C.sizeof(_cabi.RenderOpts) == 48 and C.sizeof(_cabi.Stats) == 56
+    assert _cabi.RenderOpts.tolerance.offset == 40 and _cabi.NormOpts.skip.offset == 48
+
+
+def test_no_gpu_fails_loudly():
+    """The product has no CPU path: without a CUDA device creating a context raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_cabi.FlyByError):
+        _cabi.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fly-by-cnn_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "liborc" not in src and "hostsim" not in src.replace("tests/hostsim", ""), f
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_vtk_roundtrip_ascii_binary(tmp_path):
+    P, F = synth.bumpy_sphere(4, 0)
+    pd = {"RegionId": np.arange(len(P), dtype=np.int32) % 7, "Curv": np.linspace(0, 1, len(P)).astype(np.float32)}
+    for binary in (False, True):
+        path = str(tmp_path / ("m%d.vtk" % binary))
+        readers.write_vtk(path, P, F, point_data=pd, cell_data={"cid": np.arange(len(F), dtype=np.int32)}, binary=binary)
+        m = readers.read_mesh(path)
+        assert np.array_equal(m.polys, F) and np.allclose(m.points, P, rtol=1e-7)
+        assert np.array_equal(m.point_data["RegionId"], pd["RegionId"]) and np.allclose(m.point_data["Curv"], pd["Curv"])
+        assert np.array_equal(m.cell_data["cid"], np.arange(len(F)))
+        if binary:
+            assert np.array_equal(m.points, P)
+
+
+def test_vtk_version5_offsets_connectivity(tmp_path):
+    """vtk >= 9 (what the reference's vtk==9.2.2 writes) stores cells as OFFSETS / CONNECTIVITY."""
+    path = str(tmp_path / "v5.vtk")
+    with open(path, "w") as f:
+        f.write("# vtk DataFile Version 5.1\nvtk output\nASCII\nDATASET POLYDATA\nPOINTS 4 float\n"
+                "0 0 0 1 0 0 0 1 0 0 0 1\n\nPOLYGONS 3 7\nOFFSETS vtktypeint64\n0 3 7\n"
+                "CONNECTIVITY vtktypeint64\n0 1 2 0 1 3 2\n\nPOINT_DATA 4\nNORMALS Normals float\n"
+                "0 0 1 0 0 1 0 0 1 0 0 1\n")
+    m = readers.read_mesh(path)
+    assert len(m.points) == 4 and m.polys.tolist() == [[0, 1, 2], [0, 1, 3], [0, 3, 2]]  # quad fan-triangulated
+    assert m.point_data["Normals"].shape == (4, 3)
+
+
+def test_obj_off_stl(tmp_path):
+    V, F = synth.cube()
+    obj = tmp_path / "c.obj"
+    obj.write_text("".join("v %g %g %g\n" % tuple(p) for p in V) + "".join("f %d//1 %d//1 %d//1\n" % tuple(t + 1) for t in F))
+    m = readers.read_mesh(str(obj))
+    assert np.array_equal(m.points, V) and np.array_equal(m.polys, F)
+    off = tmp_path / "c.off"
+    off.write_text("OFF\n8 12 0\n" + "".join("%g %g %g\n" % tuple(p) for p in V) + "".join("3 %d %d %d\n" % tuple(t) for t in F))
+    m = readers.read_mesh(str(off))
+    assert np.array_equal(m.points, V) and np.array_equal(m.polys, F)
+    # binary STL: 36 unmerged corners -> 8 merged points, same geometry
+    import struct
+    stl = tmp_path / "c.stl"
+    with open(stl, "wb") as f:
+        f.write(b"\0" * 80 + struct.pack("<I", len(F)))
+        for t in F:
+            f.write(struct.pack("<12fH", 0, 0, 0, *V[t].reshape(-1), 0))
+    m = readers.read_mesh(str(stl))
+    assert len(m.points) == 8 and np.array_equal(m.points[m.polys], V[F])
+    ascii_stl = tmp_path / "a.stl"
+    ascii_stl.write_text("solid c\n" + "".join(
+        "facet normal 0 0 0\nouter loop\n" + "".join("vertex %g %g %g\n" % tuple(V[i]) for i in t) + "endloop\nendfacet\n"
+        for t in F) + "endsolid c\n")
+    m2 = readers.read_mesh(str(ascii_stl))
+    assert np.array_equal(m2.points[m2.polys], V[F])
+    with pytest.raises(NotImplementedError):
+        readers.read_mesh("x.vtp")
+
+
+def test_nrrd_roundtrip_and_layout(tmp_path):
+    a = np.random.default_rng(0).random((5, 6, 7, 4)).astype(np.float32)  # [views, y, x, C]
+    for compress in (True, False):
+        path = str(tmp_path / ("o%d.nrrd" % compress))
+        nrrd.write(path, a, compress=compress)
+        b, hdr = nrrd.read(path)
+        assert np.array_equal(a, b) and b.dtype == np.float32
+        assert hdr["sizes"] == "4 7 6 5" and hdr["dimension"] == "4" and hdr["space dimension"] == "3"
+        assert hdr["kinds"] == "vector domain domain domain" and hdr["type"] == "float"
+        assert hdr["encoding"] == ("gzip" if compress else "raw")
+    # the reference's consumers reshape by element count (train_useg_flyby.py:170-174)
+    flat = np.frombuffer(a.tobytes(), np.float32)
+    assert np.array_equal(flat.reshape(5, 6, 7, 4), b)
+    nrrd.write(str(tmp_path / "one.nrrd"), a[0])  # --concatenate 0: one 2-D vector image per view
+    c, hdr = nrrd.read(str(tmp_path / "one.nrrd"))
+    assert np.array_equal(c, a[0]) and hdr["sizes"] == "4 7 6" and hdr["space dimension"] == "2"
+
+
+def test_id_codec_matches_reference_formula():
+    from flyby_b200 import utils
+    ids = np.array([-1, 0, 1, 253, 254, 255, 256, 65024, 65025, 200000, 16581374], np.int64)
+    rgb = utils.EncodeIdsRGB(ids)
+    for i, v in enumerate(ids):
+        if v < 0:
+            assert rgb[i].tolist() == [0, 0, 0]
+        else:  # utils.py:616-618
+            assert rgb[i].tolist() == [v % 255 + 1, int(v / 255) % 255, int(int(v / 255) / 255) % 255]
+    assert np.array_equal(utils.DecodeIdsRGB(rgb), ids.astype(np.int32))  # utils.py:654, background -> -1
+
+
+def test_rotation_matrix():
+    from flyby_b200 import utils
+    m = utils.GetTransform(90.0, [0, 0, 2])
+    assert np.allclose(m[:3, :3] @ [1, 0, 0], [0, 1, 0]) and np.allclose(m[3], [0, 0, 0, 1])
+    m = utils.GetTransform(120.0, [1, 1, 1])
+    assert np.allclose(m[:3, :3] @ [1, 0, 0], [0, 1, 0]) and np.isclose(np.linalg.det(m[:3, :3]), 1)
+    s = utils.Surf(np.eye(3, dtype=np.float32), np.array([[0, 1, 2]], np.int32))
+    r = utils.RotateSurf(s, 37.0, [0.3, -1, 2])
+    back = utils.RotateInverse(r, 37.0, [0.3, -1, 2])
+    assert np.allclose(back.points, s.points, atol=1e-6)
+
+
+def test_cli_option_surface_matches_reference():
+    from flyby_b200 import fly_by_features as fbf
+    parser = fbf.build_parser()
+    actions = {o: a for a in parser._actions for o in a.option_strings}
+    for flag, default in REFERENCE_FLAGS.items():
+        assert flag in actions, flag
+        assert actions[flag].default == default, (flag, actions[flag].default)
+    args = parser.parse_args("--surf m.vtk --subdivision 2 --resolution 512 --radius 2 --use_z 1 --split_z 1 --out o.nrrd".split())
+    assert (args.surf, args.subdivision, args.resolution, args.radius, args.use_z, args.split_z, args.out) == \
+        ("m.vtk", 2, 512, 2.0, 1, 1, "o.nrrd")
+    for bad in (["--subdivision", "2"], ["--surf", "a", "--dir", "b", "--spiral", "4"],
+                ["--surf", "a", "--subdivision", "1", "--spiral", "4"]):
+        with pytest.raises(SystemExit):
+            parser.parse_args(bad)
+    for unsupported in ("--model x", "--fiber 1", "--property p.txt", "--visualize 1"):
+        a = parser.parse_args(("--surf m.vtk --subdivision 1 " + unsupported).split())
+        with pytest.raises(SystemExit):
+            fbf.main(a)
+
+
+def test_flybygenerator_signature_matches_reference():
+    import inspect
+    from flyby_b200 import fly_by_features as fbf
+    p = list(inspect.signature(fbf.FlyByGenerator.__init__).parameters)
+    assert p[:7] == ["self", "sphere", "resolution", "visualize", "use_z", "split_z", "rescale_features"]
+    g = list(inspect.signature(fbf.FlyByGenerator.getFlyBy).parameters)
+    assert g == ["self", "sphere_points", "view_up_points", "focal_points"]
+    for name in ("addActor", "removeActor", "removeActors", "getFlyBy"):
+        assert hasattr(fbf.FlyByGenerator, name)
+    for name in ("ReadSurf", "GetUnitSurf", "ScaleSurf", "CreateIcosahedron", "CreateSpiral", "GetNormalsActor",
+                 "GetPointIdMapActor", "ExtractPointFeatures", "GetImage", "ComputeNormals", "RandomRotation"):
+        assert hasattr(fbf, name), name  # callers use fbf.ReadSurf etc. (predict_v3.py:23-36)

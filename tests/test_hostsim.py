@@ -1,0 +1,99 @@
+"""CPU tests of the kernels' per-element logic: tests/hostsim compiles
+fly-by-cnn_b200/csrc/flyby_core.cuh with g++ (the same code nvcc compiles for the
+device) and drives it serially.  Three schedules of the same exact decision are
+checked against the oracle: recursive-free traverse(), the per-lane state machine,
+and a 32-lane emulation of the render kernel's packet traversal (votes as loops).
+This is test infrastructure: the product never loads libhostsim.so."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from flyby_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "hostsim")], stdout=subprocess.DEVNULL)
+    return C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def sim_render(sim, U, F, N, views, radius, res, ps=1.0, sp=1.0, use_z=1, split_z=1, mode=0):
+    nv = len(views)
+    Cn = 4 if (use_z and split_z) else 3
+    feat = np.empty((nv, res, res, Cn), np.float32)
+    ids = np.empty((nv, res, res), np.int32)
+    t = np.empty((nv, res, res), np.float64)
+    work = np.zeros(3, np.int64)
+    rc = sim.sim_render(_p(U), C.c_int64(len(U)), _p(F), C.c_int64(len(F)), _p(N), _p(views), C.c_int(nv),
+                        C.c_double(radius), C.c_int(res), C.c_double(ps), C.c_double(sp), C.c_int(use_z),
+                        C.c_int(split_z), C.c_int(0), C.c_double(1.0), _p(feat), _p(ids), _p(t), _p(work),
+                        C.c_int(mode))
+    assert rc == 0
+    return feat, ids, t, work
+
+
+def sim_packet(sim, U, F, views, radius, res, ps=1.0, sp=1.0, ring=16):
+    nv = len(views)
+    ids = np.empty((nv, res, res), np.int32)
+    t = np.empty((nv, res, res), np.float64)
+    work = np.zeros(3, np.int64)
+    rc = sim.sim_render_packet(_p(U), C.c_int64(len(U)), _p(F), C.c_int64(len(F)), _p(views), C.c_int(nv),
+                               C.c_double(radius), C.c_int(res), C.c_double(ps), C.c_double(sp), C.c_int(ring),
+                               _p(ids), _p(t), _p(work))
+    assert rc == 0
+    return ids, t, work
+
+
+CASES = {
+    "bumpy12": lambda: synth.bumpy_sphere(12, 0),
+    "crown20": lambda: synth.dental_crown(20, 1),
+    "cube": lambda: synth.cube(),
+    "sphere16": lambda: (synth.icosphere(16)[0].astype(np.float32), synth.icosphere(16)[1]),  # rays through edges
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_per_ray_traversal_matches_oracle(sim, orc, name, mode):
+    P, F = CASES[name]()
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    for views, R, ps in [(orc.icosahedron(1, 2.0), 2.0, 1.0), (orc.spiral(6, 4, 4.0), 4.0, 2.0)]:
+        fo, io, to = orc.render(U, F, N, views, R, 48, plane_scale=ps, grid=False, want_t=True)
+        fs, is_, ts, work = sim_render(sim, U, F, N, views, R, 48, ps=ps, mode=mode)
+        assert np.array_equal(io, is_) and np.array_equal(to, ts) and np.array_equal(fo, fs)
+        assert work[2] <= 62  # LBVH depth bound the 64-bit trail relies on
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("ring", [16, 1])
+def test_packet_traversal_matches_oracle(sim, orc, name, ring):
+    P, F = CASES[name]()
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    for views, R, ps in [(orc.icosahedron(1, 2.0), 2.0, 1.0), (orc.spiral(6, 4, 4.0), 4.0, 2.0)]:
+        fo, io, to = orc.render(U, F, N, views, R, 50, plane_scale=ps, grid=False, want_t=True)
+        ids, t, work = sim_packet(sim, U, F, views, R, 50, ps=ps, ring=ring)
+        assert np.array_equal(io, ids) and np.array_equal(to, t)
+
+
+def test_many_duplicate_centroids_stay_within_depth_bound(sim, orc):
+    """Identical Morton codes fall back to the index bits: depth stays <= 62 and results stay exact."""
+    base = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], np.float32)
+    V = np.concatenate([base + np.array([0, 0, 1e-3 * k], np.float32) for k in range(40)])
+    F = np.arange(120, dtype=np.int32).reshape(40, 3)
+    N = orc.point_normals(V, F)
+    views = np.array([[0, 0, 2.0], [0, 0, -2.0]], np.float32)
+    fo, io, to = orc.render(V, F, N, views, 2.0, 16, plane_scale=2.0, grid=False, want_t=True)
+    fs, is_, ts, work = sim_render(sim, V, F, N, views, 2.0, 16, ps=2.0, mode=0)
+    assert np.array_equal(io, is_) and np.array_equal(to, ts) and work[2] <= 62
+    assert set(np.unique(io[0][io[0] >= 0])) == {39} and set(np.unique(io[1][io[1] >= 0])) == {0}

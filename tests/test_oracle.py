@@ -1,0 +1,229 @@
+"""CPU tests of the oracle (oracle/flyby_oracle.c): analytic known answers, the shape /
+count facts the reference documents, brute force == bucket grid, and the committed
+golden fixtures.  The reference has no tests and no golden vectors for this path
+(SURVEY.md section 4), so these are the anchors there are."""
+import os
+
+import numpy as np
+import pytest
+
+from flyby_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flyby_golden.npz")
+
+
+# ---------------------------------------------------------------- viewpoints (a3, a4)
+def test_icosahedron_counts_and_order(orc):
+    # 10 L^2 + 2 lattice points; subdivision 1 = the 12 vertices (train_useg_flyby.py:153,174: [12,512,512,4])
+    for L, n in [(1, 12), (2, 42), (3, 92), (4, 162), (10, 1002)]:
+        v = orc.icosahedron(L, 2.75)
+        assert v.shape == (n, 3) and v.dtype == np.float32
+        assert np.allclose(np.linalg.norm(v.astype(np.float64), axis=1), 2.75, rtol=1e-6)
+        assert len(np.unique(np.round(v, 4), axis=0)) == n
+    v = orc.icosahedron(2, 2.0)
+    # first inserted point = first lattice point of face (0,5,4) = icosahedron vertex 0 = south pole
+    assert np.array_equal(v[0], np.array([0, 0, -2], np.float32))
+    assert (np.abs(v[:, 2] - 2.0) < 1e-6).sum() == 1  # the north pole appears exactly once
+
+
+def test_icosahedron_float_dedupe_leaks_duplicates(orc):
+    """Hazard H1: the reference de-duplicates by float equality and leaks duplicate viewpoints
+    (its readme documents 268 ids for subdivision 5, ideal 252): the emulation shows the same effect."""
+    assert len(orc.icosahedron(2, 2.0, dedupe=1)) == 42
+    assert len(orc.icosahedron(4, 2.0, dedupe=1)) == 162
+    assert len(orc.icosahedron(3, 2.0, dedupe=1)) > 92
+    assert len(orc.icosahedron(5, 2.0, dedupe=1)) > 252
+
+
+def test_spiral(orc):
+    v = orc.spiral(64, 4, 4.0)  # predict_LU.py:39-72 setting
+    assert v.shape == (64, 3)
+    assert np.array_equal(v[0], np.array([0, 0, 4], np.float32))  # i = 0 is the north pole
+    i = np.arange(64)
+    a = i * np.pi / 64
+    ref = 4.0 * np.stack([np.sin(a) * np.cos(8 * a), np.sin(a) * np.sin(8 * a), np.cos(a)], 1)
+    assert np.allclose(v, ref, atol=1e-6)
+    assert np.all(np.diff(v[:, 2]) < 0)  # monotone descent from the pole
+
+
+# ---------------------------------------------------------------- plane and rays (a5)
+def test_view_basis_and_ray_order(orc):
+    rays, B = orc.view_rays(np.array([0, 0, 2], np.float32), 2.0, 3)         # north pole special case
+    assert np.array_equal(B, [[0, 0, 1], [1, 0, 0], [0, 1, 0]])
+    rays_s, Bs = orc.view_rays(np.array([0, 0, -2], np.float32), 2.0, 3)     # south pole special case
+    assert np.array_equal(Bs, [[0, 0, -1], [-1, 0, 0], [0, -1, 0]])
+    # 3x3 plane of side 1 centred on the viewpoint, i (x axis) fastest
+    o = rays[:, :3]
+    assert np.allclose(o[0], [-0.5, -0.5, 2]) and np.allclose(o[1], [0, -0.5, 2]) and np.allclose(o[3], [-0.5, 0, 2])
+    assert np.allclose(rays[:, 3:] - o, [0, 0, -4])                          # end = origin - n * 2R
+    sp = np.array([1.0, 2.0, 0.5], np.float32)
+    rays, B = orc.view_rays(sp, 2.0, 4, plane_scale=2.0)
+    n, x, y = B
+    assert np.allclose(n, sp / np.linalg.norm(sp))
+    assert np.allclose(x, np.cross(n, [0, 0, 1]) / np.linalg.norm(np.cross(n, [0, 0, 1])))
+    assert np.allclose(y, np.cross(n, x))
+    c = rays[:, :3].mean(0)
+    assert np.allclose(c, sp, atol=1e-6)                                     # plane centred on the viewpoint
+    assert np.allclose(np.linalg.norm(rays[3, :3] - rays[0, :3]), 2.0, atol=1e-6)
+    # plane spacing scales the plane about the viewpoint (cxx:659,746)
+    r2, _ = orc.view_rays(sp, 2.0, 4, plane_scale=2.0, spacing=0.5)
+    assert np.allclose(r2[:, :3] - sp, 0.5 * (rays[:, :3] - sp), atol=1e-6)
+
+
+# ---------------------------------------------------------------- triangle test (a7)
+def test_triangle_known_answers(orc):
+    p0, p1, p2 = [0, 0, 0], [1, 0, 0], [0, 1, 0]
+    hit, t, x, w = orc.tri_intersect([0.25, 0.25, 1], [0.25, 0.25, -1], p0, p1, p2)
+    assert hit and t == 0.5 and np.allclose(x, [0.25, 0.25, 0]) and np.allclose(w, [0.5, 0.25, 0.25])
+    # inclusive edges and vertices (vtkTriangle::EvaluatePosition weights in [0,1])
+    assert orc.tri_intersect([0.5, 0.0, 1], [0.5, 0.0, -1], p0, p1, p2)[0]
+    assert orc.tri_intersect([0.5, 0.5, 1], [0.5, 0.5, -1], p0, p1, p2)[0]
+    assert orc.tri_intersect([0, 0, 1], [0, 0, -1], p0, p1, p2)[0]
+    assert orc.tri_intersect([1, 0, 1], [1, 0, -1], p0, p1, p2)[0]
+    # outside, beyond the segment, parallel, degenerate
+    assert not orc.tri_intersect([0.75, 0.75, 1], [0.75, 0.75, -1], p0, p1, p2)[0]
+    assert not orc.tri_intersect([-1e-9, 0.5, 1], [-1e-9, 0.5, -1], p0, p1, p2)[0]
+    assert not orc.tri_intersect([0.25, 0.25, 1], [0.25, 0.25, 0.5], p0, p1, p2)[0]
+    assert not orc.tri_intersect([0, 0, 1], [1, 1, 1], p0, p1, p2)[0]
+    assert not orc.tri_intersect([0.25, 0.25, 1], [0.25, 0.25, -1], p0, p1, p1)[0]
+    # the segment end points count (0 <= t <= 1)
+    assert orc.tri_intersect([0.25, 0.25, 0], [0.25, 0.25, -1], p0, p1, p2)[1] == 0.0
+    assert orc.tri_intersect([0.25, 0.25, 1], [0.25, 0.25, 0], p0, p1, p2)[1] == 1.0
+
+
+def test_cube_tie_break_lowest_id(orc):
+    V, F = synth.cube()
+    # straight down the middle of the top face: exactly on the diagonal shared by its two triangles
+    rays = np.array([[0, 0, 3, 0, 0, -3]], np.float64)
+    ids, t, x, w = orc.cast(V, F, rays, grid=False)
+    top = [c for c in range(12) if np.all(V[F[c]][:, 2] == 1)]
+    assert ids[0] == min(top) and np.isclose(t[0], 1 / 3)
+    ids_g, t_g, _, _ = orc.cast(V, F, rays, grid=True, grid_div=4)
+    assert ids_g[0] == ids[0] and t_g[0] == t[0]
+
+
+# ---------------------------------------------------------------- whole path
+def test_sphere_analytic_depth_and_normals(orc):
+    """An icosphere seen from the +x axis: depth = R - sqrt(r^2 - d^2) and the interpolated normal is
+    radial, up to the tessellation error."""
+    V, F = synth.icosphere(24)
+    U, c, s = orc.unit_surf(V.astype(np.float32))
+    r = float(np.linalg.norm(U.max(0)))  # unit surf: bbox corner on the unit sphere
+    assert np.isclose(r, 1.0, atol=1e-6)
+    rad = np.linalg.norm(U.astype(np.float64), axis=1).mean()
+    N = orc.point_normals(U, F)
+    assert np.allclose(N, U / np.linalg.norm(U, axis=1, keepdims=True), atol=2e-3)
+    view = np.array([[2.0, 0, 0]], np.float32)
+    res = 65
+    feat, ids, t = orc.render(U, F, N, view, 2.0, res, plane_scale=1.0, want_t=True, grid=False)
+    rays, _ = orc.view_rays(view[0], 2.0, res)
+    d2 = (rays[:, 1] ** 2 + rays[:, 2] ** 2).reshape(res, res)
+    inside = d2 < (0.97 * rad) ** 2
+    outside = d2 > (1.001 * rad) ** 2
+    assert np.all(ids[0][inside] >= 0) and np.all(ids[0][outside] == -1)
+    depth = feat[0, :, :, 3]
+    expect = 2.0 - np.sqrt(np.maximum(rad ** 2 - d2, 0))
+    assert np.allclose(depth[inside], expect[inside], atol=3e-3)
+    assert np.all(depth[ids[0] < 0] == 0) and np.all(feat[0][ids[0] < 0] == 0)
+    # centre pixel: normal (1,0,0) -> encoded (1, .5, .5)
+    assert np.allclose(feat[0, res // 2, res // 2, :3], [1.0, 0.5, 0.5], atol=2e-3)
+    assert np.allclose(t[0][inside] * 4.0, depth[inside], rtol=1e-6)  # depth = t * 2R along the ray
+
+
+def test_grid_equals_brute_force(orc):
+    rng = np.random.default_rng(1)
+    for P, F in (synth.bumpy_sphere(10, 1), synth.dental_crown(12, 3)):
+        U, _, _ = orc.unit_surf(P)
+        n = 4000
+        a = rng.normal(size=(n, 3)); a /= np.linalg.norm(a, axis=1, keepdims=True)
+        b = rng.normal(size=(n, 3)); b /= np.linalg.norm(b, axis=1, keepdims=True)
+        rays = np.concatenate([a * 2, -a * 2 + b * 0.7], axis=1)
+        ib, tb, xb, wb = orc.cast(U, F, rays, grid=False)
+        for div in (0, 8, 32):
+            ig, tg, xg, wg = orc.cast(U, F, rays, grid=True, grid_div=div)
+            assert np.array_equal(ib, ig) and np.array_equal(tb, tg) and np.array_equal(wb, wg)
+        assert (ib >= 0).sum() > n // 4
+
+
+def test_channel_assembly(orc):
+    P, F = synth.bumpy_sphere(8, 2)
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    views = orc.icosahedron(1, 2.0)[:3]
+    f4, ids = orc.render(U, F, N, views, 2.0, 32, use_z=1, split_z=1, grid=False)
+    f3m, _ = orc.render(U, F, N, views, 2.0, 32, use_z=1, split_z=0, grid=False)
+    f3n, _ = orc.render(U, F, N, views, 2.0, 32, use_z=0, split_z=0, grid=False)
+    fs, _ = orc.render(U, F, N, views, 2.0, 32, use_z=1, split_z=1, normal_encoding=2, zscale=0.25, grid=False)
+    fb, _ = orc.render(U, F, N, views, 2.0, 32, use_z=0, split_z=0, normal_encoding=1, grid=False)
+    assert f4.shape[-1] == 4 and f3m.shape[-1] == 3 and f3n.shape[-1] == 3
+    assert np.array_equal(f4[..., :3], f3n)                                        # normals channels
+    assert np.allclose(f3m, f4[..., :3] * f4[..., 3:4], rtol=1e-6)                 # cxx:802-804
+    hit = ids >= 0
+    assert np.allclose(fs[..., :3][hit], (f4[..., :3][hit] - 0.5) * 2, atol=1e-6)  # signed normals
+    assert np.allclose(fs[..., 3], f4[..., 3] * 0.25, rtol=1e-6)                   # z scale
+    assert np.allclose(fb, f3n * 255.0, rtol=1e-6)                                 # 8-bit range
+
+
+def test_unit_surf_modes(orc):
+    P, F = synth.bumpy_sphere(8, 5)
+    U, c, s = orc.unit_surf(P)
+    lo, hi = P.min(0).astype(np.float64), P.max(0).astype(np.float64)
+    assert np.allclose(c, (lo + hi) / 2) and np.isclose(s, 1 / np.linalg.norm(hi - c))
+    assert np.isclose(np.linalg.norm(U.max(0)), 1.0, atol=1e-6)
+    U2, c2, s2 = orc.unit_surf(P, centre_mode=1, scale_mode=1)
+    assert np.allclose(c2, P.astype(np.float64).mean(0)) and np.isclose(np.linalg.norm(U2, axis=1).max(), 1.0, atol=1e-6)
+    U3, c3, s3 = orc.unit_surf(P, translate=[1, 2, 3], scale_factor=0.1)
+    assert np.allclose(U3, (P.astype(np.float64) - [1, 2, 3]) * 0.1, atol=1e-6)
+
+
+def test_backprojection_semantics(orc):
+    ids = np.array([[0, 0, 1, -1], [2, 2, 2, 1]], np.int32)
+    labels = np.array([[3, 3, 1, 2], [0, 4, 4, 1]], np.int32)
+    votes = orc.backproject(ids, labels, 4, 5)
+    assert votes.sum() == 7                                   # the background pixel does not vote
+    assert votes[0, 3] == 2 and votes[1, 1] == 2 and votes[2, 4] == 2 and votes[2, 0] == 1 and votes[3].sum() == 0
+    lab = orc.votes_argmax(votes, default=33)
+    assert lab.tolist() == [3, 1, 4, 33]
+    tie = np.array([[2, 5, 5, 0]], np.int32)
+    assert orc.votes_argmax(tie, default=-1).tolist() == [1]   # numpy argmax: first maximum
+    tris = np.array([[0, 1, 2], [0, 2, 3], [3, 1, 0], [4, 0, 1]], np.int32)
+    pts = orc.cells_to_points(lab, tris, 6, default=33)
+    assert pts.tolist() == [1, 33, 33, 4, 33, 33]             # vertex 0 of each cell, later cells overwrite
+
+
+def test_golden_fixtures(orc):
+    g = np.load(GOLDEN)
+    U, c, s = orc.unit_surf(g["P"])
+    assert np.array_equal(U, g["U"]) and np.array_equal(c, g["centre"]) and s == g["scale"]
+    N = orc.point_normals(U, g["F"])
+    assert np.array_equal(N, g["N"])
+    assert np.array_equal(orc.icosahedron(2, 2.0), g["ico"])
+    assert np.allclose(orc.spiral(8, 4, 4.0), g["spiral"], atol=0)
+    for grid in (False, True):
+        f4, ids, t = orc.render(U, g["F"], N, g["ico"], 2.0, 24, grid=grid, want_t=True)
+        assert np.array_equal(ids, g["ids"]) and np.array_equal(t, g["t"]) and np.array_equal(f4, g["feat4"])
+    f3, ids_s = orc.render(U, g["F"], N, g["spiral"], 4.0, 24, plane_scale=2.0, use_z=1, split_z=0, grid=True)
+    assert np.array_equal(ids_s, g["ids_spiral"]) and np.array_equal(f3, g["feat3_spiral"])
+    rays, basis = orc.view_rays(g["ico"][5], 2.0, 5)
+    assert np.array_equal(rays, g["rays_view5"]) and np.array_equal(basis, g["basis_view5"])
+    votes = orc.backproject(g["ids"], g["labels"], len(g["F"]), 5)
+    assert np.array_equal(votes, g["votes"])
+    assert np.array_equal(orc.votes_argmax(votes, default=33), g["cell_labels"])
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden(gpu_ctx):
+    g = np.load(GOLDEN)
+    gpu_ctx.set_mesh(g["P"], g["F"])
+    gpu_ctx.build()
+    uv, nrm, c, s = gpu_ctx.get_mesh()
+    assert np.array_equal(uv, g["U"]) and np.array_equal(nrm, g["N"])
+    assert gpu_ctx.views_icosahedron(2, 2.0) == 42 and np.array_equal(gpu_ctx.get_views(), g["ico"])
+    f4, ids, t = gpu_ctx.render(24, gpu_ctx.render_opts(use_z=1, split_z=1), want_t=True)
+    assert np.array_equal(ids, g["ids"]) and np.array_equal(t, g["t"]) and np.array_equal(f4, g["feat4"])
+    gpu_ctx.views_custom(g["spiral"], 4.0)
+    f3, ids_s = gpu_ctx.render(24, gpu_ctx.render_opts(use_z=1, split_z=0, plane_scale=2.0))
+    assert np.array_equal(ids_s, g["ids_spiral"]) and np.array_equal(f3, g["feat3_spiral"])
+    votes = gpu_ctx.backproject(ids, g["labels"], 5)
+    assert np.array_equal(votes, g["votes"])
+    assert np.array_equal(gpu_ctx.votes_argmax(votes, default=33), g["cell_labels"])
