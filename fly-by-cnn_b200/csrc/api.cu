@@ -104,7 +104,11 @@ int flyby_create(int device, void* stream, flyby_ctx** out) {
   for (int i = 0; i < 16; i++)
     if (cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (c->counters.reserve(8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+  if (const char* e = getenv("FLYBY_LEAF_MAX")) {
+    int v = atoi(e);
+    if (v >= 1 && v <= 8) c->leaf_max = v;
+  }
+  if (c->counters.reserve(16 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
   *out = c;
   return FLYBY_OK;
 }
@@ -117,8 +121,8 @@ void flyby_destroy(flyby_ctx* c) {
   MeshDev& m = c->mesh;
   DevBuf* bufs[] = {&m.raw_verts, &m.tris, &m.verts, &m.normals, &m.face_n, &m.adj_start, &m.adj_cur, &m.adj,
                     &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.leaf_box,
-                    &m.node_box, &m.knode, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid,
-                    &c->view_pts, &c->views, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
+                    &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid,
+                    &c->view_pts, &c->views, &c->viewsf, &c->cand, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
                     &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->counters};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; i++)
@@ -151,7 +155,7 @@ int flyby_set_mesh(flyby_ctx* c, const float* verts, int64_t V, const int32_t* t
                    const flyby_norm_opts* opts) {
   CHECK_CTX(c);
   if (!verts || V <= 0 || T < 0 || (T > 0 && !tris)) return fail(c, FLYBY_ERR_INVALID, "set_mesh: empty or null mesh");
-  if (V >= (int64_t)1 << 31 || T >= (int64_t)1 << 30) return fail(c, FLYBY_ERR_INVALID, "set_mesh: mesh too large");
+  if (V >= (int64_t)1 << 31 || T > FB_LEAF_FIRST_MASK) return fail(c, FLYBY_ERR_INVALID, "set_mesh: mesh too large");
   MeshDev& m = c->mesh;
   m.has_mesh = false;
   m.built = false;
@@ -487,8 +491,11 @@ int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {
     if (c->mesh.T > 0) { s.ms_sort = el(2, 3); s.ms_tree = el(3, 4); }
   }
   s.ms_render = el(5, 6);
-  unsigned long long h[8] = {0};
+  unsigned long long h[16] = {0};
   FB_CUDA(c, cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+  if (getenv("FLYBY_DEBUG_STATS") && h[9])
+    fprintf(stderr, "[flyby] packets %llu, lanes/packet %.2f, node visits/packet %.1f, leaf visits/packet %.1f\n", h[9],
+            (double)h[10] / h[9], (double)h[8] / h[9], (double)h[11] / h[9]);
   s.nodes_visited = (int64_t)h[1];
   s.tris_tested = (int64_t)h[2];
   s.n_hits = (int64_t)h[3];

@@ -52,6 +52,7 @@ struct MeshDev {
   DevBuf leaf_box;                        // float [T,6] boxes of sorted slots
   DevBuf node_box;                        // float [T-1,6] internal boxes (Karras numbering)
   DevBuf knode;                           // int32 [T-1,4] child0, child1, parent, flag (Karras numbering)
+  DevBuf krange;                          // int2 [T-1] first slot, triangle count of every subtree
   DevBuf remap;                           // int32 [T-1] Karras index -> final index
   DevBuf topflag;                         // int32 [T-1]
   DevBuf nodes;                           // Node [max(T-1,1)] final layout, top-of-tree first
@@ -77,6 +78,8 @@ struct flyby_ctx {
   // viewpoints
   fb::DevBuf view_pts;  // float [n,3]
   fb::DevBuf views;     // fb::View [n]
+  fb::DevBuf viewsf;    // fb::ViewF [n] float32 screening frames
+  fb::DevBuf cand;      // int4 [n_pix] candidate slots between the trace and the resolve kernel
   int n_views = 0;
   double radius = 0;
   // staging for host-side buffers
@@ -88,6 +91,7 @@ struct flyby_ctx {
   int count_work = 0;
   int64_t launches = 0;
   int sm_count = 148;
+  int leaf_max = FB_LEAF_MAX;  // triangles per collapsed leaf (FLYBY_LEAF_MAX overrides, 1..8)
   // NCCL (nccl_glue.cu)
   void* nccl_comm = nullptr;
   int nccl_rank = 0, nccl_world = 1;

@@ -22,8 +22,10 @@ struct float4 { float x, y, z, w; };  // host simulator build only
 
 #if defined(__CUDACC__)
 #define FB_HD __host__ __device__ __forceinline__
+#define FB_COLD static __host__ __device__ __noinline__
 #else
 #define FB_HD inline
+#define FB_COLD static __attribute__((noinline))
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -159,8 +161,13 @@ FB_HD double dist2seg(const double* x, const double* p1, const double* p2) {
 // vtkTriangle::EvaluatePosition for a point outside the triangle: squared distance
 // to the nearest edge / vertex, picked from the signs of the weights
 // (w[k] belongs to vertex k; pt1 = P1, pt2 = P2, pt3 = P0).  Rarely executed.
-FB_HD double outside_dist2(const double* x, const double* pt1, const double* pt2, const double* pt3,
-                           const double* w) {
+// Not inlined and fed by value: the hot path then keeps every vertex in registers
+// (an inlined copy made the render kernel spill to local memory).
+FB_COLD double outside_dist2(double x0, double x1, double x2, double a0, double a1, double a2, double b0,
+                             double b1, double b2, double c0, double c1, double c2, double w0, double w1,
+                             double w2) {
+  const double x[3] = {x0, x1, x2}, pt1[3] = {a0, a1, a2}, pt2[3] = {b0, b1, b2}, pt3[3] = {c0, c1, c2};
+  const double w[3] = {w0, w1, w2};
   double dp, d1, d2;
   if (w[1] < 0.0 && w[2] < 0.0) {
     dp = dist2pt(x, pt3); d1 = dist2seg(x, pt1, pt3); d2 = dist2seg(x, pt3, pt2);
@@ -259,7 +266,8 @@ FB_HD bool tri_exact(const double* o, const double* d, const float* P0, const fl
     }
     if (far) return false;
   }
-  if (outside_dist2(x, pt1, pt2, pt3, w) <= tol2) {
+  if (outside_dist2(x[0], x[1], x[2], pt1[0], pt1[1], pt1[2], pt2[0], pt2[1], pt2[2], pt3[0], pt3[1], pt3[2],
+                    w[0], w[1], w[2]) <= tol2) {
     *t_out = t;
     return true;
   }
@@ -270,12 +278,21 @@ FB_HD bool tri_exact(const double* o, const double* d, const float* P0, const fl
 // 64-byte node: the two child boxes live in the parent so one fetch decides
 // both descents.  Words (DESIGN.md "Data layout"):
 //   f[0..5]  child0 lo xyz, hi xyz      f[6..11] child1 lo xyz, hi xyz
-//   i[12] child0  i[13] child1   (>= 0 internal node index, < 0 leaf: ~slot)
+//   i[12] child0  i[13] child1   (>= 0 internal node index, < 0 leaf: see leaf_first / leaf_count)
 //   i[14] parent (-1 for the root)    i[15] sibling (same encoding as a child)
 struct __attribute__((aligned(16))) Node {
   float box[12];
   int32_t c0, c1, parent, sibling;
 };
+// A negative child is a LEAF: a run of consecutive Morton-sorted triangle slots (a radix-tree
+// subtree always covers a contiguous slot range, so small subtrees are collapsed into one leaf).
+//   v = ~child ;  first slot = v & LEAF_FIRST_MASK ;  count = (v >> LEAF_SHIFT) + 1   (1..8)
+#define FB_LEAF_SHIFT 27
+#define FB_LEAF_FIRST_MASK 0x07ffffff
+#define FB_LEAF_MAX 4  // triangles per collapsed leaf
+FB_HD int leaf_encode(int first, int count) { return ~(first | ((count - 1) << FB_LEAF_SHIFT)); }
+FB_HD int leaf_first(int child) { return (~child) & FB_LEAF_FIRST_MASK; }
+FB_HD int leaf_count(int child) { return ((~child) >> FB_LEAF_SHIFT) + 1; }
 
 FB_HD uint32_t expand10(uint32_t v) {
   v &= 0x3ffu;
@@ -387,6 +404,111 @@ FB_HD bool slab_fma(const float* b, const SlabRay& r, bool negx, bool negy, bool
   return tn <= tf;
 }
 
+// ---------------------------------------------------------------- float32 screening
+// The rays of one view are parallel (orthographic), so "does the ray hit the
+// triangle" is a 2-D point-in-triangle question in the view plane.  screen_tri
+// answers it in float32 with explicit error margins and returns
+//   SC_MISS  the exact test is certain to reject the triangle,
+//   SC_SURE  the exact test is certain to accept it,
+//   SC_MAYBE anything the margins cannot decide (near an edge, edge-on, slivers),
+// plus a depth interval [zlo, zhi] (distance below the view plane) that contains
+// the exact hit if there is one.  The render kernel uses it to run the long
+// double-precision test once per ray, on the few candidates that can still be
+// the nearest hit, instead of on every leaf a ray's box test touches.  It never
+// decides a result: ids, t and weights always come from tri_exact.
+struct ViewF {
+  float xf[3], yf[3], nf[3];  // view-plane basis and viewing normal
+  float rp;                   // sp . n  (distance of the plane from the origin)
+  float e_p;                  // bound on the error of a projected coordinate
+  float e_z;                  // bound on the error of a projected depth
+  float two_r;                // length of the segment (2 R)
+  float d0;                   // absolute in-plane margin on top of the rounding bounds
+  int enabled;                // 0: the view radius is tiny against the mesh, every candidate is SC_MAYBE
+};
+enum { SC_MISS = 0, SC_MAYBE = 1, SC_SURE = 2 };
+
+FB_HD void viewf_setup(const View& v, double radius, float max_abs_coord, ViewF* f) {
+  for (int k = 0; k < 3; k++) {
+    f->xf[k] = (float)v.x[k];
+    f->yf[k] = (float)v.y[k];
+    f->nf[k] = (float)v.n[k];
+  }
+  double rp = v.sp[0] * v.n[0] + v.sp[1] * v.n[1] + v.sp[2] * v.n[2];
+  f->rp = (float)rp;
+  // a projected coordinate is a 3-term float dot product of |coord| <= max_abs_coord with a
+  // unit vector rounded to float: error < 8 * 2^-24 * sqrt(3) * max_abs_coord; 2^-20 leaves 4x headroom
+  f->e_p = 9.5367431640625e-07f * (max_abs_coord + 1.0f);
+  f->e_z = 9.5367431640625e-07f * (max_abs_coord + 1.0f + fabsf((float)rp));
+  f->two_r = (float)(2.0 * radius);
+  f->d0 = 4.0f * f->e_p;
+  // the SC_SURE argument needs |n.d| > 1e-6 |n.(P1-o)| for non-grazing triangles: holds when R is not tiny
+  f->enabled = radius >= 0.05 * ((double)max_abs_coord + 1.0) ? 1 : 0;
+}
+
+// 2-D position and depth of a ray origin in the frame of its view (from the double origin)
+FB_HD void screen_ray(const View& v, const double* o, float* qx, float* qy, float* zo) {
+  double r[3] = {o[0] - v.sp[0], o[1] - v.sp[1], o[2] - v.sp[2]};
+  *qx = (float)(r[0] * v.x[0] + r[1] * v.x[1] + r[2] * v.x[2]);
+  *qy = (float)(r[0] * v.y[0] + r[1] * v.y[1] + r[2] * v.y[2]);
+  *zo = (float)(-(r[0] * v.n[0] + r[1] * v.n[1] + r[2] * v.n[2]));
+}
+
+FB_HD int screen_tri(const ViewF& V, float qx, float qy, float zo, const float* P0, const float* P1,
+                     const float* P2, float* zlo, float* zhi) {
+  if (!V.enabled) {
+    *zlo = -INFINITY;
+    *zhi = INFINITY;
+    return SC_MAYBE;
+  }
+  // projected vertices: X, Y in the view plane
+  const float ax = fmaf(P0[0], V.xf[0], fmaf(P0[1], V.xf[1], P0[2] * V.xf[2]));
+  const float ay = fmaf(P0[0], V.yf[0], fmaf(P0[1], V.yf[1], P0[2] * V.yf[2]));
+  const float bx = fmaf(P1[0], V.xf[0], fmaf(P1[1], V.xf[1], P1[2] * V.xf[2]));
+  const float by = fmaf(P1[0], V.yf[0], fmaf(P1[1], V.yf[1], P1[2] * V.yf[2]));
+  const float cx = fmaf(P2[0], V.xf[0], fmaf(P2[1], V.xf[1], P2[2] * V.xf[2]));
+  const float cy = fmaf(P2[0], V.yf[0], fmaf(P2[1], V.yf[1], P2[2] * V.yf[2]));
+  const float ep = V.e_p, m0 = 2.0f * ep + V.d0;
+  // bounding box of the projection
+  const float lox = fminf(ax, fminf(bx, cx)), hix = fmaxf(ax, fmaxf(bx, cx));
+  const float loy = fminf(ay, fminf(by, cy)), hiy = fmaxf(ay, fmaxf(by, cy));
+  *zlo = -INFINITY;
+  *zhi = INFINITY;
+  if (qx < lox - m0 || qx > hix + m0 || qy < loy - m0 || qy > hiy + m0) return SC_MISS;
+  // depth (distance below the view plane) interval of the triangle; the segment covers [zo, zo + 2R]
+  const float az = V.rp - fmaf(P0[0], V.nf[0], fmaf(P0[1], V.nf[1], P0[2] * V.nf[2]));
+  const float bz = V.rp - fmaf(P1[0], V.nf[0], fmaf(P1[1], V.nf[1], P1[2] * V.nf[2]));
+  const float cz = V.rp - fmaf(P2[0], V.nf[0], fmaf(P2[1], V.nf[1], P2[2] * V.nf[2]));
+  const float zmin = fminf(az, fminf(bz, cz)), zmax = fmaxf(az, fmaxf(bz, cz));
+  *zlo = zmin - V.e_z;
+  *zhi = zmax + V.e_z;
+  if (*zhi < zo - V.e_z || *zlo > zo + V.two_r + V.e_z) return SC_MISS;
+  // edge functions E_k = e_k x r_k.  One margin G bounds the float error of all three:
+  // moving both edge ends and the query point by ep changes E by at most 2 ep (|r|_1 + |e|_1),
+  // the products round by 2^-22 |e|_1 |r|_1, and d0 |e|_1 is the absolute distance margin;
+  // inside the (inflated) bounding box |r|_1 <= Dq and |e|_1 <= D <= Dq, Dq = L1 diameter + 2 m0.
+  const float r0x = qx - ax, r0y = qy - ay, r1x = qx - bx, r1y = qy - by, r2x = qx - cx, r2y = qy - cy;
+  const float E0 = (bx - ax) * r0y - (by - ay) * r0x;
+  const float E1 = (cx - bx) * r1y - (cy - by) * r1x;
+  const float E2 = (ax - cx) * r2y - (ay - cy) * r2x;
+  const float Dq = (hix - lox) + (hiy - loy) + 2.0f * m0;
+  const float G = fmaf(2.384185791015625e-07f * Dq, Dq, (4.0f * ep + V.d0) * Dq);
+  const float area2 = (E0 + E1) + E2;
+  const float aa = fabsf(area2);
+  if (aa <= 6.0f * G) return SC_MAYBE;  // (nearly) edge-on: orientation not reliable
+  const float s = area2 > 0.f ? 1.0f : -1.0f;
+  const float v0 = s * E0, v1 = s * E1, v2 = s * E2;
+  if (v0 < -G || v1 < -G || v2 < -G) return SC_MISS;
+  if (!(v0 > G && v1 > G && v2 > G)) return SC_MAYBE;
+  // Inside with margin.  Sure only if the triangle is not grazing -- the exact test rejects
+  // |n.d| <= 1e-6 |n.(P1-o)|.  The depth of the plane changes by at most (zmax - zmin) over a
+  // 2-D extent of at least the smallest altitude, which is >= area2 / (longest edge) >= area2 / Dq:
+  // tan(theta) <= dz Dq / area2, so dz Dq <= 500 area2 keeps cos(theta) > 1e-3 --
+  // and its depth range must lie strictly inside the segment.
+  if ((zmax - zmin + 4.0f * V.e_z) * Dq > 500.0f * (aa - 3.0f * G)) return SC_MAYBE;
+  if (*zlo <= zo + V.e_z || *zhi >= zo + V.two_r - V.e_z) return SC_MAYBE;
+  return SC_SURE;
+}
+
 // Stackless traversal: a 64-bit trail holds one "far sibling still pending" bit
 // per level, parent / sibling links walk back up.  Depth <= 62 is guaranteed by
 // the 30+32-bit key length of the LBVH.  NodeFetch: node(i) -> Node by value,
@@ -418,23 +540,25 @@ FB_HD Hit traverse(const NodeFetch& fetch, const float4* __restrict__ tv0,
       bool h = side ? h1 : h0;
       int c = side ? c1 : c0;
       if (h && c < 0) {
-        int slot = ~c;
-        float4 a = tv0[slot], b = tv1[slot], e = tv2[slot];
-        cnt.tri();
-        float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-        double t, x[3], w[3];
-        if (tri_exact(o, d, P0, P1, P2, best.t, tol2, &t, x, w)) {
+        const int first = leaf_first(c), count = leaf_count(c);
+        for (int slot = first; slot < first + count; slot++) {
+          float4 a = tv0[slot], b = tv1[slot], e = tv2[slot];
+          cnt.tri();
+          float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+          double t, x[3], w[3];
+          if (tri_exact(o, d, P0, P1, P2, best.t, tol2, &t, x, w)) {
 #if defined(__CUDA_ARCH__)
-          int cell = __float_as_int(a.w);
+            int cell = __float_as_int(a.w);
 #else
-          int cell;
-          memcpy(&cell, &a.w, 4);
+            int cell;
+            memcpy(&cell, &a.w, 4);
 #endif
-          if (t < best.t || (t == best.t && cell < best.cell)) {
-            best.t = t;
-            best.slot = slot;
-            best.cell = cell;
-            tcull = fminf(tcull, FB_F2F_RU(t) + tslack);
+            if (t < best.t || (t == best.t && cell < best.cell)) {
+              best.t = t;
+              best.slot = slot;
+              best.cell = cell;
+              tcull = fminf(tcull, FB_F2F_RU(t) + tslack);
+            }
           }
         }
       }
@@ -461,123 +585,12 @@ FB_HD Hit traverse(const NodeFetch& fetch, const float4* __restrict__ tv0,
   return best;
 }
 
-// ---------------------------------------------------------------- lane state machine
-// The render kernel drives 32 of these per warp and lets warp votes decide which
-// step runs next (trace.cu); tests/hostsim drives one at a time.  Same exact
-// decisions as traverse(); differences are purely in scheduling:
-//  * leaf tests are deferred (up to two pending slots) so that a warp can batch
-//    them and run the long double-precision test with many live lanes;
-//  * a 4-entry register stack remembers the most recent far siblings together
-//    with their entry distance, so most pops need no memory access and culled
-//    subtrees are skipped without being visited; older entries fall back to the
-//    parent / sibling links (the trail stays authoritative).
-struct Lane {
-  double o[3];
-  float of[3];
-  double best_t;
-  int32_t best_slot, best_cell;
-  float tcull;
-  uint64_t trail;
-  int32_t node;            // -1: traversal finished
-  int32_t s0, s1, s2, s3;  // short stack of pending far siblings (-1 = empty)
-  float f0, f1, f2, f3;    // their entry distances
-  int32_t p0, p1;          // pending leaf slots (-1 = none); p0 is filled first
-};
-
-FB_HD void lane_init(Lane& L, const double* o, float tslack) {
-  for (int k = 0; k < 3; k++) { L.o[k] = o[k]; L.of[k] = (float)o[k]; }
-  L.best_t = DBL_MAX;
-  L.best_slot = -1;
-  L.best_cell = 0x7fffffff;
-  L.tcull = 1.0f + tslack;
-  L.trail = 1;
-  L.node = 0;
-  L.s0 = L.s1 = L.s2 = L.s3 = -1;
-  L.f0 = L.f1 = L.f2 = L.f3 = 0.f;
-  L.p0 = L.p1 = -1;
-}
-
 FB_HD int ctz64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
   return __ffsll((long long)v) - 1;
 #else
   return __builtin_ctzll(v);
 #endif
-}
-
-// visit L.node (precondition: L.node >= 0 and no pending leaves)
-template <class NodeFetch, class Counter>
-FB_HD void lane_node_step(Lane& L, const NodeFetch& fetch, const float* invf, float slack, Counter& cnt) {
-  const Node N = fetch.node(L.node);
-  cnt.node();
-  float tn0, tn1;
-  bool h0 = slab(N.box, L.of, invf, slack, L.tcull, &tn0);
-  bool h1 = slab(N.box + 6, L.of, invf, slack, L.tcull, &tn1);
-  const int c0 = N.c0, c1 = N.c1;
-  if (h0 && c0 < 0) { L.p0 = ~c0; }
-  if (h1 && c1 < 0) { if (L.p0 < 0) L.p0 = ~c1; else L.p1 = ~c1; }
-  h0 = h0 && c0 >= 0;
-  h1 = h1 && c1 >= 0;
-  if (h0 || h1) {
-    const bool both = h0 && h1;
-    const bool swap = both && tn1 < tn0;
-    L.trail = (L.trail << 1) | (both ? 1u : 0u);
-    if (both) {
-      L.s3 = L.s2; L.s2 = L.s1; L.s1 = L.s0; L.s0 = swap ? c0 : c1;
-      L.f3 = L.f2; L.f2 = L.f1; L.f1 = L.f0; L.f0 = swap ? tn0 : tn1;
-    }
-    L.node = both ? (swap ? c1 : c0) : (h0 ? c0 : c1);
-    return;
-  }
-  // dead end: pop the nearest pending far sibling that is still within reach
-  int climbed = 0;
-  for (;;) {
-    int k = ctz64(L.trail);
-    L.trail >>= k;
-    climbed += k;
-    if (L.trail == 1) { L.node = -1; return; }
-    L.trail ^= 1;
-    int x = L.s0;
-    float fx = L.f0;
-    L.s0 = L.s1; L.s1 = L.s2; L.s2 = L.s3; L.s3 = -1;
-    L.f0 = L.f1; L.f1 = L.f2; L.f2 = L.f3;
-    if (x >= 0) {
-      if (fx <= L.tcull) { L.node = x; return; }
-      continue;  // culled by a hit found since it was pushed
-    }
-    // the entry was pushed out of the short stack: walk the links
-    int nd = L.node;
-    for (int i = 0; i < climbed; i++) nd = fetch.parent(nd);
-    L.node = fetch.sibling(nd);
-    return;
-  }
-}
-
-// test one pending leaf (precondition: L.p0 >= 0)
-template <class Counter>
-FB_HD void lane_leaf_step(Lane& L, const float4* __restrict__ tv0, const float4* __restrict__ tv1,
-                          const float4* __restrict__ tv2, const double* d, float tslack, double tol2,
-                          Counter& cnt) {
-  int slot;
-  if (L.p1 >= 0) { slot = L.p1; L.p1 = -1; } else { slot = L.p0; L.p0 = -1; }
-  float4 a = tv0[slot], b = tv1[slot], e = tv2[slot];
-  cnt.tri();
-  float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-  double t, x[3], w[3];
-  if (tri_exact(L.o, d, P0, P1, P2, L.best_t, tol2, &t, x, w)) {
-#if defined(__CUDA_ARCH__)
-    int cell = __float_as_int(a.w);
-#else
-    int cell;
-    memcpy(&cell, &a.w, 4);
-#endif
-    if (t < L.best_t || (t == L.best_t && cell < L.best_cell)) {
-      L.best_t = t;
-      L.best_slot = slot;
-      L.best_cell = cell;
-      L.tcull = fminf(L.tcull, FB_F2F_RU(t) + tslack);
-    }
-  }
 }
 
 struct NoCount {

@@ -206,11 +206,12 @@ __global__ void reorder_kernel(const float* __restrict__ v, const int32_t* __res
 
 // knode[i] = (child0, child1, parent, arrival flag); leaf children are ~slot
 __global__ void karras_kernel(const uint32_t* __restrict__ codes, int n, int4* __restrict__ knode,
-                              int32_t* __restrict__ leaf_parent) {
+                              int32_t* __restrict__ leaf_parent, int2* __restrict__ krange) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   int first, last, split;
   karras_node(codes, n, i, &first, &last, &split);
+  krange[i] = make_int2(first, last - first + 1);  // the subtree covers slots [first, first + count)
   int c0 = (split == first) ? ~split : split;
   int c1 = (split + 1 == last) ? ~(split + 1) : split + 1;
   knode[i].x = c0;
@@ -310,8 +311,18 @@ __device__ __forceinline__ int final_index(int k, const int32_t* remap, const ui
   return nontop_flag[k] ? n_top + (int)nontop_scan[k] : remap[k];
 }
 
-__global__ void layout_kernel(int n_internal, const int4* __restrict__ knode,
-                              const float* __restrict__ leaf_box, const float* __restrict__ node_box,
+// child reference in the final layout: a subtree of at most leaf_max triangles becomes one leaf
+// (its slots are contiguous), anything larger stays an internal node
+__device__ __forceinline__ int final_child(int k, const int2* krange, int leaf_max, const int32_t* remap,
+                                           const uint32_t* nontop_scan, const int32_t* nontop_flag, int n_top) {
+  if (k < 0) return k;  // single-triangle leaf: ~slot == leaf_encode(slot, 1)
+  const int2 r = krange[k];
+  if (r.y <= leaf_max) return leaf_encode(r.x, r.y);
+  return final_index(k, remap, nontop_scan, nontop_flag, n_top);
+}
+
+__global__ void layout_kernel(int n_internal, const int4* __restrict__ knode, const int2* __restrict__ krange,
+                              int leaf_max, const float* __restrict__ leaf_box, const float* __restrict__ node_box,
                               const int32_t* __restrict__ remap, const uint32_t* __restrict__ nontop_scan,
                               const int32_t* __restrict__ nontop_flag, const int32_t* __restrict__ n_top_p,
                               Node* __restrict__ nodes) {
@@ -327,13 +338,13 @@ __global__ void layout_kernel(int n_internal, const int4* __restrict__ knode,
     out.box[k] = b0[k];
     out.box[6 + k] = b1[k];
   }
-  out.c0 = kn.x < 0 ? kn.x : final_index(kn.x, remap, nontop_scan, nontop_flag, n_top);
-  out.c1 = kn.y < 0 ? kn.y : final_index(kn.y, remap, nontop_scan, nontop_flag, n_top);
+  out.c0 = final_child(kn.x, krange, leaf_max, remap, nontop_scan, nontop_flag, n_top);
+  out.c1 = final_child(kn.y, krange, leaf_max, remap, nontop_scan, nontop_flag, n_top);
   int sib = -1;
   if (kn.z >= 0) {
     int4 pn = knode[kn.z];
     int s = (pn.x == i) ? pn.y : pn.x;
-    sib = s < 0 ? s : final_index(s, remap, nontop_scan, nontop_flag, n_top);
+    sib = final_child(s, krange, leaf_max, remap, nontop_scan, nontop_flag, n_top);
     out.parent = final_index(kn.z, remap, nontop_scan, nontop_flag, n_top);
   } else {
     out.parent = -1;
@@ -375,6 +386,7 @@ int lbvh_run(flyby_ctx* c) {
   FB_CUDA(c, m.leaf_box.reserve(24 * Tz));
   FB_CUDA(c, m.node_box.reserve(24 * Tz));
   FB_CUDA(c, m.knode.reserve(16 * Tz));
+  FB_CUDA(c, m.krange.reserve(8 * Tz));
   FB_CUDA(c, m.remap.reserve(4 * Tz + 64));
   FB_CUDA(c, m.topflag.reserve(4 * Tz + 64));
   FB_CUDA(c, m.nodes.reserve(sizeof(Node) * Tz));
@@ -420,7 +432,7 @@ int lbvh_run(flyby_ctx* c) {
   }
   const int n = (int)T, ni = n - 1;
   int32_t* leaf_parent = m.idx_alt.as<int32_t>();  // sort scratch is free again
-  karras_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(k0, n, m.knode.as<int4>(), leaf_parent);
+  karras_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(k0, n, m.knode.as<int4>(), leaf_parent, m.krange.as<int2>());
   FB_LAUNCH_CHECK(c);
   refit_kernel<<<gT, 256, 0, st>>>(n, m.knode.as<int4>(), leaf_parent, m.leaf_box.as<float>(),
                                    m.node_box.as<float>());
@@ -438,7 +450,8 @@ int lbvh_run(flyby_ctx* c) {
   int rc = exclusive_scan_u32(c, nontop_scan, ni, m.scan_tmp);
   if (rc) return rc;
   layout_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(
-      ni, m.knode.as<int4>(), m.leaf_box.as<float>(), m.node_box.as<float>(), m.remap.as<int32_t>(),
+      ni, m.knode.as<int4>(), m.krange.as<int2>(), c->leaf_max, m.leaf_box.as<float>(), m.node_box.as<float>(),
+      m.remap.as<int32_t>(),
       nontop_scan, m.topflag.as<int32_t>(), n_top_dev, m.nodes.as<Node>());
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, cudaEventRecord(c->ev[4], st));

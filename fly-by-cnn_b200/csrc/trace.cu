@@ -16,28 +16,35 @@
 //
 // Roofline: algorithmic bytes per ray = 4*C + 4 (+8 with t); the
 // kernel is bound by L1/L2 node-fetch latency, not HBM.
-#include "ctx.h"
+#include "trace_common.cuh"
 
 namespace fb {
 
-const float* prep_unit_box(flyby_ctx* c);
-
 // ---------------------------------------------------------------- view setup
 __global__ void view_setup_kernel(const float* __restrict__ pts, int n, double radius, double plane_scale,
-                                  double spacing, View* __restrict__ views) {
+                                  double spacing, const float* __restrict__ ubox, View* __restrict__ views,
+                                  ViewF* __restrict__ viewsf) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   View v;
   float sp[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
   view_setup(sp, radius, plane_scale, spacing, &v);
   views[i] = v;
+  // largest |coordinate| of the unit surface bounds the float32 screening errors
+  float max_abs_coord = 0.f;
+  for (int k = 0; k < 6; k++) max_abs_coord = fmaxf(max_abs_coord, fabsf(ubox[k]));
+  ViewF f;
+  viewf_setup(v, radius, max_abs_coord, &f);
+  viewsf[i] = f;
 }
 
 int views_setup(flyby_ctx* c, const flyby_render_opts* o) {
   if (c->n_views <= 0) return fail(c, FLYBY_ERR_INVALID, "no viewpoints set");
   FB_CUDA(c, c->views.reserve(sizeof(View) * (size_t)c->n_views));
+  FB_CUDA(c, c->viewsf.reserve(sizeof(ViewF) * (size_t)c->n_views));
   view_setup_kernel<<<(unsigned)cdiv(c->n_views, 64), 64, 0, c->stream>>>(
-      c->view_pts.as<float>(), c->n_views, c->radius, o->plane_scale, o->plane_spacing, c->views.as<View>());
+      c->view_pts.as<float>(), c->n_views, c->radius, o->plane_scale, o->plane_spacing, prep_unit_box(c),
+      c->views.as<View>(), c->viewsf.as<ViewF>());
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;
 }
@@ -68,117 +75,6 @@ int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o
   return FLYBY_OK;
 }
 
-// ---------------------------------------------------------------- node fetch
-struct GlobalFetch {
-  const Node* gl;
-  __device__ __forceinline__ Node node(int i) const {
-    const float4* p = reinterpret_cast<const float4*>(gl + i);
-    Node n;
-    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-    n.box[0] = a.x; n.box[1] = a.y; n.box[2] = a.z; n.box[3] = a.w;
-    n.box[4] = b.x; n.box[5] = b.y; n.box[6] = b.z; n.box[7] = b.w;
-    n.box[8] = c.x; n.box[9] = c.y; n.box[10] = c.z; n.box[11] = c.w;
-    n.c0 = __float_as_int(d.x); n.c1 = __float_as_int(d.y);
-    n.parent = __float_as_int(d.z); n.sibling = __float_as_int(d.w);
-    return n;
-  }
-  __device__ __forceinline__ int parent(int i) const { return __ldg(&gl[i].parent); }
-  __device__ __forceinline__ int sibling(int i) const { return __ldg(&gl[i].sibling); }
-};
-
-// top-of-tree in shared memory, the rest through the read-only path
-struct TopFetch {
-  const Node* gl;
-  const Node* sm;
-  int ntop;
-  __device__ __forceinline__ Node node(int i) const {
-    Node n;
-    float4 a, b, c, d;
-    if (i < ntop) {
-      const float4* p = reinterpret_cast<const float4*>(sm + i);
-      a = p[0]; b = p[1]; c = p[2]; d = p[3];
-    } else {
-      const float4* p = reinterpret_cast<const float4*>(gl + i);
-      a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); d = __ldg(p + 3);
-    }
-    n.box[0] = a.x; n.box[1] = a.y; n.box[2] = a.z; n.box[3] = a.w;
-    n.box[4] = b.x; n.box[5] = b.y; n.box[6] = b.z; n.box[7] = b.w;
-    n.box[8] = c.x; n.box[9] = c.y; n.box[10] = c.z; n.box[11] = c.w;
-    n.c0 = __float_as_int(d.x); n.c1 = __float_as_int(d.y);
-    n.parent = __float_as_int(d.z); n.sibling = __float_as_int(d.w);
-    return n;
-  }
-  __device__ __forceinline__ int parent(int i) const {
-    return i < ntop ? sm[i].parent : __ldg(&gl[i].parent);
-  }
-  __device__ __forceinline__ int sibling(int i) const {
-    return i < ntop ? sm[i].sibling : __ldg(&gl[i].sibling);
-  }
-};
-
-struct WorkCount {
-  unsigned int nodes = 0, tris = 0;
-  __device__ __forceinline__ void node() { nodes++; }
-  __device__ __forceinline__ void tri() { tris++; }
-};
-
-// ---------------------------------------------------------------- render
-struct RenderParams {
-  const Node* nodes;
-  const int32_t* n_top_dev;
-  const float4 *tv0, *tv1, *tv2;
-  const int4* tvid;
-  const float4* normals;
-  const View* views;
-  const float* ubox;
-  int view_begin, n_views, res;
-  int use_z, split_z, enc, channels;
-  double zscale, spacing;
-  double tol2;  // tol^2 of IntersectWithLine
-  float* feat;
-  int32_t* ids;
-  double* tt;
-  unsigned long long* counters;  // [0] tile counter, [1] nodes, [2] tris, [3] hits
-  int tiles_x, tiles_y;          // padded tile grid (x even, y multiple of 4)
-  long long n_tiles;
-  int top_cap;                   // nodes that fit in the dynamic shared memory
-};
-
-#define RK_THREADS 256
-#define RK_WARPS (RK_THREADS / 32)
-#define RK_QCAP 96
-#ifdef FLYBY_DEBUG
-#define RK_MAX_ITERS (1ull << 18)
-#else
-#define RK_MAX_ITERS (1ull << 26)
-#endif
-//  // ~60 steps per ray would allow a million rays per warp
-#define RK_RETIRE 12  // retire/refill once this many lanes are finished or idle
-
-__device__ __forceinline__ void write_pixel(const RenderParams& p, int64_t pix, const float* px, int cell,
-                                            double t) {
-  if (p.feat) {
-    if (p.channels == 4) {
-      __stcs(reinterpret_cast<float4*>(p.feat) + pix, make_float4(px[0], px[1], px[2], px[3]));
-    } else {
-      float* o = p.feat + pix * 3;
-      __stcs(o, px[0]);
-      __stcs(o + 1, px[1]);
-      __stcs(o + 2, px[2]);
-    }
-  }
-  if (p.ids) __stcs(p.ids + pix, cell);
-  if (p.tt) __stcs(p.tt + pix, t);
-}
-
-// conservative float32 test of a ray against the mesh bounds (same maths as the
-// node test, so a ray rejected here would also be rejected at the root)
-__device__ __forceinline__ bool hits_bounds(const float* ubox, const double* o, const View& vw) {
-  float of[3] = {(float)o[0], (float)o[1], (float)o[2]};
-  float tn;
-  return slab(ubox, of, vw.invf, vw.slack, 1.0f + vw.tslack, &tn);
-}
-
 // Warp-cooperative packet traversal.  A warp owns a batch of up to 32 compacted
 // rays of ONE view (parallel rays from neighbouring pixels) and walks the LBVH as
 // a unit: node index and bit-trail are warp-uniform, every lane tests its own ray
@@ -191,10 +87,11 @@ __device__ __forceinline__ bool hits_bounds(const float* ubox, const double* o, 
 // Each lane still decides its own hit exactly (double precision) and keeps its
 // own cull distance, so the result equals the per-ray traversal bit for bit.
 #define RK_RING 16
+#define RK_PEND 4
 #define RK_MAX_STEPS (1u << 24)  // node visits of one packet; a tree has < 2^31 nodes, a packet visits far fewer
 
 template <bool USE_TOP, bool COUNT>
-__global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(RK_THREADS, RK_MINB) render_kernel(const RenderParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Node* top = reinterpret_cast<Node*>(smem_raw);
   uint32_t* queues = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.top_cap * sizeof(Node));
@@ -211,36 +108,7 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
   }
   if (threadIdx.x < 6) s_ubox[threadIdx.x] = p.ubox[threadIdx.x];
 
-  if (USE_TOP && ntop > 0) {
-    // one bulk async copy (TMA engine, UBLKCP) of the top-of-tree block
-    const uint32_t bytes = (uint32_t)ntop * (uint32_t)sizeof(Node);
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(top);
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-          "l"(p.nodes), "r"(bytes), "r"(bar)
-          : "memory");
-    }
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred q;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, q;\n\t}"
-          : "=r"(done)
-          : "r"(bar), "r"(0u)
-          : "memory");
-    }
-  } else {
-    __syncthreads();
-  }
+  stage_top_of_tree(top, p.nodes, USE_TOP ? ntop : 0, &s_bar);
 
   uint32_t* q = queues + warp * RK_QCAP;
   int32_t* ring = s_ring[warp];
@@ -326,16 +194,32 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
     int best_slot = -1, best_cell = 0x7fffffff;
     float tcull = active ? 1.0f + tslack : -1.0f;  // an idle lane never hits a box
 
-    // ---- packet traversal (everything below the leaf tests is warp-uniform)
+    // exact nearest hit of this lane so far (double), with its barycentric weights
+    double bw0 = 0.0, bw1 = 0.0, bw2 = 0.0;
+    auto exact_test = [&](int slot) {
+      const float4 a = __ldg(p.tv0 + slot), b = __ldg(p.tv1 + slot), e = __ldg(p.tv2 + slot);
+      if (COUNT) n_tris++;
+      const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+      double t, x[3], w[3];
+      if (tri_exact(o, d, P0, P1, P2, best_t, p.tol2, &t, x, w)) {
+        const int cell = __float_as_int(a.w);
+        if (t < best_t || (t == best_t && cell < best_cell)) {
+          best_t = t;
+          best_slot = slot;
+          best_cell = cell;
+          bw0 = w[0]; bw1 = w[1]; bw2 = w[2];
+          return true;
+        }
+      }
+      return false;
+    };
+
+    // ---- packet traversal (everything but the leaf tests is warp-uniform)
     int node = 0;
     unsigned long long trail = 1;
     int ring_head = 0, ring_count = 0;
     unsigned int steps = 0;
     for (;;) {
-      if (++steps > RK_MAX_STEPS) {  // watchdog: a traversal bug must end as an error, not a hung GPU
-        if (lane == 0) atomicAdd(p.counters + 6, 1ull);
-        break;
-      }
       const Node N = tf.node(node);
       float tn0, tn1;
       const bool h0 = slab_fma(N.box, sr, negx, negy, negz, tcull, &tn0);
@@ -344,31 +228,18 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
       const unsigned m1 = __ballot_sync(0xffffffffu, h1);
       const int c0 = N.c0, c1 = N.c1;
       if (COUNT) n_nodes += __popc(m0 | m1);
-      // leaves: every lane whose ray enters the leaf box runs the exact test
 #pragma unroll
       for (int side = 0; side < 2; side++) {
         const unsigned m = side ? m1 : m0;
         const int c = side ? c1 : c0;
         if (m != 0u && c < 0) {
-          const int slot = ~c;
-          const float4 a = __ldg(p.tv0 + slot), b = __ldg(p.tv1 + slot), e = __ldg(p.tv2 + slot);
-          if (side ? h1 : h0) {
-            if (COUNT) n_tris++;
-            const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-            double t, x[3], w[3];
-            if (tri_exact(o, d, P0, P1, P2, best_t, p.tol2, &t, x, w)) {
-              const int cell = __float_as_int(a.w);
-              if (t < best_t || (t == best_t && cell < best_cell)) {
-                best_t = t;
-                best_slot = slot;
-                best_cell = cell;
-                tcull = fminf(tcull, FB_F2F_RU(t) + tslack);
-              }
-            }
-          }
+          const bool h = side ? h1 : h0;
+          const int first = leaf_first(c), last = first + leaf_count(c);
+          // every lane whose ray enters the leaf box runs the exact test on the leaf's triangles
+          for (int slot = first; slot < last; slot++)
+            if (h && exact_test(slot)) tcull = fminf(tcull, FB_F2F_RU(best_t) + tslack);
         }
       }
-      __syncwarp();
       // internal children still wanted by at least one lane (cull distances may have shrunk)
       const bool w0 = h0 && c0 >= 0 && tn0 <= tcull;
       const bool w1 = h1 && c1 >= 0 && tn1 <= tcull;
@@ -389,6 +260,10 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
         continue;
       }
       // dead end: climb to the nearest level with a pending far sibling
+      if (++steps > RK_MAX_STEPS) {  // watchdog: a traversal bug must end as an error, not a hung GPU
+        if (lane == 0) atomicAdd(p.counters + 6, 1ull);
+        break;
+      }
       const int k = __ffsll((long long)trail) - 1;
       trail >>= k;
       if (trail == 1ull) break;
@@ -405,17 +280,16 @@ __global__ void __launch_bounds__(RK_THREADS, 2) render_kernel(const RenderParam
       }
     }
 
-    // ---- shade + write
+    // ---- shade + write (x is recomputed from t exactly as the test computed it)
     if (active) {
       float px[4] = {0.f, 0.f, 0.f, 0.f};
       double t = -1.0;
       if (best_slot >= 0) {
         n_hits++;
-        const float4 a = p.tv0[best_slot], b = p.tv1[best_slot], e = p.tv2[best_slot];
-        const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-        double x[3], w[3];
-        tri_exact(o, d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w);
+        t = best_t;
         if (p.feat) {
+          const double x[3] = {FB_ADD(o[0], FB_MUL(t, d[0])), FB_ADD(o[1], FB_MUL(t, d[1])), FB_ADD(o[2], FB_MUL(t, d[2]))};
+          const double w[3] = {bw0, bw1, bw2};
           const int4 vid = p.tvid[best_slot];
           const float4 n0 = __ldg(p.normals + vid.x), n1 = __ldg(p.normals + vid.y), n2 = __ldg(p.normals + vid.z);
           const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
@@ -445,6 +319,8 @@ __global__ void fill_miss_kernel(float* feat, int32_t* ids, double* tt, int64_t 
   if (tt) tt[i] = -1.0;
 }
 
+static int g_screen = 1;  // FLYBY_NO_SCREEN=1: fused kernel, exact test on every leaf candidate (A/B, parity checks)
+int screen_render(flyby_ctx* c, const RenderParams& p);
 static int g_use_top = 1;  // FLYBY_NO_SMEM_TOP=1 disables the shared-memory top (A/B measurements)
 
 // first_chunk / last_chunk: a render call may be split into view chunks (api.cu overlaps the
@@ -460,6 +336,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if (first_chunk) {
     FB_CUDA(c, cudaEventRecord(c->ev[5], st));
     FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 7 * sizeof(unsigned long long), st));
+    FB_CUDA(c, cudaMemsetAsync(c->counters.as<unsigned long long>() + 8, 0, 8 * sizeof(unsigned long long), st));
     c->stats.n_rays = 0;
   }
   c->stats.n_rays += n_pix;
@@ -473,6 +350,8 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if (!env_read) {
     const char* e = getenv("FLYBY_NO_SMEM_TOP");
     if (e && e[0] == '1') g_use_top = 0;
+    e = getenv("FLYBY_NO_SCREEN");
+    if (e && e[0] == '1') g_screen = 0;
     env_read = true;
   }
   RenderParams p;
@@ -494,6 +373,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   p.tiles_y = (ty + 3) & ~3;
   p.n_tiles = (long long)p.tiles_x * p.tiles_y * nv;
   p.top_cap = g_use_top ? 1024 : 0;
+  p.viewsf = c->viewsf.as<ViewF>();
   FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), st));  // tile counter
   const size_t smem = (size_t)p.top_cap * sizeof(Node) + RK_WARPS * RK_QCAP * sizeof(uint32_t);
   auto launch = [&](auto kern) -> int {
@@ -510,8 +390,17 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
     return FLYBY_OK;
   };
   int rc;
-  if (g_use_top) rc = c->count_work ? launch(render_kernel<true, true>) : launch(render_kernel<true, false>);
-  else rc = c->count_work ? launch(render_kernel<false, true>) : launch(render_kernel<false, false>);
+  if (g_screen) {
+    rc = screen_render(c, p);  // screen.cu: float32 trace kernel + exact resolve kernel
+  } else {
+    const int variant = (g_use_top ? 2 : 0) | (c->count_work ? 1 : 0);
+    switch (variant) {
+      case 0: rc = launch(render_kernel<false, false>); break;
+      case 1: rc = launch(render_kernel<false, true>); break;
+      case 2: rc = launch(render_kernel<true, false>); break;
+      default: rc = launch(render_kernel<true, true>); break;
+    }
+  }
   if (rc) return rc;
   if (last_chunk) FB_CUDA(c, cudaEventRecord(c->ev[6], st));
   return FLYBY_OK;

@@ -1,0 +1,160 @@
+// trace_common.cuh -- pieces shared by the render kernels (trace.cu: fused exact kernel,
+// screen.cu: float32 trace kernel + exact resolve kernel).
+#pragma once
+#include "ctx.h"
+
+namespace fb {
+
+const float* prep_unit_box(flyby_ctx* c);
+
+// ---------------------------------------------------------------- node fetch
+struct GlobalFetch {
+  const Node* gl;
+  __device__ __forceinline__ Node node(int i) const {
+    const float4* p = reinterpret_cast<const float4*>(gl + i);
+    Node n;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    n.box[0] = a.x; n.box[1] = a.y; n.box[2] = a.z; n.box[3] = a.w;
+    n.box[4] = b.x; n.box[5] = b.y; n.box[6] = b.z; n.box[7] = b.w;
+    n.box[8] = c.x; n.box[9] = c.y; n.box[10] = c.z; n.box[11] = c.w;
+    n.c0 = __float_as_int(d.x); n.c1 = __float_as_int(d.y);
+    n.parent = __float_as_int(d.z); n.sibling = __float_as_int(d.w);
+    return n;
+  }
+  __device__ __forceinline__ int parent(int i) const { return __ldg(&gl[i].parent); }
+  __device__ __forceinline__ int sibling(int i) const { return __ldg(&gl[i].sibling); }
+};
+
+// top-of-tree in shared memory, the rest through the read-only path
+struct TopFetch {
+  const Node* gl;
+  const Node* sm;
+  int ntop;
+  __device__ __forceinline__ Node node(int i) const {
+    Node n;
+    float4 a, b, c, d;
+    if (i < ntop) {
+      const float4* p = reinterpret_cast<const float4*>(sm + i);
+      a = p[0]; b = p[1]; c = p[2]; d = p[3];
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(gl + i);
+      a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); d = __ldg(p + 3);
+    }
+    n.box[0] = a.x; n.box[1] = a.y; n.box[2] = a.z; n.box[3] = a.w;
+    n.box[4] = b.x; n.box[5] = b.y; n.box[6] = b.z; n.box[7] = b.w;
+    n.box[8] = c.x; n.box[9] = c.y; n.box[10] = c.z; n.box[11] = c.w;
+    n.c0 = __float_as_int(d.x); n.c1 = __float_as_int(d.y);
+    n.parent = __float_as_int(d.z); n.sibling = __float_as_int(d.w);
+    return n;
+  }
+  __device__ __forceinline__ int parent(int i) const {
+    return i < ntop ? sm[i].parent : __ldg(&gl[i].parent);
+  }
+  __device__ __forceinline__ int sibling(int i) const {
+    return i < ntop ? sm[i].sibling : __ldg(&gl[i].sibling);
+  }
+};
+
+struct WorkCount {
+  unsigned int nodes = 0, tris = 0;
+  __device__ __forceinline__ void node() { nodes++; }
+  __device__ __forceinline__ void tri() { tris++; }
+};
+
+// ---------------------------------------------------------------- render
+struct RenderParams {
+  const Node* nodes;
+  const int32_t* n_top_dev;
+  const float4 *tv0, *tv1, *tv2;
+  const int4* tvid;
+  const float4* normals;
+  const View* views;
+  const float* ubox;
+  int view_begin, n_views, res;
+  int use_z, split_z, enc, channels;
+  double zscale, spacing;
+  double tol2;  // tol^2 of IntersectWithLine
+  float* feat;
+  int32_t* ids;
+  double* tt;
+  unsigned long long* counters;  // [0] tile counter, [1] nodes, [2] tris, [3] hits
+  int tiles_x, tiles_y;          // padded tile grid (x even, y multiple of 4)
+  long long n_tiles;
+  int top_cap;                   // nodes that fit in the dynamic shared memory
+  const ViewF* viewsf;           // float32 screening frame of every view
+};
+
+#ifndef RK_MINB
+#define RK_MINB 2
+#endif
+#define RK_THREADS 256
+#define RK_WARPS (RK_THREADS / 32)
+#define RK_QCAP 96
+#ifdef FLYBY_DEBUG
+#define RK_MAX_ITERS (1ull << 18)
+#else
+#define RK_MAX_ITERS (1ull << 26)
+#endif
+//  // ~60 steps per ray would allow a million rays per warp
+#define RK_RETIRE 12  // retire/refill once this many lanes are finished or idle
+
+__device__ __forceinline__ void write_pixel(const RenderParams& p, int64_t pix, const float* px, int cell,
+                                            double t) {
+  if (p.feat) {
+    if (p.channels == 4) {
+      __stcs(reinterpret_cast<float4*>(p.feat) + pix, make_float4(px[0], px[1], px[2], px[3]));
+    } else {
+      float* o = p.feat + pix * 3;
+      __stcs(o, px[0]);
+      __stcs(o + 1, px[1]);
+      __stcs(o + 2, px[2]);
+    }
+  }
+  if (p.ids) __stcs(p.ids + pix, cell);
+  if (p.tt) __stcs(p.tt + pix, t);
+}
+
+// conservative float32 test of a ray against the mesh bounds (same maths as the
+// node test, so a ray rejected here would also be rejected at the root)
+__device__ __forceinline__ bool hits_bounds(const float* ubox, const double* o, const View& vw) {
+  float of[3] = {(float)o[0], (float)o[1], (float)o[2]};
+  float tn;
+  return slab(ubox, of, vw.invf, vw.slack, 1.0f + vw.tslack, &tn);
+}
+
+
+// One bulk async copy (TMA engine, SASS UBLKCP) of the breadth-first top of the tree into shared
+// memory, completion through an mbarrier.  Must be called by every thread of the CTA.
+__device__ __forceinline__ void stage_top_of_tree(Node* top, const Node* nodes, int ntop, unsigned long long* bar_mem) {
+  if (ntop > 0) {
+    const uint32_t bytes = (uint32_t)ntop * (uint32_t)sizeof(Node);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bar_mem);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(top);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+          "l"(nodes), "r"(bytes), "r"(bar)
+          : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, q;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(0u)
+          : "memory");
+    }
+  } else {
+    __syncthreads();
+  }
+}
+
+}  // namespace fb

@@ -26,6 +26,9 @@ struct SimCount {
   void tri() { tris++; }
 };
 
+static int g_leaf_max = FB_LEAF_MAX;
+extern "C" __attribute__((visibility("default"))) void sim_set_leaf_max(int k) { g_leaf_max = k; }
+
 struct SimBvh {
   std::vector<Node> nodes;
   std::vector<float4> tv0, tv1, tv2;
@@ -90,10 +93,11 @@ static void build(const float* v, int64_t V, const int32_t* tris, int64_t T, Sim
     return;
   }
   int ni = n - 1;
-  std::vector<int> c0(ni), c1(ni), par(ni, -1);
+  std::vector<int> c0(ni), c1(ni), par(ni, -1), rfirst(ni), rcount(ni);
   for (int i = 0; i < ni; i++) {
     int first, last, split;
     karras_node(sc.data(), n, i, &first, &last, &split);
+    rfirst[i] = first; rcount[i] = last - first + 1;
     c0[i] = (split == first) ? ~split : split;
     c1[i] = (split + 1 == last) ? ~(split + 1) : split + 1;
     if (c0[i] >= 0) par[c0[i]] = i;
@@ -125,9 +129,10 @@ static void build(const float* v, int64_t V, const int32_t* tris, int64_t T, Sim
     Node nd;
     box_of(b, leaf_box, node_box, c0[i], nd.box);
     box_of(b, leaf_box, node_box, c1[i], nd.box + 6);
-    nd.c0 = c0[i]; nd.c1 = c1[i]; nd.parent = par[i];
+    auto fin = [&](int k) { return (k >= 0 && rcount[k] <= g_leaf_max) ? leaf_encode(rfirst[k], rcount[k]) : k; };
+    nd.c0 = fin(c0[i]); nd.c1 = fin(c1[i]); nd.parent = par[i];
     nd.sibling = -1;
-    if (par[i] >= 0) nd.sibling = (c0[par[i]] == i) ? c1[par[i]] : c0[par[i]];
+    if (par[i] >= 0) nd.sibling = fin((c0[par[i]] == i) ? c1[par[i]] : c0[par[i]]);
     b.nodes[i] = nd;
   }
 }
@@ -150,22 +155,9 @@ int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, co
       for (int i = 0; i < res; i++) {
         double o[3];
         view_ray(vw, res, i, j, spacing, o);
-        Hit h;
-        if (mode == 0) {
-          h = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o, vw.dir, vw.dirf, vw.invf, vw.slack,
-                       vw.tslack, 1e-20, cnt);
-        } else {
-          // the render kernel's per-lane state machine, one lane at a time; leaf tests are
-          // delayed as long as possible (mode 2) or run at once (mode 1) to cover both schedules
-          Lane L;
-          lane_init(L, o, vw.tslack);
-          while (L.node >= 0 || L.p0 >= 0) {
-            bool leaf_now = L.p0 >= 0 && (mode == 1 || L.node < 0 || L.p0 >= 0);
-            if (leaf_now) lane_leaf_step(L, b.tv0.data(), b.tv1.data(), b.tv2.data(), vw.dir, vw.tslack, 1e-20, cnt);
-            else lane_node_step(L, f, vw.invf, vw.slack, cnt);
-          }
-          h.t = L.best_t; h.slot = L.best_slot; h.cell = L.best_slot >= 0 ? L.best_cell : -1;
-        }
+        (void)mode;
+        Hit h = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o, vw.dir, vw.dirf, vw.invf, vw.slack,
+                         vw.tslack, 1e-20, cnt);
         size_t pix = ((size_t)v * res + j) * res + i;
         float px[4] = {0, 0, 0, 0};
         double t = -1.0;
@@ -218,8 +210,8 @@ static void packet_trace(const SimBvh& b, const View& vw, const double (*o)[3], 
     }
     for (int side = 0; side < 2; side++) {
       int c = side ? N.c1 : N.c0;
-      if ((side ? any1 : any0) && c < 0) {
-        int slot = ~c;
+      if ((side ? any1 : any0) && c < 0)
+       for (int slot = leaf_first(c); slot < leaf_first(c) + leaf_count(c); slot++) {
         float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
         float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
         int cell; memcpy(&cell, &a.w, 4);
@@ -303,5 +295,181 @@ int sim_render_packet(const float* verts, int64_t V, const int32_t* tris, int64_
       }
   }
   if (work) { work[0] = cnt.nodes; work[1] = cnt.tris; work[2] = b.max_depth; }
+  return 0;
+}
+
+// ---- packet traversal with float32 screening (render_kernel<.., SCREEN = true>): candidates are
+// classified by screen_tri, kept in a short per-lane list and settled by the exact test in batches.
+static void packet_trace_screen(const SimBvh& b, const View& vw, const ViewF& vf, const double (*o)[3],
+                                int n_active, int pend_cap, Hit* out, SimCount& cnt, long long* cls_count) {
+  // pend_cap > 0: fused kernel with in-loop resolution; pend_cap < 0: split design (screen.cu): the
+  // trace pass only lists candidates (|pend_cap| slots, overflow -> exact per-ray traversal in resolve)
+  const bool split = pend_cap < 0;
+  if (split) pend_cap = -pend_cap;
+  bool overflow[32] = {false};
+  const Node* nodes = b.nodes.data();
+  SlabRay sr[32];
+  double best_t[32]; int best_slot[32], best_cell[32]; float tcull[32];
+  float qx[32], qy[32], zo[32], uz[32]; int nc[32];
+  std::vector<int> cslot(32 * pend_cap); std::vector<float> clo(32 * pend_cap);
+  bool negx = vw.dirf[0] < 0.f, negy = vw.dirf[1] < 0.f, negz = vw.dirf[2] < 0.f;
+  const float inv_two_r = 1.000001f / vf.two_r;
+  for (int l = 0; l < 32; l++) {
+    float of[3] = {0, 0, 0};
+    double oo[3] = {0, 0, 0};
+    if (l < n_active) for (int k = 0; k < 3; k++) { of[k] = (float)o[l][k]; oo[k] = o[l][k]; }
+    float inv[3] = {clamp_inv(vw.dirf[0]), clamp_inv(vw.dirf[1]), clamp_inv(vw.dirf[2])};
+    slab_ray_setup(of, inv, vw.slack, &sr[l]);
+    best_t[l] = DBL_MAX; best_slot[l] = -1; best_cell[l] = 0x7fffffff;
+    tcull[l] = l < n_active ? 1.0f + vw.tslack : -1.0f;
+    screen_ray(vw, oo, &qx[l], &qy[l], &zo[l]);
+    uz[l] = INFINITY; nc[l] = 0;
+  }
+  auto exact_test = [&](int l, int slot) {
+    float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
+    float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
+    int cell; memcpy(&cell, &a.w, 4);
+    cnt.tri();
+    double t, x[3], w[3];
+    if (tri_exact(o[l], vw.dir, P0, P1, P2, best_t[l], 1e-20, &t, x, w) &&
+        (t < best_t[l] || (t == best_t[l] && cell < best_cell[l]))) {
+      best_t[l] = t; best_slot[l] = slot; best_cell[l] = cell;
+      return true;
+    }
+    return false;
+  };
+  auto resolve = [&]() {
+    for (int l = 0; l < 32; l++)
+      while (nc[l] > 0) {
+        nc[l]--;
+        int slot = cslot[l * pend_cap + nc[l]];
+        if (clo[l * pend_cap + nc[l]] <= uz[l] && exact_test(l, slot)) {
+          float zx = fmaf((float)best_t[l], vf.two_r, zo[l]) + 2.0f * vf.e_z;
+          uz[l] = fminf(uz[l], zx);
+          tcull[l] = fminf(tcull[l], FB_F2F_RU(best_t[l]) + vw.tslack);
+        }
+      }
+  };
+  int node = 0; uint64_t trail = 1;
+  std::vector<int> ring(16); int ring_head = 0, ring_count = 0;
+  for (;;) {
+    const Node N = nodes[node];
+    cnt.node();
+    bool h0[32], h1[32]; float tn0[32], tn1[32];
+    bool any0 = false, any1 = false;
+    for (int l = 0; l < 32; l++) {
+      h0[l] = slab_fma(N.box, sr[l], negx, negy, negz, tcull[l], &tn0[l]);
+      h1[l] = slab_fma(N.box + 6, sr[l], negx, negy, negz, tcull[l], &tn1[l]);
+      any0 |= h0[l]; any1 |= h1[l];
+    }
+    for (int side = 0; side < 2; side++) {
+      int c = side ? N.c1 : N.c0;
+      if ((side ? any1 : any0) && c < 0)
+       for (int slot = leaf_first(c); slot < leaf_first(c) + leaf_count(c); slot++) {
+        float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
+        float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
+        bool full = false;
+        for (int l = 0; l < 32; l++) {
+          if (!(side ? h1[l] : h0[l])) continue;
+          float zlo, zhi;
+          int cls = screen_tri(vf, qx[l], qy[l], zo[l], P0, P1, P2, &zlo, &zhi);
+          if (cls_count) cls_count[cls]++;
+          if (cls != SC_MISS && zlo <= uz[l] && !overflow[l]) {
+            if (cls == SC_SURE && zhi < uz[l]) {
+              uz[l] = zhi;
+              tcull[l] = fminf(tcull[l], fmaf(uz[l] - zo[l] + 2.0f * vf.e_z, inv_two_r, vw.tslack));
+            }
+            if (split && nc[l] == pend_cap) {  // compact, then give up on the list
+              int k = 0;
+              for (int i = 0; i < pend_cap; i++)
+                if (clo[l * pend_cap + i] <= uz[l]) { clo[l * pend_cap + k] = clo[l * pend_cap + i]; cslot[l * pend_cap + k] = cslot[l * pend_cap + i]; k++; }
+              nc[l] = k;
+            }
+            if (split && nc[l] == pend_cap) overflow[l] = true;
+            else { cslot[l * pend_cap + nc[l]] = slot; clo[l * pend_cap + nc[l]] = zlo; nc[l]++; }
+          }
+          if (!split) full |= nc[l] == pend_cap;
+        }
+        if (full) resolve();
+      }
+    }
+    int nd0 = 0, nd1 = 0, npref1 = 0, nany = 0;
+    for (int l = 0; l < 32; l++) {
+      bool w0 = h0[l] && N.c0 >= 0 && tn0[l] <= tcull[l];
+      bool w1 = h1[l] && N.c1 >= 0 && tn1[l] <= tcull[l];
+      nd0 += w0; nd1 += w1; nany += (w0 || w1);
+      npref1 += (w1 && (!w0 || tn1[l] < tn0[l]));
+    }
+    if (nd0 || nd1) {
+      bool both = nd0 && nd1;
+      bool swap = both && 2 * npref1 > nany;
+      trail = (trail << 1) | (both ? 1ull : 0ull);
+      if (both) {
+        ring_head = (ring_head + 1) % 16;
+        ring[ring_head] = swap ? N.c0 : N.c1;
+        ring_count = ring_count < 16 ? ring_count + 1 : 16;
+      }
+      node = both ? (swap ? N.c1 : N.c0) : (nd0 ? N.c0 : N.c1);
+      continue;
+    }
+    int k = ctz64(trail);
+    trail >>= k;
+    if (trail == 1ull) break;
+    trail ^= 1ull;
+    if (ring_count > 0) {
+      node = ring[ring_head];
+      ring_head = (ring_head + 15) % 16;
+      ring_count--;
+    } else {
+      int nd = node;
+      for (int i = 0; i < k; i++) nd = nodes[nd].parent;
+      node = nodes[nd].sibling;
+    }
+  }
+  resolve();
+  for (int l = 0; l < n_active; l++) {
+    if (overflow[l]) {
+      SimFetch f{nodes};
+      out[l] = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o[l], vw.dir, vw.dirf, vw.invf, vw.slack, vw.tslack,
+                        1e-20, cnt);
+      if (cls_count) cls_count[1] += 1000000;  // make overflows visible in the class counters
+      continue;
+    }
+    out[l].t = best_t[l]; out[l].slot = best_slot[l]; out[l].cell = best_slot[l] >= 0 ? best_cell[l] : -1;
+  }
+}
+
+extern "C" __attribute__((visibility("default")))
+int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* views,
+                             int n_views, double radius, int res, double plane_scale, double spacing, int pend_cap,
+                             int32_t* out_ids, double* out_t, long long* work /* nodes, exact tests, depth, miss, maybe, sure */) {
+  SimBvh b;
+  build(verts, V, tris, T, b);
+  if (b.nodes.empty()) return 1;
+  float maxc = 0.f;
+  for (int64_t i = 0; i < 3 * V; i++) maxc = fmaxf(maxc, fabsf(verts[i]));
+  SimCount cnt;
+  long long cls[3] = {0, 0, 0};
+  for (int v = 0; v < n_views; v++) {
+    View vw;
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    ViewF vf;
+    viewf_setup(vw, radius, maxc, &vf);
+    for (int ty = 0; ty < (res + 3) / 4; ty++)
+      for (int tx = 0; tx < (res + 7) / 8; tx++) {
+        double o[32][3]; int pix[32]; int n = 0;
+        for (int l = 0; l < 32; l++) {
+          int px = tx * 8 + (l & 7), py = ty * 4 + (l >> 3);
+          if (px < res && py < res) { view_ray(vw, res, px, py, spacing, o[n]); pix[n] = py * res + px; n++; }
+        }
+        Hit h[32];
+        packet_trace_screen(b, vw, vf, o, n, pend_cap, h, cnt, cls);
+        for (int l = 0; l < n; l++) {
+          size_t id = (size_t)v * res * res + pix[l];
+          out_ids[id] = h[l].cell; out_t[id] = h[l].slot >= 0 ? h[l].t : -1.0;
+        }
+      }
+  }
+  if (work) { work[0] = cnt.nodes; work[1] = cnt.tris; work[2] = b.max_depth; work[3] = cls[0]; work[4] = cls[1]; work[5] = cls[2]; }
   return 0;
 }

@@ -89,6 +89,9 @@ def test_rays(gpu_ctx, orc, ps, spacing):
 
 @pytest.mark.parametrize("name", list(MESHES))
 def test_bvh_invariants(gpu_ctx, name):
+    """Walk the LBVH from the root: every triangle slot is covered by exactly one leaf (a leaf is a run
+    of consecutive Morton-sorted slots), every stored child box is the exact bound of what hangs below
+    it, parent / sibling links are consistent, the top block is a breadth-first prefix."""
     P, F = MESHES[name]()
     uv, _, _, _ = _build(gpu_ctx, P, F)
     nodes, n_top, slots = gpu_ctx.get_bvh()
@@ -98,26 +101,40 @@ def test_bvh_invariants(gpu_ctx, name):
     link = nodes[:, 12:].view(np.int32)
     tri = uv[F[slots]]  # [T,3,3] in slot order
     leaf_lo, leaf_hi = tri.min(1), tri.max(1)
-    # every leaf referenced exactly once; every internal node except the root exactly once
-    ch = link[:, :2].reshape(-1)
-    assert sorted((~ch[ch < 0]).tolist()) == list(range(T))
-    assert sorted(ch[ch >= 0].tolist()) == list(range(1, T - 1))
+
+    def leaf_range(c):
+        v = ~int(c)
+        return v & 0x07ffffff, (v >> 27) + 1
+
+    covered = np.zeros(T, np.int32)
+    seen = set()
     assert link[0, 2] == -1
-    # boxes: compute node boxes bottom-up from the stored child boxes and compare
-    lo = np.minimum(box[:, 0:3], box[:, 6:9])
-    hi = np.maximum(box[:, 3:6], box[:, 9:12])
-    for side in (0, 1):
-        c = link[:, side]
-        b_lo, b_hi = box[:, 6 * side:6 * side + 3], box[:, 6 * side + 3:6 * side + 6]
-        isleaf = c < 0
-        assert np.array_equal(b_lo[isleaf], leaf_lo[~c[isleaf]]) and np.array_equal(b_hi[isleaf], leaf_hi[~c[isleaf]])
-        assert np.array_equal(b_lo[~isleaf], lo[c[~isleaf]]) and np.array_equal(b_hi[~isleaf], hi[c[~isleaf]])
-        # parent / sibling links
-        inner = c[~isleaf]
-        idx = np.nonzero(~isleaf)[0]
-        assert np.array_equal(link[inner, 2], idx)
-        assert np.array_equal(link[inner, 3], link[idx, 1 - side])
-    # top block is closed under "parent" (a breadth-first prefix)
+
+    def bounds(i):  # returns (lo, hi) of node i, checking everything below it
+        assert i not in seen
+        seen.add(i)
+        los, his = [], []
+        for side in (0, 1):
+            c = int(link[i, side])
+            b_lo, b_hi = box[i, 6 * side:6 * side + 3], box[i, 6 * side + 3:6 * side + 6]
+            if c < 0:
+                first, cnt = leaf_range(c)
+                assert 1 <= cnt <= 4 or cnt == 1
+                covered[first:first + cnt] += 1
+                lo, hi = leaf_lo[first:first + cnt].min(0), leaf_hi[first:first + cnt].max(0)
+            else:
+                assert link[c, 2] == i and link[c, 3] == link[i, 1 - side]
+                lo, hi = bounds(c)
+            assert np.array_equal(b_lo, lo) and np.array_equal(b_hi, hi), (i, side)
+            los.append(lo)
+            his.append(hi)
+        return np.minimum(los[0], los[1]), np.maximum(his[0], his[1])
+
+    import sys
+    sys.setrecursionlimit(10000)
+    bounds(0)
+    assert np.all(covered == 1)
+    # top block: a breadth-first prefix (every parent precedes its children)
     assert 1 <= n_top <= min(1024, T - 1)
     par = link[1:n_top, 2]
     assert np.all(par < np.arange(1, n_top))

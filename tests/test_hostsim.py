@@ -1,8 +1,9 @@
 """CPU tests of the kernels' per-element logic: tests/hostsim compiles
 fly-by-cnn_b200/csrc/flyby_core.cuh with g++ (the same code nvcc compiles for the
 device) and drives it serially.  Three schedules of the same exact decision are
-checked against the oracle: recursive-free traverse(), the per-lane state machine,
-and a 32-lane emulation of the render kernel's packet traversal (votes as loops).
+checked against the oracle: the per-ray stackless traverse(), a 32-lane emulation of
+the fused kernel's packet traversal (votes as loops), and the float32-screened
+trace + exact resolve split of screen.cu.
 This is test infrastructure: the product never loads libhostsim.so."""
 import ctypes as C
 import os
@@ -62,7 +63,7 @@ CASES = {
 
 
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0])
 def test_per_ray_traversal_matches_oracle(sim, orc, name, mode):
     P, F = CASES[name]()
     U, _, _ = orc.unit_surf(P)
