@@ -482,29 +482,34 @@ FB_HD int screen_tri(const ViewF& V, float qx, float qy, float zo, const float* 
   *zlo = zmin - V.e_z;
   *zhi = zmax + V.e_z;
   if (*zhi < zo - V.e_z || *zlo > zo + V.two_r + V.e_z) return SC_MISS;
-  // edge functions E_k = e_k x r_k.  One margin G bounds the float error of all three:
+  // edge functions E_k = e_k x r_k, each with a margin that bounds its total float error:
   // moving both edge ends and the query point by ep changes E by at most 2 ep (|r|_1 + |e|_1),
-  // the products round by 2^-22 |e|_1 |r|_1, and d0 |e|_1 is the absolute distance margin;
-  // inside the (inflated) bounding box |r|_1 <= Dq and |e|_1 <= D <= Dq, Dq = L1 diameter + 2 m0.
+  // the product rounding adds 2^-22 (|ex ry| + |ey rx|), and d0 |e|_1 (>= d0 |e|_2) is the
+  // absolute distance margin.
   const float r0x = qx - ax, r0y = qy - ay, r1x = qx - bx, r1y = qy - by, r2x = qx - cx, r2y = qy - cy;
-  const float E0 = (bx - ax) * r0y - (by - ay) * r0x;
-  const float E1 = (cx - bx) * r1y - (cy - by) * r1x;
-  const float E2 = (ax - cx) * r2y - (ay - cy) * r2x;
-  const float Dq = (hix - lox) + (hiy - loy) + 2.0f * m0;
-  const float G = fmaf(2.384185791015625e-07f * Dq, Dq, (4.0f * ep + V.d0) * Dq);
+  const float e0x = bx - ax, e0y = by - ay, e1x = cx - bx, e1y = cy - by, e2x = ax - cx, e2y = ay - cy;
+  const float p0a = e0x * r0y, p0b = e0y * r0x, p1a = e1x * r1y, p1b = e1y * r1x, p2a = e2x * r2y, p2b = e2y * r2x;
+  const float E0 = p0a - p0b, E1 = p1a - p1b, E2 = p2a - p2b;
+  const float l0 = fabsf(e0x) + fabsf(e0y), l1 = fabsf(e1x) + fabsf(e1y), l2 = fabsf(e2x) + fabsf(e2y);
+  const float k2 = 2.0f * ep, kd = k2 + V.d0, kr = 2.384185791015625e-07f;
+  const float g0 = fmaf(k2, fabsf(r0x) + fabsf(r0y), fmaf(kd, l0, kr * (fabsf(p0a) + fabsf(p0b))));
+  const float g1 = fmaf(k2, fabsf(r1x) + fabsf(r1y), fmaf(kd, l1, kr * (fabsf(p1a) + fabsf(p1b))));
+  const float g2 = fmaf(k2, fabsf(r2x) + fabsf(r2y), fmaf(kd, l2, kr * (fabsf(p2a) + fabsf(p2b))));
   const float area2 = (E0 + E1) + E2;
   const float aa = fabsf(area2);
-  if (aa <= 6.0f * G) return SC_MAYBE;  // (nearly) edge-on: orientation not reliable
+  const float G = g0 + g1 + g2;
+  if (aa <= 2.0f * G) return SC_MAYBE;  // (nearly) edge-on: orientation not reliable
   const float s = area2 > 0.f ? 1.0f : -1.0f;
   const float v0 = s * E0, v1 = s * E1, v2 = s * E2;
-  if (v0 < -G || v1 < -G || v2 < -G) return SC_MISS;
-  if (!(v0 > G && v1 > G && v2 > G)) return SC_MAYBE;
+  if (v0 < -g0 || v1 < -g1 || v2 < -g2) return SC_MISS;
+  if (!(v0 > g0 && v1 > g1 && v2 > g2)) return SC_MAYBE;
+  const float Dq = (hix - lox) + (hiy - loy);  // >= the L1 length of the longest edge
   // Inside with margin.  Sure only if the triangle is not grazing -- the exact test rejects
   // |n.d| <= 1e-6 |n.(P1-o)|.  The depth of the plane changes by at most (zmax - zmin) over a
   // 2-D extent of at least the smallest altitude, which is >= area2 / (longest edge) >= area2 / Dq:
   // tan(theta) <= dz Dq / area2, so dz Dq <= 500 area2 keeps cos(theta) > 1e-3 --
   // and its depth range must lie strictly inside the segment.
-  if ((zmax - zmin + 4.0f * V.e_z) * Dq > 500.0f * (aa - 3.0f * G)) return SC_MAYBE;
+  if ((zmax - zmin + 4.0f * V.e_z) * Dq > 500.0f * (aa - G)) return SC_MAYBE;
   if (*zlo <= zo + V.e_z || *zhi >= zo + V.two_r - V.e_z) return SC_MAYBE;
   return SC_SURE;
 }

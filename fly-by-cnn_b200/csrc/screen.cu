@@ -203,13 +203,15 @@ __global__ void __launch_bounds__(TK_THREADS, 2) trace_kernel(const TraceParams 
           }
         }
       }
-      // internal children entered by at least one lane
-      const unsigned d0 = c0 >= 0 ? m0 : 0u;
-      const unsigned d1 = c1 >= 0 ? m1 : 0u;
+      // internal children still wanted by at least one lane (cull distances may have shrunk)
+      const bool w0 = h0 && c0 >= 0 && tn0 <= tcull;
+      const bool w1 = h1 && c1 >= 0 && tn1 <= tcull;
+      const unsigned d0 = __ballot_sync(0xffffffffu, w0);
+      const unsigned d1 = __ballot_sync(0xffffffffu, w1);
       if ((d0 | d1) != 0u) {
         const bool both = d0 != 0u && d1 != 0u;
-        // near child first: majority of the lanes that reach child 1 earlier (or only child 1)
-        const unsigned pref1 = __ballot_sync(0xffffffffu, h1 && (!h0 || tn1 < tn0));
+        // near child first: majority of the lanes that want child 1 earlier (or only child 1)
+        const unsigned pref1 = __ballot_sync(0xffffffffu, w1 && (!w0 || tn1 < tn0));
         const bool swap = both && 2 * __popc(pref1) > __popc(d0 | d1);
         trail = (trail << 1) | (both ? 1ull : 0ull);
         if (both) {
