@@ -491,6 +491,8 @@ int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {
     if (c->mesh.T > 0) { s.ms_sort = el(2, 3); s.ms_tree = el(3, 4); }
   }
   s.ms_render = el(5, 6);
+  s.ms_trace = el(5, 7);
+  s.ms_resolve = el(7, 6);
   unsigned long long h[16] = {0};
   FB_CUDA(c, cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
   if (getenv("FLYBY_DEBUG_STATS") && h[9])

@@ -277,16 +277,51 @@ __global__ void __launch_bounds__(TK_THREADS, 2) trace_kernel(const TraceParams 
 }
 
 // ---------------------------------------------------------------- resolve
-__global__ void __launch_bounds__(256) resolve_kernel(const TraceParams tp, int64_t n_pix) {
+// Rare path, kept out of line so that it does not inflate the registers of resolve_kernel:
+// a ray with more candidates than the list holds (layered / degenerate geometry) is re-traced
+// exactly, on its own, with the stackless per-ray traversal.
+struct ExactHit {
+  double t, w0, w1, w2;
+  int slot, cell;
+};
+static __device__ __noinline__ ExactHit resolve_overflow(const RenderParams& p, int view, double o0, double o1, double o2) {
+  const View& vw = p.views[view];
+  const double o[3] = {o0, o1, o2};
+  const double d[3] = {vw.dir[0], vw.dir[1], vw.dir[2]};
+  GlobalFetch f{p.nodes};
+  NoCount nc;
+  float invf[3] = {vw.invf[0], vw.invf[1], vw.invf[2]};
+  const Hit h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, p.tol2, nc);
+  ExactHit r;
+  r.t = DBL_MAX; r.w0 = r.w1 = r.w2 = 0.0; r.slot = -1; r.cell = 0x7fffffff;
+  if (h.slot >= 0) {
+    const float4 a = p.tv0[h.slot], b = p.tv1[h.slot], e = p.tv2[h.slot];
+    const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+    double x[3], w[3];
+    tri_exact(o, d, P0, P1, P2, DBL_MAX, p.tol2, &r.t, x, w);
+    r.w0 = w[0]; r.w1 = w[1]; r.w2 = w[2];
+    r.slot = h.slot;
+    r.cell = h.cell;
+  }
+  return r;
+}
+
+#define RS_THREADS 128
+
+__global__ void __launch_bounds__(RS_THREADS, 4) resolve_kernel(const TraceParams tp, int64_t n_pix) {
   const RenderParams& p = tp.r;
-  const int64_t pix_id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  unsigned int hit = 0;
-  if (pix_id < n_pix) {
+  unsigned int hits = 0;
+  // persistent grid-stride loop: the warps stay resident instead of being relaunched per 128 pixels
+  for (int64_t pix_id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pix_id < n_pix;
+       pix_id += (int64_t)gridDim.x * blockDim.x) {
     const int4 cd = __ldcs(tp.cand + pix_id);
     float px[4] = {0.f, 0.f, 0.f, 0.f};
     double t = -1.0;
     int cell = -1;
     if (cd.x >= 0 || cd.w == TK_OVERFLOW) {
+      // first candidate's vertices: issue the loads before the double-precision ray setup
+      const int s0 = cd.x >= 0 ? cd.x : 0;
+      float4 a = __ldg(p.tv0 + s0), b = __ldg(p.tv1 + s0), e = __ldg(p.tv2 + s0);
       const int64_t per_view = (int64_t)p.res * p.res;
       const int v = (int)(pix_id / per_view);
       const int pix = (int)(pix_id % per_view);
@@ -297,25 +332,14 @@ __global__ void __launch_bounds__(256) resolve_kernel(const TraceParams tp, int6
       double best_t = DBL_MAX, bw[3] = {0.0, 0.0, 0.0};
       int best_slot = -1, best_cell = 0x7fffffff;
       if (cd.w == TK_OVERFLOW) {
-        // more candidates than the list holds (layered / degenerate geometry): exact per-ray traversal
-        GlobalFetch f{p.nodes};
-        NoCount nc;
-        float invf[3] = {vw.invf[0], vw.invf[1], vw.invf[2]};
-        const Hit h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, p.tol2, nc);
-        if (h.slot >= 0) {
-          const float4 a = p.tv0[h.slot], b = p.tv1[h.slot], e = p.tv2[h.slot];
-          const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-          double x[3];
-          tri_exact(o, d, P0, P1, P2, DBL_MAX, p.tol2, &best_t, x, bw);
-          best_slot = h.slot;
-          best_cell = h.cell;
-        }
+        const ExactHit r = resolve_overflow(p, p.view_begin + v, o[0], o[1], o[2]);
+        best_t = r.t; best_slot = r.slot; best_cell = r.cell;
+        bw[0] = r.w0; bw[1] = r.w1; bw[2] = r.w2;
       } else {
-#pragma unroll
         for (int i = 0; i < TK_CAND; i++) {
           const int slot = i == 0 ? cd.x : (i == 1 ? cd.y : (i == 2 ? cd.z : cd.w));
           if (slot < 0) break;
-          const float4 a = __ldg(p.tv0 + slot), b = __ldg(p.tv1 + slot), e = __ldg(p.tv2 + slot);
+          if (i > 0) { a = __ldg(p.tv0 + slot); b = __ldg(p.tv1 + slot); e = __ldg(p.tv2 + slot); }
           const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
           double tt, x[3], w[3];
           if (tri_exact(o, d, P0, P1, P2, best_t, p.tol2, &tt, x, w)) {
@@ -328,7 +352,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const TraceParams tp, int6
         }
       }
       if (best_slot >= 0) {
-        hit = 1;
+        hits++;
         t = best_t;
         cell = best_cell;
         if (p.feat) {
@@ -342,8 +366,8 @@ __global__ void __launch_bounds__(256) resolve_kernel(const TraceParams tp, int6
     }
     write_pixel(p, pix_id, px, cell, t);
   }
-  const unsigned m = __ballot_sync(0xffffffffu, hit != 0);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(p.counters + 3, (unsigned long long)__popc(m));
+  for (int o2 = 16; o2 > 0; o2 >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o2);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
 }
 
 int screen_render(flyby_ctx* c, const RenderParams& rp) {
@@ -376,7 +400,13 @@ int screen_render(flyby_ctx* c, const RenderParams& rp) {
     default: rc = launch(trace_kernel<true, true>); break;
   }
   if (rc) return rc;
-  resolve_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(tp, n_pix);
+  FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the two kernels (stats describe the last chunk's split)
+  {
+    long long grid = (long long)c->sm_count * 4 * 4;  // 4 CTAs resident per SM, 4 rounds for balance
+    const long long want = cdiv(n_pix, RS_THREADS);
+    if (grid > want) grid = want;
+    resolve_kernel<<<(unsigned)grid, RS_THREADS, 0, st>>>(tp, n_pix);
+  }
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;
 }

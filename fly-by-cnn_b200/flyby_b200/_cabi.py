@@ -36,7 +36,7 @@ class Stats(C.Structure):
     _fields_ = [("ms_normalise", C.c_float), ("ms_normals", C.c_float), ("ms_sort", C.c_float),
                 ("ms_tree", C.c_float), ("ms_render", C.c_float), ("reserved", C.c_int32),
                 ("n_rays", C.c_int64), ("n_hits", C.c_int64), ("nodes_visited", C.c_int64),
-                ("tris_tested", C.c_int64)]
+                ("tris_tested", C.c_int64), ("ms_trace", C.c_float), ("ms_resolve", C.c_float)]
 
 
 # every symbol include/flyby_b200.h declares (tests check the .so exports all of them)

@@ -82,6 +82,7 @@ typedef struct {
   int32_t reserved;
   int64_t n_rays, n_hits;
   int64_t nodes_visited, tris_tested; /* filled only by flyby_render with count_work=1 */
+  float ms_trace, ms_resolve;         /* the two kernels of ms_render: float32 trace, exact resolve */
 } flyby_stats;
 
 /* ---- lifetime ---------------------------------------------------------- */

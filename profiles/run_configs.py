@@ -1,0 +1,81 @@
+"""Measure BASELINE configs 1, 2 and 5 on one B200 (device-resident outputs, CUDA events) and check a
+sample of every config against the oracle.  Writes gpurun_out/configs.json.
+  python profiles/run_configs.py [c1 c2 c5]"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "fly-by-cnn_b200"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from flyby_b200 import _cabi, synth  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+CONFIGS = {
+    "c1": dict(mesh=lambda: synth.bumpy_sphere(71, 0), views=("ico", 2), radius=2.0, res=512, use_z=1, split_z=1),
+    "c2": dict(mesh=lambda: synth.dental_crown(100, 1), views=("spiral", 64, 4), radius=2.0, res=224, use_z=1, split_z=0),
+    "c5": dict(mesh=lambda: synth.bumpy_sphere(316, 5), views=("ico", 4), radius=2.0, res=1024, use_z=1, split_z=1),
+}
+
+
+def run(name, cfg, check_views=2):
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = _cabi.Context(0, stream=stream.cuda_stream)
+    P, F = cfg["mesh"]()
+    tp, tf = torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)
+    if cfg["views"][0] == "ico":
+        n = ctx.views_icosahedron(cfg["views"][1], cfg["radius"])
+    else:
+        n = ctx.views_spiral(cfg["views"][1], cfg["views"][2], cfg["radius"])
+    res = cfg["res"]
+    opts = ctx.render_opts(use_z=cfg["use_z"], split_z=cfg["split_z"])
+    C = ctx.channels(opts)
+    feat = torch.empty((n, res, res, C), dtype=torch.float32, device=dev)
+    ids = torch.empty((n, res, res), dtype=torch.int32, device=dev)
+    times, builds = [], []
+    for it in range(4):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        ctx.set_mesh(tp, tf)
+        ctx.build()
+        e1.record(stream)
+        ctx.render_into(res, opts, feat, ids)
+        e2.record(stream)
+        e2.synchronize()
+        builds.append(e0.elapsed_time(e1))
+        times.append(e1.elapsed_time(e2))
+    st = ctx.stats()
+    out = dict(config=name, triangles=int(len(F)), views=n, resolution=res, channels=C, rays=n * res * res,
+               build_ms=min(builds[1:]), render_ms=min(times[1:]), trace_ms=st["ms_trace"], resolve_ms=st["ms_resolve"],
+               mrays_per_s=n * res * res / (min(times[1:]) * 1e-3) / 1e6, views_per_s=n / (min(times[1:]) * 1e-3),
+               hit_fraction=st["n_hits"] / max(1, st["n_rays"]))
+    # parity on a sample of views against the oracle (brute-force-equivalent bucket grid)
+    uv, nrm, _, _ = ctx.get_mesh()
+    views = ctx.get_views()
+    sel = sorted(set(np.linspace(0, n - 1, check_views).astype(int).tolist()))
+    t0 = time.time()
+    fo, io = orc.render(uv, F, nrm, views[sel], cfg["radius"], res, use_z=cfg["use_z"], split_z=cfg["split_z"],
+                        grid=True, grid_div=64)
+    got_i = ids[sel].cpu().numpy()
+    got_f = feat[sel].cpu().numpy()
+    out["parity"] = dict(views_checked=sel, rays_checked=int(io.size), id_mismatches=int((io != got_i).sum()),
+                         features_bit_equal=bool(np.array_equal(fo, got_f)),
+                         max_rel_err=float(np.max(np.abs(fo - got_f) / np.maximum(np.abs(fo), 1e-30))) if io.size else 0.0,
+                         oracle_seconds=round(time.time() - t0, 2))
+    ctx.close()
+    return out
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "c2", "c5"]
+    results = [run(k, CONFIGS[k]) for k in which]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w") as f:
+        json.dump(results, f, indent=1)
+    for r in results:
+        print(json.dumps(r))

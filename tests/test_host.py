@@ -36,7 +36,7 @@ def test_cabi_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import ctypes as C
-    assert C.sizeof(_cabi.NormOpts) == 56 and C.sizeof(_cabi.RenderOpts) == 48 and C.sizeof(_cabi.Stats) == 56
+    assert C.sizeof(_cabi.NormOpts) == 56 and C.sizeof(_cabi.RenderOpts) == 48 and C.sizeof(_cabi.Stats) == 64
     assert _cabi.RenderOpts.tolerance.offset == 40 and _cabi.NormOpts.skip.offset == 48
 
 
