@@ -121,8 +121,8 @@ void flyby_destroy(flyby_ctx* c) {
   MeshDev& m = c->mesh;
   DevBuf* bufs[] = {&m.raw_verts, &m.tris, &m.verts, &m.normals, &m.face_n, &m.adj_start, &m.adj_cur, &m.adj,
                     &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.leaf_box,
-                    &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid,
-                    &c->view_pts, &c->views, &c->viewsf, &c->cand, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
+                    &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid, &m.trec,
+                    &c->view_pts, &c->views, &c->viewsf, &c->tc_table, &c->cand, &c->cand2, &c->pix_lists, &c->raster_tmp, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
                     &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->counters};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; i++)
@@ -275,7 +275,7 @@ int flyby_generate_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_rende
   int rc = check_render_args(c, vb, ve, res, o, false);
   if (rc) return rc;
   if (!rays_out) return fail(c, FLYBY_ERR_INVALID, "generate_rays: null output");
-  rc = views_setup(c, o);
+  rc = views_setup(c, o, res);
   if (rc) return rc;
   StageOut<double> so;
   rc = so.begin(c, c->stage_out0, rays_out, (size_t)(ve - vb) * res * res * 6);
@@ -296,7 +296,7 @@ int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   const size_t per_view = (size_t)res * res;
   const size_t n_pix = (size_t)(ve - vb) * per_view;
   const int channels = (o->use_z && o->split_z) ? 4 : 3;
-  rc = views_setup(c, o);
+  rc = views_setup(c, o, res);
   if (rc) return rc;
   StageOut<float> sf;
   StageOut<int32_t> si;
@@ -495,6 +495,9 @@ int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {
   s.ms_resolve = el(7, 6);
   unsigned long long h[16] = {0};
   FB_CUDA(c, cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+  if (getenv("FLYBY_DEBUG_STATS"))
+    fprintf(stderr, "[flyby] pixels with 1 candidate %u, with several %u, re-traced exactly (overflow) %llu\n",
+            (unsigned)(h[14] & 0xffffffffu), (unsigned)(h[14] >> 32), h[5]);
   if (getenv("FLYBY_DEBUG_STATS") && h[9])
     fprintf(stderr, "[flyby] packets %llu, lanes/packet %.2f, node visits/packet %.1f, leaf visits/packet %.1f\n", h[9],
             (double)h[10] / h[9], (double)h[8] / h[9], (double)h[11] / h[9]);

@@ -58,6 +58,7 @@ struct MeshDev {
   DevBuf nodes;                           // Node [max(T-1,1)] final layout, top-of-tree first
   DevBuf tv0, tv1, tv2;                   // float4 [T] sorted vertices; tv0.w = cell id bits
   DevBuf tvid;                            // int4 [T] sorted (pid0, pid1, pid2, cell id)
+  DevBuf trec;                            // float4 [T,4] 64-byte record per slot: v0|cell, v1|pid0, v2|pid1, pid2
   int32_t n_nodes = 0;
   int32_t* n_top_dev = nullptr;  // device word: nodes in the breadth-first top block
   double centre_scale[4] = {0, 0, 0, 1};
@@ -79,7 +80,11 @@ struct flyby_ctx {
   fb::DevBuf view_pts;  // float [n,3]
   fb::DevBuf views;     // fb::View [n]
   fb::DevBuf viewsf;    // fb::ViewF [n] float32 screening frames
-  fb::DevBuf cand;      // int4 [n_pix] candidate slots between the trace and the resolve kernel
+  fb::DevBuf tc_table;  // double [res] plane parameters i / (res - 1) of the current resolution
+  fb::DevBuf cand;      // int4 [n_pix] candidate slots between the candidate search and the resolve kernel
+  fb::DevBuf cand2;     // int4 [n_pix] candidate slots 4..7 of the scan-conversion path
+  fb::DevBuf pix_lists; // uint32 [n_pix] pixels with one candidate (front) / several candidates (back)
+  fb::DevBuf raster_tmp;  // uint32 [n_pix] nearest certain depth + int32 [n_pix] candidate counts (raster.cu)
   int n_views = 0;
   double radius = 0;
   // staging for host-side buffers
@@ -142,7 +147,7 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int prep_run(flyby_ctx* c);                       // prep.cu: unit surf + normals
 int lbvh_run(flyby_ctx* c);                       // lbvh.cu: sort + tree + layout
 int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp);  // lbvh.cu
-int views_setup(flyby_ctx* c, const flyby_render_opts* o);                      // trace.cu
+int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res);                      // trace.cu
 int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
                  int32_t* ids, double* tt, bool first_chunk = true, bool last_chunk = true);                                     // trace.cu
 int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double* rays);

@@ -423,11 +423,12 @@ struct ViewF {
   float e_z;                  // bound on the error of a projected depth
   float two_r;                // length of the segment (2 R)
   float d0;                   // absolute in-plane margin on top of the rounding bounds
+  float q0x, q0y, qdx, qdy;   // view-plane position of pixel (i, j): (q0x + i qdx, q0y + j qdy)
   int enabled;                // 0: the view radius is tiny against the mesh, every candidate is SC_MAYBE
 };
 enum { SC_MISS = 0, SC_MAYBE = 1, SC_SURE = 2 };
 
-FB_HD void viewf_setup(const View& v, double radius, float max_abs_coord, ViewF* f) {
+FB_HD void viewf_setup(const View& v, double radius, double spacing, float max_abs_coord, ViewF* f) {
   for (int k = 0; k < 3; k++) {
     f->xf[k] = (float)v.x[k];
     f->yf[k] = (float)v.y[k];
@@ -437,12 +438,29 @@ FB_HD void viewf_setup(const View& v, double radius, float max_abs_coord, ViewF*
   f->rp = (float)rp;
   // a projected coordinate is a 3-term float dot product of |coord| <= max_abs_coord with a
   // unit vector rounded to float: error < 8 * 2^-24 * sqrt(3) * max_abs_coord; 2^-20 leaves 4x headroom
-  f->e_p = 9.5367431640625e-07f * (max_abs_coord + 1.0f);
-  f->e_z = 9.5367431640625e-07f * (max_abs_coord + 1.0f + fabsf((float)rp));
+  // e_q: a ray origin is a float32-rounded plane point (vtkPlaneSource); deriving its view-plane
+  // position from the pixel index instead of the double origin is off by < 2^-22 (|sp| + plane size)
+  double spn = fabs(v.sp[0]) + fabs(v.sp[1]) + fabs(v.sp[2]);
+  double pln = fabs(v.v1[0]) + fabs(v.v1[1]) + fabs(v.v1[2]) + fabs(v.v2[0]) + fabs(v.v2[1]) + fabs(v.v2[2]);
+  float e_q = 2.384185791015625e-07f * (float)((spn + pln) * (fabs(spacing) + 1.0));
+  f->e_p = 9.5367431640625e-07f * (max_abs_coord + 1.0f) + e_q;
+  f->e_z = 9.5367431640625e-07f * (max_abs_coord + 1.0f + fabsf((float)rp)) + e_q;
   f->two_r = (float)(2.0 * radius);
   f->d0 = 4.0f * f->e_p;
+  f->q0x = f->q0y = f->qdx = f->qdy = 0.f;  // set by viewf_pixels once the resolution is known
   // the SC_SURE argument needs |n.d| > 1e-6 |n.(P1-o)| for non-grazing triangles: holds when R is not tiny
   f->enabled = radius >= 0.05 * ((double)max_abs_coord + 1.0) ? 1 : 0;
+}
+
+// pixel (i, j) of a res x res plane -> ideal view-plane position of its ray (see view_setup / view_ray):
+// o = sp + spacing ((i/(res-1) - 1/2) v1 + (j/(res-1) - 1/2) v2), v1 = s x, v2 = s y
+FB_HD void viewf_pixels(const View& v, double spacing, int res, ViewF* f) {
+  double sx = spacing * (v.v1[0] * v.x[0] + v.v1[1] * v.x[1] + v.v1[2] * v.x[2]);
+  double sy = spacing * (v.v2[0] * v.y[0] + v.v2[1] * v.y[1] + v.v2[2] * v.y[2]);
+  f->q0x = (float)(-0.5 * sx);
+  f->q0y = (float)(-0.5 * sy);
+  f->qdx = res > 1 ? (float)(sx / (double)(res - 1)) : 0.f;
+  f->qdy = res > 1 ? (float)(sy / (double)(res - 1)) : 0.f;
 }
 
 // 2-D position and depth of a ray origin in the frame of its view (from the double origin)
@@ -453,41 +471,62 @@ FB_HD void screen_ray(const View& v, const double* o, float* qx, float* qy, floa
   *zo = (float)(-(r[0] * v.n[0] + r[1] * v.n[1] + r[2] * v.n[2]));
 }
 
-FB_HD int screen_tri(const ViewF& V, float qx, float qy, float zo, const float* P0, const float* P1,
-                     const float* P2, float* zlo, float* zhi) {
-  if (!V.enabled) {
-    *zlo = -INFINITY;
-    *zhi = INFINITY;
-    return SC_MAYBE;
-  }
-  // projected vertices: X, Y in the view plane
-  const float ax = fmaf(P0[0], V.xf[0], fmaf(P0[1], V.xf[1], P0[2] * V.xf[2]));
-  const float ay = fmaf(P0[0], V.yf[0], fmaf(P0[1], V.yf[1], P0[2] * V.yf[2]));
-  const float bx = fmaf(P1[0], V.xf[0], fmaf(P1[1], V.xf[1], P1[2] * V.xf[2]));
-  const float by = fmaf(P1[0], V.yf[0], fmaf(P1[1], V.yf[1], P1[2] * V.yf[2]));
-  const float cx = fmaf(P2[0], V.xf[0], fmaf(P2[1], V.xf[1], P2[2] * V.xf[2]));
-  const float cy = fmaf(P2[0], V.yf[0], fmaf(P2[1], V.yf[1], P2[2] * V.yf[2]));
-  const float ep = V.e_p, m0 = 2.0f * ep + V.d0;
-  // bounding box of the projection
-  const float lox = fminf(ax, fminf(bx, cx)), hix = fmaxf(ax, fmaxf(bx, cx));
-  const float loy = fminf(ay, fminf(by, cy)), hiy = fmaxf(ay, fmaxf(by, cy));
-  *zlo = -INFINITY;
-  *zhi = INFINITY;
-  if (qx < lox - m0 || qx > hix + m0 || qy < loy - m0 || qy > hiy + m0) return SC_MISS;
-  // depth (distance below the view plane) interval of the triangle; the segment covers [zo, zo + 2R]
+// Per-triangle part of the screening test: the projection into the view frame and everything
+// that does not depend on the ray.  flags: bit 0 = the depth range overlaps the segment at all,
+// bit 1 = eligible for SC_SURE (not grazing, depth range strictly inside the segment).
+struct TriS {
+  float ax, ay, bx, by, cx, cy;  // projected vertices
+  float lox, hix, loy, hiy;      // bounding box of the projection
+  float zlo, zhi;                // depth interval (distance below the view plane), widened by e_z
+  float area2;                   // twice the signed projected area
+  int flags;
+};
+
+FB_HD void screen_setup(const ViewF& V, float zo, const float* P0, const float* P1, const float* P2, TriS* t) {
+  t->ax = fmaf(P0[0], V.xf[0], fmaf(P0[1], V.xf[1], P0[2] * V.xf[2]));
+  t->ay = fmaf(P0[0], V.yf[0], fmaf(P0[1], V.yf[1], P0[2] * V.yf[2]));
+  t->bx = fmaf(P1[0], V.xf[0], fmaf(P1[1], V.xf[1], P1[2] * V.xf[2]));
+  t->by = fmaf(P1[0], V.yf[0], fmaf(P1[1], V.yf[1], P1[2] * V.yf[2]));
+  t->cx = fmaf(P2[0], V.xf[0], fmaf(P2[1], V.xf[1], P2[2] * V.xf[2]));
+  t->cy = fmaf(P2[0], V.yf[0], fmaf(P2[1], V.yf[1], P2[2] * V.yf[2]));
+  t->lox = fminf(t->ax, fminf(t->bx, t->cx));
+  t->hix = fmaxf(t->ax, fmaxf(t->bx, t->cx));
+  t->loy = fminf(t->ay, fminf(t->by, t->cy));
+  t->hiy = fmaxf(t->ay, fmaxf(t->by, t->cy));
   const float az = V.rp - fmaf(P0[0], V.nf[0], fmaf(P0[1], V.nf[1], P0[2] * V.nf[2]));
   const float bz = V.rp - fmaf(P1[0], V.nf[0], fmaf(P1[1], V.nf[1], P1[2] * V.nf[2]));
   const float cz = V.rp - fmaf(P2[0], V.nf[0], fmaf(P2[1], V.nf[1], P2[2] * V.nf[2]));
   const float zmin = fminf(az, fminf(bz, cz)), zmax = fmaxf(az, fmaxf(bz, cz));
-  *zlo = zmin - V.e_z;
-  *zhi = zmax + V.e_z;
-  if (*zhi < zo - V.e_z || *zlo > zo + V.two_r + V.e_z) return SC_MISS;
+  t->zlo = zmin - V.e_z;
+  t->zhi = zmax + V.e_z;
+  t->area2 = (t->bx - t->ax) * (t->cy - t->ay) - (t->by - t->ay) * (t->cx - t->ax);
+  int flags = 0;
+  // the segment covers depths [zo, zo + 2R]
+  if (!(t->zhi < zo - V.e_z || t->zlo > zo + V.two_r + V.e_z)) flags |= 1;
+  // Sure-eligible only if the triangle is not grazing -- the exact test rejects
+  // |n.d| <= 1e-6 |n.(P1-o)|.  The depth of the plane changes by at most (zmax - zmin) over a
+  // 2-D extent of at least the smallest altitude, which is >= |area2| / (longest edge) >= |area2| / Dq
+  // (Dq = L1 size of the bounding box): tan(theta) <= dz Dq / |area2|, so dz Dq <= 500 |area2| keeps
+  // cos(theta) > 1e-3 -- and only if its depth range lies strictly inside the segment.
+  const float Dq = (t->hix - t->lox) + (t->hiy - t->loy);
+  const float amin = fabsf(t->area2) - 8.0f * V.e_p * Dq;  // |area2| less its own rounding bound
+  if ((zmax - zmin + 4.0f * V.e_z) * Dq <= 500.0f * amin && t->zlo > zo + V.e_z && t->zhi < zo + V.two_r - V.e_z)
+    flags |= 2;
+  t->flags = flags;
+}
+
+// Per-ray part: q = position of the ray in the view plane.
+FB_HD int screen_pixel(const ViewF& V, const TriS& t, float qx, float qy) {
+  if (!(t.flags & 1)) return SC_MISS;
+  const float ep = V.e_p, m0 = 2.0f * ep + V.d0;
+  if (qx < t.lox - m0 || qx > t.hix + m0 || qy < t.loy - m0 || qy > t.hiy + m0) return SC_MISS;
   // edge functions E_k = e_k x r_k, each with a margin that bounds its total float error:
   // moving both edge ends and the query point by ep changes E by at most 2 ep (|r|_1 + |e|_1),
   // the product rounding adds 2^-22 (|ex ry| + |ey rx|), and d0 |e|_1 (>= d0 |e|_2) is the
   // absolute distance margin.
-  const float r0x = qx - ax, r0y = qy - ay, r1x = qx - bx, r1y = qy - by, r2x = qx - cx, r2y = qy - cy;
-  const float e0x = bx - ax, e0y = by - ay, e1x = cx - bx, e1y = cy - by, e2x = ax - cx, e2y = ay - cy;
+  const float r0x = qx - t.ax, r0y = qy - t.ay, r1x = qx - t.bx, r1y = qy - t.by, r2x = qx - t.cx, r2y = qy - t.cy;
+  const float e0x = t.bx - t.ax, e0y = t.by - t.ay, e1x = t.cx - t.bx, e1y = t.cy - t.by;
+  const float e2x = t.ax - t.cx, e2y = t.ay - t.cy;
   const float p0a = e0x * r0y, p0b = e0y * r0x, p1a = e1x * r1y, p1b = e1y * r1x, p2a = e2x * r2y, p2b = e2y * r2x;
   const float E0 = p0a - p0b, E1 = p1a - p1b, E2 = p2a - p2b;
   const float l0 = fabsf(e0x) + fabsf(e0y), l1 = fabsf(e1x) + fabsf(e1y), l2 = fabsf(e2x) + fabsf(e2y);
@@ -496,22 +535,54 @@ FB_HD int screen_tri(const ViewF& V, float qx, float qy, float zo, const float* 
   const float g1 = fmaf(k2, fabsf(r1x) + fabsf(r1y), fmaf(kd, l1, kr * (fabsf(p1a) + fabsf(p1b))));
   const float g2 = fmaf(k2, fabsf(r2x) + fabsf(r2y), fmaf(kd, l2, kr * (fabsf(p2a) + fabsf(p2b))));
   const float area2 = (E0 + E1) + E2;
-  const float aa = fabsf(area2);
   const float G = g0 + g1 + g2;
-  if (aa <= 2.0f * G) return SC_MAYBE;  // (nearly) edge-on: orientation not reliable
+  if (fabsf(area2) <= 2.0f * G) {
+    // (nearly) edge-on: the orientation is not reliable, but every point of the triangle (and of its
+    // d0 neighbourhood) satisfies |E_k| <= |area2| + d0 |e_k| for each edge k -- it lies in the thin
+    // strip between an edge line and the opposite vertex.  Outside that strip is a certain miss.
+    const float lim = fabsf(area2) + G;
+    if (fabsf(E0) > lim + g0 || fabsf(E1) > lim + g1 || fabsf(E2) > lim + g2) return SC_MISS;
+    return SC_MAYBE;
+  }
   const float s = area2 > 0.f ? 1.0f : -1.0f;
   const float v0 = s * E0, v1 = s * E1, v2 = s * E2;
   if (v0 < -g0 || v1 < -g1 || v2 < -g2) return SC_MISS;
   if (!(v0 > g0 && v1 > g1 && v2 > g2)) return SC_MAYBE;
-  const float Dq = (hix - lox) + (hiy - loy);  // >= the L1 length of the longest edge
-  // Inside with margin.  Sure only if the triangle is not grazing -- the exact test rejects
-  // |n.d| <= 1e-6 |n.(P1-o)|.  The depth of the plane changes by at most (zmax - zmin) over a
-  // 2-D extent of at least the smallest altitude, which is >= area2 / (longest edge) >= area2 / Dq:
-  // tan(theta) <= dz Dq / area2, so dz Dq <= 500 area2 keeps cos(theta) > 1e-3 --
-  // and its depth range must lie strictly inside the segment.
-  if ((zmax - zmin + 4.0f * V.e_z) * Dq > 500.0f * (aa - G)) return SC_MAYBE;
-  if (*zlo <= zo + V.e_z || *zhi >= zo + V.two_r - V.e_z) return SC_MAYBE;
-  return SC_SURE;
+  return (t.flags & 2) ? SC_SURE : SC_MAYBE;
+}
+
+struct PixRange {
+  int i0, i1, j0, j1;
+};
+// pixels whose ray can lie within the margins of the triangle's bounding box (a superset is fine:
+// screen_pixel repeats the bounding-box test on the real coordinates)
+FB_HD PixRange pixel_range(const ViewF& V, const TriS& t, int res) {
+  const float m0 = 2.0f * V.e_p + V.d0;
+  const float ix = 1.0f / V.qdx, iy = 1.0f / V.qdy;
+  PixRange r;
+  r.i0 = (int)ceilf((t.lox - m0 - V.q0x) * ix - 0.01f);
+  r.i1 = (int)floorf((t.hix + m0 - V.q0x) * ix + 0.01f);
+  r.j0 = (int)ceilf((t.loy - m0 - V.q0y) * iy - 0.01f);
+  r.j1 = (int)floorf((t.hiy + m0 - V.q0y) * iy + 0.01f);
+  if (r.i0 < 0) r.i0 = 0;
+  if (r.j0 < 0) r.j0 = 0;
+  if (r.i1 > res - 1) r.i1 = res - 1;
+  if (r.j1 > res - 1) r.j1 = res - 1;
+  return r;
+}
+
+FB_HD int screen_tri(const ViewF& V, float qx, float qy, float zo, const float* P0, const float* P1,
+                     const float* P2, float* zlo, float* zhi) {
+  if (!V.enabled) {
+    *zlo = -INFINITY;
+    *zhi = INFINITY;
+    return SC_MAYBE;
+  }
+  TriS t;
+  screen_setup(V, zo, P0, P1, P2, &t);
+  *zlo = t.zlo;
+  *zhi = t.zhi;
+  return screen_pixel(V, t, qx, qy);
 }
 
 // Stackless traversal: a 64-bit trail holds one "far sibling still pending" bit

@@ -184,7 +184,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restri
 __global__ void reorder_kernel(const float* __restrict__ v, const int32_t* __restrict__ tris, int64_t T,
                                const uint32_t* __restrict__ idx, float4* __restrict__ tv0,
                                float4* __restrict__ tv1, float4* __restrict__ tv2,
-                               int4* __restrict__ tvid, float* __restrict__ leaf_box) {
+                               int4* __restrict__ tvid, float4* __restrict__ trec, float* __restrict__ leaf_box) {
   int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (s >= T) return;
   int cell = (int)idx[s];
@@ -202,6 +202,11 @@ __global__ void reorder_kernel(const float* __restrict__ v, const int32_t* __res
   tv1[s] = make_float4(p1[0], p1[1], p1[2], 0.f);
   tv2[s] = make_float4(p2[0], p2[1], p2[2], 0.f);
   tvid[s] = make_int4(i0, i1, i2, cell);
+  // 64-byte record of the same data for the per-pixel kernels (one fetch instead of four)
+  trec[4 * s + 0] = make_float4(p0[0], p0[1], p0[2], __int_as_float(cell));
+  trec[4 * s + 1] = make_float4(p1[0], p1[1], p1[2], __int_as_float(i0));
+  trec[4 * s + 2] = make_float4(p2[0], p2[1], p2[2], __int_as_float(i1));
+  trec[4 * s + 3] = make_float4(__int_as_float(i2), 0.f, 0.f, 0.f);
 }
 
 // knode[i] = (child0, child1, parent, arrival flag); leaf children are ~slot
@@ -394,6 +399,7 @@ int lbvh_run(flyby_ctx* c) {
   FB_CUDA(c, m.tv1.reserve(16 * Tz));
   FB_CUDA(c, m.tv2.reserve(16 * Tz));
   FB_CUDA(c, m.tvid.reserve(16 * Tz));
+  FB_CUDA(c, m.trec.reserve(64 * Tz));
 
   const unsigned gT = (unsigned)cdiv(T, 256);
   morton_kernel<<<gT, 256, 0, st>>>(m.verts.as<float>(), m.tris.as<int32_t>(), T, prep_unit_box(c),
@@ -418,7 +424,7 @@ int lbvh_run(flyby_ctx* c) {
 
   reorder_kernel<<<gT, 256, 0, st>>>(m.verts.as<float>(), m.tris.as<int32_t>(), T, v0,
                                      m.tv0.as<float4>(), m.tv1.as<float4>(), m.tv2.as<float4>(),
-                                     m.tvid.as<int4>(), m.leaf_box.as<float>());
+                                     m.tvid.as<int4>(), m.trec.as<float4>(), m.leaf_box.as<float>());
   FB_LAUNCH_CHECK(c);
   if (T == 1) {
     single_leaf_kernel<<<1, 32, 0, st>>>(m.leaf_box.as<float>(), m.nodes.as<Node>());

@@ -308,67 +308,169 @@ static __device__ __noinline__ ExactHit resolve_overflow(const RenderParams& p, 
 
 #define RS_THREADS 128
 
-__global__ void __launch_bounds__(RS_THREADS, 4) resolve_kernel(const TraceParams tp, int64_t n_pix) {
+// ---- classify: bin the pixels by their number of candidates so that the exact kernels run dense.
+//   0 candidates -> background, written here;  1 -> list1 (front of `lists`);  >= 2 -> list2 (back).
+// cnt == nullptr: candidates come from trace_kernel (empty slots are -1, cand.w == TK_OVERFLOW flags an
+// overflowed list); cnt != nullptr: they come from the scan-conversion passes (cnt[pixel] valid slots,
+// more than 2 * TK_CAND means overflow).
+__global__ void __launch_bounds__(1024) classify_kernel(const TraceParams tp, const int* __restrict__ cnt, int64_t n_pix,
+                                                       uint32_t* __restrict__ lists, unsigned int* __restrict__ n_lists) {
   const RenderParams& p = tp.r;
-  unsigned int hits = 0;
-  // persistent grid-stride loop: the warps stay resident instead of being relaunched per 128 pixels
-  for (int64_t pix_id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pix_id < n_pix;
-       pix_id += (int64_t)gridDim.x * blockDim.x) {
-    const int4 cd = __ldcs(tp.cand + pix_id);
-    float px[4] = {0.f, 0.f, 0.f, 0.f};
-    double t = -1.0;
-    int cell = -1;
-    if (cd.x >= 0 || cd.w == TK_OVERFLOW) {
-      // first candidate's vertices: issue the loads before the double-precision ray setup
-      const int s0 = cd.x >= 0 ? cd.x : 0;
-      float4 a = __ldg(p.tv0 + s0), b = __ldg(p.tv1 + s0), e = __ldg(p.tv2 + s0);
-      const int64_t per_view = (int64_t)p.res * p.res;
-      const int v = (int)(pix_id / per_view);
-      const int pix = (int)(pix_id % per_view);
-      const View& vw = p.views[p.view_begin + v];
-      double o[3];
-      view_ray(vw, p.res, pix % p.res, pix / p.res, p.spacing, o);
-      const double d[3] = {vw.dir[0], vw.dir[1], vw.dir[2]};
-      double best_t = DBL_MAX, bw[3] = {0.0, 0.0, 0.0};
-      int best_slot = -1, best_cell = 0x7fffffff;
-      if (cd.w == TK_OVERFLOW) {
-        const ExactHit r = resolve_overflow(p, p.view_begin + v, o[0], o[1], o[2]);
-        best_t = r.t; best_slot = r.slot; best_cell = r.cell;
-        bw[0] = r.w0; bw[1] = r.w1; bw[2] = r.w2;
-      } else {
-        for (int i = 0; i < TK_CAND; i++) {
-          const int slot = i == 0 ? cd.x : (i == 1 ? cd.y : (i == 2 ? cd.z : cd.w));
-          if (slot < 0) break;
-          if (i > 0) { a = __ldg(p.tv0 + slot); b = __ldg(p.tv1 + slot); e = __ldg(p.tv2 + slot); }
-          const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-          double tt, x[3], w[3];
-          if (tri_exact(o, d, P0, P1, P2, best_t, p.tol2, &tt, x, w)) {
-            const int c = __float_as_int(a.w);
-            if (tt < best_t || (tt == best_t && c < best_cell)) {
-              best_t = tt; best_slot = slot; best_cell = c;
-              bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2];
-            }
-          }
-        }
-      }
-      if (best_slot >= 0) {
-        hits++;
-        t = best_t;
-        cell = best_cell;
-        if (p.feat) {
-          const double x[3] = {FB_ADD(o[0], FB_MUL(t, d[0])), FB_ADD(o[1], FB_MUL(t, d[1])), FB_ADD(o[2], FB_MUL(t, d[2]))};
-          const int4 vid = p.tvid[best_slot];
-          const float4 n0 = __ldg(p.normals + vid.x), n1 = __ldg(p.normals + vid.y), n2 = __ldg(p.normals + vid.z);
-          const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
-          shade(o, x, bw, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px);
-        }
-      }
+  const int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int n = 0;
+  if (pix < n_pix) {
+    if (cnt) {
+      n = __ldcs(cnt + pix);
+    } else {
+      const int4 cd = __ldcs(tp.cand + pix);
+      n = cd.w == TK_OVERFLOW ? 2 * TK_CAND + 1 : (cd.x >= 0) + (cd.y >= 0) + (cd.z >= 0) + (cd.w >= 0);
     }
-    write_pixel(p, pix_id, px, cell, t);
+    if (n == 0) {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      write_pixel(p, pix, zero, -1, -1.0);
+    }
+  }
+  // block-aggregated appends (two atomics per block) keep the lists in raster order inside a block, so the
+  // later writes stay coalesced, and keep the single pair of counters out of the critical path
+  __shared__ unsigned int s_cnt[2][32], s_base[2];
+  const unsigned m1 = __ballot_sync(0xffffffffu, n == 1), m2 = __ballot_sync(0xffffffffu, n >= 2);
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (lane == 0) { s_cnt[0][warp] = __popc(m1); s_cnt[1][warp] = __popc(m2); }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    unsigned int tot = 0;
+    for (int w = 0; w < nwarps; w++) { const unsigned int c = s_cnt[threadIdx.x][w]; s_cnt[threadIdx.x][w] = tot; tot += c; }
+    s_base[threadIdx.x] = tot ? atomicAdd(n_lists + threadIdx.x, tot) : 0u;
+  }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  if (n == 1) lists[s_base[0] + s_cnt[0][warp] + __popc(m1 & lt)] = (uint32_t)pix;
+  if (n >= 2) lists[n_pix - 1 - (s_base[1] + s_cnt[1][warp] + __popc(m2 & lt))] = (uint32_t)pix;
+}
+
+struct PixelRay {
+  double o[3], d[3];
+};
+__device__ __forceinline__ PixelRay pixel_ray(const RenderParams& p, int64_t pix_id) {
+  const int64_t per_view = (int64_t)p.res * p.res;
+  const int v = (int)(pix_id / per_view);
+  const int pix = (int)(pix_id % per_view);
+  const View& vw = p.views[p.view_begin + v];
+  PixelRay r;
+  // view_ray() with the two divisions i / (res - 1) taken from the table (bit-identical values)
+  const double tc0 = p.tc[pix % p.res], tc1 = p.tc[pix / p.res];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float pf = (float)FB_ADD(FB_ADD(vw.origin[k], FB_MUL(tc0, vw.v1[k])), FB_MUL(tc1, vw.v2[k]));
+    r.o[k] = FB_ADD(FB_MUL((double)pf, p.spacing), vw.delta[k]);
+  }
+  r.d[0] = vw.dir[0]; r.d[1] = vw.dir[1]; r.d[2] = vw.dir[2];
+  return r;
+}
+
+__device__ __forceinline__ void shade_and_write(const RenderParams& p, int64_t pix_id, const PixelRay& r, double t,
+                                                const double* w, int pid0, int pid1, int pid2, int cell) {
+  float px[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.feat) {
+    const double x[3] = {FB_ADD(r.o[0], FB_MUL(t, r.d[0])), FB_ADD(r.o[1], FB_MUL(t, r.d[1])), FB_ADD(r.o[2], FB_MUL(t, r.d[2]))};
+    const float4 n0 = __ldg(p.normals + pid0), n1 = __ldg(p.normals + pid1), n2 = __ldg(p.normals + pid2);
+    const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
+    shade(r.o, x, w, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px);
+  }
+  write_pixel(p, pix_id, px, cell, t);
+}
+
+// ---- pixels with exactly one candidate (the common case): straight-line exact test, all lanes busy
+__global__ void __launch_bounds__(RS_THREADS, 4) resolve1_kernel(const TraceParams tp, const uint32_t* __restrict__ list,
+                                                                  const unsigned int* __restrict__ n_list) {
+  const RenderParams& p = tp.r;
+  const unsigned int n = *n_list;
+  unsigned int hits = 0;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int64_t pix_id = list[k];
+    const int slot = __ldcs(reinterpret_cast<const int*>(tp.cand + pix_id));
+    const float4* rec = p.trec + 4 * (int64_t)slot;
+    const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
+    const PixelRay r = pixel_ray(p, pix_id);
+    const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+    double t, x[3], w[3];
+    if (tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w)) {
+      hits++;
+      shade_and_write(p, pix_id, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
+    } else {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      write_pixel(p, pix_id, zero, -1, -1.0);
+    }
   }
   for (int o2 = 16; o2 > 0; o2 >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o2);
   if ((threadIdx.x & 31) == 0 && hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
 }
+
+// ---- pixels with several candidates (near edges, silhouettes, layered geometry) or an overflowed list
+__global__ void __launch_bounds__(RS_THREADS, 4) resolve2_kernel(const TraceParams tp, const int* __restrict__ cnt,
+                                                                  const int4* __restrict__ cand2,
+                                                                  const uint32_t* __restrict__ list_end,
+                                                                  const unsigned int* __restrict__ n_list) {
+  const RenderParams& p = tp.r;
+  const unsigned int n = *n_list;
+  unsigned int hits = 0, n_over = 0;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int64_t pix_id = *(list_end - k);
+    int4 c0 = __ldcs(tp.cand + pix_id), c1 = make_int4(-1, -1, -1, -1);
+    int nc;
+    if (cnt) {
+      nc = __ldcs(cnt + pix_id);
+      if (nc > TK_CAND && nc <= 2 * TK_CAND) c1 = __ldcs(cand2 + pix_id);
+    } else {
+      nc = c0.w == TK_OVERFLOW ? 2 * TK_CAND + 1 : (c0.x >= 0) + (c0.y >= 0) + (c0.z >= 0) + (c0.w >= 0);
+    }
+    const PixelRay r = pixel_ray(p, pix_id);
+    double best_t = DBL_MAX, bw[3] = {0.0, 0.0, 0.0};
+    int best_slot = -1, best_cell = 0x7fffffff, bp0 = 0, bp1 = 0, bp2 = 0;
+    if (nc > 2 * TK_CAND) {
+      n_over++;
+      const int64_t per_view = (int64_t)p.res * p.res;
+      const ExactHit h = resolve_overflow(p, p.view_begin + (int)(pix_id / per_view), r.o[0], r.o[1], r.o[2]);
+      best_t = h.t; best_slot = h.slot; best_cell = h.cell;
+      bw[0] = h.w0; bw[1] = h.w1; bw[2] = h.w2;
+      if (h.slot >= 0) {
+        const int4 vid = p.tvid[h.slot];
+        bp0 = vid.x; bp1 = vid.y; bp2 = vid.z;
+      }
+    } else {
+      for (int i = 0; i < nc; i++) {
+        const int4 cc = i < TK_CAND ? c0 : c1;
+        const int j = i & (TK_CAND - 1);
+        const int slot = j == 0 ? cc.x : (j == 1 ? cc.y : (j == 2 ? cc.z : cc.w));
+        const float4* rec = p.trec + 4 * (int64_t)slot;
+        const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
+        const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+        double tt, x[3], w[3];
+        if (tri_exact(r.o, r.d, P0, P1, P2, best_t, p.tol2, &tt, x, w)) {
+          const int c = __float_as_int(a.w);
+          if (tt < best_t || (tt == best_t && c < best_cell)) {
+            best_t = tt; best_slot = slot; best_cell = c;
+            bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2];
+            bp0 = __float_as_int(b.w); bp1 = __float_as_int(e.w); bp2 = __float_as_int(g.x);
+          }
+        }
+      }
+    }
+    if (best_slot >= 0) {
+      hits++;
+      shade_and_write(p, pix_id, r, best_t, bw, bp0, bp1, bp2, best_cell);
+    } else {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      write_pixel(p, pix_id, zero, -1, -1.0);
+    }
+  }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o2);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
+  if (n_over) atomicAdd(p.counters + 5, (unsigned long long)n_over);  // rays re-traced exactly (rare)
+}
+
+int resolve_launch(flyby_ctx* c, const RenderParams& rp, const int4* cand, const int* cnt, const int4* cand2);
 
 int screen_render(flyby_ctx* c, const RenderParams& rp) {
   cudaStream_t st = c->stream;
@@ -401,12 +503,27 @@ int screen_render(flyby_ctx* c, const RenderParams& rp) {
   }
   if (rc) return rc;
   FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the two kernels (stats describe the last chunk's split)
-  {
-    long long grid = (long long)c->sm_count * 4 * 4;  // 4 CTAs resident per SM, 4 rounds for balance
-    const long long want = cdiv(n_pix, RS_THREADS);
-    if (grid > want) grid = want;
-    resolve_kernel<<<(unsigned)grid, RS_THREADS, 0, st>>>(tp, n_pix);
-  }
+  return resolve_launch(c, rp, c->cand.as<int4>(), nullptr, nullptr);
+}
+
+int resolve_launch(flyby_ctx* c, const RenderParams& rp, const int4* cand, const int* cnt, const int4* cand2) {
+  const int64_t n_pix = (int64_t)rp.n_views * rp.res * rp.res;
+  cudaStream_t st = c->stream;
+  TraceParams tp;
+  tp.r = rp;
+  tp.cand = const_cast<int4*>(cand);
+  FB_CUDA(c, c->pix_lists.reserve(4 * (size_t)n_pix + 16));
+  uint32_t* lists = c->pix_lists.as<uint32_t>();
+  unsigned int* n_lists = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 14);
+  FB_CUDA(c, cudaMemsetAsync(n_lists, 0, 8, st));
+  classify_kernel<<<(unsigned)cdiv(n_pix, 1024), 1024, 0, st>>>(tp, cnt, n_pix, lists, n_lists);
+  FB_LAUNCH_CHECK(c);
+  long long grid = (long long)c->sm_count * 4 * 4;  // 4 CTAs resident per SM, 4 rounds for balance
+  const long long want = cdiv(n_pix, RS_THREADS);
+  if (grid > want) grid = want;
+  resolve1_kernel<<<(unsigned)grid, RS_THREADS, 0, st>>>(tp, lists, n_lists);
+  FB_LAUNCH_CHECK(c);
+  resolve2_kernel<<<(unsigned)grid, RS_THREADS, 0, st>>>(tp, cnt, cand2, lists + n_pix - 1, n_lists + 1);
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;
 }

@@ -22,7 +22,7 @@ namespace fb {
 
 // ---------------------------------------------------------------- view setup
 __global__ void view_setup_kernel(const float* __restrict__ pts, int n, double radius, double plane_scale,
-                                  double spacing, const float* __restrict__ ubox, View* __restrict__ views,
+                                  double spacing, int res, const float* __restrict__ ubox, View* __restrict__ views,
                                   ViewF* __restrict__ viewsf) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -34,17 +34,26 @@ __global__ void view_setup_kernel(const float* __restrict__ pts, int n, double r
   float max_abs_coord = 0.f;
   for (int k = 0; k < 6; k++) max_abs_coord = fmaxf(max_abs_coord, fabsf(ubox[k]));
   ViewF f;
-  viewf_setup(v, radius, max_abs_coord, &f);
+  viewf_setup(v, radius, spacing, max_abs_coord, &f);
+  viewf_pixels(v, spacing, res, &f);
   viewsf[i] = f;
 }
 
-int views_setup(flyby_ctx* c, const flyby_render_opts* o) {
+__global__ void tc_table_kernel(int res, double* __restrict__ tc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < res) tc[i] = (res > 1) ? FB_DIV((double)i, (double)(res - 1)) : 0.0;  // same expression as view_ray
+}
+
+int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res) {
   if (c->n_views <= 0) return fail(c, FLYBY_ERR_INVALID, "no viewpoints set");
   FB_CUDA(c, c->views.reserve(sizeof(View) * (size_t)c->n_views));
   FB_CUDA(c, c->viewsf.reserve(sizeof(ViewF) * (size_t)c->n_views));
   view_setup_kernel<<<(unsigned)cdiv(c->n_views, 64), 64, 0, c->stream>>>(
-      c->view_pts.as<float>(), c->n_views, c->radius, o->plane_scale, o->plane_spacing, prep_unit_box(c),
+      c->view_pts.as<float>(), c->n_views, c->radius, o->plane_scale, o->plane_spacing, res, prep_unit_box(c),
       c->views.as<View>(), c->viewsf.as<ViewF>());
+  FB_LAUNCH_CHECK(c);
+  FB_CUDA(c, c->tc_table.reserve(sizeof(double) * (size_t)res));
+  tc_table_kernel<<<(unsigned)cdiv(res, 256), 256, 0, c->stream>>>(res, c->tc_table.as<double>());
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;
 }
@@ -320,7 +329,9 @@ __global__ void fill_miss_kernel(float* feat, int32_t* ids, double* tt, int64_t 
 }
 
 static int g_screen = 1;  // FLYBY_NO_SCREEN=1: fused kernel, exact test on every leaf candidate (A/B, parity checks)
-int screen_render(flyby_ctx* c, const RenderParams& p);
+int screen_render(flyby_ctx* c, const RenderParams& p);  // screen.cu: LBVH trace kernel + exact resolve kernel
+int raster_render(flyby_ctx* c, const RenderParams& p);  // raster.cu: scan-conversion passes + exact resolve kernel
+static int g_mode = 2;  // FLYBY_MODE: 2 raster (default), 1 bvh (trace + resolve), 0 fused exact LBVH kernel
 static int g_use_top = 1;  // FLYBY_NO_SMEM_TOP=1 disables the shared-memory top (A/B measurements)
 
 // first_chunk / last_chunk: a render call may be split into view chunks (api.cu overlaps the
@@ -352,6 +363,10 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
     if (e && e[0] == '1') g_use_top = 0;
     e = getenv("FLYBY_NO_SCREEN");
     if (e && e[0] == '1') g_screen = 0;
+    e = getenv("FLYBY_MODE");
+    if (e && !strcmp(e, "bvh")) g_mode = 1;
+    if (e && !strcmp(e, "fused")) g_mode = 0;
+    if (!g_screen) g_mode = 0;
     env_read = true;
   }
   RenderParams p;
@@ -359,6 +374,8 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   p.n_top_dev = m.n_top_dev;
   p.tv0 = m.tv0.as<float4>(); p.tv1 = m.tv1.as<float4>(); p.tv2 = m.tv2.as<float4>();
   p.tvid = m.tvid.as<int4>();
+  p.trec = m.trec.as<float4>();
+  p.tc = c->tc_table.as<double>();
   p.normals = m.normals.as<float4>();
   p.views = c->views.as<View>();
   p.ubox = prep_unit_box(c);
@@ -390,8 +407,12 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
     return FLYBY_OK;
   };
   int rc;
-  if (g_screen) {
-    rc = screen_render(c, p);  // screen.cu: float32 trace kernel + exact resolve kernel
+  // the scan conversion needs a regular pixel grid with a positive pitch
+  const bool grid_ok = res > 1 && o->plane_scale * o->plane_spacing > 0.0;
+  if (g_mode == 2 && grid_ok) {
+    rc = raster_render(c, p);
+  } else if (g_mode >= 1) {
+    rc = screen_render(c, p);
   } else {
     const int variant = (g_use_top ? 2 : 0) | (c->count_work ? 1 : 0);
     switch (variant) {

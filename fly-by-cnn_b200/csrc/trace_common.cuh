@@ -67,6 +67,8 @@ struct RenderParams {
   const int32_t* n_top_dev;
   const float4 *tv0, *tv1, *tv2;
   const int4* tvid;
+  const float4* trec;   // 64-byte triangle records (resolve kernels)
+  const double* tc;     // [res] i / (res - 1), exactly as view_ray computes it
   const float4* normals;
   const View* views;
   const float* ubox;

@@ -454,7 +454,8 @@ int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris,
     View vw;
     view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
     ViewF vf;
-    viewf_setup(vw, radius, maxc, &vf);
+    viewf_setup(vw, radius, spacing, maxc, &vf);
+    viewf_pixels(vw, spacing, res, &vf);
     for (int ty = 0; ty < (res + 3) / 4; ty++)
       for (int tx = 0; tx < (res + 7) / 8; tx++) {
         double o[32][3]; int pix[32]; int n = 0;
@@ -471,5 +472,77 @@ int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris,
       }
   }
   if (work) { work[0] = cnt.nodes; work[1] = cnt.tris; work[2] = b.max_depth; work[3] = cls[0]; work[4] = cls[1]; work[5] = cls[2]; }
+  return 0;
+}
+
+// ---- emulation of the scan-conversion path (raster.cu + resolve_kernel): pass A nearest certain depth,
+// pass B candidate collection, then the exact decision per pixel (overflow -> exact per-ray traversal).
+extern "C" __attribute__((visibility("default")))
+int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* views,
+                      int n_views, double radius, int res, double plane_scale, double spacing, int cand_cap,
+                      int32_t* out_ids, double* out_t, long long* work /* pixel tests, exact tests, overflow pixels */) {
+  SimBvh b;
+  build(verts, V, tris, T, b);
+  if (b.nodes.empty()) return 1;
+  float maxc = 0.f;
+  for (int64_t i = 0; i < 3 * V; i++) maxc = fmaxf(maxc, fabsf(verts[i]));
+  long long n_tests = 0, n_exact = 0, n_over = 0;
+  SimCount cnt;
+  SimFetch f{b.nodes.data()};
+  for (int v = 0; v < n_views; v++) {
+    View vw;
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    ViewF vf;
+    viewf_setup(vw, radius, spacing, maxc, &vf);
+    viewf_pixels(vw, spacing, res, &vf);
+    std::vector<float> uz((size_t)res * res, INFINITY);
+    std::vector<std::vector<int>> cand((size_t)res * res);
+    for (int pass = 0; pass < 2; pass++)
+      for (int64_t slot = 0; slot < T; slot++) {
+        float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
+        float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
+        TriS t;
+        screen_setup(vf, 0.0f, P0, P1, P2, &t);
+        if (!(t.flags & 1)) continue;
+        PixRange r = pixel_range(vf, t, res);
+        for (int j = r.j0; j <= r.j1; j++)
+          for (int i = r.i0; i <= r.i1; i++) {
+            float qx = fmaf((float)i, vf.qdx, vf.q0x), qy = fmaf((float)j, vf.qdy, vf.q0y);
+            int cls = screen_pixel(vf, t, qx, qy);
+            n_tests++;
+            if (cls == SC_MISS) continue;
+            size_t pix = (size_t)j * res + i;
+            if (pass == 0) { if (cls == SC_SURE && t.zhi < uz[pix]) uz[pix] = t.zhi; }
+            else if (t.zlo <= uz[pix]) cand[pix].push_back((int)slot);
+          }
+      }
+    for (int j = 0; j < res; j++)
+      for (int i = 0; i < res; i++) {
+        size_t pix = (size_t)j * res + i;
+        double o[3];
+        view_ray(vw, res, i, j, spacing, o);
+        Hit h; h.t = DBL_MAX; h.slot = -1; h.cell = 0x7fffffff;
+        if ((int)cand[pix].size() > cand_cap) {
+          n_over++;
+          h = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o, vw.dir, vw.dirf, vw.invf, vw.slack, vw.tslack,
+                       1e-20, cnt);
+        } else {
+          for (int slot : cand[pix]) {
+            float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
+            float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
+            int cell; memcpy(&cell, &a.w, 4);
+            double t, x[3], w[3];
+            n_exact++;
+            if (tri_exact(o, vw.dir, P0, P1, P2, h.t, 1e-20, &t, x, w) && (t < h.t || (t == h.t && cell < h.cell))) {
+              h.t = t; h.slot = slot; h.cell = cell;
+            }
+          }
+          if (h.slot < 0) h.cell = -1;
+        }
+        size_t id = (size_t)v * res * res + pix;
+        out_ids[id] = h.cell; out_t[id] = h.slot >= 0 ? h.t : -1.0;
+      }
+  }
+  if (work) { work[0] = n_tests; work[1] = n_exact; work[2] = n_over; }
   return 0;
 }
