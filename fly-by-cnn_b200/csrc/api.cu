@@ -496,8 +496,8 @@ int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {
   unsigned long long h[16] = {0};
   FB_CUDA(c, cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
   if (getenv("FLYBY_DEBUG_STATS"))
-    fprintf(stderr, "[flyby] pixels with 1 candidate %u, with several %u, re-traced exactly (overflow) %llu\n",
-            (unsigned)(h[14] & 0xffffffffu), (unsigned)(h[14] >> 32), h[5]);
+    fprintf(stderr, "[flyby] pixel lists: first %u (bvh mode: 1 candidate; raster mode: several), second %u (bvh: several; raster: overflow), re-traced exactly %llu; raster spill: %u pairs, %llu pixels\n",
+            (unsigned)(h[14] & 0xffffffffu), (unsigned)(h[14] >> 32), h[5], (unsigned)(h[13] & 0xffffffffu), h[4]);
   if (getenv("FLYBY_DEBUG_STATS") && h[9])
     fprintf(stderr, "[flyby] packets %llu, lanes/packet %.2f, node visits/packet %.1f, leaf visits/packet %.1f\n", h[9],
             (double)h[10] / h[9], (double)h[8] / h[9], (double)h[11] / h[9]);

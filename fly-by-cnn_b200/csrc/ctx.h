@@ -83,8 +83,9 @@ struct flyby_ctx {
   fb::DevBuf tc_table;  // double [res] plane parameters i / (res - 1) of the current resolution
   fb::DevBuf cand;      // int4 [n_pix] candidate slots between the candidate search and the resolve kernel
   fb::DevBuf cand2;     // int4 [n_pix] candidate slots 4..7 of the scan-conversion path
-  fb::DevBuf pix_lists; // uint32 [n_pix] pixels with one candidate (front) / several candidates (back)
-  fb::DevBuf raster_tmp;  // uint32 [n_pix] nearest certain depth + int32 [n_pix] candidate counts (raster.cu)
+  fb::DevBuf pix_lists; // uint32 pixel queues between the resolve kernels
+  fb::DevBuf raster_tmp;  // uint64 [n_pix] front (depth bound, slot) + int32 [n_pix] extra counts + hi-z tiles (raster.cu)
+  fb::DevBuf raster_ovf;  // spill list of (pixel, slot) pairs beyond 8 extras + per-overflow-pixel records (raster.cu)
   int n_views = 0;
   double radius = 0;
   // staging for host-side buffers

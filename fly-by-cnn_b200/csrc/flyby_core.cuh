@@ -594,7 +594,9 @@ template <class NodeFetch, class Counter>
 FB_HD Hit traverse(const NodeFetch& fetch, const float4* __restrict__ tv0,
                    const float4* __restrict__ tv1, const float4* __restrict__ tv2, const double* o,
                    const double* d, const float* dirf, const float* invf, float slack, float tslack,
-                   double tol2, Counter& cnt) {
+                   double tol2, Counter& cnt, const ViewF* vf = nullptr, float sqx = 0.f, float sqy = 0.f,
+                   float szo = 0.f) {
+  // vf != nullptr: the float32 screening test runs first and the exact test is skipped on a certain miss
   (void)dirf;
   Hit best;
   best.t = DBL_MAX;
@@ -621,6 +623,10 @@ FB_HD Hit traverse(const NodeFetch& fetch, const float4* __restrict__ tv0,
           float4 a = tv0[slot], b = tv1[slot], e = tv2[slot];
           cnt.tri();
           float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+          if (vf) {
+            float zl, zh;
+            if (screen_tri(*vf, sqx, sqy, szo, P0, P1, P2, &zl, &zh) == SC_MISS) continue;
+          }
           double t, x[3], w[3];
           if (tri_exact(o, d, P0, P1, P2, best.t, tol2, &t, x, w)) {
 #if defined(__CUDA_ARCH__)

@@ -1,39 +1,57 @@
-// raster.cu -- triangle-centric candidate search for the fly-by views (default render path).
+// raster.cu -- the default render path: triangle-centric candidate search + exact resolve.
 //
 // The rays of a view are parallel and sit on a regular pixel grid, and a triangle of a
 // 100k-2M triangle surface covers only a few pixels.  Instead of walking the LBVH once per
 // ray packet, every triangle is projected into the view frame once and tested -- with the
-// same float32 screening predicate the trace kernel uses (flyby_core.cuh) -- against the
+// float32 screening predicate of flyby_core.cuh, which never decides a result -- against the
 // handful of pixels inside its bounding box:
-//   pass A  uz[pixel]  = min over SURE triangles of their far depth bound   (atomicMin)
-//   pass B  cand[pixel] += every triangle that is not a certain miss and whose near depth
-//           bound is not behind uz[pixel]                                   (atomicAdd slot)
-// resolve_kernel (screen.cu) then decides every pixel exactly, in double precision, from its
-// 1-2 candidates; a pixel with more than 8 candidates is re-traced exactly through the LBVH.
-// The candidate set is a superset of what the exact test can accept in front of the nearest
-// certain hit, so the result equals the LBVH traversal and the oracle bit for bit; the order
-// in which atomics land does not matter (the exact tie-break is (t, cell id)).
-//
-// Work: T x views threads, ~45 float instructions per covered pixel; bytes: 48 B per triangle
-// per view (L2 resident), 4-8 B of L2 atomics per covered pixel.
+//   pass A    front[pixel] = min over SURE triangles of (far depth bound, slot)   one 64-bit atomicMin
+//   hi-z      tile_z[8x8 tile] = max over its pixels of the front depth bound
+//   pass B    triangles behind tile_z of every tile they touch are dropped whole; for the others,
+//             every pixel that is not a certain miss, whose near depth bound is not behind
+//             front[pixel] and which is not the front triangle itself is appended to extra[pixel]
+//   resolve1  one thread per pixel in raster order: background / the exact test on the front
+//             triangle when it is the only candidate (the common case) / queue the pixel
+//   resolve2  queued pixels: exact test on the front triangle and the extras, tie-break (t, cell id)
+//   resolve3  pixels whose extras overflowed (edge-on piles at silhouettes): exact LBVH re-trace
+// The candidate set is a superset of what the exact test can accept at or in front of the
+// nearest certain hit, so the result equals the LBVH traversal and the oracle bit for bit; the
+// order in which atomics land does not matter.
 //
 // Reference replaced: the per-view / per-plane-point loops of
-// src/app/fly_by_features.cxx:652-852 (this is the search part of IntersectWithLine).
+// src/app/fly_by_features.cxx:652-852 (search = IntersectWithLine :750-758, shading :766-807)
+// and the channel assembly of src/py/fly_by_features.py:124-150.
 #include "trace_common.cuh"
 
 namespace fb {
 
 #define RT_THREADS 256
-#define RT_BIG 48  // bounding boxes with more pixels than this are rasterised by a whole warp
+#define RT_BIG 48     // bounding boxes with more pixels than this are rasterised by a whole warp
+#define RT_EXTRA 8    // extra candidates kept per pixel (two int4)
+#define RT_TILE 8     // hi-z tile edge, pixels
+#define RV_THREADS 128
 
 struct RasterParams {
   RenderParams r;
-  unsigned int* uz;  // [n_pix] ordered-float bits of the nearest certain far depth
-  int* cnt;          // [n_pix] candidates found
-  int* cand;         // [n_pix, 4] candidate slots 0..3
-  int* cand2;        // [n_pix, 4] candidate slots 4..7 (touched only by pixels that need them)
-  int T;
+  unsigned long long* front;  // [n_pix] (ordered-float far depth bound << 32) | slot of the nearest SURE triangle
+  int* cnt;                   // [n_pix] extra candidates found
+  int* extra;                 // [n_pix, 4] extra slots 0..3
+  int* extra2;                // [n_pix, 4] extra slots 4..7 (touched only by pixels that need them)
+  unsigned int* tile_z;       // [n_views, tiles, tiles] hi-z
+  uint32_t* queue;            // [2, n_pix] pixels for resolve2, pixels for resolve3
+  unsigned int* n_queue;      // [2]
+  // spill: candidates beyond RT_EXTRA of a pixel (edge-on piles at silhouettes) go to one global pair list
+  uint2* pairs;               // [pair_cap] (pixel, slot)
+  double* pair_t;             // [pair_cap] exact t of the pair, < 0 = no hit
+  unsigned int* n_spill;      // [0] pairs appended, [1] overflow pixels numbered
+  uint32_t* ov_pix;           // [pair_cap] pixel of overflow record k
+  unsigned long long *ov_prov_t, *ov_prov_cs;  // [pair_cap] best of the front + stored extras: t bits, (cell << 32) | slot
+  unsigned long long *ov_best_t, *ov_best_cs;  // [pair_cap] running minimum over everything / over the spilled pairs
+  unsigned int pair_cap;
+  int64_t n_pix;
+  int T, tiles;
 };
+#define RT_LOST 0x40000000  // cnt flag: a spilled pair found the list full, the pixel is re-traced through the LBVH
 
 __device__ __forceinline__ unsigned int ford(float f) {
   unsigned int u = __float_as_uint(f);
@@ -48,12 +66,18 @@ __device__ __forceinline__ void visit_pixel(const RasterParams& p, const ViewF& 
   if (cls == SC_MISS) return;
   const int64_t pix = view_base + (int64_t)j * res + i;
   if (PASS == 0) {
-    if (cls == SC_SURE) atomicMin(p.uz + pix, ford(t.zhi));
+    if (cls == SC_SURE) atomicMin(p.front + pix, ((unsigned long long)ford(t.zhi) << 32) | (unsigned int)slot);
   } else {
-    if (ford(t.zlo) <= __ldcg(p.uz + pix)) {
-      const int k = atomicAdd(p.cnt + pix, 1);
-      if (k < 4) p.cand[pix * 4 + k] = slot;
-      else if (k < 8) p.cand2[pix * 4 + (k - 4)] = slot;
+    const unsigned long long f = __ldg(p.front + pix);  // read-only in this pass
+    if (ford(t.zlo) <= (unsigned int)(f >> 32) && (unsigned int)f != (unsigned int)slot) {
+      const int k = atomicAdd(p.cnt + pix, 1) & (RT_LOST - 1);
+      if (k < 4) p.extra[pix * 4 + k] = slot;
+      else if (k < RT_EXTRA) p.extra2[pix * 4 + (k - 4)] = slot;
+      else {
+        const unsigned int i = atomicAdd(p.n_spill, 1u);
+        if (i < p.pair_cap) p.pairs[i] = make_uint2((unsigned int)pix, (unsigned int)slot);
+        else atomicOr(p.cnt + pix, RT_LOST);
+      }
     }
   }
 }
@@ -85,6 +109,17 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(const RasterParams p
       r = pixel_range(V, t, res);
       if (r.i1 >= r.i0 && r.j1 >= r.j0) npx = (r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
     }
+    if (PASS == 1 && npx > 0) {
+      // hi-z: behind the nearest certain hit of every pixel of every tile it touches -> cannot be a candidate
+      const int tx0 = r.i0 / RT_TILE, tx1 = r.i1 / RT_TILE, ty0 = r.j0 / RT_TILE, ty1 = r.j1 / RT_TILE;
+      if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 9) {
+        const unsigned int* tz = p.tile_z + (int64_t)view * p.tiles * p.tiles;
+        unsigned int zmax = 0u;
+        for (int ty = ty0; ty <= ty1; ty++)
+          for (int tx = tx0; tx <= tx1; tx++) zmax = max(zmax, __ldg(tz + ty * p.tiles + tx));
+        if (ford(t.zlo) > zmax) npx = 0;
+      }
+    }
   }
   // small triangles: one thread walks the pixels of its bounding box
   if (npx > 0 && npx <= RT_BIG) {
@@ -115,38 +150,301 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(const RasterParams p
   }
 }
 
-__global__ void raster_init_kernel(unsigned int* uz, int* cnt, int64_t n) {
+// ---- hi-z: one thread per pixel row of a tile (64 contiguous bytes), 8 lanes per tile
+__global__ void __launch_bounds__(256) hiz_kernel(const RasterParams p) {
+  const int res = p.r.res;
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t tile = gid / RT_TILE;
+  const int row = (int)(gid % RT_TILE);
+  const int64_t per_view = (int64_t)p.tiles * p.tiles;
+  unsigned int z = 0u;
+  const bool valid = tile < per_view * p.r.n_views;
+  if (valid) {
+    const int view = (int)(tile / per_view), tl = (int)(tile % per_view);
+    const int ty = tl / p.tiles, tx = tl % p.tiles;
+    const int j = ty * RT_TILE + row;
+    if (j < res) {
+      const unsigned long long* src = p.front + (int64_t)view * res * res + (int64_t)j * res + tx * RT_TILE;
+      const int n = min(RT_TILE, res - tx * RT_TILE);
+      for (int i = 0; i < n; i++) z = max(z, (unsigned int)(__ldcg(src + i) >> 32));
+    }
+  }
+  z = max(z, __shfl_xor_sync(0xffffffffu, z, 1));
+  z = max(z, __shfl_xor_sync(0xffffffffu, z, 2));
+  z = max(z, __shfl_xor_sync(0xffffffffu, z, 4));
+  if (valid && row == 0) p.tile_z[tile] = z;
+}
+
+__global__ void raster_init_kernel(unsigned long long* front, int* cnt, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) {
-    uz[i] = 0xffffffffu;
+    front[i] = ~0ull;
     cnt[i] = 0;
   }
 }
 
-int resolve_launch(flyby_ctx* c, const RenderParams& rp, const int4* cand, const int* cnt, const int4* cand2);  // screen.cu
+// ---- resolve1: every pixel, raster order
+__global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve1_kernel(const RasterParams rp) {
+  const RenderParams& p = rp.r;
+  const int lane = threadIdx.x & 31;
+  unsigned int hits = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // the loop bound is rounded up to whole warps so that the vote below sees all 32 lanes
+  const int64_t n_round = (rp.n_pix + 31) & ~(int64_t)31;
+  for (int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pix < n_round; pix += stride) {
+    const bool valid = pix < rp.n_pix;
+    unsigned long long f = ~0ull;
+    int nc = 0;
+    if (valid) {
+      f = __ldcs(rp.front + pix);
+      nc = __ldcs(rp.cnt + pix);
+    }
+    const unsigned mq = __ballot_sync(0xffffffffu, nc > 0);
+    if (mq) {  // queue the pixels that have more than the front candidate (one atomic per warp)
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(rp.n_queue, (unsigned int)__popc(mq));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (nc > 0) rp.queue[base + __popc(mq & ((1u << lane) - 1u))] = (uint32_t)pix;
+    }
+    if (!valid || nc > 0) continue;
+    if (f == ~0ull) {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      write_pixel(p, pix, zero, -1, -1.0);
+      continue;
+    }
+    const int slot = (int)(unsigned int)f;
+    const float4* rec = p.trec + 4 * (int64_t)slot;
+    const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
+    const PixelRay r = pixel_ray(p, pix);
+    const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+    double t, x[3], w[3];
+    if (tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w)) {
+      hits++;
+      shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
+    } else {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      write_pixel(p, pix, zero, -1, -1.0);
+    }
+  }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o2);
+  if (lane == 0 && hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
+}
+
+// ---- resolve2: queued pixels (near edges, silhouettes, layered geometry)
+__global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve2_kernel(const RasterParams rp) {
+  const RenderParams& p = rp.r;
+  const unsigned int n = *rp.n_queue;
+  unsigned int hits = 0;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int64_t pix = rp.queue[k];
+    const int nc_all = __ldcs(rp.cnt + pix);
+    if (nc_all & RT_LOST) {  // part of its candidates were lost: resolve3 re-traces it
+      rp.queue[rp.n_pix + atomicAdd(rp.n_queue + 1, 1u)] = (uint32_t)pix;
+      continue;
+    }
+    const int nc = min(nc_all, RT_EXTRA);
+    const unsigned long long f = __ldcs(rp.front + pix);
+    const int4 c0 = __ldcs(reinterpret_cast<const int4*>(rp.extra) + pix);
+    int4 c1 = make_int4(-1, -1, -1, -1);
+    if (nc > 4) c1 = __ldcs(reinterpret_cast<const int4*>(rp.extra2) + pix);
+    const PixelRay r = pixel_ray(p, pix);
+    double best_t = DBL_MAX, bw[3] = {0.0, 0.0, 0.0};
+    int best_slot = -1, best_cell = 0x7fffffff, bp0 = 0, bp1 = 0, bp2 = 0;
+    for (int i = (f == ~0ull ? 0 : -1); i < nc; i++) {
+      const int4 cc = i < 4 ? c0 : c1;
+      const int j = i & 3;
+      const int slot = i < 0 ? (int)(unsigned int)f : (j == 0 ? cc.x : (j == 1 ? cc.y : (j == 2 ? cc.z : cc.w)));
+      const float4* rec = p.trec + 4 * (int64_t)slot;
+      const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
+      const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+      double tt, x[3], w[3];
+      if (tri_exact(r.o, r.d, P0, P1, P2, best_t, p.tol2, &tt, x, w)) {
+        const int c = __float_as_int(a.w);
+        if (tt < best_t || (tt == best_t && c < best_cell)) {
+          best_t = tt; best_slot = slot; best_cell = c;
+          bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2];
+          bp0 = __float_as_int(b.w); bp1 = __float_as_int(e.w); bp2 = __float_as_int(g.x);
+        }
+      }
+    }
+    if (nc_all > RT_EXTRA) {
+      // more candidates wait in the pair list: park the best so far in overflow record k, the spill kernels finish it
+      const unsigned int k2 = atomicAdd(rp.n_spill + 1, 1u);
+      const unsigned long long tb = (unsigned long long)__double_as_longlong(best_t + 0.0);
+      rp.ov_pix[k2] = (uint32_t)pix;
+      rp.ov_prov_t[k2] = tb;
+      rp.ov_prov_cs[k2] = best_slot >= 0 ? (((unsigned long long)(unsigned int)best_cell << 32) | (unsigned int)best_slot) : ~0ull;
+      rp.ov_best_t[k2] = tb;
+      rp.ov_best_cs[k2] = ~0ull;
+      rp.cnt[pix] = -(int)(k2 + 1);
+      continue;
+    }
+    if (best_slot >= 0) {
+      hits++;
+      shade_and_write(p, pix, r, best_t, bw, bp0, bp1, bp2, best_cell);
+    } else {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      write_pixel(p, pix, zero, -1, -1.0);
+    }
+  }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o2);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
+}
+
+// ---- spill kernels: one thread per spilled (pixel, slot) pair.  The nearest hit of an overflow pixel is the
+// lexicographic minimum of (t, cell id) over its parked best and its pairs: pass 1 takes the minimum of t
+// (the bits of a non-negative double order like the value), pass 2 the minimum cell id among the pairs that
+// reach it, pass 3 shades.  Every step is a minimum, so the order of the atomics does not matter.
+__global__ void __launch_bounds__(RV_THREADS) spill_t_kernel(const RasterParams rp) {
+  const RenderParams& p = rp.r;
+  const unsigned int n = min(rp.n_spill[0], rp.pair_cap);
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint2 pr = rp.pairs[i];
+    const int k = -rp.cnt[pr.x] - 1;
+    double tt = -1.0;
+    if (k >= 0) {  // (k < 0: the pixel lost pairs and is re-traced)
+      const float4* rec = p.trec + 4 * (int64_t)pr.y;
+      const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2);
+      const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+      const PixelRay r = pixel_ray(p, pr.x);
+      double x[3], w[3], t;
+      if (tri_exact(r.o, r.d, P0, P1, P2, __longlong_as_double((long long)rp.ov_prov_t[k]), p.tol2, &t, x, w)) {
+        tt = t + 0.0;
+        atomicMin(rp.ov_best_t + k, (unsigned long long)__double_as_longlong(tt));
+      }
+    }
+    rp.pair_t[i] = tt;
+  }
+}
+
+__global__ void __launch_bounds__(RV_THREADS) spill_cell_kernel(const RasterParams rp) {
+  const RenderParams& p = rp.r;
+  const unsigned int n = min(rp.n_spill[0], rp.pair_cap);
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double tt = rp.pair_t[i];
+    if (tt < 0.0) continue;
+    const uint2 pr = rp.pairs[i];
+    const int k = -rp.cnt[pr.x] - 1;
+    if ((unsigned long long)__double_as_longlong(tt) != rp.ov_best_t[k]) continue;
+    const int cell = __float_as_int(__ldg(p.trec + 4 * (int64_t)pr.y).w);
+    atomicMin(rp.ov_best_cs + k, ((unsigned long long)(unsigned int)cell << 32) | pr.y);
+  }
+}
+
+__global__ void __launch_bounds__(RV_THREADS) spill_shade_kernel(const RasterParams rp) {
+  const RenderParams& p = rp.r;
+  const unsigned int n = rp.n_spill[1];
+  unsigned int hits = 0;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int64_t pix = rp.ov_pix[k];
+    unsigned long long cs = rp.ov_best_cs[k];
+    if (rp.ov_prov_t[k] == rp.ov_best_t[k] && rp.ov_prov_cs[k] < cs) cs = rp.ov_prov_cs[k];
+    if (cs == ~0ull) {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      write_pixel(p, pix, zero, -1, -1.0);
+      continue;
+    }
+    const int slot = (int)(unsigned int)cs;
+    const float4* rec = p.trec + 4 * (int64_t)slot;
+    const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
+    const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+    const PixelRay r = pixel_ray(p, pix);
+    double t, x[3], w[3];
+    tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w);  // hit by construction; recomputed for the weights
+    hits++;
+    shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
+  }
+  if (hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
+  if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.counters + 4, (unsigned long long)n);  // pixels finished from the spill list
+}
+
+// ---- resolve3: the few pixels with more candidates than the lists hold: one thread each re-traces
+// its ray through the LBVH (screening test first, exact test on what is left)
+__global__ void __launch_bounds__(64) raster_resolve3_kernel(const RasterParams rp) {
+  const RenderParams& p = rp.r;
+  const unsigned int n = rp.n_queue[1];
+  const int64_t per_view = (int64_t)p.res * p.res;
+  unsigned int hits = 0;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int64_t pix = rp.queue[rp.n_pix + k];
+    const int v = (int)(pix / per_view), loc = (int)(pix % per_view);
+    const ViewF* vf = p.viewsf + p.view_begin + v;
+    const float qx = fmaf((float)(loc % p.res), vf->qdx, vf->q0x), qy = fmaf((float)(loc / p.res), vf->qdy, vf->q0y);
+    const PixelRay r = pixel_ray(p, pix);
+    const ExactHit h = resolve_overflow(p, p.view_begin + v, r.o[0], r.o[1], r.o[2], vf->enabled ? vf : nullptr, qx, qy);
+    if (h.slot >= 0) {
+      hits++;
+      const int4 vid = p.tvid[h.slot];
+      const double w[3] = {h.w0, h.w1, h.w2};
+      shade_and_write(p, pix, r, h.t, w, vid.x, vid.y, vid.z, h.cell);
+    } else {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      write_pixel(p, pix, zero, -1, -1.0);
+    }
+  }
+  if (hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
+  if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.counters + 5, (unsigned long long)n);  // rays re-traced (rare)
+}
 
 int raster_render(flyby_ctx* c, const RenderParams& rp) {
   cudaStream_t st = c->stream;
   const int64_t n_pix = (int64_t)rp.n_views * rp.res * rp.res;
-  FB_CUDA(c, c->cand.reserve(sizeof(int4) * (size_t)n_pix));
-  FB_CUDA(c, c->cand2.reserve(sizeof(int4) * (size_t)n_pix));
-  FB_CUDA(c, c->raster_tmp.reserve(8 * (size_t)n_pix));
   RasterParams p;
   p.r = rp;
-  p.uz = c->raster_tmp.as<unsigned int>();
-  p.cnt = reinterpret_cast<int*>(p.uz + n_pix);
-  p.cand = c->cand.as<int>();
-  p.cand2 = c->cand2.as<int>();
+  p.n_pix = n_pix;
   p.T = (int)c->mesh.T;
-  raster_init_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(p.uz, p.cnt, n_pix);
+  p.tiles = (int)cdiv(rp.res, RT_TILE);
+  const int64_t n_tiles = (int64_t)rp.n_views * p.tiles * p.tiles;
+  FB_CUDA(c, c->cand.reserve(sizeof(int4) * (size_t)n_pix));
+  FB_CUDA(c, c->cand2.reserve(sizeof(int4) * (size_t)n_pix));
+  FB_CUDA(c, c->raster_tmp.reserve(12 * (size_t)n_pix + 4 * (size_t)n_tiles));
+  FB_CUDA(c, c->pix_lists.reserve(8 * (size_t)n_pix + 16));
+  p.front = c->raster_tmp.as<unsigned long long>();
+  p.cnt = reinterpret_cast<int*>(p.front + n_pix);
+  p.tile_z = reinterpret_cast<unsigned int*>(p.cnt + n_pix);
+  p.extra = c->cand.as<int>();
+  p.extra2 = c->cand2.as<int>();
+  p.queue = c->pix_lists.as<uint32_t>();
+  p.n_queue = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 14);
+  p.n_spill = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 13);
+  FB_CUDA(c, cudaMemsetAsync(p.n_spill, 0, 16, st));  // n_spill[2], n_queue[2]
+  const size_t cap = (size_t)(n_pix / 8 > (1 << 20) ? n_pix / 8 : (1 << 20));
+  p.pair_cap = (unsigned int)cap;
+  FB_CUDA(c, c->raster_ovf.reserve(cap * (8 + 8 + 4 + 4 * 8)));
+  p.pairs = c->raster_ovf.as<uint2>();
+  p.pair_t = reinterpret_cast<double*>(p.pairs + cap);
+  p.ov_prov_t = reinterpret_cast<unsigned long long*>(p.pair_t + cap);
+  p.ov_prov_cs = p.ov_prov_t + cap;
+  p.ov_best_t = p.ov_prov_cs + cap;
+  p.ov_best_cs = p.ov_best_t + cap;
+  p.ov_pix = reinterpret_cast<uint32_t*>(p.ov_best_cs + cap);
+  raster_init_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(p.front, p.cnt, n_pix);
   FB_LAUNCH_CHECK(c);
   dim3 grid((unsigned)cdiv(p.T, RT_THREADS), (unsigned)rp.n_views);
   raster_kernel<0><<<grid, RT_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
+  hiz_kernel<<<(unsigned)cdiv(n_tiles * RT_TILE, 256), 256, 0, st>>>(p);
+  FB_LAUNCH_CHECK(c);
   raster_kernel<1><<<grid, RT_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the candidate search and the exact resolve
-  return resolve_launch(c, rp, c->cand.as<int4>(), p.cnt, c->cand2.as<int4>());
+  long long rgrid = (long long)c->sm_count * 4 * 4;  // 4 CTAs resident per SM, 4 rounds for balance
+  const long long want = cdiv(n_pix, RV_THREADS);
+  if (rgrid > want) rgrid = want;
+  raster_resolve1_kernel<<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
+  FB_LAUNCH_CHECK(c);
+  raster_resolve2_kernel<<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
+  FB_LAUNCH_CHECK(c);
+  const unsigned sgrid = (unsigned)c->sm_count * 4;
+  spill_t_kernel<<<sgrid, RV_THREADS, 0, st>>>(p);
+  FB_LAUNCH_CHECK(c);
+  spill_cell_kernel<<<sgrid, RV_THREADS, 0, st>>>(p);
+  FB_LAUNCH_CHECK(c);
+  spill_shade_kernel<<<sgrid, RV_THREADS, 0, st>>>(p);
+  FB_LAUNCH_CHECK(c);
+  raster_resolve3_kernel<<<(unsigned)c->sm_count, 64, 0, st>>>(p);
+  FB_LAUNCH_CHECK(c);
+  return FLYBY_OK;
 }
 
 }  // namespace fb

@@ -159,4 +159,68 @@ __device__ __forceinline__ void stage_top_of_tree(Node* top, const Node* nodes, 
   }
 }
 
+// ---------------------------------------------------------------- exact resolve helpers
+struct PixelRay {
+  double o[3], d[3];
+};
+__device__ __forceinline__ PixelRay pixel_ray(const RenderParams& p, int64_t pix_id) {
+  const int64_t per_view = (int64_t)p.res * p.res;
+  const int v = (int)(pix_id / per_view);
+  const int pix = (int)(pix_id % per_view);
+  const View& vw = p.views[p.view_begin + v];
+  PixelRay r;
+  // view_ray() with the two divisions i / (res - 1) taken from the table (bit-identical values)
+  const double tc0 = p.tc[pix % p.res], tc1 = p.tc[pix / p.res];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float pf = (float)FB_ADD(FB_ADD(vw.origin[k], FB_MUL(tc0, vw.v1[k])), FB_MUL(tc1, vw.v2[k]));
+    r.o[k] = FB_ADD(FB_MUL((double)pf, p.spacing), vw.delta[k]);
+  }
+  r.d[0] = vw.dir[0]; r.d[1] = vw.dir[1]; r.d[2] = vw.dir[2];
+  return r;
+}
+
+__device__ __forceinline__ void shade_and_write(const RenderParams& p, int64_t pix_id, const PixelRay& r, double t,
+                                                const double* w, int pid0, int pid1, int pid2, int cell) {
+  float px[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.feat) {
+    const double x[3] = {FB_ADD(r.o[0], FB_MUL(t, r.d[0])), FB_ADD(r.o[1], FB_MUL(t, r.d[1])), FB_ADD(r.o[2], FB_MUL(t, r.d[2]))};
+    const float4 n0 = __ldg(p.normals + pid0), n1 = __ldg(p.normals + pid1), n2 = __ldg(p.normals + pid2);
+    const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
+    shade(r.o, x, w, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px);
+  }
+  write_pixel(p, pix_id, px, cell, t);
+}
+
+// Rare path, kept out of line so that it does not inflate the registers of resolve_kernel:
+// a ray with more candidates than the list holds (layered / degenerate geometry) is re-traced
+// exactly, on its own, with the stackless per-ray traversal.
+struct ExactHit {
+  double t, w0, w1, w2;
+  int slot, cell;
+};
+static __device__ __noinline__ ExactHit resolve_overflow(const RenderParams& p, int view, double o0, double o1, double o2,
+                                                         const ViewF* vf = nullptr, float qx = 0.f, float qy = 0.f) {
+  const View& vw = p.views[view];
+  const double o[3] = {o0, o1, o2};
+  const double d[3] = {vw.dir[0], vw.dir[1], vw.dir[2]};
+  GlobalFetch f{p.nodes};
+  NoCount nc;
+  float invf[3] = {vw.invf[0], vw.invf[1], vw.invf[2]};
+  const Hit h = traverse(f, p.tv0, p.tv1, p.tv2, o, d, vw.dirf, invf, vw.slack, vw.tslack, p.tol2, nc, vf, qx, qy, 0.0f);
+  ExactHit r;
+  r.t = DBL_MAX; r.w0 = r.w1 = r.w2 = 0.0; r.slot = -1; r.cell = 0x7fffffff;
+  if (h.slot >= 0) {
+    const float4 a = p.tv0[h.slot], b = p.tv1[h.slot], e = p.tv2[h.slot];
+    const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+    double x[3], w[3];
+    tri_exact(o, d, P0, P1, P2, DBL_MAX, p.tol2, &r.t, x, w);
+    r.w0 = w[0]; r.w1 = w[1]; r.w2 = w[2];
+    r.slot = h.slot;
+    r.cell = h.cell;
+  }
+  return r;
+}
+
+
 }  // namespace fb

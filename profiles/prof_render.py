@@ -1,4 +1,5 @@
-"""Small driver for ncu: one bench-workload mesh, build + render (2 launches of render_kernel)."""
+"""Small driver for ncu: one mesh, build + 3 renders.
+  python profiles/prof_render.py [views] [res] [mesh Lm] [ico level]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "fly-by-cnn_b200"))
@@ -8,11 +9,13 @@ from flyby_b200 import _cabi, synth
 views = int(sys.argv[1]) if len(sys.argv) > 1 else 92
 res = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dev = torch.device("cuda", 0)
-P, F = synth.bumpy_sphere(100, seed=0)
+lm = int(sys.argv[3]) if len(sys.argv) > 3 else 100      # mesh: bumpy sphere, 20 lm^2 triangles
+level = int(sys.argv[4]) if len(sys.argv) > 4 else 3     # icosahedron subdivision of the viewpoints
+P, F = synth.bumpy_sphere(lm, seed=0)
 ctx = _cabi.Context(0)
 ctx.set_mesh(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev))
 ctx.build()
-n = ctx.views_icosahedron(3, 2.0)
+n = ctx.views_icosahedron(level, 2.0)
 n = min(n, views)
 opts = ctx.render_opts(use_z=1, split_z=1)
 feat = torch.empty((n, res, res, 4), dtype=torch.float32, device=dev)

@@ -495,9 +495,19 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
     ViewF vf;
     viewf_setup(vw, radius, spacing, maxc, &vf);
     viewf_pixels(vw, spacing, res, &vf);
+    // front[pixel] = smallest (far depth bound, slot) over SURE triangles; hi-z = max per 8x8 tile
+    const int tiles = (res + 7) / 8;
     std::vector<float> uz((size_t)res * res, INFINITY);
+    std::vector<int> front((size_t)res * res, -1);
+    std::vector<float> tile_z((size_t)tiles * tiles, -INFINITY);
     std::vector<std::vector<int>> cand((size_t)res * res);
-    for (int pass = 0; pass < 2; pass++)
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1)
+        for (int j = 0; j < res; j++)
+          for (int i = 0; i < res; i++) {
+            float& tz = tile_z[(size_t)(j / 8) * tiles + i / 8];
+            tz = fmaxf(tz, uz[(size_t)j * res + i]);
+          }
       for (int64_t slot = 0; slot < T; slot++) {
         float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
         float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
@@ -505,6 +515,13 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
         screen_setup(vf, 0.0f, P0, P1, P2, &t);
         if (!(t.flags & 1)) continue;
         PixRange r = pixel_range(vf, t, res);
+        if (r.i1 < r.i0 || r.j1 < r.j0) continue;
+        if (pass == 1) {
+          float zmax = -INFINITY;
+          for (int ty = r.j0 / 8; ty <= r.j1 / 8; ty++)
+            for (int tx = r.i0 / 8; tx <= r.i1 / 8; tx++) zmax = fmaxf(zmax, tile_z[(size_t)ty * tiles + tx]);
+          if (t.zlo > zmax) continue;
+        }
         for (int j = r.j0; j <= r.j1; j++)
           for (int i = r.i0; i <= r.i1; i++) {
             float qx = fmaf((float)i, vf.qdx, vf.q0x), qy = fmaf((float)j, vf.qdy, vf.q0y);
@@ -512,21 +529,33 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
             n_tests++;
             if (cls == SC_MISS) continue;
             size_t pix = (size_t)j * res + i;
-            if (pass == 0) { if (cls == SC_SURE && t.zhi < uz[pix]) uz[pix] = t.zhi; }
-            else if (t.zlo <= uz[pix]) cand[pix].push_back((int)slot);
+            if (pass == 0) {
+              if (cls == SC_SURE && (t.zhi < uz[pix] || (t.zhi == uz[pix] && (int)slot < front[pix]))) {
+                uz[pix] = t.zhi;
+                front[pix] = (int)slot;
+              }
+            } else if (t.zlo <= uz[pix] && (int)slot != front[pix]) {
+              cand[pix].push_back((int)slot);
+            }
           }
       }
+    }
+    for (size_t pix = 0; pix < (size_t)res * res; pix++)
+      if (front[pix] >= 0 && cand_cap >= 0) cand[pix].insert(cand[pix].begin(), front[pix]);
     for (int j = 0; j < res; j++)
       for (int i = 0; i < res; i++) {
         size_t pix = (size_t)j * res + i;
         double o[3];
         view_ray(vw, res, i, j, spacing, o);
         Hit h; h.t = DBL_MAX; h.slot = -1; h.cell = 0x7fffffff;
-        if ((int)cand[pix].size() > cand_cap) {
+        if (cand_cap < 0) {  // model of the last-resort path: screened LBVH re-trace of the pixel
           n_over++;
+          float qx = fmaf((float)i, vf.qdx, vf.q0x), qy = fmaf((float)j, vf.qdy, vf.q0y);
           h = traverse(f, b.tv0.data(), b.tv1.data(), b.tv2.data(), o, vw.dir, vw.dirf, vw.invf, vw.slack, vw.tslack,
-                       1e-20, cnt);
+                       1e-20, cnt, vf.enabled ? &vf : nullptr, qx, qy, 0.0f);
         } else {
+          // more candidates than the per-pixel lists hold go through the spill list: same minimum of (t, cell id)
+          if ((int)cand[pix].size() > cand_cap) n_over++;
           for (int slot : cand[pix]) {
             float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
             float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};

@@ -262,6 +262,37 @@ def test_single_triangle_and_empty(gpu_ctx, orc):
     assert np.all(ids == -1) and np.all(feat == 0)
 
 
+def test_piled_candidates_spill_list(gpu_ctx, orc):
+    """More candidates at a pixel than the per-pixel lists of the scan-conversion path hold: 40 coincident
+    copies of a patch (every copy is an inclusive hit at the same t: lowest cell id wins), 40 near-coincident
+    layers, and a fan of edge-on triangles seen exactly along their plane (grazing: the float32 screening
+    cannot decide any of them)."""
+    base = np.array([[-0.9, -0.8, 0.1], [0.9, -0.7, 0.1], [0.1, 0.9, 0.1], [-0.8, 0.7, 0.1]], np.float32)
+    quad = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    V, F = [], []
+    for k in range(40):  # coincident copies
+        F.append(quad + len(V) * 4); V.append(base)
+    for k in range(40):  # layers 1e-7 apart: inside the float32 depth margin of each other
+        F.append(quad + len(V) * 4); V.append(base + np.array([0, 0, -0.3 - 1e-7 * k], np.float32))
+    for k in range(24):  # edge-on fan in the plane x = 0.05, seen along +-y and +-z
+        a = 0.2 * k
+        F.append(np.array([[0, 1, 2]], np.int32) + len(V) * 4)
+        V.append(np.array([[0.05, np.cos(a), np.sin(a)], [0.05, np.cos(a + 2), np.sin(a + 2)],
+                           [0.05, np.cos(a + 4), np.sin(a + 4)], [0, 0, 0]], np.float32) * np.float32(0.6)
+                 + np.array([0.05 * 0.4, 0, 0], np.float32))
+    V = np.concatenate(V).astype(np.float32); F = np.concatenate(F).astype(np.int32)
+    F = F[np.random.default_rng(3).permutation(len(F))]  # cell ids not in construction order
+    views = np.array([[0, 0, 2.0], [0, 0, -2.0], [0, 2.0, 0], [0, -2.0, 0], [2.0, 0, 0], [1.2, 1.2, 1.0]], np.float32)
+    gpu_ctx.views_custom(views, 2.0)
+    uv, nrm, _, _ = _build(gpu_ctx, V, F, skip_normalise=True)
+    opts = gpu_ctx.render_opts(use_z=1, split_z=1, plane_scale=2.0)
+    for res in (33, 128):
+        feat, ids, t = gpu_ctx.render(res, opts, want_t=True)
+        fo, io, to = orc.render(uv, F, nrm, gpu_ctx.get_views(), 2.0, res, plane_scale=2.0, grid=False, want_t=True)
+        assert int((ids != io).sum()) == 0 and np.array_equal(t, to) and np.array_equal(feat, fo)
+    assert (io[0] >= 0).sum() > 1000 and (io[4] >= 0).sum() > 0 and (io[2] >= 0).sum() == 0  # edge-on: VTK rejects grazing
+
+
 def test_bad_indices_rejected(gpu_ctx):
     from flyby_b200 import FlyByError
     V = np.zeros((3, 3), np.float32)

@@ -98,3 +98,42 @@ def test_many_duplicate_centroids_stay_within_depth_bound(sim, orc):
     fs, is_, ts, work = sim_render(sim, V, F, N, views, 2.0, 16, ps=2.0, mode=0)
     assert np.array_equal(io, is_) and np.array_equal(to, ts) and work[2] <= 62
     assert set(np.unique(io[0][io[0] >= 0])) == {39} and set(np.unique(io[1][io[1] >= 0])) == {0}
+
+
+def _sim_ids(fn, U, F, views, radius, res, ps, cap, nwork=6):
+    nv = len(views)
+    ids = np.empty((nv, res, res), np.int32)
+    t = np.empty((nv, res, res), np.float64)
+    work = np.zeros(nwork, np.int64)
+    rc = fn(_p(U), C.c_int64(len(U)), _p(F), C.c_int64(len(F)), _p(views), C.c_int(nv), C.c_double(radius), C.c_int(res),
+            C.c_double(ps), C.c_double(1.0), C.c_int(cap), _p(ids), _p(t), _p(work))
+    assert rc == 0
+    return ids, t, work
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("cap", [4, -1])
+def test_screened_trace_and_resolve_matches_oracle(sim, orc, name, cap):
+    """screen.cu's split: float32 screening at the leaves picks candidates (it never decides), the exact test
+    resolves them; cap < 0 is the split schedule, cap >= 0 the fused one with a pending list of that size."""
+    P, F = CASES[name]()
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    for views, R, ps in [(orc.icosahedron(1, 2.0), 2.0, 1.0), (orc.spiral(6, 4, 4.0), 4.0, 2.0)]:
+        fo, io, to = orc.render(U, F, N, views, R, 50, plane_scale=ps, grid=False, want_t=True)
+        ids, t, work = _sim_ids(sim.sim_render_packet_screen, U, F, views, R, 50, ps, cap)
+        assert np.array_equal(io, ids) and np.array_equal(to, t)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("cap", [8, 0, -1])
+def test_scan_conversion_matches_oracle(sim, orc, name, cap):
+    """raster.cu's schedule: front buffer from the certain hits, hi-z cull, extras per pixel, exact resolve.
+    cap 8 = the kernel's lists, 0 = every extra goes through the spill list, -1 = every pixel re-traced."""
+    P, F = CASES[name]()
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    for views, R, ps in [(orc.icosahedron(1, 2.0), 2.0, 1.0), (orc.spiral(6, 4, 4.0), 4.0, 2.0)]:
+        fo, io, to = orc.render(U, F, N, views, R, 50, plane_scale=ps, grid=False, want_t=True)
+        ids, t, work = _sim_ids(sim.sim_render_raster, U, F, views, R, 50, ps, cap, nwork=3)
+        assert np.array_equal(io, ids) and np.array_equal(to, t)
