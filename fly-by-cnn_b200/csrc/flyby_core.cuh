@@ -585,6 +585,138 @@ FB_HD int screen_tri(const ViewF& V, float qx, float qy, float zo, const float* 
   return screen_pixel(V, t, qx, qy);
 }
 
+// ---------------------------------------------------------------- scan-conversion form (raster.cu)
+// The same screening predicate with everything that does not depend on the pixel hoisted into the
+// per-triangle setup.  The per-pixel margins of screen_pixel grow with |r| = |q - vertex|; inside the
+// padded bounding box |r|_1 <= R1 = (box size)_1 + 2 m0, so
+//     g_k = k2 R1 + kd l_k + kr l_k R1   >=   the g_k screen_pixel would use at any such pixel.
+// Larger margins only turn decisions into SC_MAYBE, so the guarantees of screen_pixel carry over.
+// For a triangle whose orientation is reliable the pixels of a row that are not a certain miss form one
+// interval; raster_span bounds it (slope / intercept per edge, relative to the box corner so that the
+// rounding error stays proportional to the box size) and sigma covers the rounding of that bound.
+struct TriR {
+  float ax, ay, bx, by, cx, cy;        // projected vertices
+  float e0x, e0y, e1x, e1y, e2x, e2y;  // edges a->b, b->c, c->a
+  float g0, g1, g2, G;                 // margins of the three edge functions and their sum
+  float x0, x1, y0, y1;                // padded bounding box (lox - m0 ...)
+  float zlo, zhi;                      // depth interval, widened by e_z
+  float m0s, m1s, m2s, b0s, b1s, b2s;  // span bound of edge k: x - x0 <=/>= b_k + m_k (qy - y0)
+  float sigma;                         // slack of the span bounds
+  int flags;                           // 1 depth range overlaps the segment, 2 SURE-eligible, 4 spans usable,
+                                       // 8/16/32: edge 0/1/2 bounds the span from above (else from below), 64/128/256: edge usable
+};
+
+// projection, padded box and pixel range; false when no pixel of the view can see the triangle's box
+FB_HD bool raster_project(const ViewF& V, const float* P0, const float* P1, const float* P2, int res, TriR* t,
+                          PixRange* r) {
+  t->ax = fmaf(P0[0], V.xf[0], fmaf(P0[1], V.xf[1], P0[2] * V.xf[2]));
+  t->ay = fmaf(P0[0], V.yf[0], fmaf(P0[1], V.yf[1], P0[2] * V.yf[2]));
+  t->bx = fmaf(P1[0], V.xf[0], fmaf(P1[1], V.xf[1], P1[2] * V.xf[2]));
+  t->by = fmaf(P1[0], V.yf[0], fmaf(P1[1], V.yf[1], P1[2] * V.yf[2]));
+  t->cx = fmaf(P2[0], V.xf[0], fmaf(P2[1], V.xf[1], P2[2] * V.xf[2]));
+  t->cy = fmaf(P2[0], V.yf[0], fmaf(P2[1], V.yf[1], P2[2] * V.yf[2]));
+  const float m0 = 2.0f * V.e_p + V.d0;
+  t->x0 = fminf(t->ax, fminf(t->bx, t->cx)) - m0;
+  t->x1 = fmaxf(t->ax, fmaxf(t->bx, t->cx)) + m0;
+  t->y0 = fminf(t->ay, fminf(t->by, t->cy)) - m0;
+  t->y1 = fmaxf(t->ay, fmaxf(t->by, t->cy)) + m0;
+  const float ix = 1.0f / V.qdx, iy = 1.0f / V.qdy;
+  // a superset of the pixels inside the padded box (raster_pixel repeats the box test on the real coordinates)
+  const float fi0 = fmaxf(0.0f, ceilf((t->x0 - V.q0x) * ix - 0.01f)), fi1 = fminf((float)(res - 1), floorf((t->x1 - V.q0x) * ix + 0.01f));
+  const float fj0 = fmaxf(0.0f, ceilf((t->y0 - V.q0y) * iy - 0.01f)), fj1 = fminf((float)(res - 1), floorf((t->y1 - V.q0y) * iy + 0.01f));
+  if (!(fi1 >= fi0 && fj1 >= fj0)) return false;
+  r->i0 = (int)fi0; r->i1 = (int)fi1; r->j0 = (int)fj0; r->j1 = (int)fj1;
+  return true;
+}
+
+// the rest of the per-triangle work (depth range, flags, margins, span coefficients); zo = depth of the ray origins
+FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* P1, const float* P2, TriR* t) {
+  const float az = V.rp - fmaf(P0[0], V.nf[0], fmaf(P0[1], V.nf[1], P0[2] * V.nf[2]));
+  const float bz = V.rp - fmaf(P1[0], V.nf[0], fmaf(P1[1], V.nf[1], P1[2] * V.nf[2]));
+  const float cz = V.rp - fmaf(P2[0], V.nf[0], fmaf(P2[1], V.nf[1], P2[2] * V.nf[2]));
+  const float zmin = fminf(az, fminf(bz, cz)), zmax = fmaxf(az, fmaxf(bz, cz));
+  t->zlo = zmin - V.e_z;
+  t->zhi = zmax + V.e_z;
+  t->e0x = t->bx - t->ax; t->e0y = t->by - t->ay;
+  t->e1x = t->cx - t->bx; t->e1y = t->cy - t->by;
+  t->e2x = t->ax - t->cx; t->e2y = t->ay - t->cy;
+  const float area2 = t->e0x * (t->cy - t->ay) - t->e0y * (t->cx - t->ax);
+  const float m0 = 2.0f * V.e_p + V.d0;
+  const float Dq = ((t->x1 - t->x0) + (t->y1 - t->y0)) - 4.0f * m0;  // L1 size of the unpadded box (screen_setup's Dq)
+  int flags = 0;
+  if (!(t->zhi < zo - V.e_z || t->zlo > zo + V.two_r + V.e_z)) flags |= 1;
+  // same SURE eligibility as screen_setup, with Dq rounded up
+  const float Dq_up = fmaxf(Dq, 0.0f) * 1.000001f + 4.0f * V.e_p;
+  const float amin = fabsf(area2) - 8.0f * V.e_p * Dq_up;
+  if ((zmax - zmin + 4.0f * V.e_z) * Dq_up <= 500.0f * amin && t->zlo > zo + V.e_z && t->zhi < zo + V.two_r - V.e_z)
+    flags |= 2;
+  const float R1 = ((t->x1 - t->x0) + (t->y1 - t->y0)) * 1.000001f;  // >= |r|_1 of any vertex to any point of the padded box
+  const float l0 = fabsf(t->e0x) + fabsf(t->e0y), l1 = fabsf(t->e1x) + fabsf(t->e1y), l2 = fabsf(t->e2x) + fabsf(t->e2y);
+  const float k2 = 2.0f * V.e_p, kd = k2 + V.d0, kr = 2.384185791015625e-07f;
+  t->g0 = fmaf(k2, R1, fmaf(kd, l0, kr * l0 * R1)) * 1.000001f;
+  t->g1 = fmaf(k2, R1, fmaf(kd, l1, kr * l1 * R1)) * 1.000001f;
+  t->g2 = fmaf(k2, R1, fmaf(kd, l2, kr * l2 * R1)) * 1.000001f;
+  t->G = (t->g0 + t->g1 + t->g2) * 1.000001f;
+  // spans: only when the sign of the area is beyond doubt (the per-pixel area differs from this one by < G)
+  t->m0s = t->m1s = t->m2s = t->b0s = t->b1s = t->b2s = 0.f;
+  t->sigma = fmaf(4.0e-5f, R1, 4.76837158203125e-07f * (fabsf(t->x0) + fabsf(t->x1) + fabsf(V.q0x) + R1));
+  if (fabsf(area2) > 4.0f * t->G) {
+    flags |= 4;
+    const float s = area2 > 0.f ? 1.0f : -1.0f;
+    // not a certain miss w.r.t. edge k:  s E_k >= -g_k,  E_k = e_kx (qy - P_ky) - e_ky (qx - P_kx)
+    //   <=>  (s e_ky) (qx - P_kx) <= g_k + (s e_kx) (qy - P_ky)
+    // an edge within ~3 degrees of the row direction gives no usable bound
+    if (fabsf(t->e0y) >= 0.05f * l0) {
+      const float c = s * t->e0y, m = t->e0x / t->e0y;
+      t->m0s = m; t->b0s = (t->ax - t->x0) + t->g0 / c - m * (t->ay - t->y0);
+      flags |= 64 | (c > 0.f ? 8 : 0);
+    }
+    if (fabsf(t->e1y) >= 0.05f * l1) {
+      const float c = s * t->e1y, m = t->e1x / t->e1y;
+      t->m1s = m; t->b1s = (t->bx - t->x0) + t->g1 / c - m * (t->by - t->y0);
+      flags |= 128 | (c > 0.f ? 16 : 0);
+    }
+    if (fabsf(t->e2y) >= 0.05f * l2) {
+      const float c = s * t->e2y, m = t->e2x / t->e2y;
+      t->m2s = m; t->b2s = (t->cx - t->x0) + t->g2 / c - m * (t->cy - t->y0);
+      flags |= 256 | (c > 0.f ? 32 : 0);
+    }
+  }
+  t->flags = flags;
+}
+
+FB_HD int raster_pixel(const TriR& t, float qx, float qy) {
+  if (qx < t.x0 || qx > t.x1 || qy < t.y0 || qy > t.y1) return SC_MISS;
+  const float r0x = qx - t.ax, r0y = qy - t.ay, r1x = qx - t.bx, r1y = qy - t.by, r2x = qx - t.cx, r2y = qy - t.cy;
+  const float p0a = t.e0x * r0y, p0b = t.e0y * r0x, p1a = t.e1x * r1y, p1b = t.e1y * r1x, p2a = t.e2x * r2y, p2b = t.e2y * r2x;
+  const float E0 = p0a - p0b, E1 = p1a - p1b, E2 = p2a - p2b;
+  const float area2 = (E0 + E1) + E2;
+  if (fabsf(area2) <= 2.0f * t.G) {  // (nearly) edge-on: strip test, see screen_pixel
+    const float lim = fabsf(area2) + t.G;
+    if (fabsf(E0) > lim + t.g0 || fabsf(E1) > lim + t.g1 || fabsf(E2) > lim + t.g2) return SC_MISS;
+    return SC_MAYBE;
+  }
+  const float s = area2 > 0.f ? 1.0f : -1.0f;
+  const float v0 = s * E0, v1 = s * E1, v2 = s * E2;
+  if (v0 < -t.g0 || v1 < -t.g1 || v2 < -t.g2) return SC_MISS;
+  if (!(v0 > t.g0 && v1 > t.g1 && v2 > t.g2)) return SC_MAYBE;
+  return (t.flags & 2) ? SC_SURE : SC_MAYBE;
+}
+
+// pixels [lo, hi] of row qy outside of which raster_pixel is certain to answer SC_MISS (flags & 4 only)
+FB_HD void raster_span(const ViewF& V, const TriR& t, float qy, int i0, int i1, int* lo, int* hi) {
+  const float dy = qy - t.y0;
+  float xl = -1.0e30f, xh = 1.0e30f;
+  if (t.flags & 64) { const float x = fmaf(t.m0s, dy, t.b0s); if (t.flags & 8) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
+  if (t.flags & 128) { const float x = fmaf(t.m1s, dy, t.b1s); if (t.flags & 16) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
+  if (t.flags & 256) { const float x = fmaf(t.m2s, dy, t.b2s); if (t.flags & 32) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
+  const float ix = 1.0f / V.qdx;
+  const float fl = fmaxf((float)i0, ceilf(((t.x0 - V.q0x) + (xl - t.sigma)) * ix - 0.01f));
+  const float fh = fminf((float)i1, floorf(((t.x0 - V.q0x) + (xh + t.sigma)) * ix + 0.01f));
+  *lo = (int)fl;
+  *hi = fh >= fl ? (int)fh : (int)fl - 1;
+}
+
 // Stackless traversal: a 64-bit trail holds one "far sibling still pending" bit
 // per level, parent / sibling links walk back up.  Depth <= 62 is guaranteed by
 // the 30+32-bit key length of the LBVH.  NodeFetch: node(i) -> Node by value,

@@ -6,10 +6,8 @@
 // float32 screening predicate of flyby_core.cuh, which never decides a result -- against the
 // handful of pixels inside its bounding box:
 //   pass A    front[pixel] = min over SURE triangles of (far depth bound, slot)   one 64-bit atomicMin
-//   hi-z      tile_z[8x8 tile] = max over its pixels of the front depth bound
-//   pass B    triangles behind tile_z of every tile they touch are dropped whole; for the others,
-//             every pixel that is not a certain miss, whose near depth bound is not behind
-//             front[pixel] and which is not the front triangle itself is appended to extra[pixel]
+//   pass B    every pixel whose front is another triangle and not nearer than this triangle's near depth
+//             bound, and where this triangle is not a certain miss, appends it to extra[pixel]
 //   resolve1  one thread per pixel in raster order: background / the exact test on the front
 //             triangle when it is the only candidate (the common case) / queue the pixel
 //   resolve2  queued pixels: exact test on the front triangle and the extras, tie-break (t, cell id)
@@ -25,10 +23,9 @@
 
 namespace fb {
 
-#define RT_THREADS 256
-#define RT_BIG 48     // bounding boxes with more pixels than this are rasterised by a whole warp
+#define RT_THREADS 128
+#define RT_BIG 256   // bounding boxes with more pixels than this are rasterised by a whole warp
 #define RT_EXTRA 8    // extra candidates kept per pixel (two int4)
-#define RT_TILE 8     // hi-z tile edge, pixels
 #define RV_THREADS 128
 
 struct RasterParams {
@@ -37,7 +34,6 @@ struct RasterParams {
   int* cnt;                   // [n_pix] extra candidates found
   int* extra;                 // [n_pix, 4] extra slots 0..3
   int* extra2;                // [n_pix, 4] extra slots 4..7 (touched only by pixels that need them)
-  unsigned int* tile_z;       // [n_views, tiles, tiles] hi-z
   uint32_t* queue;            // [2, n_pix] pixels for resolve2, pixels for resolve3
   unsigned int* n_queue;      // [2]
   // spill: candidates beyond RT_EXTRA of a pixel (edge-on piles at silhouettes) go to one global pair list
@@ -49,7 +45,7 @@ struct RasterParams {
   unsigned long long *ov_best_t, *ov_best_cs;  // [pair_cap] running minimum over everything / over the spilled pairs
   unsigned int pair_cap;
   int64_t n_pix;
-  int T, tiles;
+  int T;
 };
 #define RT_LOST 0x40000000  // cnt flag: a spilled pair found the list full, the pixel is re-traced through the LBVH
 
@@ -59,31 +55,28 @@ __device__ __forceinline__ unsigned int ford(float f) {
 }
 
 template <int PASS>
-__device__ __forceinline__ void visit_pixel(const RasterParams& p, const ViewF& V, const TriS& t, int slot,
+__device__ __forceinline__ void visit_pixel(const RasterParams& p, const ViewF& V, const TriR& t, int slot,
                                             int64_t view_base, int res, int i, int j) {
-  const float qx = fmaf((float)i, V.qdx, V.q0x), qy = fmaf((float)j, V.qdy, V.q0y);
-  const int cls = screen_pixel(V, t, qx, qy);
-  if (cls == SC_MISS) return;
   const int64_t pix = view_base + (int64_t)j * res + i;
+  const float qx = fmaf((float)i, V.qdx, V.q0x), qy = fmaf((float)j, V.qdy, V.q0y);
+  const int cls = raster_pixel(t, qx, qy);
+  if (cls == SC_MISS) return;
   if (PASS == 0) {
     if (cls == SC_SURE) atomicMin(p.front + pix, ((unsigned long long)ford(t.zhi) << 32) | (unsigned int)slot);
   } else {
-    const unsigned long long f = __ldg(p.front + pix);  // read-only in this pass
-    if (ford(t.zlo) <= (unsigned int)(f >> 32) && (unsigned int)f != (unsigned int)slot) {
-      const int k = atomicAdd(p.cnt + pix, 1) & (RT_LOST - 1);
-      if (k < 4) p.extra[pix * 4 + k] = slot;
-      else if (k < RT_EXTRA) p.extra2[pix * 4 + (k - 4)] = slot;
-      else {
-        const unsigned int i = atomicAdd(p.n_spill, 1u);
-        if (i < p.pair_cap) p.pairs[i] = make_uint2((unsigned int)pix, (unsigned int)slot);
-        else atomicOr(p.cnt + pix, RT_LOST);
-      }
+    const int k = atomicAdd(p.cnt + pix, 1) & (RT_LOST - 1);
+    if (k < 4) p.extra[pix * 4 + k] = slot;
+    else if (k < RT_EXTRA) p.extra2[pix * 4 + (k - 4)] = slot;
+    else {
+      const unsigned int i2 = atomicAdd(p.n_spill, 1u);
+      if (i2 < p.pair_cap) p.pairs[i2] = make_uint2((unsigned int)pix, (unsigned int)slot);
+      else atomicOr(p.cnt + pix, RT_LOST);
     }
   }
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(RT_THREADS) raster_kernel(const RasterParams p) {
+__global__ void __launch_bounds__(RT_THREADS, 6) raster_kernel(const RasterParams p) {
   __shared__ ViewF s_vf;
   const int view = blockIdx.y;  // local view index of this render call
   {
@@ -98,81 +91,69 @@ __global__ void __launch_bounds__(RT_THREADS) raster_kernel(const RasterParams p
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * RT_THREADS + threadIdx.x;
 
-  TriS t;
+  TriR t;
   PixRange r;
   int npx = 0;
   if (slot < p.T) {
     const float4 a = __ldg(p.r.tv0 + slot), b = __ldg(p.r.tv1 + slot), e = __ldg(p.r.tv2 + slot);
     const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-    screen_setup(V, 0.0f, P0, P1, P2, &t);  // ray origins lie in the view plane: depth 0 (+- e_z)
-    if (t.flags & 1) {
-      r = pixel_range(V, t, res);
-      if (r.i1 >= r.i0 && r.j1 >= r.j0) npx = (r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
-    }
-    if (PASS == 1 && npx > 0) {
-      // hi-z: behind the nearest certain hit of every pixel of every tile it touches -> cannot be a candidate
-      const int tx0 = r.i0 / RT_TILE, tx1 = r.i1 / RT_TILE, ty0 = r.j0 / RT_TILE, ty1 = r.j1 / RT_TILE;
-      if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 9) {
-        const unsigned int* tz = p.tile_z + (int64_t)view * p.tiles * p.tiles;
-        unsigned int zmax = 0u;
-        for (int ty = ty0; ty <= ty1; ty++)
-          for (int tx = tx0; tx <= tx1; tx++) zmax = max(zmax, __ldg(tz + ty * p.tiles + tx));
-        if (ford(t.zlo) > zmax) npx = 0;
-      }
+    if (raster_project(V, P0, P1, P2, res, &t, &r)) {  // most triangles of a close-up view end here
+      raster_setup(V, 0.0f, P0, P1, P2, &t);           // ray origins lie in the view plane: depth 0 (+- e_z)
+      if (t.flags & 1) npx = (r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
     }
   }
-  // small triangles: one thread walks the pixels of its bounding box
+  // small triangles: one thread walks the rows of its bounding box, inside each row only the span that
+  // the three edges leave
   if (npx > 0 && npx <= RT_BIG) {
-    for (int j = r.j0; j <= r.j1; j++)
-      for (int i = r.i0; i <= r.i1; i++) visit_pixel<PASS>(p, V, t, slot, view_base, res, i, j);
+    const unsigned int zlo_ord = ford(t.zlo);
+    for (int j = r.j0; j <= r.j1; j++) {
+      int lo = r.i0, hi = r.i1;
+      if (t.flags & 4) raster_span(V, t, fmaf((float)j, V.qdy, V.q0y), r.i0, r.i1, &lo, &hi);
+      if (PASS == 0) {
+        for (int i = lo; i <= hi; i++) visit_pixel<0>(p, V, t, slot, view_base, res, i, j);
+      } else {
+        // cheap tests first, four independent loads in flight: most visits end at the front buffer (the
+        // triangle is the front itself, or lies behind it)
+        const unsigned long long* frow = p.front + view_base + (int64_t)j * res;
+        for (int i = lo; i <= hi; i += 4) {
+          unsigned long long f[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) f[k] = (i + k <= hi) ? __ldg(frow + i + k) : 0ull;  // 0: nothing passes
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (zlo_ord <= (unsigned int)(f[k] >> 32) && (unsigned int)f[k] != (unsigned int)slot)
+              visit_pixel<1>(p, V, t, slot, view_base, res, i + k, j);
+        }
+      }
+    }
   }
   // large triangles (coarse meshes, close-ups): the warp takes them one at a time, 32 pixels per step
   unsigned big = __ballot_sync(0xffffffffu, npx > RT_BIG);
   while (big) {
     const int src = __ffs(big) - 1;
     big &= big - 1;
-    TriS u;
-    u.ax = __shfl_sync(0xffffffffu, t.ax, src); u.ay = __shfl_sync(0xffffffffu, t.ay, src);
-    u.bx = __shfl_sync(0xffffffffu, t.bx, src); u.by = __shfl_sync(0xffffffffu, t.by, src);
-    u.cx = __shfl_sync(0xffffffffu, t.cx, src); u.cy = __shfl_sync(0xffffffffu, t.cy, src);
-    u.lox = __shfl_sync(0xffffffffu, t.lox, src); u.hix = __shfl_sync(0xffffffffu, t.hix, src);
-    u.loy = __shfl_sync(0xffffffffu, t.loy, src); u.hiy = __shfl_sync(0xffffffffu, t.hiy, src);
-    u.zlo = __shfl_sync(0xffffffffu, t.zlo, src); u.zhi = __shfl_sync(0xffffffffu, t.zhi, src);
-    u.area2 = __shfl_sync(0xffffffffu, t.area2, src);
-    u.flags = __shfl_sync(0xffffffffu, t.flags, src);
+    TriR u;
+    {
+      const float* tf = reinterpret_cast<const float*>(&t);
+      float* uf = reinterpret_cast<float*>(&u);
+#pragma unroll
+      for (int k = 0; k < (int)(sizeof(TriR) / 4); k++) uf[k] = __shfl_sync(0xffffffffu, tf[k], src);
+    }
     const int i0 = __shfl_sync(0xffffffffu, r.i0, src), i1 = __shfl_sync(0xffffffffu, r.i1, src);
     const int j0 = __shfl_sync(0xffffffffu, r.j0, src), j1 = __shfl_sync(0xffffffffu, r.j1, src);
     const int uslot = __shfl_sync(0xffffffffu, slot, src);
     const int w = i1 - i0 + 1;
     const long long n = (long long)w * (j1 - j0 + 1);
-    for (long long k = lane; k < n; k += 32)
-      visit_pixel<PASS>(p, V, u, uslot, view_base, res, i0 + (int)(k % w), j0 + (int)(k / w));
-  }
-}
-
-// ---- hi-z: one thread per pixel row of a tile (64 contiguous bytes), 8 lanes per tile
-__global__ void __launch_bounds__(256) hiz_kernel(const RasterParams p) {
-  const int res = p.r.res;
-  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t tile = gid / RT_TILE;
-  const int row = (int)(gid % RT_TILE);
-  const int64_t per_view = (int64_t)p.tiles * p.tiles;
-  unsigned int z = 0u;
-  const bool valid = tile < per_view * p.r.n_views;
-  if (valid) {
-    const int view = (int)(tile / per_view), tl = (int)(tile % per_view);
-    const int ty = tl / p.tiles, tx = tl % p.tiles;
-    const int j = ty * RT_TILE + row;
-    if (j < res) {
-      const unsigned long long* src = p.front + (int64_t)view * res * res + (int64_t)j * res + tx * RT_TILE;
-      const int n = min(RT_TILE, res - tx * RT_TILE);
-      for (int i = 0; i < n; i++) z = max(z, (unsigned int)(__ldcg(src + i) >> 32));
+    const unsigned int uz_ord = ford(u.zlo);
+    for (long long k = lane; k < n; k += 32) {
+      const int i = i0 + (int)(k % w), j = j0 + (int)(k / w);
+      if (PASS == 1) {
+        const unsigned long long f = __ldg(p.front + view_base + (int64_t)j * res + i);
+        if (uz_ord > (unsigned int)(f >> 32) || (unsigned int)f == (unsigned int)uslot) continue;
+      }
+      visit_pixel<PASS>(p, V, u, uslot, view_base, res, i, j);
     }
   }
-  z = max(z, __shfl_xor_sync(0xffffffffu, z, 1));
-  z = max(z, __shfl_xor_sync(0xffffffffu, z, 2));
-  z = max(z, __shfl_xor_sync(0xffffffffu, z, 4));
-  if (valid && row == 0) p.tile_z[tile] = z;
 }
 
 __global__ void raster_init_kernel(unsigned long long* front, int* cnt, int64_t n) {
@@ -184,12 +165,16 @@ __global__ void raster_init_kernel(unsigned long long* front, int* cnt, int64_t 
 }
 
 // ---- resolve1: every pixel, raster order
-__global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve1_kernel(const RasterParams rp) {
+#define RV_STAGE 64  // per-warp staging of queued pixels: one global atomic per 32+ entries instead of one per iteration
+__global__ void __launch_bounds__(RV_THREADS, 5) raster_resolve1_kernel(const RasterParams rp) {
   const RenderParams& p = rp.r;
+  __shared__ uint32_t s_stage[RV_THREADS / 32][RV_STAGE];
   const int lane = threadIdx.x & 31;
+  uint32_t* stage = s_stage[threadIdx.x >> 5];
+  int n_stage = 0;  // warp-uniform
   unsigned int hits = 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  // the loop bound is rounded up to whole warps so that the vote below sees all 32 lanes
+  // the loop bound is rounded up to whole warps so that the votes below see all 32 lanes
   const int64_t n_round = (rp.n_pix + 31) & ~(int64_t)31;
   for (int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pix < n_round; pix += stride) {
     const bool valid = pix < rp.n_pix;
@@ -200,11 +185,18 @@ __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve1_kernel(const Ra
       nc = __ldcs(rp.cnt + pix);
     }
     const unsigned mq = __ballot_sync(0xffffffffu, nc > 0);
-    if (mq) {  // queue the pixels that have more than the front candidate (one atomic per warp)
-      unsigned int base = 0;
-      if (lane == 0) base = atomicAdd(rp.n_queue, (unsigned int)__popc(mq));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (nc > 0) rp.queue[base + __popc(mq & ((1u << lane) - 1u))] = (uint32_t)pix;
+    if (mq) {  // pixels that have more than the front candidate go to resolve2
+      if (nc > 0) stage[n_stage + __popc(mq & ((1u << lane) - 1u))] = (uint32_t)pix;
+      n_stage += __popc(mq);
+      __syncwarp();
+      if (n_stage > RV_STAGE - 32) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(rp.n_queue, (unsigned int)n_stage);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int k = lane; k < n_stage; k += 32) rp.queue[base + k] = stage[k];
+        n_stage = 0;
+        __syncwarp();
+      }
     }
     if (!valid || nc > 0) continue;
     if (f == ~0ull) {
@@ -225,6 +217,13 @@ __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve1_kernel(const Ra
       const float zero[4] = {0.f, 0.f, 0.f, 0.f};
       write_pixel(p, pix, zero, -1, -1.0);
     }
+  }
+  __syncwarp();
+  if (n_stage) {
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(rp.n_queue, (unsigned int)n_stage);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int k = lane; k < n_stage; k += 32) rp.queue[base + k] = stage[k];
   }
   for (int o2 = 16; o2 > 0; o2 >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o2);
   if (lane == 0 && hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
@@ -393,15 +392,12 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   p.r = rp;
   p.n_pix = n_pix;
   p.T = (int)c->mesh.T;
-  p.tiles = (int)cdiv(rp.res, RT_TILE);
-  const int64_t n_tiles = (int64_t)rp.n_views * p.tiles * p.tiles;
   FB_CUDA(c, c->cand.reserve(sizeof(int4) * (size_t)n_pix));
   FB_CUDA(c, c->cand2.reserve(sizeof(int4) * (size_t)n_pix));
-  FB_CUDA(c, c->raster_tmp.reserve(12 * (size_t)n_pix + 4 * (size_t)n_tiles));
+  FB_CUDA(c, c->raster_tmp.reserve(12 * (size_t)n_pix));
   FB_CUDA(c, c->pix_lists.reserve(8 * (size_t)n_pix + 16));
   p.front = c->raster_tmp.as<unsigned long long>();
   p.cnt = reinterpret_cast<int*>(p.front + n_pix);
-  p.tile_z = reinterpret_cast<unsigned int*>(p.cnt + n_pix);
   p.extra = c->cand.as<int>();
   p.extra2 = c->cand2.as<int>();
   p.queue = c->pix_lists.as<uint32_t>();
@@ -423,12 +419,10 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   dim3 grid((unsigned)cdiv(p.T, RT_THREADS), (unsigned)rp.n_views);
   raster_kernel<0><<<grid, RT_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
-  hiz_kernel<<<(unsigned)cdiv(n_tiles * RT_TILE, 256), 256, 0, st>>>(p);
-  FB_LAUNCH_CHECK(c);
   raster_kernel<1><<<grid, RT_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the candidate search and the exact resolve
-  long long rgrid = (long long)c->sm_count * 4 * 4;  // 4 CTAs resident per SM, 4 rounds for balance
+  long long rgrid = (long long)c->sm_count * 5 * 4;  // 5 CTAs resident per SM, 4 rounds for balance
   const long long want = cdiv(n_pix, RV_THREADS);
   if (rgrid > want) rgrid = want;
   raster_resolve1_kernel<<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);

@@ -164,13 +164,15 @@ struct PixelRay {
   double o[3], d[3];
 };
 __device__ __forceinline__ PixelRay pixel_ray(const RenderParams& p, int64_t pix_id) {
-  const int64_t per_view = (int64_t)p.res * p.res;
-  const int v = (int)(pix_id / per_view);
-  const int pix = (int)(pix_id % per_view);
-  const View& vw = p.views[p.view_begin + v];
+  // a render call covers fewer than 2^32 pixels (checked by the host side): 32-bit index arithmetic
+  const uint32_t per_view = (uint32_t)p.res * (uint32_t)p.res;
+  const uint32_t v = (uint32_t)pix_id / per_view;
+  const uint32_t pix = (uint32_t)pix_id - v * per_view;
+  const View& vw = p.views[p.view_begin + (int)v];
   PixelRay r;
   // view_ray() with the two divisions i / (res - 1) taken from the table (bit-identical values)
-  const double tc0 = p.tc[pix % p.res], tc1 = p.tc[pix / p.res];
+  const uint32_t pj = pix / (uint32_t)p.res, pi = pix - pj * (uint32_t)p.res;
+  const double tc0 = p.tc[pi], tc1 = p.tc[pj];
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const float pf = (float)FB_ADD(FB_ADD(vw.origin[k], FB_MUL(tc0, vw.v1[k])), FB_MUL(tc1, vw.v2[k]));

@@ -480,13 +480,14 @@ int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris,
 extern "C" __attribute__((visibility("default")))
 int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* views,
                       int n_views, double radius, int res, double plane_scale, double spacing, int cand_cap,
-                      int32_t* out_ids, double* out_t, long long* work /* pixel tests, exact tests, overflow pixels */) {
+                      int32_t* out_ids, double* out_t, long long* work /* pixel tests, exact tests, overflow pixels, [3] span audit */) {
   SimBvh b;
   build(verts, V, tris, T, b);
   if (b.nodes.empty()) return 1;
   float maxc = 0.f;
   for (int64_t i = 0; i < 3 * V; i++) maxc = fmaxf(maxc, fabsf(verts[i]));
-  long long n_tests = 0, n_exact = 0, n_over = 0;
+  long long n_tests = 0, n_exact = 0, n_over = 0, n_span_bad = 0;
+  const bool check_spans = work && work[3] == 1;  // in: work[3] = 1 asks for the span audit; out: work[3] = violations
   SimCount cnt;
   SimFetch f{b.nodes.data()};
   for (int v = 0; v < n_views; v++) {
@@ -495,37 +496,30 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
     ViewF vf;
     viewf_setup(vw, radius, spacing, maxc, &vf);
     viewf_pixels(vw, spacing, res, &vf);
-    // front[pixel] = smallest (far depth bound, slot) over SURE triangles; hi-z = max per 8x8 tile
-    const int tiles = (res + 7) / 8;
+    // front[pixel] = smallest (far depth bound, slot) over SURE triangles
     std::vector<float> uz((size_t)res * res, INFINITY);
     std::vector<int> front((size_t)res * res, -1);
-    std::vector<float> tile_z((size_t)tiles * tiles, -INFINITY);
     std::vector<std::vector<int>> cand((size_t)res * res);
     for (int pass = 0; pass < 2; pass++) {
-      if (pass == 1)
-        for (int j = 0; j < res; j++)
-          for (int i = 0; i < res; i++) {
-            float& tz = tile_z[(size_t)(j / 8) * tiles + i / 8];
-            tz = fmaxf(tz, uz[(size_t)j * res + i]);
-          }
       for (int64_t slot = 0; slot < T; slot++) {
         float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
         float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
-        TriS t;
-        screen_setup(vf, 0.0f, P0, P1, P2, &t);
+        TriR t;
+        PixRange r;
+        if (!raster_project(vf, P0, P1, P2, res, &t, &r)) continue;
+        raster_setup(vf, 0.0f, P0, P1, P2, &t);
         if (!(t.flags & 1)) continue;
-        PixRange r = pixel_range(vf, t, res);
-        if (r.i1 < r.i0 || r.j1 < r.j0) continue;
-        if (pass == 1) {
-          float zmax = -INFINITY;
-          for (int ty = r.j0 / 8; ty <= r.j1 / 8; ty++)
-            for (int tx = r.i0 / 8; tx <= r.i1 / 8; tx++) zmax = fmaxf(zmax, tile_z[(size_t)ty * tiles + tx]);
-          if (t.zlo > zmax) continue;
-        }
-        for (int j = r.j0; j <= r.j1; j++)
-          for (int i = r.i0; i <= r.i1; i++) {
+        const bool use_spans = (long long)(r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1) <= 256 && (t.flags & 4);
+        for (int j = r.j0; j <= r.j1; j++) {
+          int lo = r.i0, hi = r.i1;
+          if (use_spans) raster_span(vf, t, fmaf((float)j, vf.qdy, vf.q0y), r.i0, r.i1, &lo, &hi);
+          if (check_spans)  // every pixel the span skips must be a certain miss
+            for (int i = r.i0; i <= r.i1; i++)
+              if ((i < lo || i > hi) && raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y)) != SC_MISS)
+                n_span_bad++;
+          for (int i = lo; i <= hi; i++) {
             float qx = fmaf((float)i, vf.qdx, vf.q0x), qy = fmaf((float)j, vf.qdy, vf.q0y);
-            int cls = screen_pixel(vf, t, qx, qy);
+            int cls = raster_pixel(t, qx, qy);
             n_tests++;
             if (cls == SC_MISS) continue;
             size_t pix = (size_t)j * res + i;
@@ -538,6 +532,7 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
               cand[pix].push_back((int)slot);
             }
           }
+        }
       }
     }
     for (size_t pix = 0; pix < (size_t)res * res; pix++)
@@ -572,6 +567,6 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
         out_ids[id] = h.cell; out_t[id] = h.slot >= 0 ? h.t : -1.0;
       }
   }
-  if (work) { work[0] = n_tests; work[1] = n_exact; work[2] = n_over; }
+  if (work) { work[0] = n_tests; work[1] = n_exact; work[2] = n_over; if (check_spans) work[3] = n_span_bad; }
   return 0;
 }

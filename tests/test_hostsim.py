@@ -100,11 +100,13 @@ def test_many_duplicate_centroids_stay_within_depth_bound(sim, orc):
     assert set(np.unique(io[0][io[0] >= 0])) == {39} and set(np.unique(io[1][io[1] >= 0])) == {0}
 
 
-def _sim_ids(fn, U, F, views, radius, res, ps, cap, nwork=6):
+def _sim_ids(fn, U, F, views, radius, res, ps, cap, nwork=6, work_in=None):
     nv = len(views)
     ids = np.empty((nv, res, res), np.int32)
     t = np.empty((nv, res, res), np.float64)
     work = np.zeros(nwork, np.int64)
+    if work_in is not None:
+        work[:len(work_in)] = work_in
     rc = fn(_p(U), C.c_int64(len(U)), _p(F), C.c_int64(len(F)), _p(views), C.c_int(nv), C.c_double(radius), C.c_int(res),
             C.c_double(ps), C.c_double(1.0), C.c_int(cap), _p(ids), _p(t), _p(work))
     assert rc == 0
@@ -135,5 +137,18 @@ def test_scan_conversion_matches_oracle(sim, orc, name, cap):
     N = orc.point_normals(U, F)
     for views, R, ps in [(orc.icosahedron(1, 2.0), 2.0, 1.0), (orc.spiral(6, 4, 4.0), 4.0, 2.0)]:
         fo, io, to = orc.render(U, F, N, views, R, 50, plane_scale=ps, grid=False, want_t=True)
-        ids, t, work = _sim_ids(sim.sim_render_raster, U, F, views, R, 50, ps, cap, nwork=3)
+        ids, t, work = _sim_ids(sim.sim_render_raster, U, F, views, R, 50, ps, cap, nwork=4, work_in=[0, 0, 0, 1])
         assert np.array_equal(io, ids) and np.array_equal(to, t)
+        assert work[3] == 0, "a row span skipped %d pixels that are not certain misses" % work[3]
+
+
+@pytest.mark.parametrize("lm,res,ps", [(24, 384, 1.0), (24, 1024, 0.25), (24, 97, 2.0), (60, 256, 1.0), (60, 640, 2.0)])
+def test_scan_conversion_spans_at_other_pixel_pitches(sim, orc, lm, res, ps):
+    """Triangles from sub-pixel size to hundreds of pixels (the row spans serve boxes of <= 48 pixels)."""
+    P, F = synth.bumpy_sphere(lm, 2)
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    views = orc.icosahedron(1, 2.0)[[0, 5, 11]]
+    fo, io, to = orc.render(U, F, N, views, 2.0, res, plane_scale=ps, grid=True, grid_div=32, want_t=True)
+    ids, t, work = _sim_ids(sim.sim_render_raster, U, F, views, 2.0, res, ps, 8, nwork=4, work_in=[0, 0, 0, 1])
+    assert np.array_equal(io, ids) and np.array_equal(to, t) and work[3] == 0
