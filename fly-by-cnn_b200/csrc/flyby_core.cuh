@@ -630,7 +630,8 @@ FB_HD bool raster_project(const ViewF& V, const float* P0, const float* P1, cons
 }
 
 // the rest of the per-triangle work (depth range, flags, margins, span coefficients); zo = depth of the ray origins
-FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* P1, const float* P2, TriR* t) {
+FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* P1, const float* P2, bool want_spans,
+                        TriR* t) {
   const float az = V.rp - fmaf(P0[0], V.nf[0], fmaf(P0[1], V.nf[1], P0[2] * V.nf[2]));
   const float bz = V.rp - fmaf(P1[0], V.nf[0], fmaf(P1[1], V.nf[1], P1[2] * V.nf[2]));
   const float cz = V.rp - fmaf(P2[0], V.nf[0], fmaf(P2[1], V.nf[1], P2[2] * V.nf[2]));
@@ -660,7 +661,7 @@ FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* 
   // spans: only when the sign of the area is beyond doubt (the per-pixel area differs from this one by < G)
   t->m0s = t->m1s = t->m2s = t->b0s = t->b1s = t->b2s = 0.f;
   t->sigma = fmaf(4.0e-5f, R1, 4.76837158203125e-07f * (fabsf(t->x0) + fabsf(t->x1) + fabsf(V.q0x) + R1));
-  if (fabsf(area2) > 4.0f * t->G) {
+  if (want_spans && fabsf(area2) > 4.0f * t->G) {
     flags |= 4;
     const float s = area2 > 0.f ? 1.0f : -1.0f;
     // not a certain miss w.r.t. edge k:  s E_k >= -g_k,  E_k = e_kx (qy - P_ky) - e_ky (qx - P_kx)
@@ -716,6 +717,52 @@ FB_HD void raster_span(const ViewF& V, const TriR& t, float qy, int i0, int i1, 
   *lo = (int)fl;
   *hi = fh >= fl ? (int)fh : (int)fl - 1;
 }
+
+// ---- front-buffer key of the single-pass scan conversion (raster.cu):
+//   [63:32] far depth bound zhi as an order-preserving integer   [31:27] thickness code   [26:0] slot
+// The thickness code c bounds the triangle's depth extent: zhi - zlo < 2^(c - 24) (c = 31: no bound), so that
+// whoever displaces a front entry can tell, without fetching the triangle, whether it can still be a candidate.
+FB_HD uint32_t ford_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  uint32_t u = __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+FB_HD float unford_bits(uint32_t u) {
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+FB_HD uint64_t front_key(float zlo, float zhi, int slot) {
+  const float thick = zhi - zlo;  // > 0: the interval is widened by e_z on both sides
+#if defined(__CUDA_ARCH__)
+  uint32_t tb = __float_as_uint(thick);
+#else
+  uint32_t tb;
+  memcpy(&tb, &thick, 4);
+#endif
+  int c = (int)((tb >> 23) & 0xffu) - 127 + 25;  // thick < 2^(e + 1) = 2^(c - 24)
+  if (!(thick > 0.0f) || c > 31) c = 31;
+  if (c < 0) c = 0;
+  return ((uint64_t)ford_bits(zhi) << 32) | ((uint64_t)c << 27) | (uint32_t)slot;
+}
+// lower bound of the near depth bound of the triangle a key belongs to (twice the coded extent: the spare
+// factor absorbs the rounding of the subtraction)
+FB_HD float front_key_zlo_lower(uint64_t key) {
+  const int c = (int)((key >> 27) & 31u);
+  if (c == 31) return -INFINITY;
+  const float zhi = unford_bits((uint32_t)(key >> 32));
+  return zhi - ldexpf(1.0f, c - 23);
+}
+#define FB_FRONT_SLOT(key) ((int)((uint32_t)(key) & 0x07ffffffu))
 
 // Stackless traversal: a 64-bit trail holds one "far sibling still pending" bit
 // per level, parent / sibling links walk back up.  Depth <= 62 is guaranteed by

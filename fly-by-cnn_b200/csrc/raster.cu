@@ -5,9 +5,9 @@
 // ray packet, every triangle is projected into the view frame once and tested -- with the
 // float32 screening predicate of flyby_core.cuh, which never decides a result -- against the
 // handful of pixels inside its bounding box:
-//   pass A    front[pixel] = min over SURE triangles of (far depth bound, slot)   one 64-bit atomicMin
-//   pass B    every pixel whose front is another triangle and not nearer than this triangle's near depth
-//             bound, and where this triangle is not a certain miss, appends it to extra[pixel]
+//   raster    front[pixel] = min over its SURE triangles of (far depth bound, slot): one 64-bit atomicMin
+//             whose return value tells the triangle whom it displaced / lost to; every triangle that is not
+//             a certain miss and can still be at or in front of the front joins extra[pixel] (settle_pixel)
 //   resolve1  one thread per pixel in raster order: background / the exact test on the front
 //             triangle when it is the only candidate (the common case) / queue the pixel
 //   resolve2  queued pixels: exact test on the front triangle and the extras, tie-break (t, cell id)
@@ -24,13 +24,20 @@
 namespace fb {
 
 #define RT_THREADS 128
+#ifndef RT_MINB
+#define RT_MINB 12
+#endif
 #define RT_BIG 256   // bounding boxes with more pixels than this are rasterised by a whole warp
 #define RT_EXTRA 8    // extra candidates kept per pixel (two int4)
+#define RT_SPAN_MIN 12 // bounding boxes up to this many pixels are walked whole (the span set-up would cost more)
 #define RV_THREADS 128
+#ifndef RV_MINB
+#define RV_MINB 5
+#endif
 
 struct RasterParams {
   RenderParams r;
-  unsigned long long* front;  // [n_pix] (ordered-float far depth bound << 32) | slot of the nearest SURE triangle
+  unsigned long long* front;  // [n_pix] front_key() of the nearest SURE triangle: far depth bound | thickness code | slot
   int* cnt;                   // [n_pix] extra candidates found
   int* extra;                 // [n_pix, 4] extra slots 0..3
   int* extra2;                // [n_pix, 4] extra slots 4..7 (touched only by pixels that need them)
@@ -49,34 +56,35 @@ struct RasterParams {
 };
 #define RT_LOST 0x40000000  // cnt flag: a spilled pair found the list full, the pixel is re-traced through the LBVH
 
-__device__ __forceinline__ unsigned int ford(float f) {
-  unsigned int u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-template <int PASS>
-__device__ __forceinline__ void visit_pixel(const RasterParams& p, const ViewF& V, const TriR& t, int slot,
-                                            int64_t view_base, int res, int i, int j) {
-  const int64_t pix = view_base + (int64_t)j * res + i;
-  const float qx = fmaf((float)i, V.qdx, V.q0x), qy = fmaf((float)j, V.qdy, V.q0y);
-  const int cls = raster_pixel(t, qx, qy);
-  if (cls == SC_MISS) return;
-  if (PASS == 0) {
-    if (cls == SC_SURE) atomicMin(p.front + pix, ((unsigned long long)ford(t.zhi) << 32) | (unsigned int)slot);
-  } else {
-    const int k = atomicAdd(p.cnt + pix, 1) & (RT_LOST - 1);
-    if (k < 4) p.extra[pix * 4 + k] = slot;
-    else if (k < RT_EXTRA) p.extra2[pix * 4 + (k - 4)] = slot;
-    else {
-      const unsigned int i2 = atomicAdd(p.n_spill, 1u);
-      if (i2 < p.pair_cap) p.pairs[i2] = make_uint2((unsigned int)pix, (unsigned int)slot);
-      else atomicOr(p.cnt + pix, RT_LOST);
-    }
+__device__ __forceinline__ void append_extra(const RasterParams& p, int64_t pix, int slot) {
+  const int k = atomicAdd(p.cnt + pix, 1) & (RT_LOST - 1);
+  if (k < 4) p.extra[pix * 4 + k] = slot;
+  else if (k < RT_EXTRA) p.extra2[pix * 4 + (k - 4)] = slot;
+  else {
+    const unsigned int i2 = atomicAdd(p.n_spill, 1u);
+    if (i2 < p.pair_cap) p.pairs[i2] = make_uint2((unsigned int)pix, (unsigned int)slot);
+    else atomicOr(p.cnt + pix, RT_LOST);
   }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(RT_THREADS, 6) raster_kernel(const RasterParams p) {
+// What a triangle does at a pixel where it is not a certain miss, given the front entry it met there
+// (`old`: the value its atomicMin replaced or kept if it is a certain hit, else the value it read):
+//   certain hit, became the front: the entry it displaced stays a candidate if its depth range can reach this one
+//   certain hit, did not:          it is a candidate if its near depth bound is not behind the front it met
+//   undecided:                     likewise
+// The front only ever moves nearer, so every test against an intermediate front is weaker than the test
+// against the final one: the extras are a superset of what pass-by-pass scan conversion would list, for any
+// order of arrival.
+__device__ __forceinline__ void settle_pixel(const RasterParams& p, int64_t pix, int cls, unsigned long long key,
+                                             unsigned long long old, unsigned int zlo_ord, float zhi) {
+  if (cls == SC_SURE && key < old) {
+    if (old != ~0ull && front_key_zlo_lower(old) <= zhi) append_extra(p, pix, FB_FRONT_SLOT(old));
+  } else if (zlo_ord <= (unsigned int)(old >> 32)) {
+    append_extra(p, pix, FB_FRONT_SLOT(key));
+  }
+}
+
+__global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const RasterParams p) {
   __shared__ ViewF s_vf;
   const int view = blockIdx.y;  // local view index of this render call
   {
@@ -97,33 +105,39 @@ __global__ void __launch_bounds__(RT_THREADS, 6) raster_kernel(const RasterParam
   if (slot < p.T) {
     const float4 a = __ldg(p.r.tv0 + slot), b = __ldg(p.r.tv1 + slot), e = __ldg(p.r.tv2 + slot);
     const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-    if (raster_project(V, P0, P1, P2, res, &t, &r)) {  // most triangles of a close-up view end here
-      raster_setup(V, 0.0f, P0, P1, P2, &t);           // ray origins lie in the view plane: depth 0 (+- e_z)
-      if (t.flags & 1) npx = (r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
+    if (raster_project(V, P0, P1, P2, res, &t, &r)) {  // triangles outside a close-up view end here
+      npx = (r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
+      raster_setup(V, 0.0f, P0, P1, P2, npx > RT_SPAN_MIN, &t);  // ray origins lie in the view plane: depth 0 (+- e_z)
+      if (!(t.flags & 1)) npx = 0;
     }
   }
   // small triangles: one thread walks the rows of its bounding box, inside each row only the span that
-  // the three edges leave
+  // the three edges leave; up to four pixels of a row are in flight at a time
   if (npx > 0 && npx <= RT_BIG) {
-    const unsigned int zlo_ord = ford(t.zlo);
+    const unsigned long long key = front_key(t.zlo, t.zhi, slot);
+    const unsigned int zlo_ord = ford_bits(t.zlo);
     for (int j = r.j0; j <= r.j1; j++) {
       int lo = r.i0, hi = r.i1;
-      if (t.flags & 4) raster_span(V, t, fmaf((float)j, V.qdy, V.q0y), r.i0, r.i1, &lo, &hi);
-      if (PASS == 0) {
-        for (int i = lo; i <= hi; i++) visit_pixel<0>(p, V, t, slot, view_base, res, i, j);
-      } else {
-        // cheap tests first, four independent loads in flight: most visits end at the front buffer (the
-        // triangle is the front itself, or lies behind it)
-        const unsigned long long* frow = p.front + view_base + (int64_t)j * res;
-        for (int i = lo; i <= hi; i += 4) {
-          unsigned long long f[4];
+      const float qy = fmaf((float)j, V.qdy, V.q0y);
+      if (t.flags & 4) raster_span(V, t, qy, r.i0, r.i1, &lo, &hi);
+      unsigned long long* frow = p.front + view_base + (int64_t)j * res;
+      for (int i = lo; i <= hi; i += 4) {
+        int cls[4];
+        unsigned long long old[4];
 #pragma unroll
-          for (int k = 0; k < 4; k++) f[k] = (i + k <= hi) ? __ldg(frow + i + k) : 0ull;  // 0: nothing passes
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (zlo_ord <= (unsigned int)(f[k] >> 32) && (unsigned int)f[k] != (unsigned int)slot)
-              visit_pixel<1>(p, V, t, slot, view_base, res, i + k, j);
+        for (int k = 0; k < 4; k++) {
+          cls[k] = SC_MISS;
+          if (i + k <= hi) cls[k] = raster_pixel(t, fmaf((float)(i + k), V.qdx, V.q0x), qy);
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          old[k] = 0ull;
+          if (cls[k] == SC_SURE) old[k] = atomicMin(frow + i + k, key);
+          else if (cls[k] == SC_MAYBE) old[k] = __ldcg(frow + i + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (cls[k] != SC_MISS) settle_pixel(p, view_base + (int64_t)j * res + i + k, cls[k], key, old[k], zlo_ord, t.zhi);
       }
     }
   }
@@ -142,16 +156,17 @@ __global__ void __launch_bounds__(RT_THREADS, 6) raster_kernel(const RasterParam
     const int i0 = __shfl_sync(0xffffffffu, r.i0, src), i1 = __shfl_sync(0xffffffffu, r.i1, src);
     const int j0 = __shfl_sync(0xffffffffu, r.j0, src), j1 = __shfl_sync(0xffffffffu, r.j1, src);
     const int uslot = __shfl_sync(0xffffffffu, slot, src);
+    const unsigned long long key = front_key(u.zlo, u.zhi, uslot);
+    const unsigned int zlo_ord = ford_bits(u.zlo);
     const int w = i1 - i0 + 1;
     const long long n = (long long)w * (j1 - j0 + 1);
-    const unsigned int uz_ord = ford(u.zlo);
     for (long long k = lane; k < n; k += 32) {
       const int i = i0 + (int)(k % w), j = j0 + (int)(k / w);
-      if (PASS == 1) {
-        const unsigned long long f = __ldg(p.front + view_base + (int64_t)j * res + i);
-        if (uz_ord > (unsigned int)(f >> 32) || (unsigned int)f == (unsigned int)uslot) continue;
-      }
-      visit_pixel<PASS>(p, V, u, uslot, view_base, res, i, j);
+      const int cls = raster_pixel(u, fmaf((float)i, V.qdx, V.q0x), fmaf((float)j, V.qdy, V.q0y));
+      if (cls == SC_MISS) continue;
+      const int64_t pix = view_base + (int64_t)j * res + i;
+      const unsigned long long old = cls == SC_SURE ? atomicMin(p.front + pix, key) : __ldcg(p.front + pix);
+      settle_pixel(p, pix, cls, key, old, zlo_ord, u.zhi);
     }
   }
 }
@@ -166,7 +181,7 @@ __global__ void raster_init_kernel(unsigned long long* front, int* cnt, int64_t 
 
 // ---- resolve1: every pixel, raster order
 #define RV_STAGE 64  // per-warp staging of queued pixels: one global atomic per 32+ entries instead of one per iteration
-__global__ void __launch_bounds__(RV_THREADS, 5) raster_resolve1_kernel(const RasterParams rp) {
+__global__ void __launch_bounds__(RV_THREADS, RV_MINB) raster_resolve1_kernel(const RasterParams rp) {
   const RenderParams& p = rp.r;
   __shared__ uint32_t s_stage[RV_THREADS / 32][RV_STAGE];
   const int lane = threadIdx.x & 31;
@@ -204,7 +219,7 @@ __global__ void __launch_bounds__(RV_THREADS, 5) raster_resolve1_kernel(const Ra
       write_pixel(p, pix, zero, -1, -1.0);
       continue;
     }
-    const int slot = (int)(unsigned int)f;
+    const int slot = FB_FRONT_SLOT(f);
     const float4* rec = p.trec + 4 * (int64_t)slot;
     const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
     const PixelRay r = pixel_ray(p, pix);
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve2_kernel(const Ra
     for (int i = (f == ~0ull ? 0 : -1); i < nc; i++) {
       const int4 cc = i < 4 ? c0 : c1;
       const int j = i & 3;
-      const int slot = i < 0 ? (int)(unsigned int)f : (j == 0 ? cc.x : (j == 1 ? cc.y : (j == 2 ? cc.z : cc.w)));
+      const int slot = i < 0 ? FB_FRONT_SLOT(f) : (j == 0 ? cc.x : (j == 1 ? cc.y : (j == 2 ? cc.z : cc.w)));
       const float4* rec = p.trec + 4 * (int64_t)slot;
       const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
       const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
@@ -417,12 +432,10 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   raster_init_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(p.front, p.cnt, n_pix);
   FB_LAUNCH_CHECK(c);
   dim3 grid((unsigned)cdiv(p.T, RT_THREADS), (unsigned)rp.n_views);
-  raster_kernel<0><<<grid, RT_THREADS, 0, st>>>(p);
-  FB_LAUNCH_CHECK(c);
-  raster_kernel<1><<<grid, RT_THREADS, 0, st>>>(p);
+  raster_kernel<<<grid, RT_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the candidate search and the exact resolve
-  long long rgrid = (long long)c->sm_count * 5 * 4;  // 5 CTAs resident per SM, 4 rounds for balance
+  long long rgrid = (long long)c->sm_count * RV_MINB * 4;  // RV_MINB CTAs resident per SM, 4 rounds for balance
   const long long want = cdiv(n_pix, RV_THREADS);
   if (rgrid > want) rgrid = want;
   raster_resolve1_kernel<<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);

@@ -480,14 +480,15 @@ int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris,
 extern "C" __attribute__((visibility("default")))
 int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* views,
                       int n_views, double radius, int res, double plane_scale, double spacing, int cand_cap,
-                      int32_t* out_ids, double* out_t, long long* work /* pixel tests, exact tests, overflow pixels, [3] span audit */) {
+                      int32_t* out_ids, double* out_t, long long* work /* [5]: pixel tests, exact tests, overflow pixels, span audit, in: order seed */) {
   SimBvh b;
   build(verts, V, tris, T, b);
   if (b.nodes.empty()) return 1;
   float maxc = 0.f;
   for (int64_t i = 0; i < 3 * V; i++) maxc = fmaxf(maxc, fabsf(verts[i]));
   long long n_tests = 0, n_exact = 0, n_over = 0, n_span_bad = 0;
-  const bool check_spans = work && work[3] == 1;  // in: work[3] = 1 asks for the span audit; out: work[3] = violations
+  const bool check_spans = work && work[3] == 1;
+  const long long order_seed = work ? work[4] : 0;  // in: work[4] != 0 shuffles the arrival order of the triangles  // in: work[3] = 1 asks for the span audit; out: work[3] = violations
   SimCount cnt;
   SimFetch f{b.nodes.data()};
   for (int v = 0; v < n_views; v++) {
@@ -496,47 +497,58 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
     ViewF vf;
     viewf_setup(vw, radius, spacing, maxc, &vf);
     viewf_pixels(vw, spacing, res, &vf);
-    // front[pixel] = smallest (far depth bound, slot) over SURE triangles
-    std::vector<float> uz((size_t)res * res, INFINITY);
-    std::vector<int> front((size_t)res * res, -1);
+    // single pass, as raster_kernel: front[pixel] = smallest front_key over the SURE triangles; what a triangle
+    // learns from the entry it displaced / lost to / read decides who joins the extras (settle_pixel).
+    // Triangles arrive in slot order, or in a seeded random order to stand in for the GPU's arbitrary one.
+    std::vector<uint64_t> front((size_t)res * res, ~0ull);
     std::vector<std::vector<int>> cand((size_t)res * res);
-    for (int pass = 0; pass < 2; pass++) {
-      for (int64_t slot = 0; slot < T; slot++) {
-        float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
-        float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
-        TriR t;
-        PixRange r;
-        if (!raster_project(vf, P0, P1, P2, res, &t, &r)) continue;
-        raster_setup(vf, 0.0f, P0, P1, P2, &t);
-        if (!(t.flags & 1)) continue;
-        const bool use_spans = (long long)(r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1) <= 256 && (t.flags & 4);
-        for (int j = r.j0; j <= r.j1; j++) {
-          int lo = r.i0, hi = r.i1;
-          if (use_spans) raster_span(vf, t, fmaf((float)j, vf.qdy, vf.q0y), r.i0, r.i1, &lo, &hi);
-          if (check_spans)  // every pixel the span skips must be a certain miss
-            for (int i = r.i0; i <= r.i1; i++)
-              if ((i < lo || i > hi) && raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y)) != SC_MISS)
-                n_span_bad++;
-          for (int i = lo; i <= hi; i++) {
-            float qx = fmaf((float)i, vf.qdx, vf.q0x), qy = fmaf((float)j, vf.qdy, vf.q0y);
-            int cls = raster_pixel(t, qx, qy);
-            n_tests++;
-            if (cls == SC_MISS) continue;
-            size_t pix = (size_t)j * res + i;
-            if (pass == 0) {
-              if (cls == SC_SURE && (t.zhi < uz[pix] || (t.zhi == uz[pix] && (int)slot < front[pix]))) {
-                uz[pix] = t.zhi;
-                front[pix] = (int)slot;
-              }
-            } else if (t.zlo <= uz[pix] && (int)slot != front[pix]) {
-              cand[pix].push_back((int)slot);
-            }
+    std::vector<int64_t> order(T);
+    for (int64_t k = 0; k < T; k++) order[k] = k;
+    if (order_seed) {
+      uint64_t st = (uint64_t)order_seed * 0x9E3779B97F4A7C15ull + (uint64_t)v;
+      for (int64_t k = T - 1; k > 0; k--) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        std::swap(order[k], order[(int64_t)((st >> 33) % (uint64_t)(k + 1))]);
+      }
+    }
+    for (int64_t oi = 0; oi < T; oi++) {
+      const int64_t slot = order[oi];
+      float4 a = b.tv0[slot], bb = b.tv1[slot], e = b.tv2[slot];
+      float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
+      TriR t;
+      PixRange r;
+      if (!raster_project(vf, P0, P1, P2, res, &t, &r)) continue;
+      const long long npx = (long long)(r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
+      raster_setup(vf, 0.0f, P0, P1, P2, npx > 12, &t);
+      if (!(t.flags & 1)) continue;
+      const uint64_t key = front_key(t.zlo, t.zhi, (int)slot);
+      const uint32_t zlo_ord = ford_bits(t.zlo);
+      const bool use_spans = npx <= 256 && (t.flags & 4);
+      for (int j = r.j0; j <= r.j1; j++) {
+        int lo = r.i0, hi = r.i1;
+        if (use_spans) raster_span(vf, t, fmaf((float)j, vf.qdy, vf.q0y), r.i0, r.i1, &lo, &hi);
+        if (check_spans)  // every pixel the span skips must be a certain miss
+          for (int i = r.i0; i <= r.i1; i++)
+            if ((i < lo || i > hi) && raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y)) != SC_MISS)
+              n_span_bad++;
+        for (int i = lo; i <= hi; i++) {
+          float qx = fmaf((float)i, vf.qdx, vf.q0x), qy = fmaf((float)j, vf.qdy, vf.q0y);
+          int cls = raster_pixel(t, qx, qy);
+          n_tests++;
+          if (cls == SC_MISS) continue;
+          size_t pix = (size_t)j * res + i;
+          const uint64_t old = front[pix];
+          if (cls == SC_SURE && key < old) front[pix] = key;
+          if (cls == SC_SURE && key < old) {
+            if (old != ~0ull && front_key_zlo_lower(old) <= t.zhi) cand[pix].push_back(FB_FRONT_SLOT(old));
+          } else if (zlo_ord <= (uint32_t)(old >> 32)) {
+            cand[pix].push_back((int)slot);
           }
         }
       }
     }
     for (size_t pix = 0; pix < (size_t)res * res; pix++)
-      if (front[pix] >= 0 && cand_cap >= 0) cand[pix].insert(cand[pix].begin(), front[pix]);
+      if (front[pix] != ~0ull && cand_cap >= 0) cand[pix].insert(cand[pix].begin(), FB_FRONT_SLOT(front[pix]));
     for (int j = 0; j < res; j++)
       for (int i = 0; i < res; i++) {
         size_t pix = (size_t)j * res + i;
