@@ -243,8 +243,8 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
         alg = algorithmic_bytes(n_rays, C, T, V)
-        # the render is a short pipeline of kernels (candidate search: raster_kernel<0>, <1>; exact decision:
-        # classify, resolve1, resolve2); the roofline is taken over the pipeline, CUDA events on its stream
+        # the render is a short pipeline of kernels (candidate search: raster_kernel; exact decision:
+        # raster_resolve1/2, spill_*); the roofline is taken over the pipeline, CUDA events on its stream
         achieved = alg / (ms_render * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "render_traffic.json")
@@ -264,9 +264,9 @@ def run_ours(args):
                 "hit_fraction": st["n_hits"] / max(1, st["n_rays"]),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "render pipeline: raster_kernel<0>, raster_kernel<1> (largest), classify_kernel, resolve1_kernel, resolve2_kernel",
+                             "kernel": "render pipeline: raster_kernel (largest), raster_resolve1_kernel, raster_resolve2_kernel, spill_*_kernel",
                              "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                             "note": "algorithmic bytes = compulsory output + mesh + BVH bytes of one render (SURVEY 8d); the pipeline is bound by float32/float64 instruction issue and L2 atomics, not by HBM"},
+                             "note": "algorithmic bytes = compulsory output + mesh + BVH bytes of one render (SURVEY 8d); the pipeline is bound by float32/float64 instruction issue and L2 atomic latency, not by HBM"},
                 "e2e": {"value": e2e_views, "unit": "views/s", "ms_per_step": ms_e2e_max,
                         "h2d_bytes_per_step": V * 12 + T * 12, "d2h_bytes_per_step": n_rays * (4 * C + 4)},
                 "gpu_launches": launches, "clocks": sampler.summary()}
@@ -281,7 +281,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
