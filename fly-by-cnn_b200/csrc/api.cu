@@ -123,7 +123,7 @@ void flyby_destroy(flyby_ctx* c) {
                     &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.leaf_box,
                     &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid, &m.trec,
                     &c->view_pts, &c->views, &c->viewsf, &c->tc_table, &c->cand, &c->cand2, &c->pix_lists, &c->raster_tmp, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
-                    &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->counters};
+                    &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->counters};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -459,6 +459,72 @@ int flyby_cells_to_points(flyby_ctx* c, const int32_t* cell_labels, int32_t dflt
   bool need = !is_device_ptr(cell_labels);
   if ((rc = so.finish(c, &need))) return rc;
   return sync_if(c, need);
+}
+
+// ---- mesh-label post-processing (postproc.cu): labels int32 [V], host or device, edited in place
+namespace {
+struct LabelsIO {
+  int32_t* user = nullptr;
+  int32_t* dev = nullptr;
+  bool host = false;
+};
+int labels_begin(flyby_ctx* c, int32_t* labels, const char* what, LabelsIO* io) {
+  if (!c->mesh.has_mesh || !c->mesh.built) return fail(c, FLYBY_ERR_INVALID, "%s: call flyby_set_mesh and flyby_build first", what);
+  if (!labels && c->mesh.V > 0) return fail(c, FLYBY_ERR_INVALID, "%s: labels is NULL", what);
+  io->user = io->dev = labels;
+  io->host = labels && !is_device_ptr(labels);
+  if (io->host) {
+    FB_CUDA(c, c->stage_in0.reserve((size_t)c->mesh.V * sizeof(int32_t) + 16));
+    io->dev = c->stage_in0.as<int32_t>();
+    FB_CUDA(c, cudaMemcpyAsync(io->dev, labels, (size_t)c->mesh.V * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  }
+  return FLYBY_OK;
+}
+int labels_end(flyby_ctx* c, const LabelsIO& io, int rc) {
+  if (rc) return rc;
+  if (io.host) {
+    FB_CUDA(c, cudaMemcpyAsync(io.user, io.dev, (size_t)c->mesh.V * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return FLYBY_OK;
+}
+}  // namespace
+
+int flyby_labels_remove_islands(flyby_ctx* c, int32_t* labels, int32_t label, int64_t min_count, int ignore_neg1) {
+  CHECK_CTX(c);
+  LabelsIO io;
+  int rc = labels_begin(c, labels, "labels_remove_islands", &io);
+  if (rc) return rc;
+  return labels_end(c, io, pp_remove_islands(c, io.dev, label, min_count, ignore_neg1));
+}
+int flyby_labels_connectivity(flyby_ctx* c, int32_t* labels, int32_t label, int32_t start_label, int64_t* n_regions) {
+  CHECK_CTX(c);
+  LabelsIO io;
+  int rc = labels_begin(c, labels, "labels_connectivity", &io);
+  if (rc) return rc;
+  return labels_end(c, io, pp_connectivity(c, io.dev, label, start_label, n_regions));
+}
+int flyby_labels_erode(flyby_ctx* c, int32_t* labels, int32_t label, int has_ignore, int32_t ignore_label,
+                       int64_t iterations, int has_target, int32_t target) {
+  CHECK_CTX(c);
+  LabelsIO io;
+  int rc = labels_begin(c, labels, "labels_erode", &io);
+  if (rc) return rc;
+  return labels_end(c, io, pp_erode(c, io.dev, label, has_ignore, ignore_label, iterations, has_target, target));
+}
+int flyby_labels_dilate(flyby_ctx* c, int32_t* labels, int32_t label, int64_t iterations, int over_target, int32_t target) {
+  CHECK_CTX(c);
+  LabelsIO io;
+  int rc = labels_begin(c, labels, "labels_dilate", &io);
+  if (rc) return rc;
+  return labels_end(c, io, pp_dilate(c, io.dev, label, iterations, over_target, target));
+}
+int flyby_labels_relabel(flyby_ctx* c, int32_t* labels, int32_t label, int32_t relabel) {
+  CHECK_CTX(c);
+  LabelsIO io;
+  int rc = labels_begin(c, labels, "labels_relabel", &io);
+  if (rc) return rc;
+  return labels_end(c, io, pp_relabel(c, io.dev, label, relabel));
 }
 
 int flyby_nccl_unique_id(flyby_ctx* c, uint8_t id_out[128]) {

@@ -90,6 +90,7 @@ struct flyby_ctx {
   double radius = 0;
   // staging for host-side buffers
   fb::DevBuf stage_feat, stage_ids, stage_t, stage_in0, stage_in1, stage_out0, stage_misc;
+  fb::DevBuf pp_tmp, pp_tmp2;  // label post-processing scratch (postproc.cu)
   fb::DevBuf counters;  // uint64 [8]: tile counter, work counters
   // stats
   cudaEvent_t ev[8] = {nullptr};
@@ -153,6 +154,13 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
                  int32_t* ids, double* tt, bool first_chunk = true, bool last_chunk = true);                                     // trace.cu
 int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double* rays);
 int trace_cast(flyby_ctx* c, const double* rays, int64_t n, double tol, int32_t* ids, double* tt, double* w);
+// postproc.cu: labels int32 [V] on the device, edited in place
+int pp_remove_islands(flyby_ctx* c, int32_t* labels, int32_t label, int64_t min_count, int ignore_neg1);
+int pp_connectivity(flyby_ctx* c, int32_t* labels, int32_t label, int32_t start_label, int64_t* n_regions);
+int pp_erode(flyby_ctx* c, int32_t* labels, int32_t label, int has_ignore, int32_t ignore_label, int64_t iterations,
+             int has_target, int32_t target);
+int pp_dilate(flyby_ctx* c, int32_t* labels, int32_t label, int64_t iterations, int over_target, int32_t target);
+int pp_relabel(flyby_ctx* c, int32_t* labels, int32_t label, int32_t relabel);
 int views_icosahedron(flyby_ctx* c, int L, double radius, int dedupe);          // views.cu
 int views_spiral(flyby_ctx* c, int n, double turns, double radius);             // views.cu
 

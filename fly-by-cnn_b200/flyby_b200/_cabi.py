@@ -47,7 +47,8 @@ SYMBOLS = [
     "flyby_generate_rays", "flyby_render", "flyby_cast", "flyby_point_features", "flyby_backproject",
     "flyby_backproject_soft", "flyby_votes_argmax", "flyby_cells_to_points", "flyby_nccl_unique_id",
     "flyby_nccl_init", "flyby_votes_allreduce", "flyby_get_stats", "flyby_set_count_work",
-    "flyby_launch_count",
+    "flyby_launch_count", "flyby_labels_remove_islands", "flyby_labels_connectivity", "flyby_labels_erode",
+    "flyby_labels_dilate", "flyby_labels_relabel",
 ]
 
 NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2}
@@ -303,6 +304,38 @@ class Context:
             out = np.empty(self.n_verts, np.int32)
         self._ck(self._lib.flyby_cells_to_points(self._h, _ptr(cell_labels), C.c_int32(default), _ptr(out)))
         return out
+
+    # ---- mesh-label post-processing (labels int32 [V], numpy or torch-cuda, edited in place) --------
+    def labels_remove_islands(self, labels, label, min_count, ignore_neg1=False):
+        _check_dtype(labels, np.int32, "labels")
+        self._ck(self._lib.flyby_labels_remove_islands(self._h, _ptr(labels), C.c_int32(label), C.c_int64(min_count),
+                                                       C.c_int(1 if ignore_neg1 else 0)))
+        return labels
+
+    def labels_connectivity(self, labels, label, start_label):
+        _check_dtype(labels, np.int32, "labels")
+        n = C.c_int64(0)
+        self._ck(self._lib.flyby_labels_connectivity(self._h, _ptr(labels), C.c_int32(label), C.c_int32(start_label),
+                                                     C.byref(n)))
+        return int(n.value)
+
+    def labels_erode(self, labels, label, ignore_label=None, iterations=None, target=None):
+        _check_dtype(labels, np.int32, "labels")
+        self._ck(self._lib.flyby_labels_erode(
+            self._h, _ptr(labels), C.c_int32(label), C.c_int(ignore_label is not None), C.c_int32(ignore_label or 0),
+            C.c_int64(-1 if iterations is None else int(iterations)), C.c_int(target is not None), C.c_int32(target or 0)))
+        return labels
+
+    def labels_dilate(self, labels, label, iterations=2, over_target=False, target=None):
+        _check_dtype(labels, np.int32, "labels")
+        self._ck(self._lib.flyby_labels_dilate(self._h, _ptr(labels), C.c_int32(label), C.c_int64(iterations),
+                                               C.c_int(1 if over_target else 0), C.c_int32(target or 0)))
+        return labels
+
+    def labels_relabel(self, labels, label, relabel):
+        _check_dtype(labels, np.int32, "labels")
+        self._ck(self._lib.flyby_labels_relabel(self._h, _ptr(labels), C.c_int32(label), C.c_int32(relabel)))
+        return labels
 
     # ---- collective ---------------------------------------------------------
     def nccl_unique_id(self):

@@ -168,6 +168,37 @@ FLYBY_API int flyby_votes_argmax(flyby_ctx* ctx, const int32_t* votes, int64_t n
 FLYBY_API int flyby_cells_to_points(flyby_ctx* ctx, const int32_t* cell_labels, int32_t dflt,
                           int32_t* point_labels_out /* [V] */);
 
+/* ---- mesh-label post-processing ------------------------ */
+/* What every predictor of the reference runs on the point labels right after the
+ * back-projection (predict_v3.py:93-133, dental_model_seg.py:228-239).  labels is
+ * int32 [V] of the current mesh (flyby_set_mesh + flyby_build), host or device,
+ * edited in place; neighbours of a point = the other points of its incident cells. */
+/* src/py/post_process.py:285-295 RemoveIslands (+ ConnectedRegion :243-255,
+ * NeighborLabel :257-281): connected regions of `label` with fewer than min_count
+ * points take the most frequent label around them (ties: the label met first in
+ * ascending point id).  As in the reference (:292) nothing is relabelled unless
+ * ignore_neg1 is set, and never to -1. */
+FLYBY_API int flyby_labels_remove_islands(flyby_ctx* ctx, int32_t* labels, int32_t label,
+                                          int64_t min_count, int ignore_neg1);
+/* :297-304 ConnectivityLabeling: the connected regions of `label`, in the order of
+ * their lowest point id, become start_label, start_label + 1, ...; n_regions
+ * (optional) returns their number. */
+FLYBY_API int flyby_labels_connectivity(flyby_ctx* ctx, int32_t* labels, int32_t label,
+                                        int32_t start_label, int64_t* n_regions);
+/* :306-346 ErodeLabel: synchronous sweeps; a point of `label` takes the label of its
+ * lowest-id neighbour whose label differs (and is not ignore_label / is target, when
+ * has_ignore / has_target); stops when a sweep changes nothing or after `iterations`
+ * sweeps (< 0: no limit, the reference's math.inf). */
+FLYBY_API int flyby_labels_erode(flyby_ctx* ctx, int32_t* labels, int32_t label, int has_ignore,
+                                 int32_t ignore_label, int64_t iterations, int has_target,
+                                 int32_t target);
+/* :348-375 DilateLabel: `iterations` synchronous sweeps; neighbours of `label` whose
+ * label differs (over_target: whose label is exactly target) join it. */
+FLYBY_API int flyby_labels_dilate(flyby_ctx* ctx, int32_t* labels, int32_t label, int64_t iterations,
+                                  int over_target, int32_t target);
+/* :377-380 ReLabel */
+FLYBY_API int flyby_labels_relabel(flyby_ctx* ctx, int32_t* labels, int32_t label, int32_t relabel);
+
 /* ---- the one collective: sum of label votes over ranks ------------------ */
 /* NCCL is loaded at run time (the libnccl.so.2 torch ships).  Rank 0 calls
  * flyby_nccl_unique_id, the host shares the 128 bytes, every rank calls

@@ -176,3 +176,43 @@ def cells_to_points(cell_labels, tris, n_points, default=0):
     lib().orc_cells_to_points(_p(cl), _p(t), C.c_int64(len(t)), C.c_int64(n_points),
                               C.c_int32(default), _p(out))
     return out
+
+
+# ---- mesh-label post-processing (oracle/postproc_oracle.c; reference src/py/post_process.py:243-380).
+# Each function returns a new label array; the reference edits its vtk array in place.
+def pp_remove_islands(tris, n_points, labels, label, min_count, ignore_neg1=False):
+    t, out = _i32(tris), _i32(labels).copy()
+    lib().orc_pp_remove_islands(_p(t), C.c_int64(len(t)), C.c_int64(n_points), _p(out), C.c_int32(label),
+                                C.c_int64(min_count), C.c_int(1 if ignore_neg1 else 0))
+    return out
+
+
+def pp_connectivity(tris, n_points, labels, label, start_label):
+    t, out = _i32(tris), _i32(labels).copy()
+    f = lib().orc_pp_connectivity
+    f.restype = C.c_int64
+    n = f(_p(t), C.c_int64(len(t)), C.c_int64(n_points), _p(out), C.c_int32(label), C.c_int32(start_label))
+    return out, int(n)
+
+
+def pp_erode(tris, n_points, labels, label, ignore_label=None, iterations=None, target=None):
+    t, out = _i32(tris), _i32(labels).copy()
+    f = lib().orc_pp_erode
+    f.restype = C.c_int64
+    f(_p(t), C.c_int64(len(t)), C.c_int64(n_points), _p(out), C.c_int32(label),
+      C.c_int(ignore_label is not None), C.c_int32(ignore_label or 0),
+      C.c_int64(-1 if iterations is None else iterations), C.c_int(target is not None), C.c_int32(target or 0))
+    return out
+
+
+def pp_dilate(tris, n_points, labels, label, iterations=2, over_target=False, target=None):
+    t, out = _i32(tris), _i32(labels).copy()
+    lib().orc_pp_dilate(_p(t), C.c_int64(len(t)), C.c_int64(n_points), _p(out), C.c_int32(label),
+                        C.c_int64(iterations), C.c_int(1 if over_target else 0), C.c_int32(target or 0))
+    return out
+
+
+def pp_relabel(labels, label, relabel):
+    out = _i32(labels).copy()
+    lib().orc_pp_relabel(_p(out), C.c_int64(len(out)), C.c_int32(label), C.c_int32(relabel))
+    return out
