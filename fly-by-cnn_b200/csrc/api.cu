@@ -379,6 +379,26 @@ int flyby_point_features(flyby_ctx* c, const int32_t* cell_ids, int64_t n_pix, c
   return sync_if(c, need);
 }
 
+int flyby_interpolate_features(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, const int32_t* cell_ids,
+                               const float* feats, int F, float zero, float* out) {
+  CHECK_CTX(c);
+  int rc = check_render_args(c, vb, ve, res, o, true);
+  if (rc) return rc;
+  if (!cell_ids || !feats || !out || F < 1) return fail(c, FLYBY_ERR_INVALID, "interpolate_features: bad arguments");
+  const size_t n_pix = (size_t)(ve - vb) * res * res;
+  if ((rc = views_setup(c, o, res))) return rc;
+  const int32_t* dids;
+  const float* dfeats;
+  if ((rc = stage_in(c, c->stage_in0, cell_ids, n_pix, &dids))) return rc;
+  if ((rc = stage_in(c, c->stage_in1, feats, (size_t)c->mesh.V * F, &dfeats))) return rc;
+  StageOut<float> so;
+  if ((rc = so.begin(c, c->stage_out0, out, n_pix * F))) return rc;
+  if ((rc = trace_interpolate(c, vb, ve, res, o, dids, dfeats, F, zero, so.dev))) return rc;
+  bool need = !is_device_ptr(cell_ids) || !is_device_ptr(feats);
+  if ((rc = so.finish(c, &need))) return rc;
+  return sync_if(c, need);
+}
+
 int flyby_backproject(flyby_ctx* c, const int32_t* cell_ids, const int32_t* labels, int64_t n_pix, int K,
                       int32_t* votes) {
   CHECK_CTX(c);

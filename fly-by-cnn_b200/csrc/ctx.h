@@ -152,6 +152,8 @@ int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp);  /
 int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res);                      // trace.cu
 int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
                  int32_t* ids, double* tt, bool first_chunk = true, bool last_chunk = true);                                     // trace.cu
+int trace_interpolate(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, const int32_t* cell_ids,
+                      const float* feats, int F, float zero, float* out);
 int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double* rays);
 int trace_cast(flyby_ctx* c, const double* rays, int64_t n, double tol, int32_t* ids, double* tt, double* w);
 // postproc.cu: labels int32 [V] on the device, edited in place

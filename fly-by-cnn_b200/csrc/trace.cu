@@ -58,6 +58,59 @@ int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res) {
   return FLYBY_OK;
 }
 
+// ---------------------------------------------------------------- barycentric lookup at the hits
+// out[pixel, f] = sum_k w_k feats[point_k(cell), f] with the exact test's weights of the cell that
+// flyby_render reported for the pixel (fly_by_features.cxx:766-790 interpolates its normals this way;
+// the vertex-colour shading of challenge-teeth/teeth_nets.py:121-153 is the same lookup).  The weights are
+// recomputed with tri_exact on the same inputs, i.e. they are the values the render used.
+__global__ void interpolate_kernel(RenderParams p, const float* __restrict__ verts, const int32_t* __restrict__ tris,
+                                   const int32_t* __restrict__ cell_ids, const float* __restrict__ feats, int F,
+                                   float zero, float* __restrict__ out, int64_t n_pix) {
+  const int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (pix >= n_pix) return;
+  const int32_t cell = cell_ids[pix];
+  float* o = out + pix * F;
+  if (cell < 0) {
+    for (int f = 0; f < F; f++) o[f] = zero;
+    return;
+  }
+  const int32_t i0 = tris[3 * (int64_t)cell], i1 = tris[3 * (int64_t)cell + 1], i2 = tris[3 * (int64_t)cell + 2];
+  const float P0[3] = {verts[3 * (int64_t)i0], verts[3 * (int64_t)i0 + 1], verts[3 * (int64_t)i0 + 2]};
+  const float P1[3] = {verts[3 * (int64_t)i1], verts[3 * (int64_t)i1 + 1], verts[3 * (int64_t)i1 + 2]};
+  const float P2[3] = {verts[3 * (int64_t)i2], verts[3 * (int64_t)i2 + 1], verts[3 * (int64_t)i2 + 2]};
+  const PixelRay r = pixel_ray(p, pix);
+  double t, x[3], w[3];
+  if (!tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w)) {  // not a hit of this ray: ids from another set-up
+    for (int f = 0; f < F; f++) o[f] = zero;
+    return;
+  }
+  for (int f = 0; f < F; f++) {
+    const double a = FB_MUL(w[0], (double)feats[(int64_t)i0 * F + f]);
+    const double b = FB_MUL(w[1], (double)feats[(int64_t)i1 * F + f]);
+    const double e = FB_MUL(w[2], (double)feats[(int64_t)i2 * F + f]);
+    o[f] = (float)FB_ADD(FB_ADD(a, b), e);
+  }
+}
+
+int trace_interpolate(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, const int32_t* cell_ids,
+                      const float* feats, int F, float zero, float* out) {
+  MeshDev& m = c->mesh;
+  const int64_t n_pix = (int64_t)(ve - vb) * res * res;
+  if (n_pix >= (int64_t)1 << 32) return fail(c, FLYBY_ERR_INVALID, "more than 2^32 rays in one call");
+  if (n_pix == 0) return FLYBY_OK;
+  RenderParams p;
+  memset(&p, 0, sizeof p);
+  p.tc = c->tc_table.as<double>();
+  p.views = c->views.as<View>();
+  p.view_begin = vb; p.n_views = ve - vb; p.res = res;
+  p.spacing = o->plane_spacing;
+  p.tol2 = o->tolerance * o->tolerance;
+  interpolate_kernel<<<(unsigned)cdiv(n_pix, 128), 128, 0, c->stream>>>(p, m.verts.as<float>(), m.tris.as<int32_t>(),
+                                                                          cell_ids, feats, F, zero, out, n_pix);
+  FB_LAUNCH_CHECK(c);
+  return FLYBY_OK;
+}
+
 // ---------------------------------------------------------------- ray dump (parity of a5)
 __global__ void rays_kernel(const View* __restrict__ views, int view_begin, int n_views, int res,
                             double spacing, double* __restrict__ out) {

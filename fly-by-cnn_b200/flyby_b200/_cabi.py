@@ -48,7 +48,7 @@ SYMBOLS = [
     "flyby_backproject_soft", "flyby_votes_argmax", "flyby_cells_to_points", "flyby_nccl_unique_id",
     "flyby_nccl_init", "flyby_votes_allreduce", "flyby_get_stats", "flyby_set_count_work",
     "flyby_launch_count", "flyby_labels_remove_islands", "flyby_labels_connectivity", "flyby_labels_erode",
-    "flyby_labels_dilate", "flyby_labels_relabel",
+    "flyby_labels_dilate", "flyby_labels_relabel", "flyby_interpolate_features",
 ]
 
 NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2}
@@ -265,6 +265,20 @@ class Context:
             out = np.empty(tuple(cell_ids.shape) + (F,), np.float32)
         self._ck(self._lib.flyby_point_features(self._h, _ptr(cell_ids), C.c_int64(n_pix), _ptr(feats),
                                                 C.c_int(F), C.c_float(zero), C.c_int(int(mode)), _ptr(out)))
+        return out
+
+    def interpolate_features(self, res, opts, cell_ids, feats, zero=0.0, out=None, view_begin=0, view_end=None):
+        """Barycentric lookup of per-point features at the hits of render() (same res / opts / view range)."""
+        ve = self.num_views() if view_end is None else view_end
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        _check_dtype(feats, np.float32, "feats")
+        F = int(feats.shape[1]) if len(feats.shape) > 1 else 1
+        if out is None:
+            out = np.empty(tuple(cell_ids.shape) + (F,), np.float32)
+        _check_dtype(out, np.float32, "out")
+        self._ck(self._lib.flyby_interpolate_features(self._h, C.c_int(view_begin), C.c_int(ve), C.c_int(res),
+                                                      C.byref(opts), _ptr(cell_ids), _ptr(feats), C.c_int(F),
+                                                      C.c_float(zero), _ptr(out)))
         return out
 
     def backproject(self, cell_ids, labels, n_classes, votes=None):

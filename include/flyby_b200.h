@@ -143,6 +143,15 @@ FLYBY_API int flyby_render(flyby_ctx* ctx, int view_begin, int view_end, int res
 FLYBY_API int flyby_cast(flyby_ctx* ctx, const double* rays, int64_t n_rays, double tolerance,
                int32_t* out_cell_ids, double* out_t, double* out_w);
 
+/* Barycentric lookup of per-point features at the hits of flyby_render (same view range, resolution and
+ * options): out[pixel, f] = sum_k w_k feats[point_k(cell), f] with the exact test's weights -- how
+ * fly_by_features.cxx:766-790 interpolates its normals, and what the vertex-colour shading of
+ * challenge-teeth/teeth_nets.py:121-153 computes.  cell_ids int32 [n_pix] as written by flyby_render;
+ * feats float32 [V,F]; out float32 [n_pix,F]; miss -> zero. */
+FLYBY_API int flyby_interpolate_features(flyby_ctx* ctx, int view_begin, int view_end, int res,
+                               const flyby_render_opts* opts, const int32_t* cell_ids, const float* feats,
+                               int n_features, float zero, float* out);
+
 /* ---- point features through the id map (utils.py:604-684) --------------- */
 /* mode 0: ids are hit cell ids, value at the cell's vertex 0 (GetPointIdColors
  * utils.py:604-621 colours a cell with its first point's id); mode 1: ids are

@@ -689,6 +689,39 @@ ORC_API void orc_point_features(const int32_t* cell_ids, int64_t n_pix, const in
   }
 }
 
+/* Barycentric lookup at the hits: out[pixel, f] = w0 f0 + w1 f1 + w2 f2 with the weights of
+ * vtkTriangle::EvaluatePosition for the cell the render reported -- how the C++ tool interpolates its
+ * normals (src/app/fly_by_features.cxx:766-790) and what the vertex-colour shading of
+ * src/py/challenge-teeth/teeth_nets.py:121-153 computes.  Products and sums in double, left to right. */
+ORC_API void orc_interpolate_features(const float* verts, const int32_t* tris, const float* views, int n_views,
+                                      double radius, int res, double plane_scale, double spacing,
+                                      const int32_t* cell_ids, const float* feats, int F, float zero, float* out) {
+  for (int v = 0; v < n_views; v++) {
+    orc_view vw;
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    for (int64_t p = 0; p < (int64_t)res * res; p++) {
+      size_t pix = (size_t)v * res * res + (size_t)p;
+      int32_t c = cell_ids[pix];
+      double o[3], t, x[3], w[3];
+      int hit = 0;
+      if (c >= 0) {
+        const int32_t* tr = tris + 3 * (int64_t)c;
+        view_ray(&vw, res, (int)(p % res), (int)(p / res), spacing, o);
+        hit = tri_hit(o, vw.dir, verts + 3 * (int64_t)tr[0], verts + 3 * (int64_t)tr[1], verts + 3 * (int64_t)tr[2],
+                      &t, x, w);
+      }
+      for (int k = 0; k < F; k++) {
+        if (!hit) { out[pix * F + k] = zero; continue; }
+        const int32_t* tr = tris + 3 * (int64_t)c;
+        double a = w[0] * (double)feats[(int64_t)tr[0] * F + k];
+        double b = w[1] * (double)feats[(int64_t)tr[1] * F + k];
+        double e = w[2] * (double)feats[(int64_t)tr[2] * F + k];
+        out[pix * F + k] = (float)((a + b) + e);
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------ */
 /* O9  back-projection of per-pixel labels onto cells                  */
 /*   src/py/dental_model_seg.py:192-199 (per cell, through pix_to_face)*/

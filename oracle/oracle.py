@@ -216,3 +216,15 @@ def pp_relabel(labels, label, relabel):
     out = _i32(labels).copy()
     lib().orc_pp_relabel(_p(out), C.c_int64(len(out)), C.c_int32(label), C.c_int32(relabel))
     return out
+
+
+def interpolate_features(verts, tris, views, radius, res, cell_ids, feats, plane_scale=1.0, spacing=1.0, zero=0.0):
+    """Barycentric lookup of per-point features at the hits (fly_by_features.cxx:766-790)."""
+    v, t, vw = _f32(verts), _i32(tris), _f32(views).reshape(-1, 3)
+    ids = _i32(cell_ids)
+    f = _f32(feats).reshape(len(feats), -1)
+    out = np.empty(ids.shape + (f.shape[1],), dtype=np.float32)
+    lib().orc_interpolate_features(_p(v), _p(t), _p(vw), C.c_int(len(vw)), C.c_double(radius), C.c_int(res),
+                                   C.c_double(plane_scale), C.c_double(spacing), _p(ids), _p(f), C.c_int(f.shape[1]),
+                                   C.c_float(zero), _p(out))
+    return out
