@@ -29,7 +29,12 @@ namespace fb {
 #endif
 #define RT_BIG 256   // bounding boxes with more pixels than this are rasterised by a whole warp
 #define RT_EXTRA 8    // extra candidates kept per pixel (two int4)
+#ifndef RT_SPAN_MIN
 #define RT_SPAN_MIN 12 // bounding boxes up to this many pixels are walked whole (the span set-up would cost more)
+#endif
+#ifndef RT_UNROLL
+#define RT_UNROLL 4    // pixels of a row in flight at a time
+#endif
 #define RV_THREADS 128
 #ifndef RV_MINB
 #define RV_MINB 5
@@ -56,13 +61,13 @@ struct RasterParams {
 };
 #define RT_LOST 0x40000000  // cnt flag: a spilled pair found the list full, the pixel is re-traced through the LBVH
 
-__device__ __forceinline__ void append_extra(const RasterParams& p, int64_t pix, int slot) {
+__device__ __forceinline__ void append_extra(const RasterParams& p, uint32_t pix, int slot) {
   const int k = atomicAdd(p.cnt + pix, 1) & (RT_LOST - 1);
-  if (k < 4) p.extra[pix * 4 + k] = slot;
-  else if (k < RT_EXTRA) p.extra2[pix * 4 + (k - 4)] = slot;
+  if (k < 4) p.extra[(size_t)pix * 4 + k] = slot;
+  else if (k < RT_EXTRA) p.extra2[(size_t)pix * 4 + (k - 4)] = slot;
   else {
     const unsigned int i2 = atomicAdd(p.n_spill, 1u);
-    if (i2 < p.pair_cap) p.pairs[i2] = make_uint2((unsigned int)pix, (unsigned int)slot);
+    if (i2 < p.pair_cap) p.pairs[i2] = make_uint2(pix, (unsigned int)slot);
     else atomicOr(p.cnt + pix, RT_LOST);
   }
 }
@@ -75,7 +80,7 @@ __device__ __forceinline__ void append_extra(const RasterParams& p, int64_t pix,
 // The front only ever moves nearer, so every test against an intermediate front is weaker than the test
 // against the final one: the extras are a superset of what pass-by-pass scan conversion would list, for any
 // order of arrival.
-__device__ __forceinline__ void settle_pixel(const RasterParams& p, int64_t pix, int cls, unsigned long long key,
+__device__ __forceinline__ void settle_pixel(const RasterParams& p, uint32_t pix, int cls, unsigned long long key,
                                              unsigned long long old, unsigned int zlo_ord, float zhi) {
   if (cls == SC_SURE && key < old) {
     if (old != ~0ull && front_key_zlo_lower(old) <= zhi) append_extra(p, pix, FB_FRONT_SLOT(old));
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
   __syncthreads();
   const ViewF& V = s_vf;
   const int res = p.r.res;
-  const int64_t view_base = (int64_t)view * res * res;
+  const uint32_t view_base = (uint32_t)view * (uint32_t)res * (uint32_t)res;  // a render call has < 2^32 pixels
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * RT_THREADS + threadIdx.x;
 
@@ -120,24 +125,25 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
       int lo = r.i0, hi = r.i1;
       const float qy = fmaf((float)j, V.qdy, V.q0y);
       if (t.flags & 4) raster_span(V, t, qy, r.i0, r.i1, &lo, &hi);
-      unsigned long long* frow = p.front + view_base + (int64_t)j * res;
-      for (int i = lo; i <= hi; i += 4) {
-        int cls[4];
-        unsigned long long old[4];
+      const uint32_t prow = view_base + (uint32_t)j * (uint32_t)res;
+      unsigned long long* frow = p.front + prow;
+      for (int i = lo; i <= hi; i += RT_UNROLL) {
+        int cls[RT_UNROLL];
+        unsigned long long old[RT_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < RT_UNROLL; k++) {
           cls[k] = SC_MISS;
           if (i + k <= hi) cls[k] = raster_pixel(t, fmaf((float)(i + k), V.qdx, V.q0x), qy);
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < RT_UNROLL; k++) {
           old[k] = 0ull;
           if (cls[k] == SC_SURE) old[k] = atomicMin(frow + i + k, key);
           else if (cls[k] == SC_MAYBE) old[k] = __ldcg(frow + i + k);
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (cls[k] != SC_MISS) settle_pixel(p, view_base + (int64_t)j * res + i + k, cls[k], key, old[k], zlo_ord, t.zhi);
+        for (int k = 0; k < RT_UNROLL; k++)
+          if (cls[k] != SC_MISS) settle_pixel(p, prow + (uint32_t)(i + k), cls[k], key, old[k], zlo_ord, t.zhi);
       }
     }
   }
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
       const int i = i0 + (int)(k % w), j = j0 + (int)(k / w);
       const int cls = raster_pixel(u, fmaf((float)i, V.qdx, V.q0x), fmaf((float)j, V.qdy, V.q0y));
       if (cls == SC_MISS) continue;
-      const int64_t pix = view_base + (int64_t)j * res + i;
+      const uint32_t pix = view_base + (uint32_t)j * (uint32_t)res + (uint32_t)i;
       const unsigned long long old = cls == SC_SURE ? atomicMin(p.front + pix, key) : __ldcg(p.front + pix);
       settle_pixel(p, pix, cls, key, old, zlo_ord, u.zhi);
     }
