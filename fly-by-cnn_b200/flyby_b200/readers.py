@@ -4,8 +4,10 @@ Covers what ``ReadSurf`` of the reference accepts for the fly-by path
 (reference src/py/utils.py:112-194): legacy VTK polydata (ASCII and BINARY,
 classic ``POLYGONS n size`` cells and the VTK >= 9 ``OFFSETS`` / ``CONNECTIVITY``
 form), Wavefront OBJ, STL (binary and ASCII, coincident vertices merged like
-vtkSTLReader does by default) and OFF (reference src/py/readers.py:15-61).
-``.vtp`` and ``.gii`` need libraries that are not in this image and raise.
+vtkSTLReader does by default), OFF (reference src/py/readers.py:15-61), VTK XML
+polydata ``.vtp`` (ascii / inline binary / appended raw or base64, optional zlib
+blocks, UInt32 or UInt64 headers) and GIFTI ``.gii`` (ASCII, Base64Binary,
+GZipBase64Binary), both parsed with the standard library only.
 Polygons with more than three vertices are fan-triangulated (the reference's
 subdivision filter and ray caster only accept triangles).
 """
@@ -263,6 +265,159 @@ def read_stl(path):
     return MeshData(uniq[order], rank[inv.reshape(-1)].reshape(-1, 3))
 
 
+# --------------------------------------------------------------------------- VTK XML polydata (.vtp)
+_XML_TYPES = {"Int8": np.int8, "UInt8": np.uint8, "Int16": np.int16, "UInt16": np.uint16, "Int32": np.int32,
+              "UInt32": np.uint32, "Int64": np.int64, "UInt64": np.uint64, "Float32": np.float32, "Float64": np.float64}
+
+
+def _b64_chars(n_bytes):
+    return (n_bytes + 2) // 3 * 4
+
+
+def _xml_block(raw, header_dt, compressed, base64_text):
+    """One data block of a VTK XML file -> bytes.  `raw` is base64 text (inline binary or base64 appended
+    data, header and payload encoded separately) or raw bytes (appended raw)."""
+    import base64
+    import zlib
+    hs = header_dt.itemsize
+    if base64_text:
+        if compressed:
+            head = np.frombuffer(base64.b64decode(raw[:_b64_chars(3 * hs)])[:3 * hs], header_dt)
+            n_head = _b64_chars((3 + int(head[0])) * hs)
+            sizes = np.frombuffer(base64.b64decode(raw[:n_head])[:(3 + int(head[0])) * hs], header_dt)[3:]
+            total = int(sizes.sum())
+            body = base64.b64decode(raw[n_head:n_head + _b64_chars(total)])
+        else:
+            n = int(np.frombuffer(base64.b64decode(raw[:_b64_chars(hs)])[:hs], header_dt)[0])
+            return base64.b64decode(raw[_b64_chars(hs):_b64_chars(hs) + _b64_chars(n)])[:n]
+    else:
+        if compressed:
+            head = np.frombuffer(raw[:3 * hs], header_dt)
+            sizes = np.frombuffer(raw[3 * hs:(3 + int(head[0])) * hs], header_dt)
+            body = raw[(3 + int(head[0])) * hs:]
+        else:
+            n = int(np.frombuffer(raw[:hs], header_dt)[0])
+            return bytes(raw[hs:hs + n])
+    out, off = [], 0
+    for sz in sizes:
+        out.append(zlib.decompress(bytes(body[off:off + int(sz)])))
+        off += int(sz)
+    return b"".join(out)
+
+
+def read_vtp(path):
+    """vtkXMLPolyDataReader for the fly-by path (reference src/py/utils.py:121-125): first piece, points, polys
+    (and triangle strips), point / cell data arrays."""
+    import xml.etree.ElementTree as ET
+    blob = open(path, "rb").read()
+    appended_raw = None
+    m = re.search(rb"<AppendedData[^>]*encoding\s*=\s*\"raw\"[^>]*>", blob)
+    if m:  # raw bytes are not XML: cut them out before parsing
+        start = blob.index(b"_", m.end()) + 1
+        end = blob.rindex(b"</AppendedData>")
+        appended_raw = blob[start:end]
+        blob = blob[:start] + blob[end:]
+    root = ET.fromstring(blob)
+    if root.tag != "VTKFile" or root.get("type") != "PolyData":
+        raise ValueError("%s is not a VTK XML PolyData file" % path)
+    if root.get("byte_order", "LittleEndian") != "LittleEndian":
+        raise NotImplementedError("big-endian .vtp")
+    comp = root.get("compressor")
+    if comp not in (None, "vtkZLibDataCompressor"):
+        raise NotImplementedError("compressor %s (only zlib is supported)" % comp)
+    header_dt = np.dtype(_XML_TYPES[root.get("header_type", "UInt32")])
+    appended_b64 = None
+    ad = root.find("AppendedData")
+    if ad is not None and appended_raw is None:
+        appended_b64 = (ad.text or "").strip()
+        appended_b64 = appended_b64[1:] if appended_b64.startswith("_") else appended_b64
+
+    def array(da):
+        dt = np.dtype(_XML_TYPES[da.get("type")])
+        fmt = da.get("format", "ascii")
+        if fmt == "ascii":
+            a = np.array((da.text or "").split(), dtype=np.float64 if dt.kind == "f" else np.int64).astype(dt)
+        elif fmt == "binary":
+            a = np.frombuffer(_xml_block("".join((da.text or "").split()), header_dt, comp is not None, True), dt)
+        elif fmt == "appended":
+            off = int(da.get("offset"))
+            if appended_raw is not None:
+                a = np.frombuffer(_xml_block(appended_raw[off:], header_dt, comp is not None, False), dt)
+            else:
+                a = np.frombuffer(_xml_block(appended_b64[off:], header_dt, comp is not None, True), dt)
+        else:
+            raise ValueError("unknown DataArray format %r" % fmt)
+        nc = int(da.get("NumberOfComponents", "1"))
+        return a.reshape(-1, nc) if nc > 1 else a
+
+    piece = root.find("PolyData").find("Piece")
+    pts = array(piece.find("Points").find("DataArray")).reshape(-1, 3)
+
+    def cells(tag):
+        el = piece.find(tag)
+        if el is None:
+            return []
+        arrs = {d.get("Name"): array(d) for d in el.findall("DataArray")}
+        if "connectivity" not in arrs or len(arrs.get("offsets", [])) == 0:
+            return []
+        conn, offs = arrs["connectivity"].astype(np.int64), arrs["offsets"].astype(np.int64)
+        return [conn[a:b].tolist() for a, b in zip(np.concatenate([[0], offs[:-1]]), offs)]
+
+    polys = _fan(cells("Polys"))
+    for strip in cells("Strips"):  # vtkTriangleFilter order: alternate the winding
+        for k in range(len(strip) - 2):
+            polys.append((strip[k], strip[k + 1], strip[k + 2]) if k % 2 == 0 else (strip[k + 1], strip[k], strip[k + 2]))
+    data = {}
+    for tag in ("PointData", "CellData"):
+        el = piece.find(tag)
+        data[tag] = {d.get("Name"): array(d) for d in el.findall("DataArray")} if el is not None else {}
+    n_poly_cells = len(cells("Polys"))
+    cd = {k: v for k, v in data["CellData"].items() if len(polys) == n_poly_cells and len(v) == n_poly_cells}
+    return MeshData(pts, np.array(polys, np.int32).reshape(-1, 3), data["PointData"], cd)
+
+
+# --------------------------------------------------------------------------- GIFTI (.gii)
+_GII_TYPES = {"NIFTI_TYPE_UINT8": np.uint8, "NIFTI_TYPE_INT32": np.int32, "NIFTI_TYPE_FLOAT32": np.float32,
+              "NIFTI_TYPE_FLOAT64": np.float64, "NIFTI_TYPE_INT64": np.int64, "NIFTI_TYPE_INT16": np.int16}
+
+
+def read_gii(path):
+    """The pointset and triangle arrays of a GIFTI surface, as nibabel's agg_data('pointset') /
+    agg_data('triangle') return them (reference src/py/utils.py:167-191); other arrays with one row per point
+    become point data named by their intent."""
+    import base64
+    import xml.etree.ElementTree as ET
+    import zlib
+    root = ET.parse(path).getroot()
+    pts = tris = None
+    extra = {}
+    for da in root.iter("DataArray"):
+        dt = np.dtype(_GII_TYPES[da.get("DataType")])
+        dims = [int(da.get("Dim%d" % k)) for k in range(int(da.get("Dimensionality", "1")))]
+        enc = da.get("Encoding")
+        text = (da.find("Data").text or "").strip()
+        if enc == "ASCII":
+            a = np.array(text.split(), dtype=np.float64 if dt.kind == "f" else np.int64).astype(dt)
+        elif enc in ("Base64Binary", "GZipBase64Binary"):
+            raw = base64.b64decode(text)
+            if enc == "GZipBase64Binary":
+                raw = zlib.decompress(raw)
+            a = np.frombuffer(raw, dt.newbyteorder(">" if da.get("Endian") == "BigEndian" else "<")).astype(dt)
+        else:
+            raise NotImplementedError("GIFTI encoding %s" % enc)
+        a = a.reshape(dims, order="F" if da.get("ArrayIndexingOrder") == "ColumnMajorOrder" else "C")
+        intent = da.get("Intent")
+        if intent == "NIFTI_INTENT_POINTSET" and pts is None:
+            pts = a
+        elif intent == "NIFTI_INTENT_TRIANGLE" and tris is None:
+            tris = a
+        else:
+            extra[intent.replace("NIFTI_INTENT_", "").lower()] = a
+    if pts is None or tris is None:
+        raise ValueError("%s has no pointset / triangle arrays" % path)
+    return MeshData(pts, tris, {k: v for k, v in extra.items() if len(v) == len(pts)}, {})
+
+
 def read_mesh(path):
     ext = os.path.splitext(path)[1].lower()
     if ext == ".vtk":
@@ -273,9 +428,10 @@ def read_mesh(path):
         return read_stl(path)
     if ext == ".off":
         return read_off(path)
-    if ext in (".vtp", ".gii"):
-        raise NotImplementedError("%s files need the vtk / nibabel packages, which are not available; "
-                                  "convert to legacy .vtk, .obj, .stl or .off" % ext)
+    if ext == ".vtp":
+        return read_vtp(path)
+    if ext == ".gii":
+        return read_gii(path)
     raise ValueError("unknown mesh extension %r" % ext)
 
 

@@ -110,8 +110,91 @@ def test_obj_off_stl(tmp_path):
         for t in F) + "endsolid c\n")
     m2 = readers.read_mesh(str(ascii_stl))
     assert np.array_equal(m2.points[m2.polys], V[F])
-    with pytest.raises(NotImplementedError):
-        readers.read_mesh("x.vtp")
+
+
+def _vtp_encode(arr, mode, header, compress):
+    """One DataArray payload as a VTK XML writer lays it out (header, then data; zlib in blocks)."""
+    import base64
+    import zlib
+    raw = np.ascontiguousarray(arr).tobytes()
+    hd = np.dtype(header)
+    if compress:
+        bs = 64  # tiny blocks so that several are exercised
+        blocks = [raw[i:i + bs] for i in range(0, len(raw), bs)] or [b""]
+        comp = [zlib.compress(b) for b in blocks]
+        head = np.array([len(blocks), bs, len(blocks[-1]) % bs] + [len(c) for c in comp], hd).tobytes()
+        body = b"".join(comp)
+    else:
+        head, body = np.array([len(raw)], hd).tobytes(), raw
+    if mode == "raw":
+        return head + body
+    return base64.b64encode(head).decode() + base64.b64encode(body).decode()
+
+
+@pytest.mark.parametrize("fmt,header,compress", [("ascii", "uint32", False), ("binary", "uint32", False),
+                                                 ("binary", "uint64", True), ("appended-raw", "uint64", False),
+                                                 ("appended-raw", "uint32", True), ("appended-base64", "uint64", True)])
+def test_vtp_variants(tmp_path, fmt, header, compress):
+    P, F = synth.bumpy_sphere(3, 0)
+    lab = (np.arange(len(P)) % 5).astype(np.int32)
+    arrays = [("Points", "Float32", 3, P.astype(np.float32)), ("connectivity", "Int64", 1, F.astype(np.int64).reshape(-1)),
+              ("offsets", "Int64", 1, (np.arange(len(F), dtype=np.int64) + 1) * 3), ("RegionId", "Int32", 1, lab),
+              ("cid", "Int32", 1, np.arange(len(F), dtype=np.int32))]
+    appended, attr = b"", {}
+    for name, typ, nc, a in arrays:
+        if fmt == "ascii":
+            attr[name] = ('format="ascii"', " ".join(repr(float(x)) if a.dtype.kind == "f" else str(int(x)) for x in a.reshape(-1)))
+        elif fmt == "binary":
+            attr[name] = ('format="binary"', _vtp_encode(a, "b64", header, compress))
+        else:
+            blk = _vtp_encode(a, "raw" if fmt == "appended-raw" else "b64", header, compress)
+            blk = blk if isinstance(blk, bytes) else blk.encode()
+            attr[name] = ('format="appended" offset="%d"' % len(appended), "")
+            appended += blk
+
+    def da(name, typ, nc, extra=""):
+        return '<DataArray type="%s" Name="%s" NumberOfComponents="%d" %s %s>%s</DataArray>' % (
+            typ, name, nc, attr[name][0], extra, attr[name][1])
+    head = '<?xml version="1.0"?>\n<VTKFile type="PolyData" version="1.0" byte_order="LittleEndian" header_type="%s"%s>\n' % (
+        {"uint32": "UInt32", "uint64": "UInt64"}[header], ' compressor="vtkZLibDataCompressor"' if compress else "")
+    body = ('<PolyData><Piece NumberOfPoints="%d" NumberOfVerts="0" NumberOfLines="0" NumberOfStrips="0" NumberOfPolys="%d">'
+            '<PointData Scalars="RegionId">%s</PointData><CellData>%s</CellData><Points>%s</Points>'
+            '<Verts></Verts><Polys>%s%s</Polys></Piece></PolyData>') % (
+        len(P), len(F), da("RegionId", "Int32", 1), da("cid", "Int32", 1), da("Points", "Float32", 3),
+        da("connectivity", "Int64", 1), da("offsets", "Int64", 1))
+    path = tmp_path / "m.vtp"
+    with open(path, "wb") as f:
+        f.write((head + body).encode())
+        if fmt.startswith("appended"):
+            f.write(b'<AppendedData encoding="%s">_' % (b"raw" if fmt == "appended-raw" else b"base64") + appended + b"</AppendedData>")
+        f.write(b"</VTKFile>\n")
+    m = readers.read_mesh(str(path))
+    assert np.array_equal(m.points, P) and np.array_equal(m.polys, F)
+    assert np.array_equal(m.point_data["RegionId"], lab) and np.array_equal(m.cell_data["cid"], np.arange(len(F)))
+
+
+@pytest.mark.parametrize("enc", ["ASCII", "Base64Binary", "GZipBase64Binary"])
+def test_gifti_surface(tmp_path, enc):
+    import base64
+    import zlib
+    P, F = synth.bumpy_sphere(3, 1)
+
+    def data(a):
+        if enc == "ASCII":
+            return " ".join(repr(float(x)) if a.dtype.kind == "f" else str(int(x)) for x in a.reshape(-1))
+        raw = a.tobytes()
+        return base64.b64encode(zlib.compress(raw) if enc == "GZipBase64Binary" else raw).decode()
+
+    def da(intent, dtype, a):
+        return ('<DataArray Intent="%s" DataType="%s" ArrayIndexingOrder="RowMajorOrder" Dimensionality="2" Dim0="%d" Dim1="3" '
+                'Encoding="%s" Endian="LittleEndian" ExternalFileName="" ExternalFileOffset=""><MetaData/><Data>%s</Data></DataArray>'
+                % (intent, dtype, len(a), enc, data(a)))
+    path = tmp_path / "s.surf.gii"
+    path.write_text('<?xml version="1.0" encoding="UTF-8"?><GIFTI Version="1.0" NumberOfDataArrays="2"><MetaData/><LabelTable/>'
+                    + da("NIFTI_INTENT_POINTSET", "NIFTI_TYPE_FLOAT32", P.astype(np.float32))
+                    + da("NIFTI_INTENT_TRIANGLE", "NIFTI_TYPE_INT32", F.astype(np.int32)) + "</GIFTI>")
+    m = readers.read_mesh(str(path))
+    assert np.array_equal(m.points, P) and np.array_equal(m.polys, F)
 
 
 def test_nrrd_roundtrip_and_layout(tmp_path):
