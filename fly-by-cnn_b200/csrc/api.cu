@@ -338,6 +338,30 @@ int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   return check_watchdog(c);
 }
 
+int flyby_render_perspective(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double view_angle_deg,
+                             double z_near, double z_far, float* out_features, int32_t* out_cell_ids, double* out_depth) {
+  CHECK_CTX(c);
+  int rc = check_render_args(c, vb, ve, res, o, true);
+  if (rc) return rc;
+  if (!(view_angle_deg > 0.0 && view_angle_deg < 180.0) || !(z_near >= 0.0) || !(z_far > z_near))
+    return fail(c, FLYBY_ERR_INVALID, "render_perspective: need 0 < view angle < 180 and 0 <= z_near < z_far");
+  const size_t n_pix = (size_t)(ve - vb) * res * res;
+  const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  const double tan_half = tan(view_angle_deg * 0.5 * 3.14159265358979323846 / 180.0);  // host libm, as the oracle
+  StageOut<float> sf;
+  StageOut<int32_t> si;
+  StageOut<double> sd;
+  if ((rc = sf.begin(c, c->stage_feat, out_features, n_pix * channels))) return rc;
+  if ((rc = si.begin(c, c->stage_ids, out_cell_ids, n_pix))) return rc;
+  if ((rc = sd.begin(c, c->stage_t, out_depth, n_pix))) return rc;
+  if ((rc = trace_render_perspective(c, vb, ve, res, o, tan_half, z_near, z_far, sf.dev, si.dev, sd.dev))) return rc;
+  bool need = false;
+  if ((rc = sf.finish(c, &need))) return rc;
+  if ((rc = si.finish(c, &need))) return rc;
+  if ((rc = sd.finish(c, &need))) return rc;
+  return sync_if(c, need);
+}
+
 int flyby_cast(flyby_ctx* c, const double* rays, int64_t n, double tolerance, int32_t* out_ids, double* out_t,
                double* out_w) {
   CHECK_CTX(c);

@@ -152,6 +152,8 @@ int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp);  /
 int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res);                      // trace.cu
 int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
                  int32_t* ids, double* tt, bool first_chunk = true, bool last_chunk = true);                                     // trace.cu
+int trace_render_perspective(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double tan_half,
+                             double z_near, double z_far, float* feat, int32_t* ids, double* depth);
 int trace_interpolate(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, const int32_t* cell_ids,
                       const float* feats, int F, float zero, float* out);
 int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double* rays);

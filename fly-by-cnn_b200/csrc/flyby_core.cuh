@@ -862,22 +862,24 @@ struct NoCount {
 // ---------------------------------------------------------------- shading
 // src/app/fly_by_features.cxx:766-807 (barycentric normal, z, pixel) and
 // src/py/fly_by_features.py:124-150 (use_z / split_z channel assembly).
-FB_HD void shade(const double* o, const double* x, const double* w, const float* n0,
-                 const float* n1, const float* n2, int use_z, int split_z, int enc, double zscale,
-                 float* px) {
+// shade_z: the same with the depth supplied by the caller (z already scaled); enc 3 = the 8-bit colour an
+// OpenGL read-back returns (round(255 c), clamped), kept as float
+FB_HD void shade_z(const double* w, const float* n0, const float* n1, const float* n2, double z, int use_z,
+                   int split_z, int enc, float* px) {
   double nn[3];
   for (int k = 0; k < 3; k++) {
     double s = FB_ADD(0.0, FB_MUL((double)n0[k], w[0]));
     s = FB_ADD(s, FB_MUL((double)n1[k], w[1]));
     nn[k] = FB_ADD(s, FB_MUL((double)n2[k], w[2]));
   }
-  double dd[3] = {FB_SUB(o[0], x[0]), FB_SUB(o[1], x[1]), FB_SUB(o[2], x[2])};
-  double z = FB_MUL(norm3(dd), zscale);
   double e[3];
   for (int k = 0; k < 3; k++) {
     if (enc == 2) e[k] = nn[k];
     else if (enc == 1) e[k] = FB_MUL(FB_ADD(FB_MUL(nn[k], 0.5), 0.5), 255.0);
-    else e[k] = FB_ADD(FB_MUL(nn[k], 0.5), 0.5);
+    else if (enc == 3) {
+      double q = floor(FB_ADD(FB_MUL(FB_ADD(FB_MUL(nn[k], 0.5), 0.5), 255.0), 0.5));
+      e[k] = q < 0.0 ? 0.0 : (q > 255.0 ? 255.0 : q);
+    } else e[k] = FB_ADD(FB_MUL(nn[k], 0.5), 0.5);
   }
   if (!use_z) {
     for (int k = 0; k < 3; k++) px[k] = (float)e[k];
@@ -886,6 +888,53 @@ FB_HD void shade(const double* o, const double* x, const double* w, const float*
     px[3] = (float)z;
   } else {
     for (int k = 0; k < 3; k++) px[k] = (float)FB_MUL(e[k], z);
+  }
+}
+
+FB_HD void shade(const double* o, const double* x, const double* w, const float* n0,
+                 const float* n1, const float* n2, int use_z, int split_z, int enc, double zscale,
+                 float* px) {
+  double dd[3] = {FB_SUB(o[0], x[0]), FB_SUB(o[1], x[1]), FB_SUB(o[2], x[2])};
+  shade_z(w, n0, n1, n2, FB_MUL(norm3(dd), zscale), use_z, split_z, enc, px);
+}
+
+// ---------------------------------------------------------------- pinhole camera (raster-compatible views)
+// What FlyByGenerator.getFlyBy sets up for OpenGL (src/py/fly_by_features.py:85-107): position = the
+// viewpoint, focal point = origin, view-up (0,0,-1), or (1,0,0) / (-1,0,0) exactly at the north / south
+// pole; vtkCamera's default view angle is 30 degrees.  f = direction of projection, s = image x (right),
+// u = image y (up, orthogonalised as vtkCamera does); rows run bottom to top as vtkWindowToImageFilter
+// returns them.  A pixel's ray goes through its centre: d = f + sx tan(a/2) s + sy tan(a/2) u, so that the
+// parameter along d is the depth along the viewing direction (the linearised z-buffer of :127-128).
+struct Camera {
+  double eye[3], f[3], s[3], u[3];
+};
+FB_HD void camera_setup(const float* spf, Camera* c) {
+  double len = FB_SQRT(FB_ADD(FB_ADD(FB_MUL((double)spf[0], (double)spf[0]), FB_MUL((double)spf[1], (double)spf[1])),
+                              FB_MUL((double)spf[2], (double)spf[2])));
+  double nz = FB_DIV((double)spf[2], len);
+  double up[3] = {0.0, 0.0, -1.0};
+  if (nz == 1.0) { up[0] = 1.0; up[2] = 0.0; }
+  else if (nz == -1.0) { up[0] = -1.0; up[2] = 0.0; }
+  for (int k = 0; k < 3; k++) {
+    c->eye[k] = (double)spf[k];
+    c->f[k] = FB_DIV(-(double)spf[k], len);
+  }
+  double s[3];
+  cross3(c->f, up, s);
+  double sl = norm3(s);
+  for (int k = 0; k < 3; k++) c->s[k] = FB_DIV(s[k], sl);
+  cross3(c->s, c->f, c->u);
+}
+// segment of pixel (i, j): from depth z_near to depth z_far along the pixel's direction
+FB_HD void camera_ray(const Camera& c, int res, int i, int j, double tan_half, double z_near, double z_far,
+                      double* o, double* d) {
+  double sx = FB_MUL(FB_SUB(FB_MUL(FB_DIV(FB_ADD((double)i, 0.5), (double)res), 2.0), 1.0), tan_half);
+  double sy = FB_MUL(FB_SUB(FB_MUL(FB_DIV(FB_ADD((double)j, 0.5), (double)res), 2.0), 1.0), tan_half);
+  double span = FB_SUB(z_far, z_near);
+  for (int k = 0; k < 3; k++) {
+    double dir = FB_ADD(FB_ADD(c.f[k], FB_MUL(sx, c.s[k])), FB_MUL(sy, c.u[k]));
+    o[k] = FB_ADD(c.eye[k], FB_MUL(dir, z_near));
+    d[k] = FB_MUL(dir, span);
   }
 }
 

@@ -58,6 +58,79 @@ int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res) {
   return FLYBY_OK;
 }
 
+// ---------------------------------------------------------------- raster-compatible (pinhole) views
+// the images FlyByGenerator.getFlyBy reads back from OpenGL (src/py/fly_by_features.py:85-152)
+// -- perspective camera at the viewpoint, one ray through every pixel centre, depth along the viewing
+// direction, 8-bit colours with normal_encoding 3 -- produced by the ray caster.  Rays are not parallel, so
+// this goes through the per-ray stackless LBVH traversal (as flyby_cast), not the scan conversion.
+__global__ void __launch_bounds__(128) persp_kernel(const Node* __restrict__ nodes, const float4* __restrict__ tv0,
+                                                    const float4* __restrict__ tv1, const float4* __restrict__ tv2,
+                                                    const int4* __restrict__ tvid, const float4* __restrict__ normals,
+                                                    int has_tris, const float* __restrict__ view_pts, int view_begin,
+                                                    int64_t n_pix, int res, double tan_half, double z_near, double z_far,
+                                                    int use_z, int split_z, int enc, int channels, double zscale,
+                                                    double tol2, float* feat, int32_t* ids, double* depth) {
+  const int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (pix >= n_pix) return;
+  const int64_t per_view = (int64_t)res * res;
+  const int v = (int)(pix / per_view), loc = (int)(pix % per_view);
+  Camera cam;
+  camera_setup(view_pts + 3 * (int64_t)(view_begin + v), &cam);
+  double o[3], d[3];
+  camera_ray(cam, res, loc % res, loc / res, tan_half, z_near, z_far, o, d);
+  float px[4] = {0.f, 0.f, 0.f, 0.f};
+  int cell = -1;
+  double z = -1.0;
+  if (has_tris) {
+    float dirf[3], invf[3];
+    double amax = 1.0;
+    for (int k = 0; k < 3; k++) {
+      dirf[k] = (float)d[k];
+      invf[k] = 1.0f / dirf[k];
+      const double reach = fabs(o[k]) + fabs(d[k]);
+      amax = reach > amax ? reach : amax;
+    }
+    const float slack = (float)(amax * 64.0 * 5.9604644775390625e-08);
+    const double dl = norm3(d);
+    const float tslack = (float)(dl > 0.0 ? 4.0 * (double)slack / dl : 0.0);
+    GlobalFetch f{nodes};
+    NoCount nc;
+    const Hit h = traverse(f, tv0, tv1, tv2, o, d, dirf, invf, slack, tslack, tol2, nc);
+    if (h.slot >= 0) {
+      const float4 a = tv0[h.slot], b = tv1[h.slot], e = tv2[h.slot];
+      const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+      double t, x[3], w[3];
+      tri_exact(o, d, P0, P1, P2, DBL_MAX, tol2, &t, x, w);
+      cell = h.cell;
+      z = FB_ADD(z_near, FB_MUL(t, FB_SUB(z_far, z_near)));
+      if (feat) {
+        const int4 vid = tvid[h.slot];
+        const float4 n0 = __ldg(normals + vid.x), n1 = __ldg(normals + vid.y), n2 = __ldg(normals + vid.z);
+        const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
+        shade_z(w, N0, N1, N2, FB_MUL(z, zscale), use_z, split_z, enc, px);
+      }
+    }
+  }
+  if (feat)
+    for (int k = 0; k < channels; k++) feat[pix * channels + k] = px[k];
+  if (ids) ids[pix] = cell;
+  if (depth) depth[pix] = z;
+}
+
+int trace_render_perspective(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double tan_half,
+                             double z_near, double z_far, float* feat, int32_t* ids, double* depth) {
+  MeshDev& m = c->mesh;
+  const int64_t n_pix = (int64_t)(ve - vb) * res * res;
+  if (n_pix == 0) return FLYBY_OK;
+  const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  persp_kernel<<<(unsigned)cdiv(n_pix, 128), 128, 0, c->stream>>>(
+      m.nodes.as<Node>(), m.tv0.as<float4>(), m.tv1.as<float4>(), m.tv2.as<float4>(), m.tvid.as<int4>(),
+      m.normals.as<float4>(), m.T > 0 ? 1 : 0, c->view_pts.as<float>(), vb, n_pix, res, tan_half, z_near, z_far,
+      o->use_z, o->split_z, o->normal_encoding, channels, o->z_scale, o->tolerance * o->tolerance, feat, ids, depth);
+  FB_LAUNCH_CHECK(c);
+  return FLYBY_OK;
+}
+
 // ---------------------------------------------------------------- barycentric lookup at the hits
 // out[pixel, f] = sum_k w_k feats[point_k(cell), f] with the exact test's weights of the cell that
 // flyby_render reported for the pixel (fly_by_features.cxx:766-790 interpolates its normals this way;

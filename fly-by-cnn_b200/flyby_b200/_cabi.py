@@ -48,10 +48,10 @@ SYMBOLS = [
     "flyby_backproject_soft", "flyby_votes_argmax", "flyby_cells_to_points", "flyby_nccl_unique_id",
     "flyby_nccl_init", "flyby_votes_allreduce", "flyby_get_stats", "flyby_set_count_work",
     "flyby_launch_count", "flyby_labels_remove_islands", "flyby_labels_connectivity", "flyby_labels_erode",
-    "flyby_labels_dilate", "flyby_labels_relabel", "flyby_interpolate_features",
+    "flyby_labels_dilate", "flyby_labels_relabel", "flyby_interpolate_features", "flyby_render_perspective",
 ]
 
-NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2}
+NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2, "uint8": 3}
 
 
 def load():
@@ -245,6 +245,25 @@ class Context:
         tt = np.empty((n, res, res), np.float64) if want_t else None
         self.render_into(res, opts, feat, ids, tt, view_begin, ve)
         return (feat, ids, tt) if want_t else (feat, ids)
+
+    def render_perspective(self, res, opts, view_angle=30.0, z_near=0.01, z_far=None, view_begin=0, view_end=None,
+                           features=None, cell_ids=None, depth=None):
+        """Pinhole views (raster-compatible): returns (features [n,res,res,C], cell_ids [n,res,res], depth [n,res,res])."""
+        ve = self.num_views() if view_end is None else view_end
+        n = ve - view_begin
+        if features is None:
+            features = np.empty((n, res, res, self.channels(opts)), np.float32)
+        if cell_ids is None:
+            cell_ids = np.empty((n, res, res), np.int32)
+        if depth is None:
+            depth = np.empty((n, res, res), np.float64)
+        _check_dtype(features, np.float32, "features")
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        _check_dtype(depth, np.float64, "depth")
+        self._ck(self._lib.flyby_render_perspective(self._h, C.c_int(view_begin), C.c_int(ve), C.c_int(res), C.byref(opts),
+                                                    C.c_double(view_angle), C.c_double(z_near), C.c_double(z_far),
+                                                    _ptr(features), _ptr(cell_ids), _ptr(depth)))
+        return features, cell_ids, depth
 
     def cast(self, rays, tolerance=1e-10):
         r = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)

@@ -14,6 +14,11 @@ Differences a caller can see (DESIGN.md "Deviations"):
    range: "byte255" (default here, the range the Python reference produces),
    "unit01" (the C++ tool's n*0.5+0.5) or "signed" (rescale_features);
  * options that need an OpenGL window, a Keras model or fibre tubes are rejected.
+
+``FlyByGenerator(..., projection="perspective")`` is the raster-compatible mode: the
+pinhole camera of the OpenGL path (view angle 30 degrees, view-up (0,0,-1), rows bottom to top, depth along
+the viewing direction, clipping range as vtkRenderer::ResetCameraClippingRange derives it from the bounds,
+8-bit colours) traced by the ray caster, for models trained on the reference's raster images.
 """
 import argparse
 import glob
@@ -31,7 +36,7 @@ from .utils import *  # noqa: F401,F403  (the reference re-exports utils through
 class FlyByGenerator():
     def __init__(self, sphere=None, resolution=224, visualize=False, use_z=False, split_z=False,
                  rescale_features=False, normal_encoding=None, plane_scale=1.0, plane_spacing=1.0,
-                 z_far=None, device=0):
+                 z_far=None, device=0, projection="orthographic", view_angle=30.0):
         if visualize:
             raise NotImplementedError("visualize needs an interactive VTK window; not available in flyby_b200")
         self.sphere = sphere
@@ -40,7 +45,13 @@ class FlyByGenerator():
         self.use_z = bool(use_z)
         self.split_z = bool(split_z)
         self.rescale_features = bool(rescale_features)
-        self.normal_encoding = normal_encoding or ("signed" if rescale_features else "byte255")
+        if projection not in ("orthographic", "perspective"):
+            raise ValueError("projection must be 'orthographic' or 'perspective'")
+        self.projection = projection
+        self.view_angle = float(view_angle)
+        # perspective = what the OpenGL read-back returns: uint8 colours (rescaled to [-1, 1] on request)
+        self.normal_encoding = normal_encoding or ("uint8" if projection == "perspective" else
+                                                   ("signed" if rescale_features else "byte255"))
         self.plane_scale = float(plane_scale)
         self.plane_spacing = float(plane_spacing)
         self.z_far = z_far
@@ -105,6 +116,8 @@ class FlyByGenerator():
         print("number of points : ", len(sphere_points))
         ctx.views_custom(sphere_points, radius)
         res = self.resolution
+        if self.projection == "perspective":
+            return self._fly_by_perspective(points, polys, kind, sphere_points)
         if kind != "normals":
             opts = ctx.render_opts(use_z=0, split_z=0, plane_scale=self.plane_scale, plane_spacing=self.plane_spacing)
             ids = np.empty((len(sphere_points), res, res), np.int32)
@@ -123,6 +136,60 @@ class FlyByGenerator():
         feat, ids = ctx.render(res, opts)
         self.last_cell_ids = ids
         return feat
+
+
+    def _fly_by_perspective(self, points, polys, kind, sphere_points):
+        """fly_by_features.py:85-152 with the ray caster behind the pinhole camera."""
+        ctx, res = self.ctx, self.resolution
+        n = len(sphere_points)
+        lo, hi = points.min(0).astype(np.float64), points.max(0).astype(np.float64)
+        feats = []
+        ids_all = np.empty((n, res, res), np.int32)
+        for i in range(n):  # the clipping range is reset per camera position (:109)
+            z_near, z_far = clipping_range(sphere_points[i], (lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]))
+            if kind != "normals":
+                opts = ctx.render_opts(use_z=0, split_z=0)
+                _, ids, _ = ctx.render_perspective(res, opts, self.view_angle, z_near, z_far, i, i + 1)
+                ids_all[i] = ids[0]
+                continue
+            z_scale = 1.0 / z_far if self.use_z and (self.rescale_features or not self.split_z) else 1.0
+            opts = ctx.render_opts(use_z=self.use_z, split_z=self.split_z, normal_encoding=self.normal_encoding,
+                                   z_scale=z_scale)
+            f, ids, _ = ctx.render_perspective(res, opts, self.view_angle, z_near, z_far, i, i + 1)
+            if self.rescale_features and self.normal_encoding == "uint8":
+                hit = ids[0] >= 0
+                if self.use_z and not self.split_z:  # colours were multiplied by z / z_far in the kernel: redo on the host
+                    raise NotImplementedError("rescale_features with use_z=1, split_z=0 in perspective mode: "
+                                              "pass normal_encoding='signed'")
+                f[0][..., :3] = np.where(hit[..., None], 2.0 * (f[0][..., :3] / 255.0) - 1.0, -1.0)  # :119-120
+            feats.append(f[0])
+            ids_all[i] = ids[0]
+        self.last_cell_ids = ids_all
+        if kind == "point_id":
+            return utils.EncodeIdsRGB(np.where(ids_all >= 0, polys[np.maximum(ids_all, 0), 0], -1))
+        if kind != "normals":
+            return utils.EncodeIdsRGB(ids_all)
+        return np.stack(feats)
+
+
+def clipping_range(position, bounds, expansion=0.5, near_tolerance=0.001):
+    """vtkRenderer::ResetCameraClippingRange(bounds) for a camera at `position` looking at the origin
+    (VTK 9 Rendering/Core/vtkRenderer.cxx, restated from memory: distance range of the eight corners of the
+    bounding box along the view direction, 1 % + expansion * span breathing room, near at least
+    near_tolerance * far; 0.001 is VTK's value for depth buffers deeper than 16 bits)."""
+    p = np.asarray(position, np.float64)
+    vn = p / np.linalg.norm(p)  # view plane normal: from the focal point (origin) to the camera
+    a, b, c = -vn
+    d = -(a * p[0] + b * p[1] + c * p[2])
+    dist = [a * bounds[i] + b * bounds[2 + j] + c * bounds[4 + k] + d for k in range(2) for j in range(2) for i in range(2)]
+    r0, r1 = min(dist), max(max(dist), 1e-18)
+    r0 = 0.99 * r0 - (r1 - r0) * expansion
+    r1 = 1.01 * r1 + (r1 - r0) * expansion
+    if r0 >= r1:
+        r0 = 0.01 * r1
+    if r0 < near_tolerance * r1:
+        r0 = near_tolerance * r1
+    return float(r0), float(r1)
 
 
 def _find_surfaces(args):

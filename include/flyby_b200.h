@@ -66,7 +66,8 @@ typedef struct {
 typedef struct {
   int32_t use_z;           /* --use_z */
   int32_t split_z;         /* --split_z */
-  int32_t normal_encoding; /* 0 n*0.5+0.5 (cxx:802-804), 1 *255 (8-bit raster range), 2 signed n (--rescale_features) */
+  int32_t normal_encoding; /* 0 n*0.5+0.5 (cxx:802-804), 1 *255 (8-bit raster range), 2 signed n (--rescale_features),
+                              3 round(255 (n*0.5+0.5)) clamped to 0..255 (the uint8 an RGB read-back returns) */
   int32_t reserved;
   double plane_scale;      /* planeScaleFactor, default 1.0 */
   double plane_spacing;    /* planeSpacing, default 1.0 */
@@ -137,6 +138,16 @@ FLYBY_API int flyby_generate_rays(flyby_ctx* ctx, int view_begin, int view_end, 
 FLYBY_API int flyby_render(flyby_ctx* ctx, int view_begin, int view_end, int res,
                  const flyby_render_opts* opts, float* out_features, int32_t* out_cell_ids,
                  double* out_t);
+/* Raster-compatible views: what FlyByGenerator.getFlyBy reads back from OpenGL
+ * (src/py/fly_by_features.py:85-152), produced by the ray caster: a pinhole camera at the viewpoint looking
+ * at the origin, view-up (0,0,-1) ((+-1,0,0) exactly at the poles, :93-98), view angle in degrees (vtkCamera
+ * default 30), one ray through the centre of every pixel, rows bottom to top as vtkWindowToImageFilter returns
+ * them.  Depth is the distance along the viewing direction (the linearised z-buffer of :127-128), clipped to
+ * [z_near, z_far]; features follow opts (use_z, split_z, z_scale; normal_encoding 3 = the 8-bit colours of the
+ * RGB read-back); plane_scale / plane_spacing are not used.  out_depth float64 (-1 = miss); any output may be NULL. */
+FLYBY_API int flyby_render_perspective(flyby_ctx* ctx, int view_begin, int view_end, int res,
+                             const flyby_render_opts* opts, double view_angle_deg, double z_near, double z_far,
+                             float* out_features, int32_t* out_cell_ids, double* out_depth);
 /* Cast caller-supplied segments (rays float64 [n,6]); same outputs per ray
  * plus barycentric weights w [n,3].  vtkCellLocator::IntersectWithLine
  * (fly_by_features.cxx:758, predict.py:128). */

@@ -622,24 +622,31 @@ ORC_API void orc_cast(const orc_grid* g, const float* verts, const int32_t* tris
 /* ------------------------------------------------------------------ */
 ORC_API int orc_channels(int use_z, int split_z) { return (use_z && split_z) ? 4 : 3; }
 
-static void shade(const double o[3], const double x[3], const double w[3], const float* normals,
-                  const int32_t* tri, int use_z, int split_z, int enc, double zscale, float* px) {
+static void shade_z(const double w[3], const float* normals, const int32_t* tri, double z, int use_z, int split_z,
+                    int enc, float* px) {
   double nn[3] = {0, 0, 0};
   for (int j = 0; j < 3; j++) {
     const float* N = normals + 3 * (int64_t)tri[j];
     for (int k = 0; k < 3; k++) nn[k] = nn[k] + (double)N[k] * w[j];
   }
-  double dd[3] = {o[0] - x[0], o[1] - x[1], o[2] - x[2]};
-  double z = norm3(dd) * zscale;
   double e[3];
   for (int k = 0; k < 3; k++) {
     if (enc == 2) e[k] = nn[k];
     else if (enc == 1) e[k] = (nn[k] * 0.5 + 0.5) * 255.0;
-    else e[k] = nn[k] * 0.5 + 0.5;
+    else if (enc == 3) { /* the uint8 colour an OpenGL RGB read-back returns */
+      double q = floor((nn[k] * 0.5 + 0.5) * 255.0 + 0.5);
+      e[k] = q < 0.0 ? 0.0 : (q > 255.0 ? 255.0 : q);
+    } else e[k] = nn[k] * 0.5 + 0.5;
   }
   if (!use_z) { for (int k = 0; k < 3; k++) px[k] = (float)e[k]; }
   else if (split_z) { for (int k = 0; k < 3; k++) px[k] = (float)e[k]; px[3] = (float)z; }
   else { for (int k = 0; k < 3; k++) px[k] = (float)(e[k] * z); }
+}
+
+static void shade(const double o[3], const double x[3], const double w[3], const float* normals,
+                  const int32_t* tri, int use_z, int split_z, int enc, double zscale, float* px) {
+  double dd[3] = {o[0] - x[0], o[1] - x[1], o[2] - x[2]};
+  shade_z(w, normals, tri, norm3(dd) * zscale, use_z, split_z, enc, px);
 }
 
 /* Whole path for a set of viewpoints.  verts are the UNIT-SURF float32 points,
@@ -669,6 +676,63 @@ ORC_API void orc_render(const float* verts, int64_t V, const int32_t* tris, int6
         float* px = out_features + pix * C;
         for (int k = 0; k < C; k++) px[k] = 0.f;
         if (id >= 0) shade(o, x, w, normals, tris + 3 * (int64_t)id, use_z, split_z, enc, zscale, px);
+      }
+    }
+  }
+  orc_grid_free(g);
+}
+
+/* ------------------------------------------------------------------ */
+/* Raster-compatible views                          */
+/*   src/py/fly_by_features.py:85-107 camera: position = viewpoint,    */
+/*   focal point = origin, view-up (0,0,-1) or (+-1,0,0) at the poles; */
+/*   vtkCamera default view angle 30; :113-131 RGB + linearised z.     */
+/* One ray through every pixel centre, rows bottom to top; the ray     */
+/* parameter is the depth along the viewing direction.                 */
+/* ------------------------------------------------------------------ */
+ORC_API void orc_render_perspective(const float* verts, int64_t V, const int32_t* tris, int64_t T,
+                                    const float* normals, const float* views, int n_views, int res,
+                                    double view_angle_deg, double z_near, double z_far, int use_z, int split_z,
+                                    int enc, double zscale, int use_grid, int grid_div, float* out_features,
+                                    int32_t* out_ids, double* out_depth) {
+  int C = orc_channels(use_z, split_z);
+  orc_grid* g = use_grid ? orc_grid_build(verts, V, tris, T, grid_div) : NULL;
+  const double tan_half = tan(view_angle_deg * 0.5 * 3.14159265358979323846 / 180.0);
+  for (int v = 0; v < n_views; v++) {
+    const float* sp = views + 3 * v;
+    double eye[3] = {sp[0], sp[1], sp[2]};
+    double len = sqrt((double)sp[0] * (double)sp[0] + (double)sp[1] * (double)sp[1] + (double)sp[2] * (double)sp[2]);
+    double nz = (double)sp[2] / len;
+    double up[3] = {0.0, 0.0, -1.0};
+    if (nz == 1.0) { up[0] = 1.0; up[2] = 0.0; }
+    else if (nz == -1.0) { up[0] = -1.0; up[2] = 0.0; }
+    double f[3] = {-(double)sp[0] / len, -(double)sp[1] / len, -(double)sp[2] / len};
+    double s[3], u[3];
+    cross3(f, up, s);
+    double sl = norm3(s);
+    for (int k = 0; k < 3; k++) s[k] = s[k] / sl;
+    cross3(s, f, u);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = 0; p < (int64_t)res * res; p++) {
+      int i = (int)(p % res), j = (int)(p / res);
+      double sx = ((((double)i + 0.5) / (double)res) * 2.0 - 1.0) * tan_half;
+      double sy = ((((double)j + 0.5) / (double)res) * 2.0 - 1.0) * tan_half;
+      double span = z_far - z_near;
+      double o[3], d[3], t, x[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+      for (int k = 0; k < 3; k++) {
+        double dir = (f[k] + sx * s[k]) + sy * u[k];
+        o[k] = eye[k] + dir * z_near;
+        d[k] = dir * span;
+      }
+      int id = g ? cast_grid(g, o, d, &t, x, w) : cast_brute(o, d, verts, tris, T, &t, x, w);
+      size_t pix = (size_t)v * res * res + (size_t)p;
+      double z = id >= 0 ? z_near + t * span : -1.0;
+      if (out_ids) out_ids[pix] = id;
+      if (out_depth) out_depth[pix] = z;
+      if (out_features) {
+        float* px = out_features + pix * C;
+        for (int k = 0; k < C; k++) px[k] = 0.f;
+        if (id >= 0) shade_z(w, normals, tris + 3 * (int64_t)id, z * zscale, use_z, split_z, enc, px);
       }
     }
   }

@@ -228,3 +228,18 @@ def interpolate_features(verts, tris, views, radius, res, cell_ids, feats, plane
                                    C.c_double(plane_scale), C.c_double(spacing), _p(ids), _p(f), C.c_int(f.shape[1]),
                                    C.c_float(zero), _p(out))
     return out
+
+
+def render_perspective(unit_verts, tris, normals, views, res, view_angle=30.0, z_near=0.01, z_far=10.0, use_z=1,
+                       split_z=1, normal_encoding=0, zscale=1.0, grid=True, grid_div=0):
+    """Pinhole views as FlyByGenerator sets the camera up (fly_by_features.py:85-131); returns (features, ids, depth)."""
+    v, t, nrm, vw = _f32(unit_verts), _i32(tris), _f32(normals), _f32(views).reshape(-1, 3)
+    nv = len(vw)
+    feats = np.empty((nv, res, res, channels(use_z, split_z)), dtype=np.float32)
+    ids = np.empty((nv, res, res), dtype=np.int32)
+    depth = np.empty((nv, res, res), dtype=np.float64)
+    lib().orc_render_perspective(_p(v), C.c_int64(len(v)), _p(t), C.c_int64(len(t)), _p(nrm), _p(vw), C.c_int(nv),
+                                 C.c_int(res), C.c_double(view_angle), C.c_double(z_near), C.c_double(z_far),
+                                 C.c_int(use_z), C.c_int(split_z), C.c_int(normal_encoding), C.c_double(zscale),
+                                 C.c_int(1 if grid else 0), C.c_int(grid_div), _p(feats), _p(ids), _p(depth))
+    return feats, ids, depth

@@ -227,3 +227,32 @@ def test_gpu_matches_golden(gpu_ctx):
     votes = gpu_ctx.backproject(ids, g["labels"], 5)
     assert np.array_equal(votes, g["votes"])
     assert np.array_equal(gpu_ctx.votes_argmax(votes, default=33), g["cell_labels"])
+
+
+def test_perspective_camera_known_answers(orc):
+    """Pinhole views of a sphere of radius r from distance R: the centre pixels see depth R - r with the normal
+    facing the camera, the silhouette subtends asin(r/R), rows run bottom to top with view-up (0,0,-1)."""
+    V, F = synth.icosphere(40)
+    V = (V * 0.5).astype(np.float32)
+    N = orc.point_normals(V, F)
+    R, res = 2.0, 201
+    views = np.array([[R, 0, 0], [0, 0, R], [0, 0, -R], [1.6, -1.0, 1.2]], np.float32)
+    feat, ids, depth = orc.render_perspective(V, F, N, views, res, view_angle=30.0, z_near=0.01, z_far=R + 1,
+                                              grid=True, grid_div=16)
+    c = res // 2
+    for v in range(4):
+        Rv = float(np.linalg.norm(views[v]))
+        assert abs(depth[v, c, c] - (Rv - 0.5)) < 2e-3
+        nrm = feat[v, c, c, :3] * 2 - 1
+        assert np.allclose(nrm, views[v] / Rv, atol=0.05) and abs(feat[v, c, c, 3] - depth[v, c, c]) < 1e-6
+        # silhouette: pixels whose ray makes an angle below asin(r/R) with the axis are hits
+        frac = (ids[v] >= 0).mean()
+        tan_s = np.tan(np.arcsin(0.5 / Rv)) / np.tan(np.radians(15.0))
+        assert abs(frac - np.pi * tan_s ** 2 / 4) < 0.01
+        assert (depth[v][ids[v] < 0] == -1).all() and (feat[v][ids[v] < 0] == 0).all()
+    # view-up (0,0,-1): for the camera on +x the top rows (large j) look towards -z
+    top, bottom = feat[0, res - 30, c, :3] * 2 - 1, feat[0, 30, c, :3] * 2 - 1
+    assert top[2] < -0.3 and bottom[2] > 0.3
+    # uint8 colours: integers in 0..255
+    f8, _, _ = orc.render_perspective(V, F, N, views[:1], 64, z_far=R + 1, normal_encoding=3)
+    assert np.array_equal(f8[..., :3], np.round(f8[..., :3])) and f8[..., :3].max() <= 255 and f8[..., :3].min() >= 0
