@@ -179,8 +179,10 @@ def run_ours(args):
     pin_meshes = [(torch.from_numpy(P).pin_memory(), torch.from_numpy(F).pin_memory()) for P, F in meshes]
     feat = torch.empty((n_views, RES, RES, C), dtype=torch.float32, device=dev)
     ids = torch.empty((n_views, RES, RES), dtype=torch.int32, device=dev)
-    feat_host = torch.empty((n_views, RES, RES, C), dtype=torch.float32).pin_memory()
-    ids_host = torch.empty((n_views, RES, RES), dtype=torch.int32).pin_memory()
+    # two sets of pinned host outputs: the streaming call fills one while the other is being consumed
+    feat_hosts = [torch.empty((n_views, RES, RES, C), dtype=torch.float32).pin_memory() for _ in range(2)]
+    ids_hosts = [torch.empty((n_views, RES, RES), dtype=torch.int32).pin_memory() for _ in range(2)]
+    feat_host, ids_host = feat_hosts[0], ids_hosts[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     T, V = len(meshes[0][1]), len(meshes[0][0])
 
@@ -195,6 +197,32 @@ def run_ours(args):
         ctx.set_mesh(P.numpy(), F.numpy())
         ctx.build()
         ctx.render_into(RES, opts, feat_host.numpy(), ids_host.numpy())  # D2H inside, returns after the copy
+
+    def step_e2e_stream(k):
+        """the same through flyby_render_async: returns when queued; this mesh's copy-out overlaps the next mesh"""
+        P, F = pin_meshes[k % MESH_POOL]
+        ctx.set_mesh(P.numpy(), F.numpy())
+        ctx.build()
+        ctx.render_into(RES, opts, feat_hosts[k % 2].numpy(), ids_hosts[k % 2].numpy(), wait=False)
+
+    def timed_stream(steps, warmup):
+        """K streamed steps timed as a whole (every step's H2D, device work and D2H lie inside the region)"""
+        for k in range(warmup):
+            step_e2e_stream(k)
+        ctx.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            flush.zero_()
+            step_e2e_stream(warmup + k)
+        ctx.synchronize()  # both streams: every host buffer is complete
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        return max(wall_ms, e0.elapsed_time(e1)) / steps
 
     def barrier():
         if world > 1:
@@ -227,14 +255,15 @@ def run_ours(args):
     ms_step, ms_render, ms_trace = timed(step_resident, args.steps, args.warmup, collect_render=True)
     launches = ctx.launch_count() - l0
     st = ctx.stats()
-    ms_e2e, _, _ = timed(step_e2e, max(2, min(args.steps, 5)), 1)
+    ms_e2e, _, _ = timed(step_e2e, max(2, min(args.steps, 8)), 1)
+    ms_e2e_stream = timed_stream(max(4, min(args.steps, 12)), 2)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    t = torch.tensor([ms_step, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, ms_e2e, ms_e2e_stream], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step_max, ms_e2e_max = float(t[0]), float(t[1])
+    ms_step_max, ms_e2e_max, ms_e2e_stream_max = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -268,7 +297,13 @@ def run_ours(args):
                              "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                              "note": "algorithmic bytes = compulsory output + mesh + BVH bytes of one render (SURVEY 8d); the pipeline is bound by float32/float64 instruction issue and L2 atomic latency, not by HBM"},
                 "e2e": {"value": e2e_views, "unit": "views/s", "ms_per_step": ms_e2e_max,
-                        "h2d_bytes_per_step": V * 12 + T * 12, "d2h_bytes_per_step": n_rays * (4 * C + 4)},
+                        "h2d_bytes_per_step": V * 12 + T * 12, "d2h_bytes_per_step": n_rays * (4 * C + 4),
+                        "mode": "blocking flyby_render per mesh: pinned H2D of the mesh, build, render in view chunks, "
+                                "chunked D2H of features + ids overlapping the remaining chunks; PCIe-bound "
+                                "(profiles/pcie_bw.py: 8.5 ms for these 482 MB at 57 GB/s)",
+                        "streamed_ms_per_step": ms_e2e_stream_max,
+                        "streamed_note": "flyby_render_async (copy-out of mesh n overlaps mesh n+1), K meshes timed as a "
+                                         "whole incl. pipeline drain; no faster here because the copy-out alone fills the step"},
                 "gpu_launches": launches, "clocks": sampler.summary()}
         if cpu is not None:
             line["cpu_baseline"] = cpu

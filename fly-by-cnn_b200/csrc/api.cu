@@ -123,12 +123,15 @@ void flyby_destroy(flyby_ctx* c) {
                     &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.leaf_box,
                     &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid, &m.trec,
                     &c->view_pts, &c->views, &c->viewsf, &c->tc_table, &c->cand, &c->cand2, &c->pix_lists, &c->raster_tmp, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
-                    &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->counters};
+                    &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->counters,
+                    &c->async_feat[0], &c->async_feat[1], &c->async_ids[0], &c->async_ids[1], &c->async_t[0], &c->async_t[1]};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 16; i++)
     if (c->chunk_ev[i]) cudaEventDestroy(c->chunk_ev[i]);
+  for (int i = 0; i < 2; i++)
+    if (c->async_done[i]) cudaEventDestroy(c->async_done[i]);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -148,7 +151,10 @@ static int check_watchdog(flyby_ctx* c) {
 
 int flyby_synchronize(flyby_ctx* c) {
   CHECK_CTX(c);
-  return check_watchdog(c);
+  int rc = check_watchdog(c);
+  if (rc) return rc;
+  FB_CUDA(c, cudaStreamSynchronize(c->copy_stream));  // copy-outs of flyby_render_async
+  return FLYBY_OK;
 }
 
 int flyby_set_mesh(flyby_ctx* c, const float* verts, int64_t V, const int32_t* tris, int64_t T,
@@ -336,6 +342,64 @@ int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   }
   FB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
   return check_watchdog(c);
+}
+
+// Streaming form of flyby_render for host outputs: returns as soon as the work is queued.  The render goes to
+// one of two device staging sets and is copied out chunk by chunk on the copy stream; the next call (next
+// mesh) renders into the other set while those copies run, so a stream of meshes is bound by
+// max(device time, PCIe time) instead of their sum.  The host buffers are complete after flyby_synchronize
+// (or once the call after next has returned its status -- it waits for this set to drain before reusing it).
+int flyby_render_async(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* out_features,
+                       int32_t* out_cell_ids, double* out_t) {
+  CHECK_CTX(c);
+  const bool any_host = (out_features && !is_device_ptr(out_features)) || (out_cell_ids && !is_device_ptr(out_cell_ids)) ||
+                        (out_t && !is_device_ptr(out_t));
+  if (!any_host) return flyby_render(c, vb, ve, res, o, out_features, out_cell_ids, out_t);
+  if ((out_features && is_device_ptr(out_features)) || (out_cell_ids && is_device_ptr(out_cell_ids)) ||
+      (out_t && is_device_ptr(out_t)))
+    return fail(c, FLYBY_ERR_INVALID, "render_async: outputs must be all host or all device memory");
+  int rc = check_render_args(c, vb, ve, res, o, true);
+  if (rc) return rc;
+  const size_t per_view = (size_t)res * res;
+  const size_t n_pix = (size_t)(ve - vb) * per_view;
+  const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  if ((rc = views_setup(c, o, res))) return rc;
+  const int s = c->async_flip;
+  c->async_flip ^= 1;
+  for (int i = 0; i < 2; i++)
+    if (!c->async_done[i]) FB_CUDA(c, cudaEventCreateWithFlags(&c->async_done[i], cudaEventDisableTiming));
+  float* df = nullptr;
+  int32_t* di = nullptr;
+  double* dt = nullptr;
+  // growing a staging buffer frees the old one: drain the copies that may still read it first
+  if ((out_features && c->async_feat[s].cap < n_pix * channels * sizeof(float)) ||
+      (out_cell_ids && c->async_ids[s].cap < n_pix * sizeof(int32_t)) || (out_t && c->async_t[s].cap < n_pix * sizeof(double)))
+    FB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  if (out_features) { FB_CUDA(c, c->async_feat[s].reserve(n_pix * channels * sizeof(float))); df = c->async_feat[s].as<float>(); }
+  if (out_cell_ids) { FB_CUDA(c, c->async_ids[s].reserve(n_pix * sizeof(int32_t))); di = c->async_ids[s].as<int32_t>(); }
+  if (out_t) { FB_CUDA(c, c->async_t[s].reserve(n_pix * sizeof(double))); dt = c->async_t[s].as<double>(); }
+  FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->async_done[s], 0));  // the set's previous copy-out (two calls ago)
+  const int nv = ve - vb;
+  int n_chunks = nv < 8 ? 1 : (nv + 11) / 12;
+  if (n_chunks > 16) n_chunks = 16;
+  int bounds[17];
+  for (int k = 0; k <= n_chunks; k++) bounds[k] = vb + (int)((long long)nv * k / n_chunks);
+  for (int k = 0; k < n_chunks; k++) {
+    const size_t off = (size_t)(bounds[k] - vb) * per_view;
+    const size_t cnt = (size_t)(bounds[k + 1] - bounds[k]) * per_view;
+    rc = trace_render(c, bounds[k], bounds[k + 1], res, o, df ? df + off * channels : nullptr, di ? di + off : nullptr,
+                      dt ? dt + off : nullptr, k == 0, k == n_chunks - 1);
+    if (rc) return rc;
+    FB_CUDA(c, cudaEventRecord(c->chunk_ev[k], c->stream));
+    FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[k], 0));
+    if (df)
+      FB_CUDA(c, cudaMemcpyAsync(out_features + off * channels, df + off * channels, cnt * channels * sizeof(float),
+                                 cudaMemcpyDeviceToHost, c->copy_stream));
+    if (di) FB_CUDA(c, cudaMemcpyAsync(out_cell_ids + off, di + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (dt) FB_CUDA(c, cudaMemcpyAsync(out_t + off, dt + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  FB_CUDA(c, cudaEventRecord(c->async_done[s], c->copy_stream));
+  return FLYBY_OK;
 }
 
 int flyby_render_perspective(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double view_angle_deg,

@@ -91,6 +91,10 @@ struct flyby_ctx {
   // staging for host-side buffers
   fb::DevBuf stage_feat, stage_ids, stage_t, stage_in0, stage_in1, stage_out0, stage_misc;
   fb::DevBuf pp_tmp, pp_tmp2;  // label post-processing scratch (postproc.cu)
+  // flyby_render_async: two sets of device staging so that the copy-out of call n overlaps the work of call n + 1
+  fb::DevBuf async_feat[2], async_ids[2], async_t[2];
+  cudaEvent_t async_done[2] = {nullptr, nullptr};  // recorded on copy_stream behind the copies of a set
+  int async_flip = 0;
   fb::DevBuf counters;  // uint64 [8]: tile counter, work counters
   // stats
   cudaEvent_t ev[8] = {nullptr};

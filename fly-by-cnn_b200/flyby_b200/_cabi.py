@@ -49,6 +49,7 @@ SYMBOLS = [
     "flyby_nccl_init", "flyby_votes_allreduce", "flyby_get_stats", "flyby_set_count_work",
     "flyby_launch_count", "flyby_labels_remove_islands", "flyby_labels_connectivity", "flyby_labels_erode",
     "flyby_labels_dilate", "flyby_labels_relabel", "flyby_interpolate_features", "flyby_render_perspective",
+    "flyby_render_async",
 ]
 
 NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2, "uint8": 3}
@@ -227,14 +228,17 @@ class Context:
                                                C.byref(opts), _ptr(out)))
         return out
 
-    def render_into(self, res, opts, features=None, cell_ids=None, t=None, view_begin=0, view_end=None):
-        """Render into caller buffers (numpy = host staging + sync; torch cuda tensors = in place, async)."""
+    def render_into(self, res, opts, features=None, cell_ids=None, t=None, view_begin=0, view_end=None, wait=True):
+        """Render into caller buffers (numpy = host staging + sync; torch cuda tensors = in place, async).
+        wait=False with host buffers: streaming form (flyby_render_async) -- the buffers are complete after
+        synchronize(); alternate between two sets of (pinned) host buffers."""
         ve = self.num_views() if view_end is None else view_end
         _check_dtype(features, np.float32, "features")
         _check_dtype(cell_ids, np.int32, "cell_ids")
         _check_dtype(t, np.float64, "t")
-        self._ck(self._lib.flyby_render(self._h, C.c_int(view_begin), C.c_int(ve), C.c_int(res), C.byref(opts),
-                                        _ptr(features), _ptr(cell_ids), _ptr(t)))
+        fn = self._lib.flyby_render if wait else self._lib.flyby_render_async
+        self._ck(fn(self._h, C.c_int(view_begin), C.c_int(ve), C.c_int(res), C.byref(opts),
+                    _ptr(features), _ptr(cell_ids), _ptr(t)))
 
     def render(self, res, opts, view_begin=0, view_end=None, want_t=False):
         """Render to new numpy arrays: (features [n,res,res,C], cell_ids [n,res,res][, t])."""

@@ -138,6 +138,14 @@ FLYBY_API int flyby_generate_rays(flyby_ctx* ctx, int view_begin, int view_end, 
 FLYBY_API int flyby_render(flyby_ctx* ctx, int view_begin, int view_end, int res,
                  const flyby_render_opts* opts, float* out_features, int32_t* out_cell_ids,
                  double* out_t);
+/* Streaming form for host outputs (batch extraction, BASELINE config 3): returns once the work is queued; the
+ * render goes to one of two device staging sets and is copied out on a second stream while the next call's
+ * mesh is uploaded, built and rendered, so a stream of meshes runs at max(device time, PCIe time).  The host
+ * buffers (pinned memory, or the copies serialise) are complete after flyby_synchronize; alternate between two
+ * host buffers.  With device outputs it is flyby_render. */
+FLYBY_API int flyby_render_async(flyby_ctx* ctx, int view_begin, int view_end, int res,
+                       const flyby_render_opts* opts, float* out_features, int32_t* out_cell_ids,
+                       double* out_t);
 /* Raster-compatible views: what FlyByGenerator.getFlyBy reads back from OpenGL
  * (src/py/fly_by_features.py:85-152), produced by the ray caster: a pinhole camera at the viewpoint looking
  * at the origin, view-up (0,0,-1) ((+-1,0,0) exactly at the poles, :93-98), view angle in degrees (vtkCamera

@@ -144,3 +144,34 @@ def test_labeling_driver_single_process(orc):
     assert np.array_equal(voter.votes, ref)
     assert np.array_equal(voter.point_labels(default=33), orc.cells_to_points(orc.votes_argmax(ref, 33), F, len(P), 33))
     ctx.close()
+
+
+def test_render_async_streams_meshes(gpu_ctx):
+    """flyby_render_async: consecutive meshes through the two staging sets give what the blocking call gives."""
+    torch = pytest.importorskip("torch")
+    from flyby_b200 import synth
+    gpu_ctx.views_icosahedron(2, 2.0)
+    opts = gpu_ctx.render_opts()
+    res = 96
+    meshes = [synth.bumpy_sphere(20 + 4 * k, k) for k in range(5)]
+    want = []
+    for P, F in meshes:
+        gpu_ctx.set_mesh(P, F)
+        gpu_ctx.build()
+        want.append(gpu_ctx.render(res, opts, want_t=True))
+    n = gpu_ctx.num_views()
+    bufs = [(torch.empty((n, res, res, 4), dtype=torch.float32).pin_memory(), torch.empty((n, res, res), dtype=torch.int32).pin_memory(),
+             torch.empty((n, res, res), dtype=torch.float64).pin_memory()) for _ in range(2)]
+    for k, (P, F) in enumerate(meshes):
+        gpu_ctx.set_mesh(P, F)
+        gpu_ctx.build()
+        f, i, t = bufs[k % 2]
+        gpu_ctx.render_into(res, opts, f.numpy(), i.numpy(), t.numpy(), wait=False)
+        if k >= 1:  # the previous mesh's buffers: complete once everything queued so far has drained
+            gpu_ctx.synchronize()
+            pf, pi, pt = bufs[(k - 1) % 2]
+            assert np.array_equal(pf.numpy(), want[k - 1][0]) and np.array_equal(pi.numpy(), want[k - 1][1])
+            assert np.array_equal(pt.numpy(), want[k - 1][2])
+    gpu_ctx.synchronize()
+    f, i, t = bufs[(len(meshes) - 1) % 2]
+    assert np.array_equal(f.numpy(), want[-1][0]) and np.array_equal(i.numpy(), want[-1][1])
