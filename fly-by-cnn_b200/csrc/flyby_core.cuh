@@ -551,26 +551,9 @@ FB_HD int screen_pixel(const ViewF& V, const TriS& t, float qx, float qy) {
   return (t.flags & 2) ? SC_SURE : SC_MAYBE;
 }
 
-struct PixRange {
+struct PixRange {  // pixels of a view that can see a projected bounding box
   int i0, i1, j0, j1;
 };
-// pixels whose ray can lie within the margins of the triangle's bounding box (a superset is fine:
-// screen_pixel repeats the bounding-box test on the real coordinates)
-FB_HD PixRange pixel_range(const ViewF& V, const TriS& t, int res) {
-  const float m0 = 2.0f * V.e_p + V.d0;
-  const float ix = 1.0f / V.qdx, iy = 1.0f / V.qdy;
-  PixRange r;
-  r.i0 = (int)ceilf((t.lox - m0 - V.q0x) * ix - 0.01f);
-  r.i1 = (int)floorf((t.hix + m0 - V.q0x) * ix + 0.01f);
-  r.j0 = (int)ceilf((t.loy - m0 - V.q0y) * iy - 0.01f);
-  r.j1 = (int)floorf((t.hiy + m0 - V.q0y) * iy + 0.01f);
-  if (r.i0 < 0) r.i0 = 0;
-  if (r.j0 < 0) r.j0 = 0;
-  if (r.i1 > res - 1) r.i1 = res - 1;
-  if (r.j1 > res - 1) r.j1 = res - 1;
-  return r;
-}
-
 FB_HD int screen_tri(const ViewF& V, float qx, float qy, float zo, const float* P0, const float* P1,
                      const float* P2, float* zlo, float* zhi) {
   if (!V.enabled) {

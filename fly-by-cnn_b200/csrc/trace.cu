@@ -222,7 +222,6 @@ int trace_rays(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o
 // Each lane still decides its own hit exactly (double precision) and keeps its
 // own cull distance, so the result equals the per-ray traversal bit for bit.
 #define RK_RING 16
-#define RK_PEND 4
 #define RK_MAX_STEPS (1u << 24)  // node visits of one packet; a tree has < 2^31 nodes, a packet visits far fewer
 
 template <bool USE_TOP, bool COUNT>

@@ -1,5 +1,5 @@
-// trace_common.cuh -- pieces shared by the render kernels (trace.cu: fused exact kernel,
-// screen.cu: float32 trace kernel + exact resolve kernel).
+// trace_common.cuh -- pieces shared by the render kernels (raster.cu: scan conversion + exact resolve,
+// screen.cu: float32 LBVH trace kernel + exact resolve, trace.cu: fused exact LBVH kernel, pinhole views).
 #pragma once
 #include "ctx.h"
 
@@ -92,13 +92,6 @@ struct RenderParams {
 #define RK_THREADS 256
 #define RK_WARPS (RK_THREADS / 32)
 #define RK_QCAP 96
-#ifdef FLYBY_DEBUG
-#define RK_MAX_ITERS (1ull << 18)
-#else
-#define RK_MAX_ITERS (1ull << 26)
-#endif
-//  // ~60 steps per ray would allow a million rays per warp
-#define RK_RETIRE 12  // retire/refill once this many lanes are finished or idle
 
 __device__ __forceinline__ void write_pixel(const RenderParams& p, int64_t pix, const float* px, int cell,
                                             double t) {
