@@ -428,7 +428,7 @@ struct ViewF {
 };
 enum { SC_MISS = 0, SC_MAYBE = 1, SC_SURE = 2 };
 
-FB_HD void viewf_setup(const View& v, double radius, double spacing, float max_abs_coord, ViewF* f) {
+FB_HD void viewf_setup(const View& v, double radius, double spacing, float max_abs_coord, double tol, ViewF* f) {
   for (int k = 0; k < 3; k++) {
     f->xf[k] = (float)v.x[k];
     f->yf[k] = (float)v.y[k];
@@ -436,17 +436,24 @@ FB_HD void viewf_setup(const View& v, double radius, double spacing, float max_a
   }
   double rp = v.sp[0] * v.n[0] + v.sp[1] * v.n[1] + v.sp[2] * v.n[2];
   f->rp = (float)rp;
-  // a projected coordinate is a 3-term float dot product of |coord| <= max_abs_coord with a
-  // unit vector rounded to float: error < 8 * 2^-24 * sqrt(3) * max_abs_coord; 2^-20 leaves 4x headroom
-  // e_q: a ray origin is a float32-rounded plane point (vtkPlaneSource); deriving its view-plane
-  // position from the pixel index instead of the double origin is off by < 2^-22 (|sp| + plane size)
-  double spn = fabs(v.sp[0]) + fabs(v.sp[1]) + fabs(v.sp[2]);
-  double pln = fabs(v.v1[0]) + fabs(v.v1[1]) + fabs(v.v1[2]) + fabs(v.v2[0]) + fabs(v.v2[1]) + fabs(v.v2[2]);
-  float e_q = 2.384185791015625e-07f * (float)((spn + pln) * (fabs(spacing) + 1.0));
-  f->e_p = 9.5367431640625e-07f * (max_abs_coord + 1.0f) + e_q;
+  // e_proj: a projected coordinate is a 3-term float dot product (two fmaf and a product: three roundings of
+  // partial sums bounded by |P|_2 |x|_2) of a point with |coord| <= max_abs_coord and a unit vector rounded to
+  // float (one more 2^-24 |P|_2): error <= 4 * 2^-24 * sqrt(3) * max_abs_coord; twice that is used.
+  // e_q: the view-plane position of a ray is taken from the pixel index, q = fmaf(i, qd, q0).  The ray the exact
+  // test sees starts at a float32-rounded plane point (vtkPlaneSource): off by <= 2^-24 |spacing| |pf|_2 with
+  // |pf|_2 <= |sp|_2 + |v1|_2 + |v2|_2; evaluating q in float adds <= 2 * 2^-24 |spacing| max(|v1|_2, |v2|_2)
+  // (rounding of qd times i, of q0 and of the fmaf).  Twice the sum is used.
+  const double sp2 = sqrt(v.sp[0] * v.sp[0] + v.sp[1] * v.sp[1] + v.sp[2] * v.sp[2]);
+  const double v12 = sqrt(v.v1[0] * v.v1[0] + v.v1[1] * v.v1[1] + v.v1[2] * v.v1[2]);
+  const double v22 = sqrt(v.v2[0] * v.v2[0] + v.v2[1] * v.v2[1] + v.v2[2] * v.v2[2]);
+  const float e_q = (float)(1.1920928955078125e-07 * fabs(spacing) * (sp2 + v12 + v22 + 2.0 * (v12 > v22 ? v12 : v22)) * 1.0001) + 1.0e-12f;
+  f->e_p = 8.3e-07f * max_abs_coord + e_q;
   f->e_z = 9.5367431640625e-07f * (max_abs_coord + 1.0f + fabsf((float)rp)) + e_q;
   f->two_r = (float)(2.0 * radius);
-  f->d0 = 4.0f * f->e_p;
+  // d0: absolute in-plane margin on top of the rounding bounds.  It has to cover what the exact test itself
+  // adds at a boundary: its dist^2 <= tol^2 acceptance just outside an edge (tol = 1e-10 by default) and its
+  // own double rounding (< 1e-11 in these units for the triangles that get past the strip test).
+  f->d0 = f->e_p + (float)(2.0 * fabs(tol)) + 1.0e-9f;
   f->q0x = f->q0y = f->qdx = f->qdy = 0.f;  // set by viewf_pixels once the resolution is known
   // the SC_SURE argument needs |n.d| > 1e-6 |n.(P1-o)| for non-grazing triangles: holds when R is not tiny
   f->enabled = radius >= 0.05 * ((double)max_abs_coord + 1.0) ? 1 : 0;

@@ -22,7 +22,7 @@ namespace fb {
 
 // ---------------------------------------------------------------- view setup
 __global__ void view_setup_kernel(const float* __restrict__ pts, int n, double radius, double plane_scale,
-                                  double spacing, int res, const float* __restrict__ ubox, View* __restrict__ views,
+                                  double spacing, double tol, int res, const float* __restrict__ ubox, View* __restrict__ views,
                                   ViewF* __restrict__ viewsf) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -34,7 +34,7 @@ __global__ void view_setup_kernel(const float* __restrict__ pts, int n, double r
   float max_abs_coord = 0.f;
   for (int k = 0; k < 6; k++) max_abs_coord = fmaxf(max_abs_coord, fabsf(ubox[k]));
   ViewF f;
-  viewf_setup(v, radius, spacing, max_abs_coord, &f);
+  viewf_setup(v, radius, spacing, max_abs_coord, tol, &f);
   viewf_pixels(v, spacing, res, &f);
   viewsf[i] = f;
 }
@@ -49,7 +49,7 @@ int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res) {
   FB_CUDA(c, c->views.reserve(sizeof(View) * (size_t)c->n_views));
   FB_CUDA(c, c->viewsf.reserve(sizeof(ViewF) * (size_t)c->n_views));
   view_setup_kernel<<<(unsigned)cdiv(c->n_views, 64), 64, 0, c->stream>>>(
-      c->view_pts.as<float>(), c->n_views, c->radius, o->plane_scale, o->plane_spacing, res, prep_unit_box(c),
+      c->view_pts.as<float>(), c->n_views, c->radius, o->plane_scale, o->plane_spacing, o->tolerance, res, prep_unit_box(c),
       c->views.as<View>(), c->viewsf.as<ViewF>());
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, c->tc_table.reserve(sizeof(double) * (size_t)res));

@@ -454,7 +454,7 @@ int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris,
     View vw;
     view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
     ViewF vf;
-    viewf_setup(vw, radius, spacing, maxc, &vf);
+    viewf_setup(vw, radius, spacing, maxc, 1e-10, &vf);
     viewf_pixels(vw, spacing, res, &vf);
     for (int ty = 0; ty < (res + 3) / 4; ty++)
       for (int tx = 0; tx < (res + 7) / 8; tx++) {
@@ -480,13 +480,13 @@ int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris,
 extern "C" __attribute__((visibility("default")))
 int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* views,
                       int n_views, double radius, int res, double plane_scale, double spacing, int cand_cap,
-                      int32_t* out_ids, double* out_t, long long* work /* [5]: pixel tests, exact tests, overflow pixels, span audit, in: order seed */) {
+                      int32_t* out_ids, double* out_t, long long* work /* [7]: pixel tests, exact tests, overflow pixels, span audit, in: order seed, out: unsound decisions, MAYBE box pixels */) {
   SimBvh b;
   build(verts, V, tris, T, b);
   if (b.nodes.empty()) return 1;
   float maxc = 0.f;
   for (int64_t i = 0; i < 3 * V; i++) maxc = fmaxf(maxc, fabsf(verts[i]));
-  long long n_tests = 0, n_exact = 0, n_over = 0, n_span_bad = 0;
+  long long n_tests = 0, n_exact = 0, n_over = 0, n_span_bad = 0, n_unsound = 0, n_maybe = 0;
   const bool check_spans = work && work[3] == 1;
   const long long order_seed = work ? work[4] : 0;  // in: work[4] != 0 shuffles the arrival order of the triangles  // in: work[3] = 1 asks for the span audit; out: work[3] = violations
   SimCount cnt;
@@ -495,7 +495,7 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
     View vw;
     view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
     ViewF vf;
-    viewf_setup(vw, radius, spacing, maxc, &vf);
+    viewf_setup(vw, radius, spacing, maxc, 1e-10, &vf);
     viewf_pixels(vw, spacing, res, &vf);
     // single pass, as raster_kernel: front[pixel] = smallest front_key over the SURE triangles; what a triangle
     // learns from the entry it displaced / lost to / read decides who joins the extras (settle_pixel).
@@ -527,10 +527,23 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
       for (int j = r.j0; j <= r.j1; j++) {
         int lo = r.i0, hi = r.i1;
         if (use_spans) raster_span(vf, t, fmaf((float)j, vf.qdy, vf.q0y), r.i0, r.i1, &lo, &hi);
-        if (check_spans)  // every pixel the span skips must be a certain miss
-          for (int i = r.i0; i <= r.i1; i++)
-            if ((i < lo || i > hi) && raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y)) != SC_MISS)
-              n_span_bad++;
+        if (check_spans)
+          for (int i = r.i0; i <= r.i1; i++) {
+            // every pixel the span skips must be a certain miss
+            const int c2 = raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y));
+            if ((i < lo || i > hi) && c2 != SC_MISS) n_span_bad++;
+            // soundness of the predicate itself: MISS => the exact test rejects, SURE => it accepts
+            if (c2 != SC_MAYBE) {
+              double o[3], tt, xx[3], ww[3];
+              view_ray(vw, res, i, j, spacing, o);
+              const bool ex = tri_exact(o, vw.dir, P0, P1, P2, DBL_MAX, 1e-20, &tt, xx, ww);
+              if ((c2 == SC_MISS && ex) || (c2 == SC_SURE && !ex)) n_unsound++;
+              if (c2 == SC_SURE && ex) {  // and the hit depth lies inside [zlo, zhi]
+                const double z = tt * 2.0 * radius;
+                if (z < (double)t.zlo || z > (double)t.zhi) n_unsound++;
+              }
+            } else n_maybe++;
+          }
         for (int i = lo; i <= hi; i++) {
           float qx = fmaf((float)i, vf.qdx, vf.q0x), qy = fmaf((float)j, vf.qdy, vf.q0y);
           int cls = raster_pixel(t, qx, qy);
@@ -579,6 +592,6 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
         out_ids[id] = h.cell; out_t[id] = h.slot >= 0 ? h.t : -1.0;
       }
   }
-  if (work) { work[0] = n_tests; work[1] = n_exact; work[2] = n_over; if (check_spans) work[3] = n_span_bad; }
+  if (work) { work[0] = n_tests; work[1] = n_exact; work[2] = n_over; if (check_spans) { work[3] = n_span_bad; work[5] = n_unsound; work[6] = n_maybe; } }
   return 0;
 }
