@@ -641,7 +641,9 @@ FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* 
   const float amin = fabsf(area2) - 8.0f * V.e_p * Dq_up;
   if ((zmax - zmin + 4.0f * V.e_z) * Dq_up <= 500.0f * amin && t->zlo > zo + V.e_z && t->zhi < zo + V.two_r - V.e_z)
     flags |= 2;
-  const float R1 = ((t->x1 - t->x0) + (t->y1 - t->y0)) * 1.000001f;  // >= |r|_1 of any vertex to any point of the padded box
+  // >= |r|_1 from any vertex to any pixel raster_project lets through: the padded box plus the slack of its
+  // pixel range (0.01 pixel per side and the rounding of the index arithmetic, < 0.02 pixel in all)
+  const float R1 = ((t->x1 - t->x0) + (t->y1 - t->y0) + 0.04f * (fabsf(V.qdx) + fabsf(V.qdy))) * 1.000001f;
   const float l0 = fabsf(t->e0x) + fabsf(t->e0y), l1 = fabsf(t->e1x) + fabsf(t->e1y), l2 = fabsf(t->e2x) + fabsf(t->e2y);
   const float k2 = 2.0f * V.e_p, kd = k2 + V.d0, kr = 2.384185791015625e-07f;
   t->g0 = fmaf(k2, R1, fmaf(kd, l0, kr * l0 * R1)) * 1.000001f;
@@ -676,8 +678,8 @@ FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* 
   t->flags = flags;
 }
 
+// q must be a pixel of the range raster_project returned (that is what bounds |r| in the margins)
 FB_HD int raster_pixel(const TriR& t, float qx, float qy) {
-  if (qx < t.x0 || qx > t.x1 || qy < t.y0 || qy > t.y1) return SC_MISS;
   const float r0x = qx - t.ax, r0y = qy - t.ay, r1x = qx - t.bx, r1y = qy - t.by, r2x = qx - t.cx, r2y = qy - t.cy;
   const float p0a = t.e0x * r0y, p0b = t.e0y * r0x, p1a = t.e1x * r1y, p1b = t.e1y * r1x, p2a = t.e2x * r2y, p2b = t.e2y * r2x;
   const float E0 = p0a - p0b, E1 = p1a - p1b, E2 = p2a - p2b;
