@@ -535,7 +535,22 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   // the scan conversion needs a regular pixel grid with a positive pitch
   const bool grid_ok = res > 1 && o->plane_scale * o->plane_spacing > 0.0;
   if (g_mode == 2 && grid_ok) {
-    rc = raster_render(c, p);
+    // the per-pixel scratch of the scan conversion (~58 B / pixel) is sized for at most 2^26 pixels at a time:
+    // long view lists are rendered in slabs of whole views, each straight into its part of the outputs
+    const int64_t per_view = (int64_t)res * res;
+    int slab = (int)(((int64_t)1 << 26) / per_view);
+    if (slab < 1) slab = 1;
+    rc = FLYBY_OK;
+    for (int v0 = 0; v0 < nv && rc == FLYBY_OK; v0 += slab) {
+      RenderParams q = p;
+      q.view_begin = vb + v0;
+      q.n_views = nv - v0 < slab ? nv - v0 : slab;
+      const int64_t off = (int64_t)v0 * per_view;
+      if (feat) q.feat = feat + off * channels;
+      if (ids) q.ids = ids + off;
+      if (tt) q.tt = tt + off;
+      rc = raster_render(c, q);
+    }
   } else if (g_mode >= 1) {
     rc = screen_render(c, p);
   } else {
