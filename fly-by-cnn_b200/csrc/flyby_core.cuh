@@ -424,6 +424,7 @@ struct ViewF {
   float two_r;                // length of the segment (2 R)
   float d0;                   // absolute in-plane margin on top of the rounding bounds
   float q0x, q0y, qdx, qdy;   // view-plane position of pixel (i, j): (q0x + i qdx, q0y + j qdy)
+  float iqx, iqy;             // 1 / qdx, 1 / qdy
   int enabled;                // 0: the view radius is tiny against the mesh, every candidate is SC_MAYBE
 };
 enum { SC_MISS = 0, SC_MAYBE = 1, SC_SURE = 2 };
@@ -454,7 +455,7 @@ FB_HD void viewf_setup(const View& v, double radius, double spacing, float max_a
   // adds at a boundary: its dist^2 <= tol^2 acceptance just outside an edge (tol = 1e-10 by default) and its
   // own double rounding (< 1e-11 in these units for the triangles that get past the strip test).
   f->d0 = f->e_p + (float)(2.0 * fabs(tol)) + 1.0e-9f;
-  f->q0x = f->q0y = f->qdx = f->qdy = 0.f;  // set by viewf_pixels once the resolution is known
+  f->q0x = f->q0y = f->qdx = f->qdy = f->iqx = f->iqy = 0.f;  // set by viewf_pixels once the resolution is known
   // the SC_SURE argument needs |n.d| > 1e-6 |n.(P1-o)| for non-grazing triangles: holds when R is not tiny
   f->enabled = radius >= 0.05 * ((double)max_abs_coord + 1.0) ? 1 : 0;
 }
@@ -468,6 +469,8 @@ FB_HD void viewf_pixels(const View& v, double spacing, int res, ViewF* f) {
   f->q0y = (float)(-0.5 * sy);
   f->qdx = res > 1 ? (float)(sx / (double)(res - 1)) : 0.f;
   f->qdy = res > 1 ? (float)(sy / (double)(res - 1)) : 0.f;
+  f->iqx = 1.0f / f->qdx;
+  f->iqy = 1.0f / f->qdy;
 }
 
 // 2-D position and depth of a ray origin in the frame of its view (from the double origin)
@@ -610,7 +613,7 @@ FB_HD bool raster_project(const ViewF& V, const float* P0, const float* P1, cons
   t->x1 = fmaxf(t->ax, fmaxf(t->bx, t->cx)) + m0;
   t->y0 = fminf(t->ay, fminf(t->by, t->cy)) - m0;
   t->y1 = fmaxf(t->ay, fmaxf(t->by, t->cy)) + m0;
-  const float ix = 1.0f / V.qdx, iy = 1.0f / V.qdy;
+  const float ix = V.iqx, iy = V.iqy;
   // a superset of the pixels inside the padded box (raster_pixel repeats the box test on the real coordinates)
   const float fi0 = fmaxf(0.0f, ceilf((t->x0 - V.q0x) * ix - 0.01f)), fi1 = fminf((float)(res - 1), floorf((t->x1 - V.q0x) * ix + 0.01f));
   const float fj0 = fmaxf(0.0f, ceilf((t->y0 - V.q0y) * iy - 0.01f)), fj1 = fminf((float)(res - 1), floorf((t->y1 - V.q0y) * iy + 0.01f));
@@ -703,7 +706,7 @@ FB_HD void raster_span(const ViewF& V, const TriR& t, float qy, int i0, int i1, 
   if (t.flags & 64) { const float x = fmaf(t.m0s, dy, t.b0s); if (t.flags & 8) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
   if (t.flags & 128) { const float x = fmaf(t.m1s, dy, t.b1s); if (t.flags & 16) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
   if (t.flags & 256) { const float x = fmaf(t.m2s, dy, t.b2s); if (t.flags & 32) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
-  const float ix = 1.0f / V.qdx;
+  const float ix = V.iqx;
   const float fl = fmaxf((float)i0, ceilf(((t.x0 - V.q0x) + (xl - t.sigma)) * ix - 0.01f));
   const float fh = fminf((float)i1, floorf(((t.x0 - V.q0x) + (xh + t.sigma)) * ix + 0.01f));
   *lo = (int)fl;
@@ -752,7 +755,11 @@ FB_HD float front_key_zlo_lower(uint64_t key) {
   const int c = (int)((key >> 27) & 31u);
   if (c == 31) return -INFINITY;
   const float zhi = unford_bits((uint32_t)(key >> 32));
+#if defined(__CUDA_ARCH__)
+  return zhi - __int_as_float((c + 104) << 23);  // 2^(c - 23), built from its exponent field
+#else
   return zhi - ldexpf(1.0f, c - 23);
+#endif
 }
 #define FB_FRONT_SLOT(key) ((int)((uint32_t)(key) & 0x07ffffffu))
 
