@@ -642,7 +642,8 @@ FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* 
   // same SURE eligibility as screen_setup, with Dq rounded up
   const float Dq_up = fmaxf(Dq, 0.0f) * 1.000001f + 4.0f * V.e_p;
   const float amin = fabsf(area2) - 8.0f * V.e_p * Dq_up;
-  if ((zmax - zmin + 4.0f * V.e_z) * Dq_up <= 500.0f * amin && t->zlo > zo + V.e_z && t->zhi < zo + V.two_r - V.e_z)
+  if (V.enabled && (zmax - zmin + 4.0f * V.e_z) * Dq_up <= 500.0f * amin && t->zlo > zo + V.e_z &&
+      t->zhi < zo + V.two_r - V.e_z)
     flags |= 2;
   // >= |r|_1 from any vertex to any pixel raster_project lets through: the padded box plus the slack of its
   // pixel range (0.01 pixel per side and the rounding of the index arithmetic, < 0.02 pixel in all)
