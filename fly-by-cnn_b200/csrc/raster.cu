@@ -19,6 +19,8 @@
 // Reference replaced: the per-view / per-plane-point loops of
 // src/app/fly_by_features.cxx:652-852 (search = IntersectWithLine :750-758, shading :766-807)
 // and the channel assembly of src/py/fly_by_features.py:124-150.
+#include <stdlib.h>
+
 #include "trace_common.cuh"
 
 namespace fb {
@@ -425,7 +427,15 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   p.n_queue = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 14);
   p.n_spill = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 13);
   FB_CUDA(c, cudaMemsetAsync(p.n_spill, 0, 16, st));  // n_spill[2], n_queue[2]
-  const size_t cap = (size_t)(n_pix / 8 > (1 << 20) ? n_pix / 8 : (1 << 20));
+  size_t cap = (size_t)(n_pix / 8 > (1 << 20) ? n_pix / 8 : (1 << 20));
+  {  // FLYBY_PAIR_CAP: test hook that shrinks the spill list so that the LBVH re-trace of resolve3 gets exercised
+    static long env_cap = -1;
+    if (env_cap < 0) {
+      const char* e = getenv("FLYBY_PAIR_CAP");
+      env_cap = e ? atol(e) : 0;
+    }
+    if (env_cap > 0) cap = (size_t)env_cap;
+  }
   p.pair_cap = (unsigned int)cap;
   FB_CUDA(c, c->raster_ovf.reserve(cap * (8 + 8 + 4 + 4 * 8)));
   p.pairs = c->raster_ovf.as<uint2>();

@@ -13,6 +13,7 @@ from flyby_b200 import synth
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
+ROOT_DIR = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
 
 
 def _build(ctx, P, F, **kw):
@@ -369,3 +370,48 @@ def test_config1_full_size(gpu_ctx, orc):
     assert r["t_bit_equal"] and r["feat_bit_equal"]
     st = gpu_ctx.stats()
     assert st["n_hits"] == r["hits"]
+
+
+def test_tiny_radius_and_lost_pairs_fallback(orc, tmp_path):
+    """Two rarely taken paths, in a fresh process because one of them is switched by an environment variable read
+    once: (1) a view radius that is tiny against the mesh (view planes inside the surface: the float32 screening
+    declares nothing certain), (2) a spill list too small for the piled candidates, so that pixels are re-traced
+    through the LBVH (raster_resolve3_kernel)."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "lost.py"
+    script.write_text('''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from flyby_b200 import _cabi, synth
+from oracle import oracle as orc
+ctx = _cabi.Context(0)
+# (2) 30 coincident copies of a patch: ~29 extras per covered pixel, far more pairs than FLYBY_PAIR_CAP=64 holds
+base = np.array([[-0.9, -0.8, 0.1], [0.9, -0.7, 0.1], [0.1, 0.9, 0.1], [-0.8, 0.7, 0.1]], np.float32)
+V = np.concatenate([base] * 30); F = np.concatenate([np.array([[0, 1, 2], [0, 2, 3]], np.int32) + 4 * k for k in range(30)])
+ctx.set_mesh(V, F, skip_normalise=True); ctx.build()
+ctx.views_custom(np.array([[0, 0, 2.0], [1.0, 1.0, 1.4]], np.float32), 2.0)
+opts = ctx.render_opts(plane_scale=2.0)
+feat, ids, t = ctx.render(48, opts, want_t=True)
+ctx.stats()  # with FLYBY_DEBUG_STATS set this prints the counters of the render to stderr
+N = orc.point_normals(V, F)
+fo, io, to = orc.render(V, F, N, ctx.get_views(), 2.0, 48, plane_scale=2.0, grid=False, want_t=True)
+assert (ids != io).sum() == 0 and np.array_equal(t, to) and np.array_equal(feat, fo) and (io >= 0).sum() > 500
+assert set(np.unique(io[io >= 0])) <= {0, 1}
+# (1) radius 0.02 around a unit mesh
+P, F2 = synth.bumpy_sphere(16, 3)
+ctx.set_mesh(P, F2); ctx.build()
+uv, nrm, _, _ = ctx.get_mesh()
+ctx.views_icosahedron(1, 0.02)
+opts = ctx.render_opts(plane_scale=3.0)
+feat, ids, t = ctx.render(40, opts, want_t=True)
+fo, io, to = orc.render(uv, F2, nrm, ctx.get_views(), 0.02, 40, plane_scale=3.0, grid=False, want_t=True)
+assert (ids != io).sum() == 0 and np.array_equal(t, to) and np.array_equal(feat, fo)
+print("ok", int((io >= 0).sum()))
+''' % (ROOT_DIR, os.path.join(ROOT_DIR, "fly-by-cnn_b200")))
+    env = dict(os.environ, FLYBY_PAIR_CAP="64", FLYBY_DEBUG_STATS="1")
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+    first = [ln for ln in out.stderr.splitlines() if "re-traced exactly" in ln][0]
+    assert "re-traced exactly 0;" not in first, first  # the LBVH fallback really ran
