@@ -175,3 +175,37 @@ def test_render_async_streams_meshes(gpu_ctx):
     gpu_ctx.synchronize()
     f, i, t = bufs[(len(meshes) - 1) % 2]
     assert np.array_equal(f.numpy(), want[-1][0]) and np.array_equal(i.numpy(), want[-1][1])
+
+
+def test_two_contexts_interleaved_on_one_gpu(gpu_ctx):
+    """Independent contexts on their own streams may overlap on the device: results equal the sequential ones."""
+    torch = pytest.importorskip("torch")
+    from flyby_b200 import _cabi, synth
+    dev = torch.device("cuda", 0)
+    meshes = [synth.bumpy_sphere(30 + 3 * k, k) for k in range(6)]
+    gpu_ctx.views_icosahedron(2, 2.0)
+    opts = gpu_ctx.render_opts()
+    want = []
+    for P, F in meshes:
+        gpu_ctx.set_mesh(P, F)
+        gpu_ctx.build()
+        want.append(gpu_ctx.render(128, opts))
+    pair = []
+    for _ in range(2):
+        s = torch.cuda.Stream(device=dev)
+        c = _cabi.Context(0, stream=s.cuda_stream)
+        n = c.views_icosahedron(2, 2.0)
+        pair.append((c, s, [torch.empty((n, 128, 128, 4), dtype=torch.float32, device=dev) for _ in range(3)],
+                     [torch.empty((n, 128, 128), dtype=torch.int32, device=dev) for _ in range(3)]))
+    dm = [(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)) for P, F in meshes]
+    for k, (P, F) in enumerate(dm):          # nothing waits between the calls: the two streams run side by side
+        c, s, fs, is_ = pair[k % 2]
+        c.set_mesh(P, F)
+        c.build()
+        c.render_into(128, opts, fs[k // 2], is_[k // 2])
+    torch.cuda.synchronize()
+    for k in range(len(meshes)):
+        c, s, fs, is_ = pair[k % 2]
+        assert np.array_equal(fs[k // 2].cpu().numpy(), want[k][0]) and np.array_equal(is_[k // 2].cpu().numpy(), want[k][1])
+    for c, _, _, _ in pair:
+        c.close()
