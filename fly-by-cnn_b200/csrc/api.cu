@@ -78,6 +78,8 @@ extern "C" {
 
 int flyby_abi_version(void) { return FLYBY_ABI_VERSION; }
 
+void flyby_destroy(flyby_ctx* c);
+
 int flyby_create(int device, void* stream, flyby_ctx** out) {
   if (!out) return FLYBY_ERR_INVALID;
   *out = nullptr;
@@ -95,20 +97,20 @@ int flyby_create(int device, void* stream, flyby_ctx** out) {
   if (stream) {
     c->stream = (cudaStream_t)stream;
   } else {
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
     c->own_stream = true;
   }
   for (int i = 0; i < 8; i++)
-    if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+    if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
   for (int i = 0; i < 16; i++)
-    if (cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char* e = getenv("FLYBY_LEAF_MAX")) {
     int v = atoi(e);
     if (v >= 1 && v <= 8) c->leaf_max = v;
   }
-  if (c->counters.reserve(16 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return FLYBY_ERR_CUDA; }
+  if (c->counters.reserve(16 * sizeof(unsigned long long)) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
   *out = c;
   return FLYBY_OK;
 }
@@ -117,6 +119,7 @@ void flyby_destroy(flyby_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   nccl_destroy(c);
   MeshDev& m = c->mesh;
   DevBuf* bufs[] = {&m.raw_verts, &m.tris, &m.verts, &m.normals, &m.face_n, &m.adj_start, &m.adj_cur, &m.adj,
