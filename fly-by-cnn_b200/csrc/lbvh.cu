@@ -228,25 +228,54 @@ __global__ void karras_kernel(const uint32_t* __restrict__ codes, int n, int4* _
 }
 
 // bottom-up: the second thread to reach a node merges its children's boxes
-__global__ void refit_kernel(int n, int4* knode, const int32_t* __restrict__ leaf_parent,
-                             const float* __restrict__ leaf_box, float* node_box) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  int node = leaf_parent[s];
-  while (node >= 0) {
-    __threadfence();
-    if (atomicAdd(&knode[node].w, 1) == 0) return;  // first arrival leaves
-    __threadfence();
-    int c0 = __ldcg(&knode[node].x), c1 = __ldcg(&knode[node].y);
-    const float* b0 = c0 < 0 ? leaf_box + 6 * (int64_t)(~c0) : node_box + 6 * (int64_t)c0;
-    const float* b1 = c1 < 0 ? leaf_box + 6 * (int64_t)(~c1) : node_box + 6 * (int64_t)c1;
+// Refit without a dependency chain: the subtree of internal node i covers the Morton-sorted slots
+// krange[i] = [first, first + count), so its box is a range union of leaf boxes.  Two levels of pre-reduced
+// boxes (32-leaf chunks, 1024-leaf super chunks) keep a range query at <= 62 leaves + 62 chunks + count / 1024
+// super chunks; min / max are exact and order independent, so the boxes equal the bottom-up ones bit for bit.
+__global__ void __launch_bounds__(256) box_reduce32_kernel(const float* __restrict__ in, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float b[6];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      __stcg(&node_box[6 * (int64_t)node + k], fminf(__ldcg(b0 + k), __ldcg(b1 + k)));
-      __stcg(&node_box[6 * (int64_t)node + 3 + k], fmaxf(__ldcg(b0 + 3 + k), __ldcg(b1 + 3 + k)));
+  for (int k = 0; k < 6; k++) b[k] = i < n ? in[6 * (int64_t)i + k] : (k < 3 ? INFINITY : -INFINITY);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const float v = __shfl_xor_sync(0xffffffffu, b[k], o);
+      b[k] = k < 3 ? fminf(b[k], v) : fmaxf(b[k], v);
     }
-    node = __ldcg(&knode[node].z);
+  if ((threadIdx.x & 31) == 0 && i < n)
+#pragma unroll
+    for (int k = 0; k < 6; k++) out[6 * (int64_t)(i >> 5) + k] = b[k];
+}
+
+__device__ __forceinline__ void box_merge(float* b, const float* __restrict__ src, int64_t idx) {
+  const float* p = src + 6 * idx;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b[k] = fminf(b[k], __ldg(p + k));
+    b[3 + k] = fmaxf(b[3 + k], __ldg(p + 3 + k));
   }
+}
+
+__global__ void __launch_bounds__(256) refit_range_kernel(int n_internal, const int2* __restrict__ krange,
+                                                          const float* __restrict__ leaf_box,
+                                                          const float* __restrict__ chunk_box,
+                                                          const float* __restrict__ super_box, float* __restrict__ node_box) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal) return;
+  const int2 r = krange[i];
+  int a = r.x;
+  const int e = r.x + r.y;  // [a, e)
+  float b[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  // leaves up to the next chunk boundary, chunks up to the next super boundary, supers, then back down
+  while (a < e && (a & 31)) box_merge(b, leaf_box, a++);
+  while (a + 32 <= e && (a & 1023)) { box_merge(b, chunk_box, a >> 5); a += 32; }
+  while (a + 1024 <= e) { box_merge(b, super_box, a >> 10); a += 1024; }
+  while (a + 32 <= e) { box_merge(b, chunk_box, a >> 5); a += 32; }
+  while (a < e) box_merge(b, leaf_box, a++);
+#pragma unroll
+  for (int k = 0; k < 6; k++) node_box[6 * (int64_t)i + k] = b[k];
 }
 
 // breadth-first prefix of the tree (at most ntop_max nodes) -> remap[karras] = rank
@@ -440,9 +469,19 @@ int lbvh_run(flyby_ctx* c) {
   int32_t* leaf_parent = m.idx_alt.as<int32_t>();  // sort scratch is free again
   karras_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(k0, n, m.knode.as<int4>(), leaf_parent, m.krange.as<int2>());
   FB_LAUNCH_CHECK(c);
-  refit_kernel<<<gT, 256, 0, st>>>(n, m.knode.as<int4>(), leaf_parent, m.leaf_box.as<float>(),
-                                   m.node_box.as<float>());
-  FB_LAUNCH_CHECK(c);
+  {
+    const int n_chunk = (n + 31) / 32, n_super = (n_chunk + 31) / 32;
+    FB_CUDA(c, m.hist.reserve(sizeof(float) * 6 * ((size_t)n_chunk + (size_t)n_super) + 64));  // sort scratch, free again
+    float* chunk_box = m.hist.as<float>();
+    float* super_box = chunk_box + 6 * (size_t)n_chunk;
+    box_reduce32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(m.leaf_box.as<float>(), n, chunk_box);
+    FB_LAUNCH_CHECK(c);
+    box_reduce32_kernel<<<(unsigned)cdiv(n_chunk, 256), 256, 0, st>>>(chunk_box, n_chunk, super_box);
+    FB_LAUNCH_CHECK(c);
+    refit_range_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(ni, m.krange.as<int2>(), m.leaf_box.as<float>(), chunk_box,
+                                                                 super_box, m.node_box.as<float>());
+    FB_LAUNCH_CHECK(c);
+  }
   // top-of-tree first: flag = 1 for every node, the BFS clears it for the top set
   int32_t* n_top_dev = m.remap.as<int32_t>() + ni;  // one spare word behind the table
   fill_u32_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(m.topflag.as<uint32_t>(), ni, 1u);
