@@ -103,28 +103,31 @@ __global__ void morton_kernel(const float* __restrict__ v, const int32_t* __rest
 }
 
 // ============================================================ radix sort
-// Stable LSD sort of (code, index) pairs, 8 bits per pass.  Per pass:
+// Stable LSD sort of (code, index) pairs.  The Morton codes have 30 bits: three passes of 10 bits.  Per pass:
 //   radix_hist_kernel   per-block digit histogram -> hist[digit][block]
 //   exclusive scan      over the digit-major table = global base per (digit, block)
 //   radix_scatter_kernel stable ranking inside the block with warp match votes
 #define RS_THREADS 256
 #define RS_ITEMS 8
 #define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 keys per block, 256 per warp
+#define RS_BITS 10
+#define RS_RADIX (1 << RS_BITS)
+#define RS_PASSES 3
 
 __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist,
                   int nblocks) {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
+  __shared__ uint32_t h[RS_RADIX];
+  for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) h[d] = 0;
   __syncthreads();
   int64_t base = (int64_t)blockIdx.x * RS_TILE;
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; k++) {
     int64_t i = base + k * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & (RS_RADIX - 1u)], 1u);
   }
   __syncthreads();
-  hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) hist[(int64_t)d * nblocks + blockIdx.x] = h[d];
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -132,11 +135,11 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restri
                      int shift, const uint32_t* __restrict__ hist_scanned, int nblocks,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
   // per-warp digit counts, turned into per-warp bases, then used as running cursors
-  __shared__ uint32_t cnt[8][256];
-  __shared__ uint32_t gbase[256];
+  __shared__ uint32_t cnt[8][RS_RADIX];
+  __shared__ uint32_t gbase[RS_RADIX];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 8 * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
-  gbase[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+  for (int i = threadIdx.x; i < 8 * RS_RADIX; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+  for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) gbase[d] = hist_scanned[(int64_t)d * nblocks + blockIdx.x];
   __syncthreads();
   const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (RS_TILE / 8);
   uint32_t k[RS_ITEMS], v[RS_ITEMS];
@@ -146,16 +149,16 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restri
     bool ok = i < n;
     k[r] = ok ? keys[i] : 0u;
     v[r] = ok ? vals[i] : 0u;
-    if (ok) atomicAdd(&cnt[warp][(k[r] >> shift) & 255u], 1u);
+    if (ok) atomicAdd(&cnt[warp][(k[r] >> shift) & (RS_RADIX - 1u)], 1u);
   }
   __syncthreads();
-  // exclusive prefix over warps for each digit (thread d owns digit d)
-  {
+  // exclusive prefix over warps for each digit (every thread owns RS_RADIX / RS_THREADS digits)
+  for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) {
     uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
-      uint32_t t = cnt[w][threadIdx.x];
-      cnt[w][threadIdx.x] = run;
+      uint32_t t = cnt[w][d];
+      cnt[w][d] = run;
       run += t;
     }
   }
@@ -164,8 +167,8 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restri
   for (int r = 0; r < RS_ITEMS; r++) {
     int64_t i = wbase + r * 32 + lane;
     bool ok = i < n;
-    uint32_t d = (k[r] >> shift) & 255u;
-    uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : (0x100u | (uint32_t)lane));
+    uint32_t d = (k[r] >> shift) & (RS_RADIX - 1u);
+    uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : (RS_RADIX | (uint32_t)lane));
     uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     uint32_t pos = 0;
     if (ok) pos = gbase[d] + cnt[warp][d] + rank;
@@ -416,7 +419,7 @@ int lbvh_run(flyby_ctx* c) {
   FB_CUDA(c, m.codes_alt.reserve(4 * Tz));
   FB_CUDA(c, m.idx.reserve(4 * Tz));
   FB_CUDA(c, m.idx_alt.reserve(4 * Tz));
-  FB_CUDA(c, m.hist.reserve(4 * 256 * (size_t)nblocks));
+  FB_CUDA(c, m.hist.reserve(4 * RS_RADIX * (size_t)nblocks));
   FB_CUDA(c, m.leaf_box.reserve(24 * Tz));
   FB_CUDA(c, m.node_box.reserve(24 * Tz));
   FB_CUDA(c, m.knode.reserve(16 * Tz));
@@ -436,11 +439,11 @@ int lbvh_run(flyby_ctx* c) {
   FB_LAUNCH_CHECK(c);
   uint32_t *k0 = m.codes.as<uint32_t>(), *k1 = m.codes_alt.as<uint32_t>();
   uint32_t *v0 = m.idx.as<uint32_t>(), *v1 = m.idx_alt.as<uint32_t>();
-  for (int pass = 0; pass < 4; pass++) {
-    int shift = 8 * pass;
+  for (int pass = 0; pass < RS_PASSES; pass++) {
+    int shift = RS_BITS * pass;
     radix_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, T, shift, m.hist.as<uint32_t>(), nblocks);
     FB_LAUNCH_CHECK(c);
-    int rc = exclusive_scan_u32(c, m.hist.as<uint32_t>(), 256 * (int64_t)nblocks, m.scan_tmp);
+    int rc = exclusive_scan_u32(c, m.hist.as<uint32_t>(), RS_RADIX * (int64_t)nblocks, m.scan_tmp);
     if (rc) return rc;
     radix_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, v0, T, shift, m.hist.as<uint32_t>(),
                                                          nblocks, k1, v1);
@@ -448,7 +451,7 @@ int lbvh_run(flyby_ctx* c) {
     uint32_t* t = k0; k0 = k1; k1 = t;
     t = v0; v0 = v1; v1 = t;
   }
-  // after 4 passes the sorted data is back in codes / idx
+  // after an odd number of passes the sorted data sits in the alternate buffers: k0 / v0 point at it
   FB_CUDA(c, cudaEventRecord(c->ev[3], st));
 
   reorder_kernel<<<gT, 256, 0, st>>>(m.verts.as<float>(), m.tris.as<int32_t>(), T, v0,
@@ -466,7 +469,7 @@ int lbvh_run(flyby_ctx* c) {
     return FLYBY_OK;
   }
   const int n = (int)T, ni = n - 1;
-  int32_t* leaf_parent = m.idx_alt.as<int32_t>();  // sort scratch is free again
+  int32_t* leaf_parent = reinterpret_cast<int32_t*>(v1);  // the sort's spare index buffer is free again
   karras_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(k0, n, m.knode.as<int4>(), leaf_parent, m.krange.as<int2>());
   FB_LAUNCH_CHECK(c);
   {
@@ -490,7 +493,7 @@ int lbvh_run(flyby_ctx* c) {
                                      m.topflag.as<int32_t>(), n_top_dev);
   FB_LAUNCH_CHECK(c);
   // scan of the non-top flags (kept separately: the layout needs flag and rank)
-  uint32_t* nontop_scan = m.codes_alt.as<uint32_t>();
+  uint32_t* nontop_scan = k1;  // the sort's spare key buffer
   FB_CUDA(c, cudaMemcpyAsync(nontop_scan, m.topflag.p, 4 * (size_t)ni, cudaMemcpyDeviceToDevice, st));
   int rc = exclusive_scan_u32(c, nontop_scan, ni, m.scan_tmp);
   if (rc) return rc;
