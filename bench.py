@@ -142,7 +142,14 @@ def cpu_baseline_sample():
         t0 = time.perf_counter()
         orc.render(U, F, N, views[1:1 + nv], RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=div)
         out[name] = nv / (time.perf_counter() - t0)
-    return {"value": out["vtk_buckets"], "unit": "views/s", "cores": orc.num_threads(), "kind": "port",
+    cores = orc.num_threads()
+    orc.set_threads(1)  # the reference's own loop is serial: one view, one thread
+    t0 = time.perf_counter()
+    orc.render(U, F, N, views[1:2], RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=0)
+    single = 1.0 / (time.perf_counter() - t0)
+    orc.set_threads(cores)
+    return {"value": out["vtk_buckets"], "unit": "views/s", "cores": cores, "kind": "port",
+            "single_thread_views_per_s": single,
             "sample": "4 views at res 512 of the bench mesh, oracle port of vtkCellLocator (VTK default bucket "
                       "rule) + VTK triangle test, OpenMP over rays, ray loop only",
             "tuned_grid64_views_per_s": out["tuned_grid64"]}

@@ -50,6 +50,15 @@ ORC_API int orc_num_threads(void) {
 #endif
 }
 
+/* the reference's ray loop is serial (fly_by_features.cxx:652,742; predict.py:83,123): n = 1 times it that way */
+ORC_API void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ */
 /* O1  unit surface                                                    */
 /*   src/py/utils.py:249-290 (ScaleSurf, canonical)                    */

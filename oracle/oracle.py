@@ -51,6 +51,11 @@ def set_tolerance(tol):
     lib().orc_set_tolerance(C.c_double(tol))
 
 
+def set_threads(n):
+    """OpenMP threads of the ray loops (1 = the reference's serial loop)."""
+    lib().orc_set_threads(C.c_int(int(n)))
+
+
 def num_threads():
     return lib().orc_num_threads()
 
