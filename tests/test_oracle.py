@@ -211,6 +211,42 @@ def test_golden_fixtures(orc):
     assert np.array_equal(orc.votes_argmax(votes, default=33), g["cell_labels"])
 
 
+GOLDEN_EXT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flyby_golden_ext.npz")
+
+
+def test_golden_fixtures_widened_rows(orc):
+    g, e = np.load(GOLDEN), np.load(GOLDEN_EXT)
+    F, V, lab = g["F"], len(g["U"]), e["labels_in"]
+    assert np.array_equal(orc.pp_remove_islands(F, V, lab, 1, 30, True), e["islands"])
+    conn, n = orc.pp_connectivity(F, V, lab, 2, 10)
+    assert n == int(e["n_regions"]) and np.array_equal(conn, e["connectivity"])
+    assert np.array_equal(orc.pp_dilate(F, V, lab, 3, 2), e["dilate"])
+    assert np.array_equal(orc.pp_erode(F, V, lab, 0, ignore_label=1), e["erode"])
+    assert np.array_equal(orc.pp_erode(F, V, lab, 2, iterations=2, target=3), e["erode2"])
+    assert np.array_equal(orc.interpolate_features(g["U"], F, g["ico"][:8], 2.0, 24, g["ids"][:8], e["feats"], zero=-1.0), e["interp"])
+    pf, pi, pd = orc.render_perspective(g["U"], F, g["N"], g["ico"][:6], 20, 30.0, 0.01, 3.0, normal_encoding=3, grid=False)
+    assert np.array_equal(pf, e["persp_feat"]) and np.array_equal(pi, e["persp_ids"]) and np.array_equal(pd, e["persp_depth"])
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_widened_rows(gpu_ctx):
+    g, e = np.load(GOLDEN), np.load(GOLDEN_EXT)
+    gpu_ctx.set_mesh(g["P"], g["F"])
+    gpu_ctx.build()
+    lab = e["labels_in"]
+    assert np.array_equal(gpu_ctx.labels_remove_islands(lab.copy(), 1, 30, True), e["islands"])
+    got = lab.copy()
+    assert gpu_ctx.labels_connectivity(got, 2, 10) == int(e["n_regions"]) and np.array_equal(got, e["connectivity"])
+    assert np.array_equal(gpu_ctx.labels_dilate(lab.copy(), 3, 2), e["dilate"])
+    assert np.array_equal(gpu_ctx.labels_erode(lab.copy(), 0, ignore_label=1), e["erode"])
+    assert np.array_equal(gpu_ctx.labels_erode(lab.copy(), 2, iterations=2, target=3), e["erode2"])
+    gpu_ctx.views_icosahedron(2, 2.0)
+    opts = gpu_ctx.render_opts(use_z=1, split_z=1)
+    assert np.array_equal(gpu_ctx.interpolate_features(24, opts, g["ids"][:8], e["feats"], zero=-1.0, view_end=8), e["interp"])
+    pf, pi, pd = gpu_ctx.render_perspective(20, gpu_ctx.render_opts(normal_encoding="uint8"), 30.0, 0.01, 3.0, view_end=6)
+    assert np.array_equal(pf, e["persp_feat"]) and np.array_equal(pi, e["persp_ids"]) and np.array_equal(pd, e["persp_depth"])
+
+
 @pytest.mark.gpu
 def test_gpu_matches_golden(gpu_ctx):
     g = np.load(GOLDEN)
