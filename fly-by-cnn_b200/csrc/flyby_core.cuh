@@ -608,6 +608,10 @@ FB_HD bool raster_project(const ViewF& V, const float* P0, const float* P1, cons
   t->by = fmaf(P1[0], V.yf[0], fmaf(P1[1], V.yf[1], P1[2] * V.yf[2]));
   t->cx = fmaf(P2[0], V.xf[0], fmaf(P2[1], V.xf[1], P2[2] * V.xf[2]));
   t->cy = fmaf(P2[0], V.yf[0], fmaf(P2[1], V.yf[1], P2[2] * V.yf[2]));
+  // a triangle with a NaN coordinate can never be hit by the exact test (every comparison fails): drop it here,
+  // fminf / fmaxf would otherwise hide the NaN and every pixel of the box would be undecided
+  const float chk = ((t->ax + t->bx) + t->cx) + ((t->ay + t->by) + t->cy);
+  if (chk != chk) return false;
   const float m0 = 2.0f * V.e_p + V.d0;
   t->x0 = fminf(t->ax, fminf(t->bx, t->cx)) - m0;
   t->x1 = fmaxf(t->ax, fmaxf(t->bx, t->cx)) + m0;

@@ -415,3 +415,22 @@ print("ok", int((io >= 0).sum()))
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
     first = [ln for ln in out.stderr.splitlines() if "re-traced exactly" in ln][0]
     assert "re-traced exactly 0;" not in first, first  # the LBVH fallback really ran
+
+
+def test_non_finite_vertices_are_never_hit(gpu_ctx, orc):
+    """A NaN coordinate poisons only the triangles that use it (the exact test rejects them, as the oracle does)."""
+    P, F = synth.bumpy_sphere(10, 6)
+    U, _, _ = orc.unit_surf(P)
+    U = U.copy()
+    U[[5, 77, 300]] = np.nan
+    uv, nrm, _, _ = _build(gpu_ctx, U, F, skip_normalise=True)
+    gpu_ctx.views_icosahedron(1, 2.0)
+    opts = gpu_ctx.render_opts(plane_scale=2.0)
+    feat, ids, t = gpu_ctx.render(64, opts, want_t=True)
+    N = orc.point_normals(U, F)
+    fo, io, to = orc.render(U, F, N, gpu_ctx.get_views(), 2.0, 64, plane_scale=2.0, grid=False, want_t=True)
+    assert int((ids != io).sum()) == 0 and np.array_equal(t, to)
+    bad = np.isin(F, [5, 77, 300]).any(axis=1)
+    assert not np.isin(io[io >= 0], np.nonzero(bad)[0]).any() and (io >= 0).sum() > 1000
+    hit = io >= 0
+    assert np.array_equal(feat[hit], fo[hit], equal_nan=True)  # points next to a poisoned triangle get NaN normals on both sides
