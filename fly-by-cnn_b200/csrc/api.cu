@@ -103,6 +103,16 @@ int flyby_create(int device, void* stream, flyby_ctx** out) {
   for (int i = 0; i < 8; i++)
     if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
+  {
+    const char* e = getenv("FLYBY_NO_SIDE_TREE");  // debugging: build the tree on the main stream
+    if (!(e && e[0] == '1')) {
+      int prio_lo = 0, prio_hi = 0;  // the many small tree kernels slip in ahead of the big render grids
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ev_sorted, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ev_tree, cudaEventDisableTiming) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
+    }
+  }
   for (int i = 0; i < 16; i++)
     if (cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -120,10 +130,11 @@ void flyby_destroy(flyby_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->side_stream) cudaStreamSynchronize(c->side_stream);
   nccl_destroy(c);
   MeshDev& m = c->mesh;
   DevBuf* bufs[] = {&m.raw_verts, &m.tris, &m.verts, &m.normals, &m.face_n, &m.adj_start, &m.adj_cur, &m.adj,
-                    &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.leaf_box,
+                    &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.tree_scan_tmp, &m.leaf_box,
                     &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid, &m.trec,
                     &c->view_pts, &c->views, &c->viewsf, &c->tc_table, &c->cand, &c->cand2, &c->pix_lists, &c->raster_tmp, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
                     &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->counters,
@@ -136,6 +147,9 @@ void flyby_destroy(flyby_ctx* c) {
   for (int i = 0; i < 2; i++)
     if (c->async_done[i]) cudaEventDestroy(c->async_done[i]);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_sorted) cudaEventDestroy(c->ev_sorted);
+  if (c->ev_tree) cudaEventDestroy(c->ev_tree);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -157,6 +171,7 @@ int flyby_synchronize(flyby_ctx* c) {
   int rc = check_watchdog(c);
   if (rc) return rc;
   FB_CUDA(c, cudaStreamSynchronize(c->copy_stream));  // copy-outs of flyby_render_async
+  if (c->side_stream) FB_CUDA(c, cudaStreamSynchronize(c->side_stream));  // tree build behind the last flyby_build
   return FLYBY_OK;
 }
 
@@ -221,6 +236,7 @@ int flyby_get_bvh(flyby_ctx* c, int64_t* n_nodes, int32_t* n_top, void* nodes_ou
   CHECK_CTX(c);
   MeshDev& m = c->mesh;
   if (!m.built) return fail(c, FLYBY_ERR_INVALID, "get_bvh: mesh not built");
+  { int rc = wait_tree(c); if (rc) return rc; }
   if (n_nodes) *n_nodes = m.n_nodes;
   if (n_top) {
     *n_top = 0;
@@ -656,6 +672,7 @@ int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {
   CHECK_CTX(c);
   if (!out) return FLYBY_ERR_INVALID;
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->side_stream) FB_CUDA(c, cudaStreamSynchronize(c->side_stream));
   flyby_stats s = c->stats;
   auto el = [&](int a, int b) -> float {
     float ms = 0.f;

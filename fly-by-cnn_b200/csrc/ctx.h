@@ -49,6 +49,7 @@ struct MeshDev {
   DevBuf codes, codes_alt, idx, idx_alt;  // uint32 [T] radix sort ping-pong
   DevBuf hist;                            // uint32 [256 * nblocks]
   DevBuf scan_tmp;                        // scan block totals
+  DevBuf tree_scan_tmp;                   // the same for the scan of the tree build (runs on the side stream)
   DevBuf leaf_box;                        // float [T,6] boxes of sorted slots
   DevBuf node_box;                        // float [T-1,6] internal boxes (Karras numbering)
   DevBuf knode;                           // int32 [T-1,4] child0, child1, parent, flag (Karras numbering)
@@ -72,6 +73,12 @@ struct flyby_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;  // D2H of finished view chunks overlaps the next chunk's render
+  // The LBVH topology / boxes / layout are not read by the scan-conversion render: they are built on a side
+  // stream behind the sort, concurrently with whatever the main stream does next.  Everything that reads the
+  // tree, and the next build, waits for ev_tree first (fb::wait_tree).
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_sorted = nullptr, ev_tree = nullptr;
+  bool tree_pending = false;
   cudaEvent_t chunk_ev[16] = {nullptr};
   char err[512] = {0};
   flyby_norm_opts norm;
@@ -152,7 +159,8 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // stage launchers (each file implements its own)
 int prep_run(flyby_ctx* c);                       // prep.cu: unit surf + normals
 int lbvh_run(flyby_ctx* c);                       // lbvh.cu: sort + tree + layout
-int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp);  // lbvh.cu
+int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp, cudaStream_t st = nullptr);  // lbvh.cu (st: default c->stream)
+int wait_tree(flyby_ctx* c);  // lbvh.cu: make the main stream wait for the side-stream tree build
 int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res);                      // trace.cu
 int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
                  int32_t* ids, double* tt, bool first_chunk = true, bool last_chunk = true);                                     // trace.cu

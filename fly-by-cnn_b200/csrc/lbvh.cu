@@ -60,27 +60,33 @@ __global__ void scan_add_kernel(uint32_t* data, int64_t n, const uint32_t* __res
     if (i < n) data[i] += off;
 }
 
-static int scan_rec(flyby_ctx* c, uint32_t* data, int64_t n, uint32_t* tmp) {
+static int scan_rec(flyby_ctx* c, uint32_t* data, int64_t n, uint32_t* tmp, cudaStream_t st) {
   int64_t nb = cdiv(n, SCAN_TILE);
-  scan_tile_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(data, n, nb > 1 ? tmp : nullptr);
+  scan_tile_kernel<<<(unsigned)nb, 256, 0, st>>>(data, n, nb > 1 ? tmp : nullptr);
   FB_LAUNCH_CHECK(c);
   if (nb > 1) {
-    int rc = scan_rec(c, tmp, nb, tmp + nb);
+    int rc = scan_rec(c, tmp, nb, tmp + nb, st);
     if (rc) return rc;
-    scan_add_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(data, n, tmp);
+    scan_add_kernel<<<(unsigned)nb, 256, 0, st>>>(data, n, tmp);
     FB_LAUNCH_CHECK(c);
   }
   return FLYBY_OK;
 }
 
-int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp) {
+int wait_tree(flyby_ctx* c) {
+  if (c->tree_pending) FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tree, 0));
+  return FLYBY_OK;
+}
+
+int exclusive_scan_u32(flyby_ctx* c, uint32_t* data, int64_t n, DevBuf& tmp, cudaStream_t st) {
+  if (!st) st = c->stream;
   if (n <= 0) return FLYBY_OK;
   // total temp over all recursion levels < n/2048 + n/2048^2 + ... + 8
   size_t need = 0;
   for (int64_t m = cdiv(n, SCAN_TILE); m > 1; m = cdiv(m, SCAN_TILE)) need += (size_t)m;
   need += 16;
   FB_CUDA(c, tmp.reserve(need * sizeof(uint32_t)));
-  return scan_rec(c, data, n, tmp.as<uint32_t>());
+  return scan_rec(c, data, n, tmp.as<uint32_t>(), st);
 }
 
 // ============================================================ Morton codes
@@ -412,6 +418,11 @@ int lbvh_run(flyby_ctx* c) {
   const int64_t T = m.T;
   m.n_nodes = 0;
   m.n_top_dev = nullptr;
+  {  // the previous mesh's tree build (side stream) may still read the scratch this build overwrites
+    int rc = wait_tree(c);
+    if (rc) return rc;
+    c->tree_pending = false;
+  }
   if (T == 0) return FLYBY_OK;
   const int nblocks = (int)cdiv(T, RS_TILE);
   const size_t Tz = (size_t)T;
@@ -469,40 +480,51 @@ int lbvh_run(flyby_ctx* c) {
     return FLYBY_OK;
   }
   const int n = (int)T, ni = n - 1;
+  // From here on nothing is needed by the scan-conversion render: topology, boxes and layout go to the side
+  // stream, ordered behind the sort / reorder by ev_sorted; readers of the tree call wait_tree().
+  cudaStream_t ss = c->side_stream ? c->side_stream : st;
+  if (ss != st) {
+    FB_CUDA(c, cudaEventRecord(c->ev_sorted, st));
+    FB_CUDA(c, cudaStreamWaitEvent(ss, c->ev_sorted, 0));
+  }
   int32_t* leaf_parent = reinterpret_cast<int32_t*>(v1);  // the sort's spare index buffer is free again
-  karras_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(k0, n, m.knode.as<int4>(), leaf_parent, m.krange.as<int2>());
+  karras_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, ss>>>(k0, n, m.knode.as<int4>(), leaf_parent, m.krange.as<int2>());
   FB_LAUNCH_CHECK(c);
   {
     const int n_chunk = (n + 31) / 32, n_super = (n_chunk + 31) / 32;
     FB_CUDA(c, m.hist.reserve(sizeof(float) * 6 * ((size_t)n_chunk + (size_t)n_super) + 64));  // sort scratch, free again
     float* chunk_box = m.hist.as<float>();
     float* super_box = chunk_box + 6 * (size_t)n_chunk;
-    box_reduce32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(m.leaf_box.as<float>(), n, chunk_box);
+    box_reduce32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ss>>>(m.leaf_box.as<float>(), n, chunk_box);
     FB_LAUNCH_CHECK(c);
-    box_reduce32_kernel<<<(unsigned)cdiv(n_chunk, 256), 256, 0, st>>>(chunk_box, n_chunk, super_box);
+    box_reduce32_kernel<<<(unsigned)cdiv(n_chunk, 256), 256, 0, ss>>>(chunk_box, n_chunk, super_box);
     FB_LAUNCH_CHECK(c);
-    refit_range_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(ni, m.krange.as<int2>(), m.leaf_box.as<float>(), chunk_box,
+    refit_range_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, ss>>>(ni, m.krange.as<int2>(), m.leaf_box.as<float>(), chunk_box,
                                                                  super_box, m.node_box.as<float>());
     FB_LAUNCH_CHECK(c);
   }
   // top-of-tree first: flag = 1 for every node, the BFS clears it for the top set
   int32_t* n_top_dev = m.remap.as<int32_t>() + ni;  // one spare word behind the table
-  fill_u32_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(m.topflag.as<uint32_t>(), ni, 1u);
+  fill_u32_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, ss>>>(m.topflag.as<uint32_t>(), ni, 1u);
   FB_LAUNCH_CHECK(c);
-  top_bfs_kernel<<<1, 1024, 0, st>>>(m.knode.as<int4>(), ni, FB_NTOP_MAX, m.remap.as<int32_t>(),
+  top_bfs_kernel<<<1, 1024, 0, ss>>>(m.knode.as<int4>(), ni, FB_NTOP_MAX, m.remap.as<int32_t>(),
                                      m.topflag.as<int32_t>(), n_top_dev);
   FB_LAUNCH_CHECK(c);
   // scan of the non-top flags (kept separately: the layout needs flag and rank)
   uint32_t* nontop_scan = k1;  // the sort's spare key buffer
-  FB_CUDA(c, cudaMemcpyAsync(nontop_scan, m.topflag.p, 4 * (size_t)ni, cudaMemcpyDeviceToDevice, st));
-  int rc = exclusive_scan_u32(c, nontop_scan, ni, m.scan_tmp);
+  FB_CUDA(c, cudaMemcpyAsync(nontop_scan, m.topflag.p, 4 * (size_t)ni, cudaMemcpyDeviceToDevice, ss));
+  int rc = exclusive_scan_u32(c, nontop_scan, ni, m.tree_scan_tmp, ss);
   if (rc) return rc;
-  layout_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, st>>>(
+  layout_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, ss>>>(
       ni, m.knode.as<int4>(), m.krange.as<int2>(), c->leaf_max, m.leaf_box.as<float>(), m.node_box.as<float>(),
       m.remap.as<int32_t>(),
       nontop_scan, m.topflag.as<int32_t>(), n_top_dev, m.nodes.as<Node>());
   FB_LAUNCH_CHECK(c);
-  FB_CUDA(c, cudaEventRecord(c->ev[4], st));
+  FB_CUDA(c, cudaEventRecord(c->ev[4], ss));
+  if (ss != st) {
+    FB_CUDA(c, cudaEventRecord(c->ev_tree, ss));
+    c->tree_pending = true;
+  }
   m.n_nodes = ni;
   m.n_top_dev = n_top_dev;
   return FLYBY_OK;

@@ -465,6 +465,10 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   FB_LAUNCH_CHECK(c);
   spill_shade_kernel<<<sgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
+  {  // the fallback walks the LBVH, which flyby_build finishes on the side stream
+    int rc = wait_tree(c);
+    if (rc) return rc;
+  }
   raster_resolve3_kernel<<<(unsigned)c->sm_count, 64, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;

@@ -123,6 +123,7 @@ int trace_render_perspective(flyby_ctx* c, int vb, int ve, int res, const flyby_
   const int64_t n_pix = (int64_t)(ve - vb) * res * res;
   if (n_pix == 0) return FLYBY_OK;
   const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  { int rc = wait_tree(c); if (rc) return rc; }
   persp_kernel<<<(unsigned)cdiv(n_pix, 128), 128, 0, c->stream>>>(
       m.nodes.as<Node>(), m.tv0.as<float4>(), m.tv1.as<float4>(), m.tv2.as<float4>(), m.tvid.as<int4>(),
       m.normals.as<float4>(), m.T > 0 ? 1 : 0, c->view_pts.as<float>(), vb, n_pix, res, tan_half, z_near, z_far,
@@ -552,8 +553,10 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
       rc = raster_render(c, q);
     }
   } else if (g_mode >= 1) {
+    if ((rc = wait_tree(c))) return rc;
     rc = screen_render(c, p);
   } else {
+    if ((rc = wait_tree(c))) return rc;
     const int variant = (g_use_top ? 2 : 0) | (c->count_work ? 1 : 0);
     switch (variant) {
       case 0: rc = launch(render_kernel<false, false>); break;
@@ -610,6 +613,7 @@ __global__ void cast_kernel(const Node* __restrict__ nodes, const float4* __rest
 int trace_cast(flyby_ctx* c, const double* rays, int64_t n, double tol, int32_t* ids, double* tt, double* w) {
   MeshDev& m = c->mesh;
   if (n <= 0) return FLYBY_OK;
+  { int rc = wait_tree(c); if (rc) return rc; }
   cast_kernel<<<(unsigned)cdiv(n, 128), 128, 0, c->stream>>>(
       m.nodes.as<Node>(), m.tv0.as<float4>(), m.tv1.as<float4>(), m.tv2.as<float4>(), m.T > 0 ? 1 : 0,
       rays, n, tol * tol, ids, tt, w);

@@ -17,7 +17,12 @@
  *    cudaPointerGetAttributes).  Device buffers are used in place and the call
  *    returns without synchronising (work is ordered on the context stream);
  *    host buffers are staged through context-owned device scratch and the call
- *    returns after the copy back completed.
+ *    returns after the copy back completed.  Two internal streams work behind
+ *    the context stream and are ordered against it with events: one copies
+ *    finished view chunks to the host, one finishes the LBVH of flyby_build
+ *    (which the default render path does not read) while the caller goes on;
+ *    everything a caller can observe is ordered on the context stream, and
+ *    flyby_synchronize waits for all three.
  *  - there is no CPU implementation behind this API: without a CUDA device
  *    flyby_create fails with FLYBY_ERR_CUDA.
  */
