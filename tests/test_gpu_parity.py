@@ -411,6 +411,7 @@ assert (ids != io).sum() == 0 and np.array_equal(t, to) and np.array_equal(feat,
 print("ok", int((io >= 0).sum()))
 ''' % (ROOT_DIR, os.path.join(ROOT_DIR, "fly-by-cnn_b200")))
     env = dict(os.environ, FLYBY_PAIR_CAP="64", FLYBY_DEBUG_STATS="1")
+    env.pop("FLYBY_MODE", None)  # this test is about the default (scan-conversion) path
     out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
     first = [ln for ln in out.stderr.splitlines() if "re-traced exactly" in ln][0]
