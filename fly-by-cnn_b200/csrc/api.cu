@@ -109,6 +109,7 @@ int flyby_create(int device, void* stream, flyby_ctx** out) {
       int prio_lo = 0, prio_hi = 0;  // the many small tree kernels slip in ahead of the big render grids
       cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
       if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ev_unit, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&c->ev_sorted, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&c->ev_tree, cudaEventDisableTiming) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
     }
@@ -147,6 +148,7 @@ void flyby_destroy(flyby_ctx* c) {
   for (int i = 0; i < 2; i++)
     if (c->async_done[i]) cudaEventDestroy(c->async_done[i]);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_unit) cudaEventDestroy(c->ev_unit);
   if (c->ev_sorted) cudaEventDestroy(c->ev_sorted);
   if (c->ev_tree) cudaEventDestroy(c->ev_tree);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
@@ -181,6 +183,7 @@ int flyby_set_mesh(flyby_ctx* c, const float* verts, int64_t V, const int32_t* t
   if (!verts || V <= 0 || T < 0 || (T > 0 && !tris)) return fail(c, FLYBY_ERR_INVALID, "set_mesh: empty or null mesh");
   if (V >= (int64_t)1 << 31 || T > FB_LEAF_FIRST_MASK) return fail(c, FLYBY_ERR_INVALID, "set_mesh: mesh too large");
   MeshDev& m = c->mesh;
+  { int rc = wait_tree(c); if (rc) return rc; }  // the previous build's side-stream work still reads the triangles
   m.has_mesh = false;
   m.built = false;
   if (opts) c->norm = *opts; else memset(&c->norm, 0, sizeof c->norm);
@@ -199,6 +202,11 @@ int flyby_build(flyby_ctx* c) {
   CHECK_CTX(c);
   MeshDev& m = c->mesh;
   if (!m.has_mesh) return fail(c, FLYBY_ERR_INVALID, "build: call flyby_set_mesh first");
+  {  // side-stream work of the previous build may still read what this build overwrites
+    int rc0 = wait_tree(c);
+    if (rc0) return rc0;
+    c->tree_pending = false;
+  }
   // index validation first: an out-of-range index must never reach a gather
   int32_t* bad = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 7);
   FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
@@ -214,6 +222,10 @@ int flyby_build(flyby_ctx* c) {
   if (rc) return rc;
   rc = lbvh_run(c);
   if (rc) return rc;
+  if (c->side_stream) {  // normals + tree are complete when this event fires
+    FB_CUDA(c, cudaEventRecord(c->ev_tree, c->side_stream));
+    c->tree_pending = true;
+  }
   m.built = true;
   return FLYBY_OK;
 }
@@ -222,6 +234,7 @@ int flyby_get_mesh(flyby_ctx* c, float* unit_verts, float* normals, double* cent
   CHECK_CTX(c);
   MeshDev& m = c->mesh;
   if (!m.built) return fail(c, FLYBY_ERR_INVALID, "get_mesh: mesh not built");
+  { int rc = wait_tree(c); if (rc) return rc; }
   if (unit_verts)
     FB_CUDA(c, cudaMemcpyAsync(unit_verts, m.verts.p, sizeof(float) * 3 * (size_t)m.V, cudaMemcpyDefault, c->stream));
   if (normals)  // device layout is float4 per point
@@ -598,6 +611,7 @@ struct LabelsIO {
 int labels_begin(flyby_ctx* c, int32_t* labels, const char* what, LabelsIO* io) {
   if (!c->mesh.has_mesh || !c->mesh.built) return fail(c, FLYBY_ERR_INVALID, "%s: call flyby_set_mesh and flyby_build first", what);
   if (!labels && c->mesh.V > 0) return fail(c, FLYBY_ERR_INVALID, "%s: labels is NULL", what);
+  { int rc = wait_tree(c); if (rc) return rc; }  // the adjacency CSR is finished on the side stream
   io->user = io->dev = labels;
   io->host = labels && !is_device_ptr(labels);
   if (io->host) {
@@ -682,7 +696,8 @@ int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {
   if (c->mesh.built) {
     s.ms_normalise = el(0, 1);
     s.ms_normals = el(1, 2);
-    if (c->mesh.T > 0) { s.ms_sort = el(2, 3); s.ms_tree = el(3, 4); }
+    // with the side stream the normals (events 1 -> 2) run beside the sort, which then starts at event 1
+    if (c->mesh.T > 0) { s.ms_sort = c->side_stream ? el(1, 3) : el(2, 3); s.ms_tree = el(3, 4); }
   }
   s.ms_render = el(5, 6);
   s.ms_trace = el(5, 7);

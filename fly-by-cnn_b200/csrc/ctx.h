@@ -73,11 +73,13 @@ struct flyby_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;  // D2H of finished view chunks overlaps the next chunk's render
-  // The LBVH topology / boxes / layout are not read by the scan-conversion render: they are built on a side
-  // stream behind the sort, concurrently with whatever the main stream does next.  Everything that reads the
-  // tree, and the next build, waits for ev_tree first (fb::wait_tree).
+  // Two parts of flyby_build are not read by the candidate search of the default render path: the point normals
+  // (+ the adjacency CSR behind them; first needed by the shading of the resolve kernels) and the LBVH topology /
+  // boxes / layout.  They run on a side stream -- normals behind the unit surface (ev_unit), tree behind the sort
+  // (ev_sorted) -- concurrently with whatever the main stream does next.  Everything that reads them, the next
+  // flyby_set_mesh and the next flyby_build wait for ev_tree first (fb::wait_tree).
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_sorted = nullptr, ev_tree = nullptr;
+  cudaEvent_t ev_unit = nullptr, ev_sorted = nullptr, ev_tree = nullptr;
   bool tree_pending = false;
   cudaEvent_t chunk_ev[16] = {nullptr};
   char err[512] = {0};

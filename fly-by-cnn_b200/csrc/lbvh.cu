@@ -418,11 +418,6 @@ int lbvh_run(flyby_ctx* c) {
   const int64_t T = m.T;
   m.n_nodes = 0;
   m.n_top_dev = nullptr;
-  {  // the previous mesh's tree build (side stream) may still read the scratch this build overwrites
-    int rc = wait_tree(c);
-    if (rc) return rc;
-    c->tree_pending = false;
-  }
   if (T == 0) return FLYBY_OK;
   const int nblocks = (int)cdiv(T, RS_TILE);
   const size_t Tz = (size_t)T;
@@ -521,10 +516,6 @@ int lbvh_run(flyby_ctx* c) {
       nontop_scan, m.topflag.as<int32_t>(), n_top_dev, m.nodes.as<Node>());
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, cudaEventRecord(c->ev[4], ss));
-  if (ss != st) {
-    FB_CUDA(c, cudaEventRecord(c->ev_tree, ss));
-    c->tree_pending = true;
-  }
   m.n_nodes = ni;
   m.n_top_dev = n_top_dev;
   return FLYBY_OK;

@@ -300,25 +300,30 @@ int prep_run(flyby_ctx* c) {
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, cudaEventRecord(c->ev[1], st));
 
-  // point normals
-  FB_CUDA(c, cudaMemsetAsync(m.adj_start.p, 0, sizeof(uint32_t) * (size_t)(V + 1), st));
-  FB_CUDA(c, cudaMemsetAsync(m.adj_cur.p, 0, sizeof(uint32_t) * (size_t)(V + 1), st));
+  // point normals: not needed before the shading, so they go to the side stream (see ctx.h)
+  cudaStream_t ss = c->side_stream ? c->side_stream : st;
+  if (ss != st) {
+    FB_CUDA(c, cudaEventRecord(c->ev_unit, ss));
+    FB_CUDA(c, cudaStreamWaitEvent(ss, c->ev_unit, 0));
+  }
+  FB_CUDA(c, cudaMemsetAsync(m.adj_start.p, 0, sizeof(uint32_t) * (size_t)(V + 1), ss));
+  FB_CUDA(c, cudaMemsetAsync(m.adj_cur.p, 0, sizeof(uint32_t) * (size_t)(V + 1), ss));
   if (T > 0) {
-    face_normal_kernel<<<(unsigned)cdiv(T, 256), 256, 0, st>>>(
+    face_normal_kernel<<<(unsigned)cdiv(T, 256), 256, 0, ss>>>(
         m.verts.as<float>(), m.tris.as<int32_t>(), T, m.face_n.as<float>(), m.adj_start.as<uint32_t>());
     FB_LAUNCH_CHECK(c);
   }
-  int rc = exclusive_scan_u32(c, m.adj_start.as<uint32_t>(), V + 1, m.scan_tmp);
+  int rc = exclusive_scan_u32(c, m.adj_start.as<uint32_t>(), V + 1, ss != st ? m.tree_scan_tmp : m.scan_tmp, ss);
   if (rc) return rc;
   if (T > 0) {
-    adj_fill_kernel<<<(unsigned)cdiv(T, 256), 256, 0, st>>>(
+    adj_fill_kernel<<<(unsigned)cdiv(T, 256), 256, 0, ss>>>(
         m.tris.as<int32_t>(), T, m.adj_start.as<uint32_t>(), m.adj_cur.as<uint32_t>(), m.adj.as<int32_t>());
     FB_LAUNCH_CHECK(c);
   }
-  point_normal_kernel<<<(unsigned)cdiv(V, 128), 128, 0, st>>>(
+  point_normal_kernel<<<(unsigned)cdiv(V, 128), 128, 0, ss>>>(
       V, m.adj_start.as<uint32_t>(), m.adj.as<int32_t>(), m.face_n.as<float>(), m.normals.as<float4>());
   FB_LAUNCH_CHECK(c);
-  FB_CUDA(c, cudaEventRecord(c->ev[2], st));
+  FB_CUDA(c, cudaEventRecord(c->ev[2], ss));
   return FLYBY_OK;
 }
 

@@ -451,6 +451,10 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   raster_kernel<<<grid, RT_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the candidate search and the exact resolve
+  {  // the shading needs the point normals, the last-resort fallback the LBVH: both are finished on the side stream
+    int rc = wait_tree(c);
+    if (rc) return rc;
+  }
   long long rgrid = (long long)c->sm_count * RV_MINB * 4;  // RV_MINB CTAs resident per SM, 4 rounds for balance
   const long long want = cdiv(n_pix, RV_THREADS);
   if (rgrid > want) rgrid = want;
@@ -465,10 +469,6 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   FB_LAUNCH_CHECK(c);
   spill_shade_kernel<<<sgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
-  {  // the fallback walks the LBVH, which flyby_build finishes on the side stream
-    int rc = wait_tree(c);
-    if (rc) return rc;
-  }
   raster_resolve3_kernel<<<(unsigned)c->sm_count, 64, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;

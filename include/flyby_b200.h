@@ -82,7 +82,10 @@ typedef struct {
 } flyby_render_opts;
 
 /* Per-stage device timings of the last build/render on this context (ms, CUDA
- * events on the context stream) and traversal counters (when enabled). */
+ * events) and traversal counters (when enabled).  ms_normals and ms_tree are
+ * measured on the internal side stream, where those two stages run beside the
+ * sort and the start of the render: they overlap other work and do not add up
+ * to the duration of flyby_build. */
 typedef struct {
   float ms_normalise, ms_normals, ms_sort, ms_tree, ms_render;
   int32_t reserved;
