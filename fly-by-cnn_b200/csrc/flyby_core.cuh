@@ -646,8 +646,11 @@ FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* 
   // same SURE eligibility as screen_setup, with Dq rounded up
   const float Dq_up = fmaxf(Dq, 0.0f) * 1.000001f + 4.0f * V.e_p;
   const float amin = fabsf(area2) - 8.0f * V.e_p * Dq_up;
-  if (V.enabled && (zmax - zmin + 4.0f * V.e_z) * Dq_up <= 500.0f * amin && t->zlo > zo + V.e_z &&
-      t->zhi < zo + V.two_r - V.e_z)
+  // V.enabled (a guard of the LBVH screening for radii that are tiny against the mesh) is not needed here: the exact
+  // test's plane rejection |n.d| <= 1e-6 |n.(P1 - o)| cannot fire for a triangle that passes this test whatever the
+  // radius, because its depth range lies inside the segment: |n.(P1 - o)| = |n| cos(theta) z_hit <= |n| 2R cos(theta)
+  // while |n.d| = |n| 2R cos(theta) -- a ratio of at most 1 against the 1e-6 of the rejection
+  if ((zmax - zmin + 4.0f * V.e_z) * Dq_up <= 500.0f * amin && t->zlo > zo + V.e_z && t->zhi < zo + V.two_r - V.e_z)
     flags |= 2;
   // >= |r|_1 from any vertex to any pixel raster_project lets through: the padded box plus the slack of its
   // pixel range (0.01 pixel per side and the rounding of the index arithmetic, < 0.02 pixel in all)
