@@ -104,6 +104,9 @@ def run_reference(args):
     N = orc.point_normals(U, F)
     views = orc.icosahedron(SUBDIVISION, RADIUS)
     sample_views = 2  # per step
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # otherwise silently make this arm single-threaded
+    orc.set_threads(_host_threads())
     cores = orc.num_threads()
 
     def step(k):
@@ -129,9 +132,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_sample():
     from oracle import oracle as orc
     from flyby_b200 import synth
+    orc.set_threads(_host_threads())
     P, F = synth.bumpy_sphere(LM, seed=0)
     U, _, _ = orc.unit_surf(P)
     N = orc.point_normals(U, F)
