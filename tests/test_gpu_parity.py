@@ -435,3 +435,35 @@ def test_non_finite_vertices_are_never_hit(gpu_ctx, orc):
     assert not np.isin(io[io >= 0], np.nonzero(bad)[0]).any() and (io >= 0).sum() > 1000
     hit = io >= 0
     assert np.array_equal(feat[hit], fo[hit], equal_nan=True)  # points next to a poisoned triangle get NaN normals on both sides
+
+
+def test_independent_algorithms_agree_at_bench_size(gpu_ctx, tmp_path):
+    """Size-independent cross-check at the full bench workload (24.1 M rays, 200 000 triangles): the scan-conversion
+    pipeline and the LBVH packet traversal share only the exact triangle test; their hit ids, hit parameters and
+    feature tensors must have identical digests (the LBVH mode runs in a fresh process: the mode is read once)."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    P, F = synth.bumpy_sphere(100, 0)
+    gpu_ctx.set_mesh(P, F)
+    gpu_ctx.build()
+    gpu_ctx.views_icosahedron(3, 2.0)
+    feat, ids, t = gpu_ctx.render(512, gpu_ctx.render_opts(use_z=1, split_z=1), want_t=True)
+    mine = [hashlib.sha1(a.tobytes()).hexdigest() for a in (ids, t, feat)]
+    assert (ids >= 0).sum() > 20_000_000
+    script = tmp_path / "bvh_digest.py"
+    script.write_text('''
+import sys, hashlib
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from flyby_b200 import _cabi, synth
+ctx = _cabi.Context(0)
+P, F = synth.bumpy_sphere(100, 0)
+ctx.set_mesh(P, F); ctx.build(); ctx.views_icosahedron(3, 2.0)
+feat, ids, t = ctx.render(512, ctx.render_opts(use_z=1, split_z=1), want_t=True)
+print(" ".join(hashlib.sha1(a.tobytes()).hexdigest() for a in (ids, t, feat)))
+''' % (ROOT_DIR, os.path.join(ROOT_DIR, "fly-by-cnn_b200")))
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, FLYBY_MODE="bvh"))
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == mine
