@@ -467,3 +467,46 @@ print(" ".join(hashlib.sha1(a.tobytes()).hexdigest() for a in (ids, t, feat)))
                          env=dict(os.environ, FLYBY_MODE="bvh"))
     assert out.returncode == 0, out.stderr
     assert out.stdout.split() == mine
+
+
+_C5_DIGEST = '''
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from flyby_b200 import _cabi, synth
+dev = torch.device("cuda", 0)
+ctx = _cabi.Context(0)
+P, F = synth.bumpy_sphere(316, 5)                      # 1 997 120 triangles
+ctx.set_mesh(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)); ctx.build()
+n = ctx.views_icosahedron(4, 2.0)                      # 162 views
+res = 1024
+feat = torch.empty((n, res, res, 4), dtype=torch.float32, device=dev)
+ids = torch.empty((n, res, res), dtype=torch.int32, device=dev)
+t = torch.empty((n, res, res), dtype=torch.float64, device=dev)
+ctx.render_into(res, ctx.render_opts(use_z=1, split_z=1), feat, ids, t)
+ctx.synchronize()
+def digest(x):                                         # position-weighted sum of the raw bits, wrapping in int64
+    b = x.reshape(-1).view(torch.int64 if x.element_size() == 8 else torch.int32).to(torch.int64)
+    w = (torch.arange(b.numel(), device=dev, dtype=torch.int64) %% 1000003) + 1
+    return int((b * w).sum())
+print(int((ids >= 0).sum()), digest(ids), digest(t), digest(feat[..., :2].contiguous()), digest(feat[..., 2:].contiguous()))
+'''
+
+
+def test_config5_full_size_cross_check(tmp_path):
+    """BASELINE config 5 in full (2 M triangles, 162 views at 1024^2, 170 M rays): the two independent searches
+    agree on every id, hit parameter and feature (position-weighted digests computed on the device)."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "c5.py"
+    script.write_text(_C5_DIGEST % (ROOT_DIR, os.path.join(ROOT_DIR, "fly-by-cnn_b200")))
+    outs = []
+    for mode in ("raster", "bvh"):
+        env = dict(os.environ)
+        env.pop("FLYBY_MODE", None)
+        if mode != "raster":
+            env["FLYBY_MODE"] = mode
+        out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append(out.stdout.split())
+    assert outs[0] == outs[1] and int(outs[0][0]) > 100_000_000
