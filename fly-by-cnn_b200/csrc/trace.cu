@@ -541,6 +541,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
     const int64_t per_view = (int64_t)res * res;
     int slab = (int)(((int64_t)1 << 26) / per_view);
     if (slab < 1) slab = 1;
+    if (slab > 65535) slab = 65535;  // gridDim.y of raster_kernel
     rc = FLYBY_OK;
     for (int v0 = 0; v0 < nv && rc == FLYBY_OK; v0 += slab) {
       RenderParams q = p;
