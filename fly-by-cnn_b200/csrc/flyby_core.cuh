@@ -80,7 +80,7 @@ struct View {
   float tslack;                    // slack in units of the segment parameter
 };
 
-FB_HD void view_setup(const float* spf, double radius, double plane_scale, double spacing, View* v) {
+FB_HD void view_setup(const float* spf, double radius, double plane_scale, double spacing, View* v, double tol = 0.0) {
   for (int k = 0; k < 3; k++) v->sp[k] = (double)spf[k];
   double len = norm3(v->sp);
   for (int k = 0; k < 3; k++) v->n[k] = FB_DIV(v->sp[k], len);
@@ -117,8 +117,9 @@ FB_HD void view_setup(const float* spf, double radius, double plane_scale, doubl
                    fabs(v->dir[k]);
     if (reach > amax) amax = reach;
   }
-  // float32 rounding of origin/direction moves a ray by < 4 ulp(amax); 64 ulp of slack
-  v->slack = (float)(amax * 64.0 * 5.9604644775390625e-08);
+  // float32 rounding of origin/direction moves a ray by < 4 ulp(amax); 64 ulp of slack.  The exact test also
+  // accepts a point within tol of a triangle (dist^2 <= tol^2), i.e. up to tol outside its box: 2 tol more.
+  v->slack = (float)(amax * 64.0 * 5.9604644775390625e-08 + 2.0 * fabs(tol));
   double dl = norm3(v->dir);
   v->tslack = (float)(dl > 0.0 ? 4.0 * (double)v->slack / dl : 0.0);
 }

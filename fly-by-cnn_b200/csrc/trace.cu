@@ -28,7 +28,7 @@ __global__ void view_setup_kernel(const float* __restrict__ pts, int n, double r
   if (i >= n) return;
   View v;
   float sp[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
-  view_setup(sp, radius, plane_scale, spacing, &v);
+  view_setup(sp, radius, plane_scale, spacing, &v, tol);
   views[i] = v;
   // largest |coordinate| of the unit surface bounds the float32 screening errors
   float max_abs_coord = 0.f;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) persp_kernel(const Node* __restrict__ nod
       const double reach = fabs(o[k]) + fabs(d[k]);
       amax = reach > amax ? reach : amax;
     }
-    const float slack = (float)(amax * 64.0 * 5.9604644775390625e-08);
+    const float slack = (float)(amax * 64.0 * 5.9604644775390625e-08 + 2.0 * sqrt(tol2));  // + the test's own tolerance
     const double dl = norm3(d);
     const float tslack = (float)(dl > 0.0 ? 4.0 * (double)slack / dl : 0.0);
     GlobalFetch f{nodes};
@@ -593,7 +593,7 @@ __global__ void cast_kernel(const Node* __restrict__ nodes, const float4* __rest
       double reach = fabs(o[k]) + fabs(d[k]);
       amax = reach > amax ? reach : amax;
     }
-    float slack = (float)(amax * 64.0 * 5.9604644775390625e-08);
+    float slack = (float)(amax * 64.0 * 5.9604644775390625e-08 + 2.0 * sqrt(tol2));  // + the test's own tolerance
     double dl = norm3(d);
     float tslack = (float)(dl > 0.0 ? 4.0 * (double)slack / dl : 0.0);
     GlobalFetch f{nodes};

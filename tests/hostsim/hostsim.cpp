@@ -150,7 +150,7 @@ int sim_render(const float* verts, int64_t V, const int32_t* tris, int64_t T, co
   SimFetch f{b.nodes.data()};
   for (int v = 0; v < n_views; v++) {
     View vw;
-    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw, 1e-10);
     for (int j = 0; j < res; j++)
       for (int i = 0; i < res; i++) {
         double o[3];
@@ -275,7 +275,7 @@ int sim_render_packet(const float* verts, int64_t V, const int32_t* tris, int64_
   SimCount cnt;
   for (int v = 0; v < n_views; v++) {
     View vw;
-    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw, 1e-10);
     // 8x4 tiles like the kernel (no bounds compaction: partial tiles run with idle lanes)
     for (int ty = 0; ty < (res + 3) / 4; ty++)
       for (int tx = 0; tx < (res + 7) / 8; tx++) {
@@ -452,7 +452,7 @@ int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris,
   long long cls[3] = {0, 0, 0};
   for (int v = 0; v < n_views; v++) {
     View vw;
-    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw, 1e-10);
     ViewF vf;
     viewf_setup(vw, radius, spacing, maxc, 1e-10, &vf);
     viewf_pixels(vw, spacing, res, &vf);
@@ -493,7 +493,7 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
   SimFetch f{b.nodes.data()};
   for (int v = 0; v < n_views; v++) {
     View vw;
-    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw);
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw, 1e-10);
     ViewF vf;
     viewf_setup(vw, radius, spacing, maxc, 1e-10, &vf);
     viewf_pixels(vw, spacing, res, &vf);

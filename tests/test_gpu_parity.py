@@ -510,3 +510,15 @@ def test_config5_full_size_cross_check(tmp_path):
         assert out.returncode == 0, out.stderr[-2000:]
         outs.append(out.stdout.split())
     assert outs[0] == outs[1] and int(outs[0][0]) > 100_000_000
+
+
+def test_randomised_parity(gpu_ctx, orc):
+    """A short run of profiles/fuzz_parity.py: random meshes (slivers, zero-area and duplicate cells, lattice
+    vertices), viewpoints, radii from inside the mesh to far away, plane scales, spacings, resolutions, tolerances
+    up to 1e-5, plus random segments through flyby_cast -- everything bit-equal to the brute-force oracle."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(ROOT_DIR, "profiles", "fuzz_parity.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    assert fuzz.run(60, 11, context=gpu_ctx) == 0
