@@ -119,3 +119,15 @@ def test_edge_cases(gpu_ctx, orc):
     n = gpu_ctx.labels_connectivity(got, 2, 10)
     ref, n_ref = orc.pp_connectivity(F, 9, lab2, 2, 10)
     assert n == n_ref == 2 and np.array_equal(got, ref)
+
+
+def test_randomised_widened_rows(gpu_ctx, orc):
+    """A short run of profiles/fuzz_widened.py: pinhole views, barycentric lookup, votes and the label
+    post-processing on random meshes (incl. triangle soups with isolated points) and random label fields."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("fuzz_widened", os.path.join(root, "profiles", "fuzz_widened.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    assert fuzz.run(30, 4, context=gpu_ctx) == 0
