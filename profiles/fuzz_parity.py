@@ -61,6 +61,9 @@ def one_case(case):
     ctx.set_mesh(P, F, skip_normalise=skip)
     ctx.build()
     uv, nrm, _, _ = ctx.get_mesh()
+    pre_ok = np.array_equal(nrm, orc.point_normals(uv, F), equal_nan=True)      # vtkPolyDataNormals restatement
+    if not skip:
+        pre_ok = pre_ok and np.array_equal(uv, orc.unit_surf(P)[0])               # GetUnitSurf restatement
     ext = float(np.abs(uv).max())
     radius = float(ext * rng.choice([0.3, 1.2, 2.0, 4.0, 10.0]))
     nv = int(rng.integers(1, 6))
@@ -83,7 +86,7 @@ def one_case(case):
     feat, ids, t = ctx.render(res, opts, want_t=True)
     orc.set_tolerance(tol)
     fo, io, to = orc.render(uv, F, nrm, views, radius, res, plane_scale=ps, spacing=sp, grid=False, want_t=True, **cfg)
-    ok = np.array_equal(ids, io) and np.array_equal(t, to) and np.array_equal(feat, fo, equal_nan=True)
+    ok = pre_ok and np.array_equal(ids, io) and np.array_equal(t, to) and np.array_equal(feat, fo, equal_nan=True)
     # arbitrary segments through the same mesh (flyby_cast): the per-ray LBVH traversal with the same tolerance
     nseg = 2000
     a = rng.uniform(-1.5, 1.5, (nseg, 3)) * ext
