@@ -138,7 +138,7 @@ void flyby_destroy(flyby_ctx* c) {
                     &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.tree_scan_tmp, &m.leaf_box,
                     &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid, &m.trec,
                     &c->view_pts, &c->views, &c->viewsf, &c->tc_table, &c->cand, &c->cand2, &c->pix_lists, &c->raster_tmp, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
-                    &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->counters,
+                    &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->raster_big, &c->counters,
                     &c->async_feat[0], &c->async_feat[1], &c->async_ids[0], &c->async_ids[1], &c->async_t[0], &c->async_t[1]};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; i++)

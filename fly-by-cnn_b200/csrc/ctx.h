@@ -94,6 +94,7 @@ struct flyby_ctx {
   fb::DevBuf cand2;     // int4 [n_pix] candidate slots 4..7 of the scan-conversion path
   fb::DevBuf pix_lists; // uint32 pixel queues between the resolve kernels
   fb::DevBuf raster_tmp;  // uint64 [n_pix] front (depth bound, slot) + int32 [n_pix] extra counts + hi-z tiles (raster.cu)
+  fb::DevBuf raster_big;  // queue of big triangles (slot, view, first band, rows per band) for raster_big_kernel
   fb::DevBuf raster_ovf;  // spill list of (pixel, slot) pairs beyond 8 extras + per-overflow-pixel records (raster.cu)
   int n_views = 0;
   double radius = 0;

@@ -31,6 +31,7 @@ namespace fb {
 #endif
 #define RT_BIG 256   // bounding boxes with more pixels than this are rasterised by a whole warp
 #define RT_EXTRA 8    // extra candidates kept per pixel (two int4)
+#define RT_BAND 4096  // pixels of a big triangle's box handled by one warp of raster_big_kernel
 #ifndef RT_SPAN_MIN
 #define RT_SPAN_MIN 12 // bounding boxes up to this many pixels are walked whole (the span set-up would cost more)
 #endif
@@ -58,6 +59,10 @@ struct RasterParams {
   unsigned long long *ov_prov_t, *ov_prov_cs;  // [pair_cap] best of the front + stored extras: t bits, (cell << 32) | slot
   unsigned long long *ov_best_t, *ov_best_cs;  // [pair_cap] running minimum over everything / over the spilled pairs
   unsigned int pair_cap;
+  // triangles of more than RT_BIG pixels are queued and rasterised in row bands by the whole grid (raster_big_kernel)
+  int4* big;                        // [big_cap] slot, local view, first band, rows per band
+  unsigned long long* big_counter;  // (entries << 32) | bands, advanced by one 64-bit atomicAdd per entry
+  unsigned int big_cap;
   int64_t n_pix;
   int T;
 };
@@ -149,7 +154,21 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
       }
     }
   }
-  // large triangles (coarse meshes, close-ups): the warp takes them one at a time, 32 pixels per step
+  // large triangles (coarse meshes, close-ups) are queued for raster_big_kernel, which spreads them over the grid in
+  // bands of about RT_BAND pixels; only if the queue is full does this warp take them itself, one at a time
+  if (npx > RT_BIG) {
+    const int w = r.i1 - r.i0 + 1, rows = r.j1 - r.j0 + 1;
+    int rpb = RT_BAND / w;
+    rpb = rpb < 1 ? 1 : (rpb > rows ? rows : rpb);
+    const unsigned int nb = (unsigned int)((rows + rpb - 1) / rpb);
+    const unsigned long long at = atomicAdd(p.big_counter, (1ull << 32) | nb);
+    const unsigned int e = (unsigned int)(at >> 32);
+    if (e < p.big_cap) {
+      const bool fits = (at & 0xffffffffull) + nb < 0x80000000ull;  // the band counter must never carry into the entry count
+      p.big[e] = make_int4(slot, view, (int)(unsigned int)(at & 0xffffffffull), fits ? rpb : 0);
+      if (fits) npx = 0;
+    }
+  }
   unsigned big = __ballot_sync(0xffffffffu, npx > RT_BIG);
   while (big) {
     const int src = __ffs(big) - 1;
@@ -171,6 +190,54 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
     for (long long k = lane; k < n; k += 32) {
       const int i = i0 + (int)(k % w), j = j0 + (int)(k / w);
       const int cls = raster_pixel(u, fmaf((float)i, V.qdx, V.q0x), fmaf((float)j, V.qdy, V.q0y));
+      if (cls == SC_MISS) continue;
+      const uint32_t pix = view_base + (uint32_t)j * (uint32_t)res + (uint32_t)i;
+      const unsigned long long old = cls == SC_SURE ? atomicMin(p.front + pix, key) : __ldcg(p.front + pix);
+      settle_pixel(p, pix, cls, key, old, zlo_ord, u.zhi);
+    }
+  }
+}
+
+// ---- big triangles, band by band.  Entry e covers the bands [big[e].z, big[e + 1].z); a warp finds the entry of
+// its band by bisection (the bases grow with the entry index: both come from one atomic), redoes the triangle's
+// set-up (cheap next to a band of pixels) and walks the band 32 pixels at a time.
+__global__ void __launch_bounds__(128) raster_big_kernel(const RasterParams p) {
+  const unsigned long long total = *p.big_counter;
+  unsigned int n_ent = (unsigned int)(total >> 32);
+  if (n_ent > p.big_cap) n_ent = p.big_cap;  // entries beyond the capacity were rasterised inline by raster_kernel
+  const unsigned int n_bands = (unsigned int)(total & 0xffffffffull);
+  if (n_ent == 0) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned int warps = gridDim.x * (blockDim.x >> 5);
+  const int res = p.r.res;
+  for (unsigned int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n_bands; b += warps) {
+    unsigned int lo = 0, hi = n_ent - 1;  // the entry with the largest first band <= b (entry 0 starts at band 0)
+    while (lo < hi) {
+      const unsigned int mid = (lo + hi + 1) >> 1;
+      if ((unsigned int)p.big[mid].z <= b) lo = mid; else hi = mid - 1;
+    }
+    const int4 ent = p.big[lo];
+    const int slot = ent.x, view = ent.y, rpb = ent.w;
+    if (rpb <= 0) continue;  // an entry that was not accepted
+    const ViewF& V = p.r.viewsf[p.r.view_begin + view];
+    const float4 a = __ldg(p.r.tv0 + slot), bb = __ldg(p.r.tv1 + slot), e = __ldg(p.r.tv2 + slot);
+    const float P0[3] = {a.x, a.y, a.z}, P1[3] = {bb.x, bb.y, bb.z}, P2[3] = {e.x, e.y, e.z};
+    TriR u;
+    PixRange r;
+    if (!raster_project(V, P0, P1, P2, res, &u, &r)) continue;
+    raster_setup(V, 0.0f, P0, P1, P2, false, &u);
+    const int jb = r.j0 + (int)(b - (unsigned int)ent.z) * rpb;
+    if (jb > r.j1) continue;  // a band of an entry that lies behind the stored ones
+    const int je = min(r.j1, jb + rpb - 1);
+    const unsigned long long key = front_key(u.zlo, u.zhi, slot);
+    const unsigned int zlo_ord = ford_bits(u.zlo);
+    const uint32_t view_base = (uint32_t)view * (uint32_t)res * (uint32_t)res;
+    const float qdx = V.qdx, q0x = V.q0x, qdy = V.qdy, q0y = V.q0y;
+    const int w = r.i1 - r.i0 + 1;
+    const int n = w * (je - jb + 1);
+    for (int k = lane; k < n; k += 32) {
+      const int i = r.i0 + k % w, j = jb + k / w;
+      const int cls = raster_pixel(u, fmaf((float)i, qdx, q0x), fmaf((float)j, qdy, q0y));
       if (cls == SC_MISS) continue;
       const uint32_t pix = view_base + (uint32_t)j * (uint32_t)res + (uint32_t)i;
       const unsigned long long old = cls == SC_SURE ? atomicMin(p.front + pix, key) : __ldcg(p.front + pix);
@@ -426,7 +493,11 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   p.queue = c->pix_lists.as<uint32_t>();
   p.n_queue = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 14);
   p.n_spill = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 13);
-  FB_CUDA(c, cudaMemsetAsync(p.n_spill, 0, 16, st));  // n_spill[2], n_queue[2]
+  p.big_counter = c->counters.as<unsigned long long>() + 12;
+  FB_CUDA(c, cudaMemsetAsync(p.big_counter, 0, 24, st));  // big_counter, n_spill[2], n_queue[2]
+  p.big_cap = 1u << 20;
+  FB_CUDA(c, c->raster_big.reserve(sizeof(int4) * (size_t)p.big_cap));
+  p.big = c->raster_big.as<int4>();
   size_t cap = (size_t)(n_pix / 8 > (1 << 20) ? n_pix / 8 : (1 << 20));
   {  // FLYBY_PAIR_CAP: test hook that shrinks the spill list so that the LBVH re-trace of resolve3 gets exercised
     static long env_cap = -1;
@@ -449,6 +520,8 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   FB_LAUNCH_CHECK(c);
   dim3 grid((unsigned)cdiv(p.T, RT_THREADS), (unsigned)rp.n_views);
   raster_kernel<<<grid, RT_THREADS, 0, st>>>(p);
+  FB_LAUNCH_CHECK(c);
+  raster_big_kernel<<<(unsigned)c->sm_count * 8, 128, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the candidate search and the exact resolve
   {  // the shading needs the point normals, the last-resort fallback the LBVH: both are finished on the side stream
