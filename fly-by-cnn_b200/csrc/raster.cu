@@ -496,6 +496,14 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   p.big_counter = c->counters.as<unsigned long long>() + 12;
   FB_CUDA(c, cudaMemsetAsync(p.big_counter, 0, 24, st));  // big_counter, n_spill[2], n_queue[2]
   p.big_cap = 1u << 20;
+  {  // FLYBY_BIG_CAP: test hook that shrinks the queue so that the inline fallback of raster_kernel gets exercised
+    static long env_big = -1;
+    if (env_big < 0) {
+      const char* e = getenv("FLYBY_BIG_CAP");
+      env_big = e ? atol(e) : 0;
+    }
+    if (env_big > 0 && env_big < (long)p.big_cap) p.big_cap = (unsigned int)env_big;
+  }
   FB_CUDA(c, c->raster_big.reserve(sizeof(int4) * (size_t)p.big_cap));
   p.big = c->raster_big.as<int4>();
   size_t cap = (size_t)(n_pix / 8 > (1 << 20) ? n_pix / 8 : (1 << 20));

@@ -373,10 +373,10 @@ def test_config1_full_size(gpu_ctx, orc):
 
 
 def test_tiny_radius_and_lost_pairs_fallback(orc, tmp_path):
-    """Two rarely taken paths, in a fresh process because one of them is switched by an environment variable read
-    once: (1) a view radius that is tiny against the mesh (view planes inside the surface: the float32 screening
-    declares nothing certain), (2) a spill list too small for the piled candidates, so that pixels are re-traced
-    through the LBVH (raster_resolve3_kernel)."""
+    """Rarely taken paths, in a fresh process because two of them are switched by environment variables read
+    once: (1) a view radius that is tiny against the mesh (view planes inside the surface), (2) a spill list too
+    small for the piled candidates, so that pixels are re-traced through the LBVH (raster_resolve3_kernel),
+    (3) a queue of big triangles that is full, so that raster_kernel rasterises them inline."""
     import os
     import subprocess
     import sys
@@ -399,6 +399,16 @@ N = orc.point_normals(V, F)
 fo, io, to = orc.render(V, F, N, ctx.get_views(), 2.0, 48, plane_scale=2.0, grid=False, want_t=True)
 assert (ids != io).sum() == 0 and np.array_equal(t, to) and np.array_equal(feat, fo) and (io >= 0).sum() > 500
 assert set(np.unique(io[io >= 0])) <= {0, 1}
+# (3) a queue of big triangles too small for a cube seen from twelve sides (FLYBY_BIG_CAP=3): the rest is
+# rasterised inline by the warp that owns the triangle
+P, F3 = synth.cube()
+ctx.set_mesh(P, F3, skip_normalise=True); ctx.build()
+ctx.views_icosahedron(1, 3.0)
+opts = ctx.render_opts(plane_scale=4.0)
+feat, ids, t = ctx.render(96, opts, want_t=True)
+N = orc.point_normals(P, F3)
+fo, io, to = orc.render(P, F3, N, ctx.get_views(), 3.0, 96, plane_scale=4.0, grid=False, want_t=True)
+assert (ids != io).sum() == 0 and np.array_equal(t, to) and np.array_equal(feat, fo) and (io >= 0).sum() > 10000
 # (1) radius 0.02 around a unit mesh
 P, F2 = synth.bumpy_sphere(16, 3)
 ctx.set_mesh(P, F2); ctx.build()
@@ -410,7 +420,7 @@ fo, io, to = orc.render(uv, F2, nrm, ctx.get_views(), 0.02, 40, plane_scale=3.0,
 assert (ids != io).sum() == 0 and np.array_equal(t, to) and np.array_equal(feat, fo)
 print("ok", int((io >= 0).sum()))
 ''' % (ROOT_DIR, os.path.join(ROOT_DIR, "fly-by-cnn_b200")))
-    env = dict(os.environ, FLYBY_PAIR_CAP="64", FLYBY_DEBUG_STATS="1")
+    env = dict(os.environ, FLYBY_PAIR_CAP="64", FLYBY_BIG_CAP="3", FLYBY_DEBUG_STATS="1")
     env.pop("FLYBY_MODE", None)  # this test is about the default (scan-conversion) path
     out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
