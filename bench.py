@@ -195,6 +195,7 @@ def run_ours(args):
 
     meshes = [synth.bumpy_sphere(LM, seed=rank * MESH_POOL + k) for k in range(MESH_POOL)]
     dev_meshes = [(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)) for P, F in meshes]
+    torch.cuda.synchronize()  # uploads ran on torch's default stream; the contexts work on their own streams
     pin_meshes = [(torch.from_numpy(P).pin_memory(), torch.from_numpy(F).pin_memory()) for P, F in meshes]
     feat = torch.empty((n_views, RES, RES, C), dtype=torch.float32, device=dev)
     ids = torch.empty((n_views, RES, RES), dtype=torch.int32, device=dev)

@@ -29,7 +29,7 @@ namespace fb {
 #ifndef RT_MINB
 #define RT_MINB 12
 #endif
-#define RT_BIG 256   // bounding boxes with more pixels than this are rasterised by a whole warp
+#define RT_BIG 96    // bounding boxes with more pixels than this go to raster_big_kernel (row bands over the whole grid)
 #define RT_EXTRA 8    // extra candidates kept per pixel (two int4)
 #define RT_BAND 4096  // pixels of a big triangle's box handled by one warp of raster_big_kernel
 #ifndef RT_SPAN_MIN

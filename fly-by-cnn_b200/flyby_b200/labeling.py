@@ -33,11 +33,14 @@ class CellVoter:
         if use_torch:
             import torch
             self.votes = torch.zeros((self.n_cells, self.K), dtype=torch.int32, device="cuda:%d" % ctx.device)
+            # the zero fill ran on torch's stream; the vote kernels run on the context's: order them once here
+            torch.cuda.current_stream(self.votes.device).synchronize()
         else:
             self.votes = np.zeros((self.n_cells, self.K), np.int32)
 
     def add(self, cell_ids, labels):
-        """cell_ids int32 [...], labels int32 [...] (same shape): one vote per hit pixel."""
+        """cell_ids int32 [...], labels int32 [...] (same shape): one vote per hit pixel.  Torch tensors must be
+        complete on the context's stream (synchronise the stream that produced them first)."""
         self.ctx.backproject(cell_ids, labels, self.K, votes=self.votes)
 
     def add_logits(self, cell_ids, logits):
@@ -53,14 +56,20 @@ class CellVoter:
 
     def cell_labels(self, default=0):
         """int32 [n_cells] argmax label (lowest label wins ties), ``default`` where no pixel voted."""
-        return self.ctx.votes_argmax(self.votes, default=default,
-                                     out=self._empty(self.n_cells) if self.use_torch else None)
+        out = self.ctx.votes_argmax(self.votes, default=default,
+                                    out=self._empty(self.n_cells) if self.use_torch else None)
+        if self.use_torch:
+            self.ctx.synchronize()  # the result is handed to torch code, which runs on another stream
+        return out
 
     def point_labels(self, default=0):
         """int32 [n_points]: every cell hands its label to its first point (highest cell id wins)."""
         cl = self.cell_labels(default)
-        return self.ctx.cells_to_points(cl, default=default,
-                                        out=self._empty(self.ctx.n_verts) if self.use_torch else None)
+        out = self.ctx.cells_to_points(cl, default=default,
+                                       out=self._empty(self.ctx.n_verts) if self.use_torch else None)
+        if self.use_torch:
+            self.ctx.synchronize()
+        return out
 
     def _empty(self, n):
         import torch

@@ -7,6 +7,7 @@ from flyby_b200 import _cabi, synth
 dev = torch.device("cuda", 0)
 meshes = [synth.bumpy_sphere(100, seed=k) for k in range(4)]
 dm = [(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)) for P, F in meshes]
+torch.cuda.synchronize()
 def make():
     s = torch.cuda.Stream(device=dev)
     c = _cabi.Context(0, stream=s.cuda_stream)

@@ -18,6 +18,7 @@ lab[flip] = rng.integers(0, 5, flip.sum()).astype(np.int32)
 ctx = _cabi.Context(0)
 ctx.set_mesh(P, F, skip_normalise=True); ctx.build()
 dev = torch.from_numpy(lab).cuda()
+torch.cuda.synchronize()
 
 
 def gpu(fn):

@@ -13,7 +13,9 @@ lm = int(sys.argv[3]) if len(sys.argv) > 3 else 100      # mesh: bumpy sphere, 2
 level = int(sys.argv[4]) if len(sys.argv) > 4 else 3     # icosahedron subdivision of the viewpoints
 P, F = synth.bumpy_sphere(lm, seed=0)
 ctx = _cabi.Context(0)
-ctx.set_mesh(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev))
+tp, tf = torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)
+torch.cuda.synchronize()
+ctx.set_mesh(tp, tf)
 ctx.build()
 n = ctx.views_icosahedron(level, 2.0)
 n = min(n, views)

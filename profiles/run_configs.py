@@ -28,6 +28,7 @@ def run(name, cfg, check_views=2):
     ctx = _cabi.Context(0, stream=stream.cuda_stream)
     P, F = cfg["mesh"]()
     tp, tf = torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)
+    torch.cuda.synchronize()
     if cfg["views"][0] == "ico":
         n = ctx.views_icosahedron(cfg["views"][1], cfg["radius"])
     else:
@@ -81,7 +82,9 @@ def run_c4():
     torch.cuda.set_stream(stream)
     ctx = _cabi.Context(0, stream=stream.cuda_stream)
     P, F = synth.dental_crown(100, 1)
-    ctx.set_mesh(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev))
+    tp, tf = torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)
+    torch.cuda.synchronize()
+    ctx.set_mesh(tp, tf)
     ctx.build()
     n = ctx.views_icosahedron(2, 2.0)
     res, K = 224, 34

@@ -523,7 +523,7 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
       if (!(t.flags & 1)) continue;
       const uint64_t key = front_key(t.zlo, t.zhi, (int)slot);
       const uint32_t zlo_ord = ford_bits(t.zlo);
-      const bool use_spans = npx <= 256 && (t.flags & 4);
+      const bool use_spans = npx <= 96 && (t.flags & 4);  // RT_BIG of raster.cu
       for (int j = r.j0; j <= r.j1; j++) {
         int lo = r.i0, hi = r.i1;
         if (use_spans) raster_span(vf, t, fmaf((float)j, vf.qdy, vf.q0y), r.i0, r.i1, &lo, &hi);

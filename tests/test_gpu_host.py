@@ -198,6 +198,7 @@ def test_two_contexts_interleaved_on_one_gpu(gpu_ctx):
         pair.append((c, s, [torch.empty((n, 128, 128, 4), dtype=torch.float32, device=dev) for _ in range(3)],
                      [torch.empty((n, 128, 128), dtype=torch.int32, device=dev) for _ in range(3)]))
     dm = [(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)) for P, F in meshes]
+    torch.cuda.synchronize()  # the uploads ran on torch's stream; the contexts work on their own streams
     for k, (P, F) in enumerate(dm):          # nothing waits between the calls: the two streams run side by side
         c, s, fs, is_ = pair[k % 2]
         c.set_mesh(P, F)

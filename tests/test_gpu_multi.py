@@ -39,6 +39,7 @@ def _worker(rank, world_size, port, tmpdir):
         gidx = torch.arange(b * res * res, e * res * res, device=dev, dtype=torch.int64).reshape(ids.shape)
         labels = ((gidx * 5) % K).to(torch.int32)
         voter = labeling.CellVoter(ctx, K, use_torch=True)
+        torch.cuda.synchronize()                            # labels were computed on torch's stream
         voter.add(ids, labels)
         voter.reduce()                                      # ncclAllReduce on the context stream
         ctx.synchronize()

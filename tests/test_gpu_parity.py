@@ -343,6 +343,7 @@ def test_torch_device_buffers(gpu_ctx, orc):
     P, F = synth.bumpy_sphere(24, 2)
     dev = torch.device("cuda:0")
     tp, tf = torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)
+    torch.cuda.synchronize()  # uploads ran on torch's stream, the context works on its own
     gpu_ctx.set_mesh(tp, tf)
     gpu_ctx.build()
     n = gpu_ctx.views_icosahedron(1, 2.0)
@@ -355,6 +356,7 @@ def test_torch_device_buffers(gpu_ctx, orc):
     assert np.array_equal(ids.cpu().numpy(), i2) and np.array_equal(feat.cpu().numpy(), f2)
     labels = (ids % 7).to(torch.int32)
     votes = torch.zeros((len(F), 7), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # labels / votes were produced on torch's stream
     gpu_ctx.backproject(ids, labels, 7, votes=votes)
     gpu_ctx.synchronize()
     assert np.array_equal(votes.cpu().numpy(), orc.backproject(i2, labels.cpu().numpy(), len(F), 7))
@@ -486,7 +488,9 @@ from flyby_b200 import _cabi, synth
 dev = torch.device("cuda", 0)
 ctx = _cabi.Context(0)
 P, F = synth.bumpy_sphere(316, 5)                      # 1 997 120 triangles
-ctx.set_mesh(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)); ctx.build()
+tp, tf = torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)
+torch.cuda.synchronize()
+ctx.set_mesh(tp, tf); ctx.build()
 n = ctx.views_icosahedron(4, 2.0)                      # 162 views
 res = 1024
 feat = torch.empty((n, res, res, 4), dtype=torch.float32, device=dev)

@@ -68,6 +68,7 @@ def test_predictor_sequence_matches_oracle(gpu_ctx, orc):
 
     torch = pytest.importorskip("torch")
     got = torch.from_numpy(lab.copy()).cuda()
+    torch.cuda.synchronize()  # the upload ran on torch's stream, the context works on its own
     gpu_ctx.labels_dilate(got, 3, 2)
     lo, hi = int(got.min()), int(got.max())
     for label in range(lo, hi + 1):
