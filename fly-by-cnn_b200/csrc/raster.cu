@@ -10,8 +10,12 @@
 //             a certain miss and can still be at or in front of the front joins extra[pixel] (settle_pixel)
 //   resolve1  one thread per pixel in raster order: background / the exact test on the front
 //             triangle when it is the only candidate (the common case) / queue the pixel
+//   big       triangles whose box exceeds RT_BIG pixels are queued by `raster` and walked here in row bands
+//             spread over the whole grid (coarse meshes, close-ups), with the same settle_pixel
 //   resolve2  queued pixels: exact test on the front triangle and the extras, tie-break (t, cell id)
-//   resolve3  pixels whose extras overflowed (edge-on piles at silhouettes): exact LBVH re-trace
+//   spill     pixels with more than 8 extras (edge-on piles at silhouettes): the rest of their candidates
+//             sits in one global (pixel, slot) list; three small kernels take the minimum of (t, cell id)
+//   resolve3  last resort, only when that list itself was full: exact LBVH re-trace of the pixel
 // The candidate set is a superset of what the exact test can accept at or in front of the
 // nearest certain hit, so the result equals the LBVH traversal and the oracle bit for bit; the
 // order in which atomics land does not matter.
