@@ -111,7 +111,9 @@ int flyby_create(int device, void* stream, flyby_ctx** out) {
       if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
           cudaEventCreateWithFlags(&c->ev_unit, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&c->ev_sorted, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&c->ev_tree, cudaEventDisableTiming) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
+          cudaEventCreateWithFlags(&c->ev_tree, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ev_front, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ev_front_free, cudaEventDisableTiming) != cudaSuccess) { flyby_destroy(c); return FLYBY_ERR_CUDA; }
     }
   }
   for (int i = 0; i < 16; i++)
@@ -151,6 +153,8 @@ void flyby_destroy(flyby_ctx* c) {
   if (c->ev_unit) cudaEventDestroy(c->ev_unit);
   if (c->ev_sorted) cudaEventDestroy(c->ev_sorted);
   if (c->ev_tree) cudaEventDestroy(c->ev_tree);
+  if (c->ev_front) cudaEventDestroy(c->ev_front);
+  if (c->ev_front_free) cudaEventDestroy(c->ev_front_free);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -93,7 +93,12 @@ struct flyby_ctx {
   fb::DevBuf cand;      // int4 [n_pix] candidate slots between the candidate search and the resolve kernel
   fb::DevBuf cand2;     // int4 [n_pix] candidate slots 4..7 of the scan-conversion path
   fb::DevBuf pix_lists; // uint32 pixel queues between the resolve kernels
-  fb::DevBuf raster_tmp;  // uint64 [n_pix] front (depth bound, slot) + int32 [n_pix] extra counts + hi-z tiles (raster.cu)
+  fb::DevBuf raster_tmp;  // uint64 [cap] front (depth bound, slot) + int32 [cap] extra counts, cap = pixels the allocation holds (raster.cu)
+  // After a render the side stream re-initialises the pixels it used, beside whatever the main stream does next
+  // (upload, unit surface and sort of the next mesh): pixels [0, front_clean) hold "no front, no extras" once
+  // ev_front fires.  Only raster.cu touches raster_tmp.
+  int64_t front_clean = 0;
+  cudaEvent_t ev_front = nullptr, ev_front_free = nullptr;
   fb::DevBuf raster_big;  // queue of big triangles (slot, view, first band, rows per band) for raster_big_kernel
   fb::DevBuf raster_ovf;  // spill list of (pixel, slot) pairs beyond 8 extras + per-overflow-pixel records (raster.cu)
   int n_views = 0;

@@ -303,8 +303,8 @@ int prep_run(flyby_ctx* c) {
   // point normals: not needed before the shading, so they go to the side stream (see ctx.h)
   cudaStream_t ss = c->side_stream ? c->side_stream : st;
   if (ss != st) {
-    FB_CUDA(c, cudaEventRecord(c->ev_unit, ss));
-    FB_CUDA(c, cudaStreamWaitEvent(ss, c->ev_unit, 0));
+    FB_CUDA(c, cudaEventRecord(c->ev_unit, st));  // the unit surface is complete on the main stream ...
+    FB_CUDA(c, cudaStreamWaitEvent(ss, c->ev_unit, 0));  // ... before the side stream reads it
   }
   FB_CUDA(c, cudaMemsetAsync(m.adj_start.p, 0, sizeof(uint32_t) * (size_t)(V + 1), ss));
   FB_CUDA(c, cudaMemsetAsync(m.adj_cur.p, 0, sizeof(uint32_t) * (size_t)(V + 1), ss));

@@ -488,10 +488,16 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   p.T = (int)c->mesh.T;
   FB_CUDA(c, c->cand.reserve(sizeof(int4) * (size_t)n_pix));
   FB_CUDA(c, c->cand2.reserve(sizeof(int4) * (size_t)n_pix));
-  FB_CUDA(c, c->raster_tmp.reserve(12 * (size_t)n_pix));
+  {
+    const size_t cap0 = c->raster_tmp.cap;
+    FB_CUDA(c, c->raster_tmp.reserve(12 * (size_t)n_pix));  // (growing it frees the old buffer: cudaFree waits for the device)
+    if (c->raster_tmp.cap != cap0) c->front_clean = 0;      // a new allocation: nothing is initialised
+  }
   FB_CUDA(c, c->pix_lists.reserve(8 * (size_t)n_pix + 16));
+  // the counts sit behind the fronts of the whole allocation, so that both keep their place when n_pix changes
+  const size_t cap_pix = c->raster_tmp.cap / 12;
   p.front = c->raster_tmp.as<unsigned long long>();
-  p.cnt = reinterpret_cast<int*>(p.front + n_pix);
+  p.cnt = reinterpret_cast<int*>(p.front + cap_pix);
   p.extra = c->cand.as<int>();
   p.extra2 = c->cand2.as<int>();
   p.queue = c->pix_lists.as<uint32_t>();
@@ -528,8 +534,15 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   p.ov_best_t = p.ov_prov_cs + cap;
   p.ov_best_cs = p.ov_best_t + cap;
   p.ov_pix = reinterpret_cast<uint32_t*>(p.ov_best_cs + cap);
-  raster_init_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(p.front, p.cnt, n_pix);
-  FB_LAUNCH_CHECK(c);
+  // front / count: what the side stream re-initialised behind the previous render is taken as it is (its event
+  // is waited for in any case: the buffer must not be written while that kernel runs), the rest is set here
+  const int64_t clean = c->front_clean;
+  c->front_clean = 0;  // dirty from here on
+  if (c->ev_front) FB_CUDA(c, cudaStreamWaitEvent(st, c->ev_front, 0));  // (no-op before the first record)
+  if (n_pix > clean) {
+    raster_init_kernel<<<(unsigned)cdiv(n_pix - clean, 256), 256, 0, st>>>(p.front + clean, p.cnt + clean, n_pix - clean);
+    FB_LAUNCH_CHECK(c);
+  }
   dim3 grid((unsigned)cdiv(p.T, RT_THREADS), (unsigned)rp.n_views);
   raster_kernel<<<grid, RT_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
@@ -556,6 +569,17 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   FB_LAUNCH_CHECK(c);
   raster_resolve3_kernel<<<(unsigned)c->sm_count, 64, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
+  if (c->side_stream && c->ev_front) {
+    // the next render's initialisation, off the critical path: the side stream runs it beside the upload / unit
+    // surface / sort of the next mesh (or right away, when the next render follows at once)
+    FB_CUDA(c, cudaEventRecord(c->ev_front_free, st));
+    FB_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->ev_front_free, 0));
+    const int64_t n_init = clean > n_pix ? clean : n_pix;  // (pixels beyond n_pix are still clean)
+    raster_init_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, c->side_stream>>>(p.front, p.cnt, n_pix);
+    FB_LAUNCH_CHECK(c);
+    FB_CUDA(c, cudaEventRecord(c->ev_front, c->side_stream));
+    c->front_clean = n_init;
+  }
   return FLYBY_OK;
 }
 

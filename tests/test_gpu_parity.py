@@ -294,6 +294,38 @@ def test_piled_candidates_spill_list(gpu_ctx, orc):
     assert (io[0] >= 0).sum() > 1000 and (io[4] >= 0).sum() > 0 and (io[2] >= 0).sum() == 0  # edge-on: VTK rejects grazing
 
 
+def test_context_reuse_equals_fresh_contexts():
+    """A context keeps grow-only scratch (front buffer, candidate lists, spill list, queues) between renders:
+    renders of changing sizes and meshes on ONE context (piled candidates that go through the spill list, then
+    fewer pixels, then more pixels than ever before) must equal the same renders on fresh contexts."""
+    from flyby_b200 import _cabi
+    base = np.array([[-0.9, -0.8, 0.1], [0.9, -0.7, 0.1], [0.1, 0.9, 0.1], [-0.8, 0.7, 0.1]], np.float32)
+    Vp = np.concatenate([base + np.array([0, 0, -1e-7 * k], np.float32) for k in range(30)]).astype(np.float32)
+    Fp = np.concatenate([np.array([[0, 1, 2], [0, 2, 3]], np.int32) + 4 * k for k in range(30)])
+    Pb, Fb = synth.bumpy_sphere(24, 2)
+    Pc, Fc = synth.cube()
+    jobs = [("piled", Vp, Fp, 96, 2.0), ("bumpy", Pb, Fb, 40, 1.0), ("cube", Pc, Fc, 64, 4.0), ("piled", Vp, Fp, 33, 2.0),
+            ("bumpy", Pb, Fb, 150, 2.0), ("piled", Vp, Fp, 96, 2.0), ("bumpy", Pb, Fb, 40, 1.0)]
+
+    def run(ctx, job):
+        _, P, F, res, ps = job
+        ctx.set_mesh(P, F)
+        ctx.build()
+        ctx.views_icosahedron(1, 2.0)
+        return ctx.render(res, ctx.render_opts(use_z=1, split_z=1, plane_scale=ps), want_t=True)
+
+    one = _cabi.Context(0)
+    got = [run(one, j) for j in jobs]
+    one.close()
+    for j, g in zip(jobs, got):
+        fresh = _cabi.Context(0)
+        want = run(fresh, j)
+        fresh.close()
+        for a, b in zip(g, want):
+            assert np.array_equal(a, b), j[0]
+    assert (got[0][1] >= 0).sum() > 1000 and (got[4][1] >= 0).sum() > 1000
+
+
 def test_bad_indices_rejected(gpu_ctx):
     from flyby_b200 import FlyByError
     V = np.zeros((3, 3), np.float32)
