@@ -198,6 +198,11 @@ def run_ours(args):
     meshes = [synth.bumpy_sphere(LM, seed=rank * MESH_POOL + k) for k in range(MESH_POOL)]
     dev_meshes = [(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)) for P, F in meshes]
     torch.cuda.synchronize()  # uploads ran on torch's default stream; the contexts work on their own streams
+    # pinned host buffers are allocated (first-touched) on the NUMA node the GPU hangs off: with several ranks the
+    # copy-outs then do not cross sockets.  The affinity is restored afterwards (the CPU arm uses all cores).
+    from flyby_b200 import dist as fdist
+    numa = fdist.near_gpu(local)
+    numa.__enter__()
     pin_meshes = [(torch.from_numpy(P).pin_memory(), torch.from_numpy(F).pin_memory()) for P, F in meshes]
     feat = torch.empty((n_views, RES, RES, C), dtype=torch.float32, device=dev)
     ids = torch.empty((n_views, RES, RES), dtype=torch.int32, device=dev)
@@ -205,6 +210,9 @@ def run_ours(args):
     feat_hosts = [torch.empty((n_views, RES, RES, C), dtype=torch.float32).pin_memory() for _ in range(2)]
     ids_hosts = [torch.empty((n_views, RES, RES), dtype=torch.int32).pin_memory() for _ in range(2)]
     feat_host, ids_host = feat_hosts[0], ids_hosts[0]
+    for hb in feat_hosts + ids_hosts:
+        hb.zero_()  # touch every page while the affinity holds
+    numa.__exit__(None, None, None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     T, V = len(meshes[0][1]), len(meshes[0][0])
 
@@ -402,6 +410,7 @@ def run_ours(args):
                                 + " per mesh: pinned H2D of the mesh, build, render in view chunks, chunked D2H of the "
                                   "feature tensor (what fly_by_features.py --out holds) into pinned host memory; "
                                   "PCIe-bound (profiles/pcie_bw.py: 57 GB/s pinned D2H on this box)",
+                        "host_buffers_numa_node": numa.node,
                         "blocking_ms_per_step": ms_e2e_max,
                         "streamed_ms_per_step": ms_e2e_stream_max,
                         "streamed_note": "flyby_render_async (copy-out of mesh n overlaps upload/build/render of mesh "

@@ -34,6 +34,65 @@ def shard_items(items, rank, world_size):
     return list(items[b:e])
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def gpu_numa_cpus(device_index):
+    """(numa node, set of CPUs) the GPU hangs off, from sysfs; (None, empty set) where that is not exposed."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None, set()
+        return node, _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None, set()
+
+
+class near_gpu:
+    """Context manager: run the body on the CPUs of the GPU's NUMA node, then restore the affinity.  Pinned
+    staging buffers allocated inside are first-touched on that node, so that the copy-out of every rank of a
+    multi-GPU batch extraction stays on its own socket (one process per GPU, by-mesh sharding).
+
+        with near_gpu(local_rank):
+            host = torch.empty(shape).pin_memory()
+    """
+
+    def __init__(self, device_index):
+        self.node, self.cpus = gpu_numa_cpus(device_index)
+        self.saved = None
+
+    def __enter__(self):
+        import os
+        try:
+            cur = os.sched_getaffinity(0)
+            want = cur & self.cpus
+            if want and want != cur:
+                os.sched_setaffinity(0, want)
+                self.saved = cur
+        except (AttributeError, OSError):
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except OSError:
+                pass
+        return False
+
+
 def init_nccl(ctx, group=None):
     """Create the library-side NCCL communicator: rank 0 makes the unique id, torch.distributed carries it."""
     import torch.distributed as dist

@@ -79,3 +79,15 @@ def test_allreduce_is_identity_without_process_group():
     v = np.arange(12, dtype=np.int32).reshape(3, 4)
     assert fd.allreduce_votes(v) is v and fd.world() == (0, 1)
     assert fd.gather_view_slabs(v, 3) is v
+
+
+def test_numa_helpers_without_gpu():
+    """near_gpu is a no-op where sysfs does not expose the GPU's node (this container); the cpulist parser is exact."""
+    import os
+    from flyby_b200 import dist as fdist
+    assert fdist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert fdist._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    with fdist.near_gpu(0) as n:
+        assert n.node is None or isinstance(n.node, int)
+    assert os.sched_getaffinity(0) == before
