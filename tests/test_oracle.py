@@ -292,3 +292,56 @@ def test_perspective_camera_known_answers(orc):
     # uint8 colours: integers in 0..255
     f8, _, _ = orc.render_perspective(V, F, N, views[:1], 64, z_far=R + 1, normal_encoding=3)
     assert np.array_equal(f8[..., :3], np.round(f8[..., :3])) and f8[..., :3].max() <= 255 and f8[..., :3].min() >= 0
+
+
+def test_oracle_agrees_with_an_independent_ray_caster(orc):
+    """The oracle restates VTK's plane-hit + dominant-axis projection.  A different algorithm -- Moeller-Trumbore in
+    numpy float64, brute force over all triangles -- must find the same nearest cell and the same segment parameter on
+    every ray that does not graze an edge (those are counted: VTK's inclusive weights and tolerance band decide them,
+    Moeller-Trumbore's do not)."""
+    from flyby_b200 import synth
+    P, F = synth.bumpy_sphere(10, 7)          # 2000 triangles
+    U, _, _ = orc.unit_surf(P)
+    rng = np.random.default_rng(5)
+    n = 1500
+    o = rng.normal(size=(n, 3)); o = 2.5 * o / np.linalg.norm(o, axis=1, keepdims=True)
+    target = rng.uniform(-0.6, 0.6, (n, 3))
+    e = o + 2.0 * (target - o)                # segments through the mesh, some missing it
+    e[:100] = o[:100] + 0.2 * (target[:100] - o[:100])   # too short to reach it
+    rays = np.concatenate([o, e], axis=1)
+    ids, t, x, w = orc.cast(U, F, rays, grid=True)
+    ids_b, t_b, _, _ = orc.cast(U, F, rays, grid=False)
+    assert np.array_equal(ids, ids_b) and np.array_equal(t, t_b)
+
+    V0, V1, V2 = (U[F[:, k]].astype(np.float64) for k in range(3))
+    e1, e2 = V1 - V0, V2 - V0
+    best_t = np.full(n, np.inf); best_id = np.full(n, -1); margin = np.full(n, np.inf)
+    for k in range(n):
+        d = e[k] - o[k]
+        pv = np.cross(d, e2)
+        det = np.einsum("ij,ij->i", e1, pv)
+        ok = np.abs(det) > 1e-300
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        tv = o[k] - V0
+        u = np.einsum("ij,ij->i", tv, pv) * inv
+        qv = np.cross(tv, e1)
+        v = (qv @ d) * inv
+        tt = np.einsum("ij,ij->i", e2, qv) * inv
+        edge = np.minimum(np.minimum(u, v), 1.0 - u - v)          # > 0 inside
+        hit = ok & (edge >= 0) & (tt >= 0) & (tt <= 1)
+        near = ok & (np.abs(edge) < 1e-9) & (tt >= -1e-9) & (tt <= 1 + 1e-9)
+        if near.any():
+            margin[k] = 0.0                                          # a grazing candidate exists on this ray
+        if hit.any():
+            tmin = tt[hit].min()
+            cand = np.nonzero(hit & (tt == tmin))[0]
+            best_t[k], best_id[k] = tmin, cand.min()
+    clear = margin > 0
+    assert clear.sum() > n - 10                                      # grazing rays are rare in a random sample
+    assert np.array_equal(ids[clear], best_id[clear])
+    h = clear & (ids >= 0)
+    assert h.sum() > 800 and (ids[clear] < 0).sum() > 100
+    assert np.allclose(t[h], best_t[h], rtol=1e-11, atol=0)
+    # the hit point and the weights the oracle returns describe the same point
+    recon = w[h, 0:1] * U[F[ids[h], 0]] + w[h, 1:2] * U[F[ids[h], 1]] + w[h, 2:3] * U[F[ids[h], 2]]
+    assert np.abs(recon - x[h]).max() < 1e-9
