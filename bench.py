@@ -132,7 +132,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mrays_per_s": value * RES * RES / 1e6, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def _host_threads():
@@ -426,13 +426,29 @@ def run_ours(args):
                 "clocks": sampler.summary()}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_json_out = None
+
+
+def emit(obj):
+    """The one JSON line, on the process's original stdout."""
+    out = _json_out if _json_out is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries the JSON line only: whatever a library prints there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) is sent to stderr by pointing file descriptor 1 at it
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
