@@ -271,3 +271,29 @@ def test_flybygenerator_signature_matches_reference():
     for name in ("ReadSurf", "GetUnitSurf", "ScaleSurf", "CreateIcosahedron", "CreateSpiral", "GetNormalsActor",
                  "GetPointIdMapActor", "ExtractPointFeatures", "GetImage", "ComputeNormals", "RandomRotation"):
         assert hasattr(fbf, name), name  # callers use fbf.ReadSurf etc. (predict_v3.py:23-36)
+
+
+def test_no_stream_waits_for_an_event_recorded_on_itself():
+    """Source lint for the cross-stream hand-offs of the CUDA library: a cudaStreamWaitEvent that directly follows
+    the cudaEventRecord of the same event must name a different stream -- recording on the waiting stream orders
+    nothing (that slip once let the side stream's point normals race the main stream's unit surface)."""
+    import glob
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fly-by-cnn_b200", "csrc")
+    rec = re.compile(r"cudaEventRecord\(\s*([^,]+?)\s*,\s*([^)]+?)\s*\)")
+    wait = re.compile(r"cudaStreamWaitEvent\(\s*([^,]+?)\s*,\s*([^,]+?)\s*,")
+    pairs = 0
+    for path in glob.glob(os.path.join(root, "*.cu")):
+        lines = open(path).read().splitlines()
+        for i, ln in enumerate(lines):
+            m = wait.search(ln)
+            if not m:
+                continue
+            stream, event = m.group(1), m.group(2)
+            for back in lines[max(0, i - 3):i][::-1]:
+                r = rec.search(back)
+                if r and r.group(1) == event:
+                    pairs += 1
+                    assert r.group(2) != stream, "%s:%d waits on %s for an event recorded on it" % (path, i + 1, stream)
+                    break
+    assert pairs >= 4  # unit surface, sort, front buffer, chunked copy-out
