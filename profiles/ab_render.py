@@ -1,7 +1,11 @@
 """A/B driver for kernel experiments: the bench workload's render (200 k triangles, 92 views, 512^2) through one or
 more builds of libflyby_b200.so, interleaved, with a digest of the outputs so that a variant that changes results is
 seen at once.
-  python profiles/ab_render.py ab/A.so ab/B.so ...        (each library runs in its own subprocess)"""
+  python profiles/ab_render.py ab/A.so ab/B.so ...        (each library runs in its own subprocess)
+Variants are built beside the in-tree library, which stays untouched:
+  make -C fly-by-cnn_b200 -j LIB=../ab/A.so
+  touch fly-by-cnn_b200/csrc/raster.cu; make -C fly-by-cnn_b200 -j EXTRA="-DRT_MINB=10" LIB=../ab/B.so
+(ab/ is git-ignored and travels to the GPU box with gpurun.)"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "fly-by-cnn_b200"))
