@@ -345,3 +345,16 @@ def test_oracle_agrees_with_an_independent_ray_caster(orc):
     # the hit point and the weights the oracle returns describe the same point
     recon = w[h, 0:1] * U[F[ids[h], 0]] + w[h, 1:2] * U[F[ids[h], 1]] + w[h, 2:3] * U[F[ids[h], 2]]
     assert np.abs(recon - x[h]).max() < 1e-9
+
+
+def test_oracle_pinned_against_vtk_when_available():
+    """Runs oracle/pin_vtk.py (the reference's own VTK calls against the oracle) where vtk is importable; skipped in
+    the build environment of this repository, where it is not -- the reason DESIGN.md says "parity unpinned"."""
+    import pytest
+    pytest.importorskip("vtk")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "pin_vtk.py")], capture_output=True, text=True,
+                         timeout=1800)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
