@@ -247,6 +247,41 @@ def _write(out_np, path, concatenate, suffix=""):
         utils.WriteImage(utils.GetImage(out_np), path)
 
 
+def cxx_scale_factor(args):
+    """--scale_factor multiplies (src/py/utils.py:285); the C++ tool's --scaleFactor divides
+    (src/app/fly_by_features.cxx:448) and -1 means "derive it from the shape" (:426)."""
+    sf = getattr(args, "scaleFactor", -1)
+    if sf is not None and sf != -1:
+        if sf == 0:
+            raise SystemExit("--scaleFactor 0: the C++ tool divides by it")
+        if args.scale_factor is not None:
+            raise SystemExit("--scale_factor and --scaleFactor are two spellings of one setting: give one")
+        return 1.0 / sf
+    return args.scale_factor
+
+
+def cxx_rotation(surf, args, rng=None):
+    """The C++ tool's --randomRotation / --applyRotation --rotationAngle --rotationVector
+    (src/app/fly_by_features.cxx:310-347): the rotation is applied to the surface as read, BEFORE centring and
+    scaling (the Python --random_rotation rotates the unit surface, fly_by_features.py:286-287).  Axis of the
+    random rotation: a normalised Gaussian vector, angle uniform in [0, 360); --rotationAngle -1 draws the angle."""
+    if not (getattr(args, "applyRotation", 0) or getattr(args, "randomRotation", 0)):
+        return surf
+    rng = rng or np.random.default_rng()
+    angle, vec = args.rotationAngle, list(args.rotationVector)
+    if args.randomRotation:
+        v = rng.normal(size=3)
+        vec = list(v / np.linalg.norm(v))
+        angle = float(rng.uniform(0.0, 360.0))
+    if angle == -1:
+        angle = float(rng.uniform(0.0, 360.0))
+    if len(vec) != 3:
+        raise SystemExit("--rotationVector needs three components")
+    if args.verbose:
+        print("Apply rotation: angle:", angle, "vector:", vec)
+    return utils.RotateSurf(surf, angle, vec)
+
+
 def main(args):
     for name in ("fiberBundle", "fiber", "property", "view_features", "model", "visualize"):
         if getattr(args, name, None):
@@ -271,7 +306,9 @@ def main(args):
             print("Number of sphere points:", sphere.GetNumberOfPoints())
             print("Reading:", fobj["surf"])
         surf = utils.ReadSurf(fobj["surf"])
-        surf = utils.GetUnitSurf(surf, args.translate, args.scale_factor, device=device)
+        surf = cxx_rotation(surf, args)
+        surf = utils.GetUnitSurf(surf, args.translate, cxx_scale_factor(args), device=device,
+                                 centre_mode=1 if args.useCenterOfMass else 0, scale_mode=1 if args.useMagnitude else 0)
         if args.random_rotation or fobj.get("rotate"):
             surf, rotationAngle, rotationVector = utils.RandomRotation(surf)
             if args.verbose:
@@ -368,8 +405,18 @@ def build_parser():
 
     # options of the reference's C++ tool (src/app/fly_by_features.xml:62-76) and of this implementation
     engine = parser.add_argument_group('Ray-cast engine')
-    engine.add_argument('--plane_scale', type=float, default=1.0, help='planeScaleFactor: side length of the view plane')
-    engine.add_argument('--plane_spacing', type=float, default=1.0, help='planeSpacing')
+    engine.add_argument('--plane_scale', '--planeScaleFactor', dest='plane_scale', type=float, default=1.0,
+                        help='planeScaleFactor: side length of the view plane')
+    engine.add_argument('--plane_spacing', '--planeSpacing', dest='plane_spacing', type=float, default=1.0, help='planeSpacing')
+    engine.add_argument('--scaleFactor', type=float, default=-1,
+                        help='C++ tool: the centred shape is DIVIDED by this value (-1: derive it from the shape)')
+    engine.add_argument('--useCenterOfMass', type=int, default=0, help='C++ tool: centre on the centre of mass of the points')
+    engine.add_argument('--useMagnitude', type=int, default=0, help='C++ tool: scale by the largest point magnitude')
+    engine.add_argument('--randomRotation', type=int, default=0, help='C++ tool: random rotation before centring and scaling')
+    engine.add_argument('--applyRotation', type=int, default=0, help='C++ tool: apply --rotationAngle about --rotationVector before centring and scaling')
+    engine.add_argument('--rotationAngle', type=float, default=-1, help='C++ tool: angle in degrees (-1: random)')
+    engine.add_argument('--rotationVector', type=lambda s: [float(x) for x in s.split(',')], default=[1.0, 0.0, 0.0],
+                        help='C++ tool: rotation axis, comma separated')
     engine.add_argument('--normal_encoding', type=str, default=None, choices=[None, 'byte255', 'unit01', 'signed'],
                         help='value range of the normal channels (default byte255, signed with --rescale_features)')
     engine.add_argument('--device', type=int, default=0, help='CUDA device')

@@ -120,13 +120,15 @@ def CreateSpiral(sphereRadius=4, numberOfSpiralSamples=64, numberOfSpiralTurns=4
 
 
 # --------------------------------------------------------------------------- normalisation
-def ScaleSurf(surf, mean_arr=None, scale_factor=None, copy=True, device=0):
+def ScaleSurf(surf, mean_arr=None, scale_factor=None, copy=True, device=0, centre_mode=0, scale_mode=0):
     """reference src/py/utils.py:249-290: centre on the bounding-box middle (or ``mean_arr``), scale by
-    1/|bbox_max - centre| (or ``scale_factor``).  Returns (surf, mean_arr, scale_factor)."""
+    1/|bbox_max - centre| (or ``scale_factor``).  Returns (surf, mean_arr, scale_factor).
+    ``centre_mode=1`` / ``scale_mode=1`` are the C++ tool's --useCenterOfMass / --useMagnitude
+    (src/app/fly_by_features.cxx:397-403, 429-435): centre of mass of the points, 1 / largest point magnitude."""
     out = surf.copy() if copy else surf
     ctx = default_context(device)
     ctx.set_mesh(np.ascontiguousarray(surf.points, np.float32), np.ascontiguousarray(surf.polys, np.int32),
-                 translate=mean_arr, scale_factor=scale_factor)
+                 centre_mode=centre_mode, scale_mode=scale_mode, translate=mean_arr, scale_factor=scale_factor)
     ctx.build()
     unit, normals, centre, scale = ctx.get_mesh()
     out.points = unit
@@ -135,9 +137,9 @@ def ScaleSurf(surf, mean_arr=None, scale_factor=None, copy=True, device=0):
     return out, centre, scale
 
 
-def GetUnitSurf(surf, mean_arr=None, scale_factor=None, copy=True, device=0):
+def GetUnitSurf(surf, mean_arr=None, scale_factor=None, copy=True, device=0, centre_mode=0, scale_mode=0):
     """reference src/py/utils.py:341-343"""
-    unit_surf, _, _ = ScaleSurf(surf, mean_arr, scale_factor, copy, device)
+    unit_surf, _, _ = ScaleSurf(surf, mean_arr, scale_factor, copy, device, centre_mode, scale_mode)
     return unit_surf
 
 

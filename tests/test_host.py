@@ -259,6 +259,33 @@ def test_cli_option_surface_matches_reference():
             fbf.main(a)
 
 
+def test_cli_options_of_the_cxx_tool():
+    """src/app/fly_by_features.xml:62-154: --planeSpacing / --planeScaleFactor are the C++ spellings of the plane
+    options, --scaleFactor DIVIDES (the Python --scale_factor multiplies), --useCenterOfMass / --useMagnitude pick
+    the normalisation, --applyRotation / --randomRotation rotate the surface as read, before centring and scaling
+    (fly_by_features.cxx:310-347)."""
+    from flyby_b200 import fly_by_features as fbf
+    from flyby_b200 import utils
+    parser = fbf.build_parser()
+    base = "--surf m.vtk --subdivision 2 "
+    a = parser.parse_args((base + "--planeScaleFactor 2 --planeSpacing 0.5 --scaleFactor 4 --useCenterOfMass 1 "
+                                  "--useMagnitude 1").split())
+    assert (a.plane_scale, a.plane_spacing, a.useCenterOfMass, a.useMagnitude) == (2.0, 0.5, 1, 1)
+    assert fbf.cxx_scale_factor(a) == 0.25
+    d = parser.parse_args(base.split())
+    assert fbf.cxx_scale_factor(d) is None and (d.scaleFactor, d.rotationAngle, d.rotationVector) == (-1, -1, [1.0, 0.0, 0.0])
+    with pytest.raises(SystemExit):
+        fbf.cxx_scale_factor(parser.parse_args((base + "--scaleFactor 2 --scale_factor 0.5").split()))
+    surf = utils.Surf(np.array([[1, 0, 0], [0, 2, 0], [0, 0, 3]], np.float32), np.array([[0, 1, 2]], np.int32), {}, {})
+    assert fbf.cxx_rotation(surf, d) is surf                                   # no rotation asked for
+    r = fbf.cxx_rotation(surf, parser.parse_args((base + "--applyRotation 1 --rotationAngle 90 --rotationVector 0,0,1").split()))
+    assert np.allclose(r.points, [[0, 1, 0], [-2, 0, 0], [0, 0, 3]], atol=1e-6)  # RotateWXYZ(90, z): x -> y, y -> -x
+    rr = fbf.cxx_rotation(surf, parser.parse_args((base + "--randomRotation 1").split()), rng=np.random.default_rng(1))
+    assert np.allclose(np.linalg.norm(rr.points, axis=1), [1, 2, 3], atol=1e-5) and not np.allclose(rr.points, surf.points)
+    ra = fbf.cxx_rotation(surf, parser.parse_args((base + "--applyRotation 1").split()), rng=np.random.default_rng(2))
+    assert np.allclose(ra.points[0, 0], 1.0, atol=1e-6)                        # random angle about the default axis x
+
+
 def test_flybygenerator_signature_matches_reference():
     import inspect
     from flyby_b200 import fly_by_features as fbf
