@@ -268,8 +268,8 @@ def cxx_rotation(surf, args, rng=None):
     if not (getattr(args, "applyRotation", 0) or getattr(args, "randomRotation", 0)):
         return surf
     rng = rng or np.random.default_rng()
-    angle, vec = args.rotationAngle, list(args.rotationVector)
-    if args.randomRotation:
+    angle, vec = getattr(args, "rotationAngle", -1), list(getattr(args, "rotationVector", [1.0, 0.0, 0.0]))
+    if getattr(args, "randomRotation", 0):
         v = rng.normal(size=3)
         vec = list(v / np.linalg.norm(v))
         angle = float(rng.uniform(0.0, 360.0))
@@ -277,7 +277,7 @@ def cxx_rotation(surf, args, rng=None):
         angle = float(rng.uniform(0.0, 360.0))
     if len(vec) != 3:
         raise SystemExit("--rotationVector needs three components")
-    if args.verbose:
+    if getattr(args, "verbose", 0):
         print("Apply rotation: angle:", angle, "vector:", vec)
     return utils.RotateSurf(surf, angle, vec)
 
@@ -308,7 +308,8 @@ def main(args):
         surf = utils.ReadSurf(fobj["surf"])
         surf = cxx_rotation(surf, args)
         surf = utils.GetUnitSurf(surf, args.translate, cxx_scale_factor(args), device=device,
-                                 centre_mode=1 if args.useCenterOfMass else 0, scale_mode=1 if args.useMagnitude else 0)
+                                 centre_mode=1 if getattr(args, "useCenterOfMass", 0) else 0,
+                                 scale_mode=1 if getattr(args, "useMagnitude", 0) else 0)
         if args.random_rotation or fobj.get("rotate"):
             surf, rotationAngle, rotationVector = utils.RandomRotation(surf)
             if args.verbose:
