@@ -287,6 +287,8 @@ def main(args):
         if getattr(args, name, None):
             raise SystemExit("--%s is not supported by flyby_b200 (needs VTK tube filters / colour maps / Keras / "
                              "an OpenGL window); see DESIGN.md" % name)
+    if getattr(args, "flyByCompose", None) is not None:  # the C++ spelling of --concatenate (fly_by_features.cxx:1049)
+        args.concatenate = 1 if args.flyByCompose else 0
     filenames = _find_surfaces(args)
     device = getattr(args, "device", 0)
     if args.subdivision:
@@ -409,6 +411,10 @@ def build_parser():
     engine.add_argument('--plane_scale', '--planeScaleFactor', dest='plane_scale', type=float, default=1.0,
                         help='planeScaleFactor: side length of the view plane')
     engine.add_argument('--plane_spacing', '--planeSpacing', dest='plane_spacing', type=float, default=1.0, help='planeSpacing')
+    engine.add_argument('--flyByCompose', type=int, default=None,
+                        help='C++ tool: 1 = one stacked volume, 0 = one file per view (sets --concatenate)')
+    engine.add_argument('--useOctree', type=int, default=0,
+                        help='C++ tool: choice of its CPU search structure; accepted, no effect (the results are the same)')
     engine.add_argument('--scaleFactor', type=float, default=-1,
                         help='C++ tool: the centred shape is DIVIDED by this value (-1: derive it from the shape)')
     engine.add_argument('--useCenterOfMass', type=int, default=0, help='C++ tool: centre on the centre of mass of the points')

@@ -272,7 +272,9 @@ def test_cli_options_of_the_cxx_tool():
                                   "--useMagnitude 1").split())
     assert (a.plane_scale, a.plane_spacing, a.useCenterOfMass, a.useMagnitude) == (2.0, 0.5, 1, 1)
     assert fbf.cxx_scale_factor(a) == 0.25
+    assert parser.parse_args((base + "--flyByCompose 0 --useOctree 1").split()).flyByCompose == 0
     d = parser.parse_args(base.split())
+    assert d.flyByCompose is None and d.concatenate == 1
     assert fbf.cxx_scale_factor(d) is None and (d.scaleFactor, d.rotationAngle, d.rotationVector) == (-1, -1, [1.0, 0.0, 0.0])
     with pytest.raises(SystemExit):
         fbf.cxx_scale_factor(parser.parse_args((base + "--scaleFactor 2 --scale_factor 0.5").split()))
