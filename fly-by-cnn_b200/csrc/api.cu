@@ -16,6 +16,10 @@ int nccl_init(flyby_ctx*, const uint8_t*, int, int);
 void nccl_destroy(flyby_ctx*);
 int nccl_votes_allreduce(flyby_ctx*, int32_t*, int64_t, int);
 const double* prep_centre_scale(flyby_ctx* c);
+int label_point_ids(flyby_ctx*, const int32_t*, int64_t, int32_t*);
+int label_backproject_points(flyby_ctx*, const int32_t*, const int32_t*, int64_t, int, int32_t*);
+int winding_detect(flyby_ctx* c, int* flags_dev);  // winding.cu
+int winding_fix(flyby_ctx* c, int* flags_dev);
 
 // input: device pointers are used in place, host pointers are copied to `stage`
 template <class T>
@@ -63,6 +67,22 @@ static int sync_if(flyby_ctx* c, bool need) {
 __global__ void check_tris_kernel(const int32_t* __restrict__ tris, int64_t n, int64_t V, int32_t* bad) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n && (tris[i] < 0 || tris[i] >= V)) atomicAdd(bad, 1);
+}
+
+// Entry points that read m.tris without a build (flyby_set_mesh only) validate the indices first, once per mesh.
+static int ensure_tris_checked(flyby_ctx* c) {
+  MeshDev& m = c->mesh;
+  if (m.tris_ok || m.T <= 0) return FLYBY_OK;
+  int32_t* bad = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 7);
+  FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
+  check_tris_kernel<<<(unsigned)cdiv(3 * m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), 3 * m.T, m.V, bad);
+  FB_LAUNCH_CHECK(c);
+  int32_t nbad = 0;
+  FB_CUDA(c, cudaMemcpyAsync(&nbad, bad, 4, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (nbad) return fail(c, FLYBY_ERR_INVALID, "%d triangle indices outside [0, n_verts)", nbad);
+  m.tris_ok = true;
+  return FLYBY_OK;
 }
 
 }  // namespace fb
@@ -140,11 +160,13 @@ void flyby_destroy(flyby_ctx* c) {
                     &m.reduce, &m.codes, &m.codes_alt, &m.idx, &m.idx_alt, &m.hist, &m.scan_tmp, &m.tree_scan_tmp, &m.leaf_box,
                     &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid, &m.trec,
                     &c->view_pts, &c->views, &c->viewsf, &c->tc_table, &c->cand, &c->cand2, &c->pix_lists, &c->raster_tmp, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
-                    &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->raster_big, &c->counters,
+                    &m.flip, &m.edge_tab, &m.orient, &m.scalars, &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->raster_big, &c->counters,
                     &c->async_feat[0], &c->async_feat[1], &c->async_ids[0], &c->async_ids[1], &c->async_t[0], &c->async_t[1]};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (cudaEvent_t e : c->slab_ev)
+    if (e) cudaEventDestroy(e);
   for (int i = 0; i < 16; i++)
     if (c->chunk_ev[i]) cudaEventDestroy(c->chunk_ev[i]);
   for (int i = 0; i < 2; i++)
@@ -190,7 +212,11 @@ int flyby_set_mesh(flyby_ctx* c, const float* verts, int64_t V, const int32_t* t
   { int rc = wait_tree(c); if (rc) return rc; }  // the previous build's side-stream work still reads the triangles
   m.has_mesh = false;
   m.built = false;
+  m.tris_ok = false;
+  m.n_scalars = 0;
+  m.n_flipped = 0;
   if (opts) c->norm = *opts; else memset(&c->norm, 0, sizeof c->norm);
+  if (c->norm.consistency < 0 || c->norm.consistency > 2) return fail(c, FLYBY_ERR_INVALID, "set_mesh: consistency must be 0, 1 or 2");
   FB_CUDA(c, m.raw_verts.reserve(sizeof(float) * 3 * (size_t)V));
   FB_CUDA(c, m.tris.reserve(sizeof(int32_t) * 3 * (size_t)(T > 0 ? T : 1)));
   FB_CUDA(c, cudaMemcpyAsync(m.raw_verts.p, verts, sizeof(float) * 3 * (size_t)V, cudaMemcpyDefault, c->stream));
@@ -211,17 +237,29 @@ int flyby_build(flyby_ctx* c) {
     if (rc0) return rc0;
     c->tree_pending = false;
   }
-  // index validation first: an out-of-range index must never reach a gather
+  // index validation first: an out-of-range index must never reach a gather.  The winding check of
+  // vtkPolyDataNormals' consistency pass (winding.cu) shares the one host synchronisation of the build.
   int32_t* bad = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 7);
   FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
-  if (m.T > 0) {
+  if (m.T > 0 && !m.tris_ok) {
     check_tris_kernel<<<(unsigned)cdiv(3 * m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), 3 * m.T, m.V, bad);
     FB_LAUNCH_CHECK(c);
   }
-  int32_t nbad = 0;
-  FB_CUDA(c, cudaMemcpyAsync(&nbad, bad, 4, cudaMemcpyDeviceToHost, c->stream));
+  const bool wind = c->norm.consistency != 2 && m.T > 0 && m.n_flipped == 0;
+  if (wind) { int rcw = winding_detect(c, bad + 1); if (rcw) return rcw; }
+  int32_t chk[2] = {0, 0};
+  FB_CUDA(c, cudaMemcpyAsync(chk, bad, 8, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (nbad) return fail(c, FLYBY_ERR_INVALID, "build: %d triangle indices outside [0, n_verts)", nbad);
+  if (chk[0]) return fail(c, FLYBY_ERR_INVALID, "build: %d triangle indices outside [0, n_verts)", chk[0]);
+  m.tris_ok = true;
+  if (wind && (chk[1] & 1)) {
+    if (c->norm.consistency == 0)
+      return fail(c, FLYBY_ERR_UNSUPPORTED,
+                  "build: inconsistently wound cells (two cells traverse a shared edge in the same direction); "
+                  "vtkPolyDataNormals would reverse cells -- set flyby_norm_opts.consistency = 1 to reproduce that, 2 to use the cells as given");
+    int rcw = winding_fix(c, bad + 1);
+    if (rcw) return rcw;
+  }
   int rc = prep_run(c);
   if (rc) return rc;
   rc = lbvh_run(c);
@@ -337,7 +375,7 @@ int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if (rc) return rc;
   const size_t per_view = (size_t)res * res;
   const size_t n_pix = (size_t)(ve - vb) * per_view;
-  const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  const int channels = ((o->use_z && o->split_z) ? 4 : 3) + c->mesh.n_scalars;  // floats per pixel of out_features
   rc = views_setup(c, o, res);
   if (rc) return rc;
   StageOut<float> sf;
@@ -398,7 +436,7 @@ int flyby_render_async(flyby_ctx* c, int vb, int ve, int res, const flyby_render
   if (rc) return rc;
   const size_t per_view = (size_t)res * res;
   const size_t n_pix = (size_t)(ve - vb) * per_view;
-  const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  const int channels = ((o->use_z && o->split_z) ? 4 : 3) + c->mesh.n_scalars;  // floats per pixel of out_features
   if ((rc = views_setup(c, o, res))) return rc;
   const int s = c->async_flip;
   c->async_flip ^= 1;
@@ -493,6 +531,7 @@ int flyby_point_features(flyby_ctx* c, const int32_t* cell_ids, int64_t n_pix, c
   const int32_t* dids;
   const float* dfeats;
   int rc;
+  if (mode == 0 && (rc = ensure_tris_checked(c))) return rc;  // mode 1 never reads the triangles
   if ((rc = stage_in(c, c->stage_in0, cell_ids, (size_t)n_pix, &dids))) return rc;
   if ((rc = stage_in(c, c->stage_in1, feats, (size_t)c->mesh.V * F, &dfeats))) return rc;
   StageOut<float> so;
@@ -501,6 +540,52 @@ int flyby_point_features(flyby_ctx* c, const int32_t* cell_ids, int64_t n_pix, c
   bool need = !is_device_ptr(cell_ids) || !is_device_ptr(feats);
   if ((rc = so.finish(c, &need))) return rc;
   return sync_if(c, need);
+}
+
+int flyby_point_ids(flyby_ctx* c, const int32_t* cell_ids, int64_t n_pix, int32_t* out) {
+  CHECK_CTX(c);
+  if (!c->mesh.has_mesh) return fail(c, FLYBY_ERR_INVALID, "point_ids: no mesh");
+  if (!cell_ids || !out || n_pix < 0) return fail(c, FLYBY_ERR_INVALID, "point_ids: bad arguments");
+  int rc;
+  if ((rc = ensure_tris_checked(c))) return rc;
+  const int32_t* dids;
+  if ((rc = stage_in(c, c->stage_in0, cell_ids, (size_t)n_pix, &dids))) return rc;
+  StageOut<int32_t> so;
+  if ((rc = so.begin(c, c->stage_out0, out, (size_t)n_pix))) return rc;
+  if ((rc = label_point_ids(c, dids, n_pix, so.dev))) return rc;
+  bool need = !is_device_ptr(cell_ids);
+  if ((rc = so.finish(c, &need))) return rc;
+  return sync_if(c, need);
+}
+
+int flyby_set_point_scalars(flyby_ctx* c, const float* feats, int S, int mode, float zero) {
+  CHECK_CTX(c);
+  MeshDev& m = c->mesh;
+  if (!m.has_mesh) return fail(c, FLYBY_ERR_INVALID, "set_point_scalars: call flyby_set_mesh first");
+  if (S < 0 || S > 64 || (S > 0 && !feats)) return fail(c, FLYBY_ERR_INVALID, "set_point_scalars: 0 <= n_scalars <= 64 and a feature array");
+  if (mode != 0 && mode != 1) return fail(c, FLYBY_ERR_UNSUPPORTED, "set_point_scalars: mode must be 0 (vertex 0) or 1 (barycentric)");
+  m.n_scalars = 0;
+  if (S == 0) return FLYBY_OK;
+  FB_CUDA(c, m.scalars.reserve(sizeof(float) * (size_t)m.V * S));
+  FB_CUDA(c, cudaMemcpyAsync(m.scalars.p, feats, sizeof(float) * (size_t)m.V * S, cudaMemcpyDefault, c->stream));
+  m.n_scalars = S;
+  m.scalar_mode = mode;
+  m.scalar_zero = zero;
+  return FLYBY_OK;
+}
+
+int flyby_get_winding(flyby_ctx* c, int64_t* n_flipped, uint8_t* flipped) {
+  CHECK_CTX(c);
+  MeshDev& m = c->mesh;
+  if (!m.built) return fail(c, FLYBY_ERR_INVALID, "get_winding: mesh not built");
+  if (n_flipped) *n_flipped = m.n_flipped;
+  if (flipped && m.T > 0) {
+    if (m.n_flipped > 0) FB_CUDA(c, cudaMemcpyAsync(flipped, m.flip.p, (size_t)m.T, cudaMemcpyDefault, c->stream));
+    else if (is_device_ptr(flipped)) FB_CUDA(c, cudaMemsetAsync(flipped, 0, (size_t)m.T, c->stream));
+    else memset(flipped, 0, (size_t)m.T);
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return FLYBY_OK;
 }
 
 int flyby_interpolate_features(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, const int32_t* cell_ids,
@@ -541,6 +626,33 @@ int flyby_backproject(flyby_ctx* c, const int32_t* cell_ids, const int32_t* labe
     FB_CUDA(c, cudaMemcpyAsync(dvotes, votes, nv * 4, cudaMemcpyHostToDevice, c->stream));
   }
   if ((rc = label_backproject(c, dids, dlab, n_pix, K, dvotes))) return rc;
+  bool need = !is_device_ptr(cell_ids) || !is_device_ptr(labels);
+  if (host_votes) {
+    FB_CUDA(c, cudaMemcpyAsync(votes, dvotes, nv * 4, cudaMemcpyDeviceToHost, c->stream));
+    need = true;
+  }
+  return sync_if(c, need);
+}
+
+int flyby_backproject_points(flyby_ctx* c, const int32_t* cell_ids, const int32_t* labels, int64_t n_pix, int K,
+                             int32_t* votes) {
+  CHECK_CTX(c);
+  if (!c->mesh.has_mesh) return fail(c, FLYBY_ERR_INVALID, "backproject_points: no mesh");
+  if (!cell_ids || !labels || !votes || K < 1 || n_pix < 0) return fail(c, FLYBY_ERR_INVALID, "backproject_points: bad arguments");
+  const int32_t *dids, *dlab;
+  int rc;
+  if ((rc = ensure_tris_checked(c))) return rc;
+  if ((rc = stage_in(c, c->stage_in0, cell_ids, (size_t)n_pix, &dids))) return rc;
+  if ((rc = stage_in(c, c->stage_in1, labels, (size_t)n_pix, &dlab))) return rc;
+  const size_t nv = (size_t)c->mesh.V * K;
+  int32_t* dvotes = votes;
+  bool host_votes = !is_device_ptr(votes);
+  if (host_votes) {
+    FB_CUDA(c, c->stage_out0.reserve(nv * 4 + 4));
+    dvotes = c->stage_out0.as<int32_t>();
+    FB_CUDA(c, cudaMemcpyAsync(dvotes, votes, nv * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  if ((rc = label_backproject_points(c, dids, dlab, n_pix, K, dvotes))) return rc;
   bool need = !is_device_ptr(cell_ids) || !is_device_ptr(labels);
   if (host_votes) {
     FB_CUDA(c, cudaMemcpyAsync(votes, dvotes, nv * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -596,6 +708,7 @@ int flyby_cells_to_points(flyby_ctx* c, const int32_t* cell_labels, int32_t dflt
   if (!cell_labels || !out) return fail(c, FLYBY_ERR_INVALID, "cells_to_points: bad arguments");
   const int32_t* dl;
   int rc;
+  if ((rc = ensure_tris_checked(c))) return rc;
   if ((rc = stage_in(c, c->stage_in0, cell_labels, (size_t)c->mesh.T, &dl))) return rc;
   StageOut<int32_t> so;
   if ((rc = so.begin(c, c->stage_out0, out, (size_t)c->mesh.V))) return rc;
@@ -704,8 +817,17 @@ int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {
     if (c->mesh.T > 0) { s.ms_sort = c->side_stream ? el(1, 3) : el(2, 3); s.ms_tree = el(3, 4); }
   }
   s.ms_render = el(5, 6);
-  s.ms_trace = el(5, 7);
-  s.ms_resolve = el(7, 6);
+  s.ms_trace = s.ms_resolve = 0.f;  // sums over the pixel slabs / view chunks of the last render
+  for (int k = 0; k < c->n_slab_ev && k < flyby_ctx::kMaxSlabEv; k++) {
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, c->slab_ev[3 * k], c->slab_ev[3 * k + 1]) == cudaSuccess &&
+        cudaEventElapsedTime(&b, c->slab_ev[3 * k + 1], c->slab_ev[3 * k + 2]) == cudaSuccess) {
+      s.ms_trace += a;
+      s.ms_resolve += b;
+    } else {
+      cudaGetLastError();
+    }
+  }
   unsigned long long h[16] = {0};
   FB_CUDA(c, cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
   if (getenv("FLYBY_DEBUG_STATS"))

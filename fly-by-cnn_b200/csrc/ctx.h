@@ -64,6 +64,14 @@ struct MeshDev {
   int32_t* n_top_dev = nullptr;  // device word: nodes in the breadth-first top block
   double centre_scale[4] = {0, 0, 0, 1};
   bool has_mesh = false, built = false;
+  bool tris_ok = false;   // every index of tris lies in [0, V): checked once per flyby_set_mesh (api.cu ensure_tris_checked)
+  // winding consistency pass (winding.cu): bytes [T], 1 = the cell was reversed to (p2,p1,p0); empty when nothing flipped
+  DevBuf flip, edge_tab, orient;
+  int64_t n_flipped = 0;
+  // per-point scalars written by the render behind the feature channels (flyby_set_point_scalars)
+  DevBuf scalars;        // float [V, n_scalars]
+  int n_scalars = 0, scalar_mode = 0;
+  float scalar_zero = 0.f;
 };
 
 }  // namespace fb
@@ -113,6 +121,10 @@ struct flyby_ctx {
   fb::DevBuf counters;  // uint64 [8]: tile counter, work counters
   // stats
   cudaEvent_t ev[8] = {nullptr};
+  // candidate search / exact resolve boundaries of every pixel slab of the last render (ms_trace / ms_resolve are sums)
+  static const int kMaxSlabEv = 32;
+  cudaEvent_t slab_ev[3 * kMaxSlabEv] = {nullptr};
+  int n_slab_ev = 0;
   flyby_stats stats;
   int count_work = 0;
   int64_t launches = 0;
@@ -163,6 +175,20 @@ inline bool is_device_ptr(const void* p) {
 }
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// stage boundaries of one pixel slab of a render: which = 0 start of the candidate search, 1 start of the exact
+// resolve, 2 end (advances to the next slab).  flyby_get_stats sums the two intervals over the slabs.
+inline int slab_mark(flyby_ctx* c, int which) {
+  const int k = c->n_slab_ev;
+  if (k < flyby_ctx::kMaxSlabEv) {
+    cudaEvent_t& e = c->slab_ev[3 * k + which];
+    if (!e && cudaEventCreate(&e) != cudaSuccess) return fail(c, FLYBY_ERR_CUDA, "cudaEventCreate failed");
+    cudaError_t err = cudaEventRecord(e, c->stream);
+    if (err != cudaSuccess) return fail(c, FLYBY_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(err));
+  }
+  if (which == 2) c->n_slab_ev = k + 1;
+  return FLYBY_OK;
+}
 
 // stage launchers (each file implements its own)
 int prep_run(flyby_ctx* c);                       // prep.cu: unit surf + normals

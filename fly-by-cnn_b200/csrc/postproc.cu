@@ -87,7 +87,9 @@ static int components(flyby_ctx* c, const int32_t* labels, int32_t label, int32_
   const Links L{m.adj_start.as<uint32_t>(), m.adj.as<int32_t>(), m.tris.as<int32_t>()};
   cc_init_kernel<<<g, 256, 0, st>>>(labels, label, V, comp, size);
   FB_LAUNCH_CHECK(c);
-  for (int round = 0; round < 64; round++) {
+  // a losing atomicMin drops a link until the next round finds it again through its edge, so the number of rounds
+  // is not bounded by log V (long thin regions need more): loop until a round joins nothing
+  for (int64_t round = 0; round <= V; round++) {
     FB_CUDA(c, cudaMemsetAsync(changed_dev, 0, sizeof(int), st));
     cc_hook_kernel<<<g, 256, 0, st>>>(L, V, comp, changed_dev);
     FB_LAUNCH_CHECK(c);

@@ -543,12 +543,13 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
     raster_init_kernel<<<(unsigned)cdiv(n_pix - clean, 256), 256, 0, st>>>(p.front + clean, p.cnt + clean, n_pix - clean);
     FB_LAUNCH_CHECK(c);
   }
+  { int rc = slab_mark(c, 0); if (rc) return rc; }
   dim3 grid((unsigned)cdiv(p.T, RT_THREADS), (unsigned)rp.n_views);
   raster_kernel<<<grid, RT_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   raster_big_kernel<<<(unsigned)c->sm_count * 8, 128, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
-  FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the candidate search and the exact resolve
+  { int rc = slab_mark(c, 1); if (rc) return rc; }  // between the candidate search and the exact resolve
   {  // the shading needs the point normals, the last-resort fallback the LBVH: both are finished on the side stream
     int rc = wait_tree(c);
     if (rc) return rc;
@@ -569,6 +570,7 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   FB_LAUNCH_CHECK(c);
   raster_resolve3_kernel<<<(unsigned)c->sm_count, 64, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
+  { int rc = slab_mark(c, 2); if (rc) return rc; }
   if (c->side_stream && c->ev_front) {
     // the next render's initialisation, off the critical path: the side stream runs it beside the upload / unit
     // surface / sort of the next mesh (or right away, when the next render follows at once)

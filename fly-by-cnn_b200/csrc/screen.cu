@@ -433,6 +433,7 @@ int screen_render(flyby_ctx* c, const RenderParams& rp) {
     return FLYBY_OK;
   };
   int rc;
+  if ((rc = slab_mark(c, 0))) return rc;
   const int variant = (rp.top_cap > 0 ? 2 : 0) | (c->count_work ? 1 : 0);
   switch (variant) {
     case 0: rc = launch(trace_kernel<false, false>); break;
@@ -441,8 +442,9 @@ int screen_render(flyby_ctx* c, const RenderParams& rp) {
     default: rc = launch(trace_kernel<true, true>); break;
   }
   if (rc) return rc;
-  FB_CUDA(c, cudaEventRecord(c->ev[7], st));  // between the two kernels (stats describe the last chunk's split)
-  return resolve_launch(c, rp, c->cand.as<int4>(), nullptr, nullptr);
+  if ((rc = slab_mark(c, 1))) return rc;  // between the two kernels
+  if ((rc = resolve_launch(c, rp, c->cand.as<int4>(), nullptr, nullptr))) return rc;
+  return slab_mark(c, 2);
 }
 
 int resolve_launch(flyby_ctx* c, const RenderParams& rp, const int4* cand, const int* cnt, const int4* cand2) {

@@ -139,12 +139,12 @@ int trace_render_perspective(flyby_ctx* c, int vb, int ve, int res, const flyby_
 // recomputed with tri_exact on the same inputs, i.e. they are the values the render used.
 __global__ void interpolate_kernel(RenderParams p, const float* __restrict__ verts, const int32_t* __restrict__ tris,
                                    const int32_t* __restrict__ cell_ids, const float* __restrict__ feats, int F,
-                                   float zero, float* __restrict__ out, int64_t n_pix) {
+                                   float zero, float* __restrict__ out, int64_t n_pix, int64_t T) {
   const int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (pix >= n_pix) return;
   const int32_t cell = cell_ids[pix];
   float* o = out + pix * F;
-  if (cell < 0) {
+  if (cell < 0 || cell >= T) {  // miss, or an id that does not belong to this mesh: never reaches a gather
     for (int f = 0; f < F; f++) o[f] = zero;
     return;
   }
@@ -180,7 +180,7 @@ int trace_interpolate(flyby_ctx* c, int vb, int ve, int res, const flyby_render_
   p.spacing = o->plane_spacing;
   p.tol2 = o->tolerance * o->tolerance;
   interpolate_kernel<<<(unsigned)cdiv(n_pix, 128), 128, 0, c->stream>>>(p, m.verts.as<float>(), m.tris.as<int32_t>(),
-                                                                          cell_ids, feats, F, zero, out, n_pix);
+                                                                          cell_ids, feats, F, zero, out, n_pix, m.T);
   FB_LAUNCH_CHECK(c);
   return FLYBY_OK;
 }
@@ -432,6 +432,11 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINB) render_kernel(const Rende
         }
       }
       write_pixel(p, (int64_t)pid, px, best_slot >= 0 ? best_cell : -1, t);
+      if (best_slot >= 0 && p.n_scal) {
+        const double w[3] = {bw0, bw1, bw2};
+        const int4 vid = p.tvid[best_slot];
+        write_hit_scalars(p, (int64_t)pid, w, vid.x, vid.y, vid.z, best_cell);
+      }
     }
     __syncwarp();
   }
@@ -446,10 +451,15 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINB) render_kernel(const Rende
   if (lane == 0 && n_hits) atomicAdd(p.counters + 3, (unsigned long long)n_hits);
 }
 
-__global__ void fill_miss_kernel(float* feat, int32_t* ids, double* tt, int64_t n_pix, int channels) {
+__global__ void fill_miss_kernel(float* feat, int32_t* ids, double* tt, int64_t n_pix, int channels, int n_scal,
+                                 float scal_zero) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_pix) return;
-  if (feat) for (int k = 0; k < channels; k++) feat[i * channels + k] = 0.f;
+  if (feat) {
+    float* o = feat + i * (channels + n_scal);
+    for (int k = 0; k < channels; k++) o[k] = 0.f;
+    for (int k = 0; k < n_scal; k++) o[channels + k] = scal_zero;
+  }
   if (ids) ids[i] = -1;
   if (tt) tt[i] = -1.0;
 }
@@ -457,7 +467,7 @@ __global__ void fill_miss_kernel(float* feat, int32_t* ids, double* tt, int64_t 
 static int g_screen = 1;  // FLYBY_NO_SCREEN=1: fused kernel, exact test on every leaf candidate (A/B, parity checks)
 int screen_render(flyby_ctx* c, const RenderParams& p);  // screen.cu: LBVH trace kernel + exact resolve kernel
 int raster_render(flyby_ctx* c, const RenderParams& p);  // raster.cu: scan-conversion passes + exact resolve kernel
-static int g_mode = 2;  // FLYBY_MODE: 2 raster (default), 1 bvh (trace + resolve), 0 fused exact LBVH kernel
+static int g_mode = 2;  // what flyby_render_opts.mode 0 means; FLYBY_MODE (A/B runs): 2 raster, 1 bvh, 0 fused
 static int g_use_top = 1;  // FLYBY_NO_SMEM_TOP=1 disables the shared-memory top (A/B measurements)
 
 // first_chunk / last_chunk: a render call may be split into view chunks (api.cu overlaps the
@@ -471,6 +481,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if (n_pix >= (int64_t)1 << 32) return fail(c, FLYBY_ERR_INVALID, "more than 2^32 rays in one render call");
   const int channels = (o->use_z && o->split_z) ? 4 : 3;
   if (first_chunk) {
+    c->n_slab_ev = 0;
     FB_CUDA(c, cudaEventRecord(c->ev[5], st));
     FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 7 * sizeof(unsigned long long), st));
     FB_CUDA(c, cudaMemsetAsync(c->counters.as<unsigned long long>() + 8, 0, 8 * sizeof(unsigned long long), st));
@@ -478,7 +489,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   }
   c->stats.n_rays += n_pix;
   if (m.T == 0) {
-    fill_miss_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(feat, ids, tt, n_pix, channels);
+    fill_miss_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(feat, ids, tt, n_pix, channels, m.n_scalars, m.scalar_zero);
     FB_LAUNCH_CHECK(c);
     if (last_chunk) FB_CUDA(c, cudaEventRecord(c->ev[6], st));
     return FLYBY_OK;
@@ -517,6 +528,16 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   p.n_tiles = (long long)p.tiles_x * p.tiles_y * nv;
   p.top_cap = g_use_top ? 1024 : 0;
   p.viewsf = c->viewsf.as<ViewF>();
+  p.scal = m.n_scalars > 0 ? m.scalars.as<float>() : nullptr;
+  p.n_scal = m.n_scalars; p.scal_mode = m.scalar_mode; p.scal_zero = m.scalar_zero;
+  p.stride = channels + m.n_scalars;
+  p.flip = m.n_flipped > 0 ? m.flip.as<uint8_t>() : nullptr;
+  // flyby_render_opts.mode: 0 default (g_mode: raster unless FLYBY_MODE says otherwise), 1 raster, 2 bvh, 3 fused
+  int mode = g_mode;
+  if (o->mode == 1) mode = 2;
+  else if (o->mode == 2) mode = 1;
+  else if (o->mode == 3) mode = 0;
+  else if (o->mode != 0) return fail(c, FLYBY_ERR_INVALID, "render: unknown mode %d", o->mode);
   FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), st));  // tile counter
   const size_t smem = (size_t)p.top_cap * sizeof(Node) + RK_WARPS * RK_QCAP * sizeof(uint32_t);
   auto launch = [&](auto kern) -> int {
@@ -535,7 +556,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   int rc;
   // the scan conversion needs a regular pixel grid with a positive pitch
   const bool grid_ok = res > 1 && o->plane_scale * o->plane_spacing > 0.0;
-  if (g_mode == 2 && grid_ok) {
+  if (mode == 2 && grid_ok) {
     // the per-pixel scratch of the scan conversion (~58 B / pixel) is sized for at most 2^26 pixels at a time:
     // long view lists are rendered in slabs of whole views, each straight into its part of the outputs
     const int64_t per_view = (int64_t)res * res;
@@ -548,16 +569,17 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
       q.view_begin = vb + v0;
       q.n_views = nv - v0 < slab ? nv - v0 : slab;
       const int64_t off = (int64_t)v0 * per_view;
-      if (feat) q.feat = feat + off * channels;
+      if (feat) q.feat = feat + off * p.stride;
       if (ids) q.ids = ids + off;
       if (tt) q.tt = tt + off;
       rc = raster_render(c, q);
     }
-  } else if (g_mode >= 1) {
+  } else if (mode >= 1) {
     if ((rc = wait_tree(c))) return rc;
     rc = screen_render(c, p);
   } else {
     if ((rc = wait_tree(c))) return rc;
+    if ((rc = slab_mark(c, 0))) return rc;
     const int variant = (g_use_top ? 2 : 0) | (c->count_work ? 1 : 0);
     switch (variant) {
       case 0: rc = launch(render_kernel<false, false>); break;
@@ -565,6 +587,8 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
       case 2: rc = launch(render_kernel<true, false>); break;
       default: rc = launch(render_kernel<true, true>); break;
     }
+    if (!rc) rc = slab_mark(c, 1);  // one kernel searches and resolves: all of it counts as the search
+    if (!rc) rc = slab_mark(c, 2);
   }
   if (rc) return rc;
   if (last_chunk) FB_CUDA(c, cudaEventRecord(c->ev[6], st));

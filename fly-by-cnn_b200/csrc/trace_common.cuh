@@ -84,6 +84,11 @@ struct RenderParams {
   long long n_tiles;
   int top_cap;                   // nodes that fit in the dynamic shared memory
   const ViewF* viewsf;           // float32 screening frame of every view
+  // per-point scalars behind the feature channels (flyby_set_point_scalars): pixel stride = channels + n_scal
+  const float* scal;             // [V, n_scal] or nullptr
+  const uint8_t* flip;           // [T] cells reversed by the consistency pass (their vertex 0 is p2), or nullptr
+  int n_scal, scal_mode, stride;
+  float scal_zero;
 };
 
 #ifndef RK_MINB
@@ -96,17 +101,43 @@ struct RenderParams {
 __device__ __forceinline__ void write_pixel(const RenderParams& p, int64_t pix, const float* px, int cell,
                                             double t) {
   if (p.feat) {
-    if (p.channels == 4) {
+    if (p.stride == 4) {
       __stcs(reinterpret_cast<float4*>(p.feat) + pix, make_float4(px[0], px[1], px[2], px[3]));
     } else {
-      float* o = p.feat + pix * 3;
+      float* o = p.feat + pix * p.stride;
       __stcs(o, px[0]);
       __stcs(o + 1, px[1]);
       __stcs(o + 2, px[2]);
+      if (p.channels == 4) __stcs(o + 3, px[3]);
+      if (cell < 0)  // background: the scalar channels get `zero` (--zero); hits write theirs in write_hit_scalars
+        for (int k = 0; k < p.n_scal; k++) __stcs(o + p.channels + k, p.scal_zero);
     }
   }
   if (p.ids) __stcs(p.ids + pix, cell);
   if (p.tt) __stcs(p.tt + pix, t);
+}
+
+// Scalar channels of a hit pixel (src/py/fly_by_features.py:385-392 concatenates them behind the image channels).
+// mode 0: the value at the cell's vertex 0 -- what the reference reads back through the point-id colour map
+// (GetPointIdColors utils.py:604-621 colours a cell with its first point; ExtractPointFeaturesClass :644-662);
+// mode 1: sum_k w_k f_k with the exact test's weights, products and sums in double, left to right
+// (fly_by_features.cxx:766-793), the expression of interpolate_kernel / orc_interpolate_features.
+__device__ __forceinline__ void write_hit_scalars(const RenderParams& p, int64_t pix, const double* w, int pid0, int pid1,
+                                                  int pid2, int cell) {
+  if (!p.n_scal || !p.feat) return;
+  float* o = p.feat + pix * p.stride + p.channels;
+  const int S = p.n_scal;
+  if (p.scal_mode == 0) {
+    const int v0 = (p.flip && p.flip[cell]) ? pid2 : pid0;  // vertex 0 of the cell as the caller numbered it
+    for (int k = 0; k < S; k++) __stcs(o + k, __ldg(p.scal + (int64_t)v0 * S + k));
+  } else {
+    for (int k = 0; k < S; k++) {
+      const double a = FB_MUL(w[0], (double)__ldg(p.scal + (int64_t)pid0 * S + k));
+      const double b = FB_MUL(w[1], (double)__ldg(p.scal + (int64_t)pid1 * S + k));
+      const double e = FB_MUL(w[2], (double)__ldg(p.scal + (int64_t)pid2 * S + k));
+      __stcs(o + k, (float)FB_ADD(FB_ADD(a, b), e));
+    }
+  }
 }
 
 // conservative float32 test of a ray against the mesh bounds (same maths as the
@@ -185,6 +216,7 @@ __device__ __forceinline__ void shade_and_write(const RenderParams& p, int64_t p
     shade(r.o, x, w, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px);
   }
   write_pixel(p, pix_id, px, cell, t);
+  write_hit_scalars(p, pix_id, w, pid0, pid1, pid2, cell);
 }
 
 // Rare path, kept out of line so that it does not inflate the registers of resolve_kernel:

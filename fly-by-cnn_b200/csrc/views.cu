@@ -23,7 +23,7 @@ __constant__ int c_ico_faces[20][3] = {
     {0, 5, 4},  {0, 4, 3},  {0, 3, 2},  {0, 2, 1},   {0, 1, 5},  {5, 1, 9},  {5, 9, 10},
     {5, 10, 4}, {4, 10, 6}, {4, 6, 3},  {3, 6, 7},   {3, 7, 2},  {2, 7, 8},  {2, 8, 1},
     {1, 8, 9},  {9, 8, 11}, {9, 11, 10}, {10, 11, 6}, {6, 11, 7}, {7, 11, 8}};
-#define FB_ICO_SOLID_SCALE (1.0 / 0.58285)
+#define FB_ICO_SOLID_SCALE (1.0 / 0.58778524999243)
 
 __device__ __forceinline__ bool face_has(int f, int v) {
   return c_ico_faces[f][0] == v || c_ico_faces[f][1] == v || c_ico_faces[f][2] == v;
@@ -133,24 +133,33 @@ int views_icosahedron(flyby_ctx* c, int L, double radius, int dedupe) {
   return FLYBY_OK;
 }
 
-__global__ void spiral_kernel(int n, double turns, double radius, float* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double pi = 3.14159265358979323846;
-  double c = FB_MUL(2.0, turns);
-  double angle = FB_DIV(FB_MUL((double)i, pi), (double)n);
-  double sa = sin(angle), ca = cos(angle);
-  double sc = sin(FB_MUL(c, angle)), cc = cos(FB_MUL(c, angle));
-  out[3 * i + 0] = (float)FB_MUL(FB_MUL(radius, sa), cc);
-  out[3 * i + 1] = (float)FB_MUL(FB_MUL(radius, sa), sc);
-  out[3 * i + 2] = (float)FB_MUL(radius, ca);
-}
-
+// CreateSpiral (utils.py:52-89) calls libm's sin / cos from Python; device sin / cos may differ from
+// libm in the last bit, and one float32 ulp of a viewpoint moves every plane point of that view.  The N
+// points (64 in the reference's callers) are therefore computed on the host with libm, in the
+// reference's expression order, and uploaded: bit-equal to the reference (tests/golden/ref_views.npz).
 int views_spiral(flyby_ctx* c, int n, double turns, double radius) {
   if (n < 1) return fail(c, FLYBY_ERR_INVALID, "spiral needs at least one sample");
   FB_CUDA(c, c->view_pts.reserve(sizeof(float) * 3 * (size_t)n));
-  spiral_kernel<<<(unsigned)cdiv(n, 128), 128, 0, c->stream>>>(n, turns, radius, c->view_pts.as<float>());
-  FB_LAUNCH_CHECK(c);
+  const double pi = 3.141592653589793;  // math.pi
+  const double cturn = 2.0 * turns;
+  float* h = (float*)malloc(sizeof(float) * 3 * (size_t)n);
+  if (!h) return fail(c, FLYBY_ERR_INVALID, "spiral: out of host memory");
+  for (int i = 0; i < n; i++) {
+    volatile double angle = ((double)i * pi) / (double)n;
+    volatile double sa = sin(angle), ca = cos(angle);
+    volatile double ta = cturn * angle;
+    volatile double x = radius * sa, y = radius * sa;
+    x = x * cos(ta);
+    y = y * sin(ta);
+    volatile double z = radius * ca;
+    h[3 * i + 0] = (float)x;
+    h[3 * i + 1] = (float)y;
+    h[3 * i + 2] = (float)z;
+  }
+  cudaError_t e = cudaMemcpyAsync(c->view_pts.p, h, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  free(h);
+  FB_CUDA(c, e);
   c->n_views = n;
   c->radius = radius;
   return FLYBY_OK;

@@ -11,24 +11,31 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libflyby_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
 
 class FlyByError(RuntimeError):
-    pass
+    """status = the flyby_status the C call returned (0 when the error was raised by this layer)."""
+
+    def __init__(self, msg, status=0):
+        RuntimeError.__init__(self, msg)
+        self.status = status
+
+
+ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED = 1, 2, 3, 4
 
 
 class NormOpts(C.Structure):
     _fields_ = [("centre_mode", C.c_int32), ("scale_mode", C.c_int32), ("has_translate", C.c_int32),
                 ("has_scale", C.c_int32), ("translate", C.c_double * 3), ("scale_factor", C.c_double),
-                ("skip", C.c_int32), ("reserved", C.c_int32)]
+                ("skip", C.c_int32), ("consistency", C.c_int32)]
 
 
 class RenderOpts(C.Structure):
     _fields_ = [("use_z", C.c_int32), ("split_z", C.c_int32), ("normal_encoding", C.c_int32),
-                ("reserved", C.c_int32), ("plane_scale", C.c_double), ("plane_spacing", C.c_double),
+                ("mode", C.c_int32), ("plane_scale", C.c_double), ("plane_spacing", C.c_double),
                 ("z_scale", C.c_double), ("tolerance", C.c_double)]
 
 
@@ -49,10 +56,13 @@ SYMBOLS = [
     "flyby_nccl_init", "flyby_votes_allreduce", "flyby_get_stats", "flyby_set_count_work",
     "flyby_launch_count", "flyby_labels_remove_islands", "flyby_labels_connectivity", "flyby_labels_erode",
     "flyby_labels_dilate", "flyby_labels_relabel", "flyby_interpolate_features", "flyby_render_perspective",
-    "flyby_render_async",
+    "flyby_render_async", "flyby_set_point_scalars", "flyby_get_winding", "flyby_point_ids",
+    "flyby_backproject_points",
 ]
 
 NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2, "uint8": 3}
+RENDER_MODES = {"default": 0, "raster": 1, "bvh": 2, "fused": 3}
+CONSISTENCY = {"check": 0, "fix": 1, "off": 2}
 
 
 def load():
@@ -117,6 +127,7 @@ class Context:
         self.device = int(device)
         self.n_verts = 0
         self.n_tris = 0
+        self.n_scalars = 0
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -132,14 +143,17 @@ class Context:
     def _ck(self, rc):
         if rc != 0:
             msg = self._lib.flyby_last_error(self._h)
-            raise FlyByError("flyby status %d: %s" % (rc, msg.decode() if msg else ""))
+            raise FlyByError("flyby status %d: %s" % (rc, msg.decode() if msg else ""), status=rc)
 
     def synchronize(self):
         self._ck(self._lib.flyby_synchronize(self._h))
 
     # ---- mesh ---------------------------------------------------------------
     def set_mesh(self, verts, tris, centre_mode=0, scale_mode=0, translate=None, scale_factor=None,
-                 skip_normalise=False):
+                 skip_normalise=False, consistency="check"):
+        """consistency: what vtkPolyDataNormals' consistency pass means for this mesh -- "check" (build() raises
+        FlyByError(status=ERR_UNSUPPORTED) if cells are inconsistently wound), "fix" (reverse cells as VTK does),
+        "off" (cells as given)."""
         _check_dtype(verts, np.float32, "verts")
         _check_dtype(tris, np.int32, "tris")
         V = int(verts.shape[0])
@@ -154,12 +168,37 @@ class Context:
             o.has_scale = 1
             o.scale_factor = float(scale_factor)
         o.skip = 1 if skip_normalise else 0
+        o.consistency = CONSISTENCY[consistency] if isinstance(consistency, str) else int(consistency)
+        self.n_scalars = 0
         self._ck(self._lib.flyby_set_mesh(self._h, _ptr(verts), C.c_int64(V), _ptr(tris), C.c_int64(T),
                                           C.byref(o)))
         self.n_verts, self.n_tris = V, T
 
     def build(self):
         self._ck(self._lib.flyby_build(self._h))
+
+    def set_point_scalars(self, feats, mode="vertex0", zero=0.0):
+        """Per-point scalars [V,S] that render() writes behind the feature channels (None / S = 0 removes them)."""
+        if feats is None:
+            self._ck(self._lib.flyby_set_point_scalars(self._h, None, C.c_int(0), C.c_int(0), C.c_float(0.0)))
+            self.n_scalars = 0
+            return
+        _check_dtype(feats, np.float32, "feats")
+        S = int(feats.shape[1]) if len(feats.shape) > 1 else 1
+        if int(feats.shape[0]) != self.n_verts:
+            raise FlyByError("point scalars need one row per mesh point (%d), got %d" % (self.n_verts, int(feats.shape[0])))
+        m = {"vertex0": 0, "barycentric": 1}[mode] if isinstance(mode, str) else int(mode)
+        self._ck(self._lib.flyby_set_point_scalars(self._h, _ptr(feats), C.c_int(S), C.c_int(m), C.c_float(zero)))
+        if isinstance(feats, np.ndarray):
+            self.synchronize()      # the copy from (possibly pinned) host memory is asynchronous
+        self.n_scalars = S
+
+    def get_winding(self):
+        """(number of cells the consistency pass reversed, uint8 [T] flags)."""
+        n = C.c_int64(0)
+        flags = np.zeros(self.n_tris, np.uint8)
+        self._ck(self._lib.flyby_get_winding(self._h, C.byref(n), _ptr(flags)))
+        return int(n.value), flags
 
     def get_mesh(self):
         """(unit_verts [V,3] f32, normals [V,3] f32, centre [3], scale) as numpy."""
@@ -208,8 +247,10 @@ class Context:
     # ---- rendering ----------------------------------------------------------
     @staticmethod
     def render_opts(use_z=1, split_z=1, normal_encoding="unit01", plane_scale=1.0, plane_spacing=1.0,
-                    z_scale=1.0, tolerance=1e-10):
+                    z_scale=1.0, tolerance=1e-10, mode="default"):
+        """mode: "default" | "raster" | "bvh" | "fused" -- the search engine; results are bit-identical."""
         o = RenderOpts()
+        o.mode = RENDER_MODES[mode] if isinstance(mode, str) else int(mode)
         o.use_z, o.split_z = int(bool(use_z)), int(bool(split_z))
         o.normal_encoding = NORMAL_ENCODINGS[normal_encoding] if isinstance(normal_encoding, str) \
             else int(normal_encoding)
@@ -220,6 +261,10 @@ class Context:
     @staticmethod
     def channels(opts):
         return 4 if (opts.use_z and opts.split_z) else 3
+
+    def out_channels(self, opts):
+        """floats per pixel of flyby_render's feature output: image channels + point scalars."""
+        return self.channels(opts) + self.n_scalars
 
     def generate_rays(self, res, opts, view_begin=0, view_end=None):
         ve = self.num_views() if view_end is None else view_end
@@ -244,7 +289,7 @@ class Context:
         """Render to new numpy arrays: (features [n,res,res,C], cell_ids [n,res,res][, t])."""
         ve = self.num_views() if view_end is None else view_end
         n = ve - view_begin
-        feat = np.empty((n, res, res, self.channels(opts)), np.float32)
+        feat = np.empty((n, res, res, self.out_channels(opts)), np.float32)
         ids = np.empty((n, res, res), np.int32)
         tt = np.empty((n, res, res), np.float64) if want_t else None
         self.render_into(res, opts, feat, ids, tt, view_begin, ve)
@@ -289,6 +334,26 @@ class Context:
         self._ck(self._lib.flyby_point_features(self._h, _ptr(cell_ids), C.c_int64(n_pix), _ptr(feats),
                                                 C.c_int(F), C.c_float(zero), C.c_int(int(mode)), _ptr(out)))
         return out
+
+    def point_ids(self, cell_ids, out=None):
+        """Vertex 0 of every hit cell (-1 = background): the decoded point-id map of GetPointIdMapActor."""
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        if out is None:
+            out = np.empty(tuple(cell_ids.shape), np.int32)
+        _check_dtype(out, np.int32, "out")
+        self._ck(self._lib.flyby_point_ids(self._h, _ptr(cell_ids), C.c_int64(int(np.prod(cell_ids.shape))), _ptr(out)))
+        return out
+
+    def backproject_points(self, cell_ids, labels, n_classes, votes=None):
+        """Per-point votes [V,K]: every hit pixel votes for vertex 0 of its cell (predict_v3.py:59-69)."""
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        _check_dtype(labels, np.int32, "labels")
+        if votes is None:
+            votes = np.zeros((self.n_verts, n_classes), np.int32)
+        _check_dtype(votes, np.int32, "votes")
+        self._ck(self._lib.flyby_backproject_points(self._h, _ptr(cell_ids), _ptr(labels),
+                                                    C.c_int64(int(np.prod(cell_ids.shape))), C.c_int(n_classes), _ptr(votes)))
+        return votes
 
     def interpolate_features(self, res, opts, cell_ids, feats, zero=0.0, out=None, view_begin=0, view_end=None):
         """Barycentric lookup of per-point features at the hits of render() (same res / opts / view range)."""

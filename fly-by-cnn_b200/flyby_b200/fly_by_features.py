@@ -59,7 +59,19 @@ class FlyByGenerator():
         self.actors = []
         self.ctx = Context(device)
         self.last_cell_ids = None  # int32 [V, res, res] hit cell ids of the last getFlyBy (-1 = background)
-        self._built_for = None
+        self._built_for = None     # (points, polys) the context currently holds a build of
+        self._views_for = None
+        self._scalars = None       # (float32 [V,S], mode, zero): written by the render behind the image channels
+        # vtkPolyDataNormals runs its consistency pass in the reference (utils.py:493-501): "fix" reverses
+        # inconsistently wound cells as VTK does; costs nothing on a consistent mesh
+        self.consistency = "fix"
+
+    def setPointScalars(self, feats, mode="vertex0", zero=0.0):
+        """Per-point arrays [V,S] that getFlyBy appends to every pixel in the same render pass (the reference
+        renders a second, point-id image and looks the values up in Python: fly_by_features.py:334-402,
+        utils.py:639-684).  mode "vertex0" = the reference's lookup, "barycentric" = the C++ tool's
+        interpolation (fly_by_features.cxx:766-793).  None removes them."""
+        self._scalars = None if feats is None else (np.ascontiguousarray(feats, np.float32).reshape(len(feats), -1), mode, float(zero))
 
     # --- reference API ---------------------------------------------------------
     def removeActor(self, actor):
@@ -100,11 +112,13 @@ class FlyByGenerator():
                                       "belong to the OpenGL camera path")
         points, polys, kind = self._mesh()
         ctx = self.ctx
-        # meshes handed to the generator are already normalised by GetUnitSurf (as in the reference);
-        # the LBVH build takes well under a millisecond, so it is simply redone per call
-        ctx.set_mesh(np.ascontiguousarray(points, np.float32), np.ascontiguousarray(polys, np.int32),
-                     skip_normalise=True)
-        ctx.build()
+        # meshes handed to the generator are already normalised by GetUnitSurf (as in the reference); the upload and
+        # the build are skipped when the context still holds this very mesh (same arrays, e.g. n_rotations of views)
+        if self._built_for is None or self._built_for[0] is not points or self._built_for[1] is not polys:
+            ctx.set_mesh(np.ascontiguousarray(points, np.float32), np.ascontiguousarray(polys, np.int32),
+                         skip_normalise=True, consistency=self.consistency)
+            ctx.build()
+            self._built_for = (points, polys)
         if sphere_points is None:
             if self.sphere is None:
                 raise RuntimeError("getFlyBy: no viewpoints")
@@ -113,7 +127,6 @@ class FlyByGenerator():
         else:
             sphere_points = np.asarray(sphere_points, dtype=np.float32).reshape(-1, 3)
             radius = float(np.linalg.norm(sphere_points[0]))
-        print("number of points : ", len(sphere_points))
         ctx.views_custom(sphere_points, radius)
         res = self.resolution
         if self.projection == "perspective":
@@ -133,6 +146,10 @@ class FlyByGenerator():
             z_scale = 1.0 / z_far  # fly_by_features.py:138-146
         opts = ctx.render_opts(use_z=self.use_z, split_z=self.split_z, normal_encoding=self.normal_encoding,
                                plane_scale=self.plane_scale, plane_spacing=self.plane_spacing, z_scale=z_scale)
+        if self._scalars is not None:
+            ctx.set_point_scalars(self._scalars[0], mode=self._scalars[1], zero=self._scalars[2])
+        else:
+            ctx.set_point_scalars(None)
         feat, ids = ctx.render(res, opts)
         self.last_cell_ids = ids
         return feat
@@ -233,18 +250,26 @@ def _find_surfaces(args):
     return filenames
 
 
-def _write(out_np, path, concatenate, suffix=""):
-    """reference src/py/fly_by_features.py:404-424"""
+def _write(out_np, path, concatenate, suffix="", cxx_spacing=None):
+    """reference src/py/fly_by_features.py:404-424.  cxx_spacing = planeSpacing selects the C++ tool's output
+    contract instead (src/app/fly_by_features.cxx:1047-1110): itk::Image<itk::RGBPixel<double>, 3> of size
+    (res, res, views) with spacing (planeSpacing, planeSpacing, 1) -- `type: double`, component kind RGB-color."""
+    def image(a):
+        if cxx_spacing is None:
+            return utils.GetImage(a)
+        from . import nrrd  # values are the float32 results widened to double (the C++ tool computes them in double)
+        return nrrd.Image(np.asarray(a, np.float64), spacing=[float(cxx_spacing)] * 2 + [1.0] * (np.ndim(a) - 3),
+                          kind="RGB-color")
     if not concatenate:
         if not os.path.exists(path):
             os.makedirs(path)
         for i in range(out_np.shape[0]):
             name = os.path.join(path, str(i) + suffix + ".nrrd")
             print("Writing:", name)
-            utils.WriteImage(utils.GetImage(out_np[i]), name)
+            utils.WriteImage(image(out_np[i]), name)
     else:
         print("Writing:", path)
-        utils.WriteImage(utils.GetImage(out_np), path)
+        utils.WriteImage(image(out_np), path)
 
 
 def cxx_scale_factor(args):
@@ -287,8 +312,14 @@ def main(args):
         if getattr(args, name, None):
             raise SystemExit("--%s is not supported by flyby_b200 (needs VTK tube filters / colour maps / Keras / "
                              "an OpenGL window); see DESIGN.md" % name)
-    if getattr(args, "flyByCompose", None) is not None:  # the C++ spelling of --concatenate (fly_by_features.cxx:1049)
+    cxx_spacing = None
+    if getattr(args, "flyByCompose", None) is not None:
+        # the C++ tool's spelling: its output contract applies (fly_by_features.cxx:802-807,1047-1110) -- one RGB image
+        # of doubles per view, pixel = (n * 0.5 + 0.5) * depth, stacked into a volume when flyByCompose is 1
         args.concatenate = 1 if args.flyByCompose else 0
+        args.use_z, args.split_z, args.rescale_features = 1, 0, 0
+        args.normal_encoding = "unit01"
+        cxx_spacing = getattr(args, "plane_spacing", 1.0)
     filenames = _find_surfaces(args)
     device = getattr(args, "device", 0)
     if args.subdivision:
@@ -297,6 +328,8 @@ def main(args):
         sphere = utils.CreateSpiral(args.radius, args.spiral, args.turns, device=device)
     kw = dict(plane_scale=getattr(args, "plane_scale", 1.0), plane_spacing=getattr(args, "plane_spacing", 1.0),
               normal_encoding=getattr(args, "normal_encoding", None), device=device)
+    if cxx_spacing is not None:
+        kw["z_far"] = 1.0  # the C++ tool multiplies by the depth itself, not by depth / z_far
     flyby = FlyByGenerator(sphere, args.resolution, use_z=args.use_z, split_z=args.split_z,
                            rescale_features=args.rescale_features, **kw)
     flyby_features = None
@@ -321,11 +354,20 @@ def main(args):
                 print("Saving rotation:", out_filename)
                 np.save(out_filename, utils.GetTransform(rotationAngle, rotationVector).ravel())
         flyby.addActor(utils.GetNormalsActor(surf))
+        # --point_features ... --point_features_concat 1: the arrays ride along in the render (vertex-0 lookup, the
+        # reference's semantics), instead of a second id-map render + RGB decode + host concatenate
+        fused_names = []
+        if args.point_features and args.point_features_concat and args.extract_components is None:
+            fused_names = list(args.point_features)
+            flyby.setPointScalars(np.concatenate([utils.PointFeatureArray(surf, n) for n in fused_names], axis=1),
+                                  mode="vertex0", zero=args.zero)
+        else:
+            flyby.setPointScalars(None)
         out_np = flyby.getFlyBy()
         if args.extract_components is not None:
             out_np = out_np[:, :, :, args.extract_components[0]:args.extract_components[1]]
             print(out_np.shape)
-        if flyby_features is not None:
+        if flyby_features is not None and (args.out_point_id or not fused_names):
             flyby_features.addActor(utils.GetPointIdMapActor(surf))
             out_point_ids_rgb_np = flyby_features.getFlyBy()
             if args.out_point_id:
@@ -334,7 +376,7 @@ def main(args):
                 else:
                     name = os.path.splitext(fobj["out"])
                     _write(out_point_ids_rgb_np, name[0] + "_point_id_map" + name[1], 1)
-            if args.point_features:
+            if args.point_features and not fused_names:
                 for point_features_name in args.point_features:
                     print("Extracting:", point_features_name)
                     out_features_np = utils.ExtractPointFeatures(surf, out_point_ids_rgb_np, point_features_name,
@@ -347,7 +389,7 @@ def main(args):
                         name = os.path.splitext(fobj["out"])
                         _write(out_features_np, name[0] + "_" + point_features_name + name[1], 1)
             flyby_features.removeActors()
-        _write(out_np, fobj["out"], args.concatenate)
+        _write(out_np, fobj["out"], args.concatenate, cxx_spacing=cxx_spacing)
         flyby.removeActors()
 
 

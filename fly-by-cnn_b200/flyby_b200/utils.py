@@ -103,8 +103,12 @@ def ReadImage(fName):
 
 
 # --------------------------------------------------------------------------- viewpoints
-def CreateIcosahedron(radius, sl=1, dedupe=0, device=0):
-    """reference src/py/utils.py:36-50 (+ LinearSubdivisionFilter.py:42-67, utils.py:22-31)."""
+def CreateIcosahedron(radius, sl=1, dedupe=1, device=0):
+    """reference src/py/utils.py:36-50 (+ LinearSubdivisionFilter.py:42-67, utils.py:22-31).
+
+    dedupe=1 (default) reproduces the reference's point list bit for bit, including the duplicate viewpoints its
+    float-equality point locator lets through (94 instead of 92 points at sl=3; tests/golden/ref_views.npz was
+    computed by the reference's own LinearSubdivisionFilter).  dedupe=0 is the exact lattice (10 sl^2 + 2)."""
     if sl < 1:
         raise ValueError("number of subdivisions must be >= 1")
     ctx = default_context(device)
@@ -241,19 +245,25 @@ def DecodeIdsRGB(rgb):
     return (rgb[..., 2] * 255 * 255 + rgb[..., 1] * 255 + rgb[..., 0] - 1).astype(np.int32)
 
 
-def ExtractPointFeatures(surf, point_ids_rgb, point_features_name, zero=0, use_multi=True, device=0):
-    """reference src/py/utils.py:664-684: per pixel, the named point-data array (or the coordinates for
-    "coords"/"points") at the point id coded in the id map; ``zero`` where nothing was hit.
-    ``point_ids_rgb`` is the uint8 RGB map ([..., 3]); an int32 array of point ids ([...]) is accepted too."""
-    a = np.asarray(point_ids_rgb)
-    ids = DecodeIdsRGB(a) if (a.ndim >= 2 and a.shape[-1] == 3 and a.dtype != np.int32) else a.astype(np.int32)
+def PointFeatureArray(surf, point_features_name):
+    """float32 [V, n_components] of a named point-data array, or the coordinates for "coords" / "points"
+    (reference src/py/utils.py:668-675)."""
     if point_features_name in ("coords", "points"):
         feats = np.ascontiguousarray(surf.points, dtype=np.float32)
     else:
         if point_features_name not in surf.point_data:
             raise KeyError("point data array %r not found" % point_features_name)
         feats = np.ascontiguousarray(surf.point_data[point_features_name], dtype=np.float32)
-    feats = feats.reshape(len(surf.points), -1)
+    return feats.reshape(len(surf.points), -1)
+
+
+def ExtractPointFeatures(surf, point_ids_rgb, point_features_name, zero=0, use_multi=True, device=0):
+    """reference src/py/utils.py:664-684: per pixel, the named point-data array (or the coordinates for
+    "coords"/"points") at the point id coded in the id map; ``zero`` where nothing was hit.
+    ``point_ids_rgb`` is the uint8 RGB map ([..., 3]); an int32 array of point ids ([...]) is accepted too."""
+    a = np.asarray(point_ids_rgb)
+    ids = DecodeIdsRGB(a) if (a.ndim >= 2 and a.shape[-1] == 3 and a.dtype != np.int32) else a.astype(np.int32)
+    feats = PointFeatureArray(surf, point_features_name)
     ctx = default_context(device)
     ctx.set_mesh(np.ascontiguousarray(surf.points, np.float32), np.ascontiguousarray(surf.polys, np.int32),
                  skip_normalise=True)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FLYBY_ABI_VERSION 1
+#define FLYBY_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FLYBY_API __attribute__((visibility("default")))
@@ -63,7 +63,12 @@ typedef struct {
   double translate[3];
   double scale_factor;
   int32_t skip;          /* 1 = mesh is already normalised, use the points as given */
-  int32_t reserved;
+  int32_t consistency;   /* winding consistency pass of vtkPolyDataNormals (utils.py:493-501, cxx:472-478):
+                            0 check: flyby_build fails with FLYBY_ERR_UNSUPPORTED when two cells traverse a shared
+                              edge in the same direction (VTK would reverse cells; nothing is reordered silently);
+                            1 fix:   reproduce VTK -- every edge-connected component is oriented like its lowest
+                              cell id, reversed cells become (p2,p1,p0) as vtkPolyData::ReverseCell leaves them;
+                            2 off:   use the cells as given (ConsistencyOff) */
 } flyby_norm_opts;
 
 /* Render options: src/py/fly_by_features.py:124-150 (channel assembly) and
@@ -73,7 +78,11 @@ typedef struct {
   int32_t split_z;         /* --split_z */
   int32_t normal_encoding; /* 0 n*0.5+0.5 (cxx:802-804), 1 *255 (8-bit raster range), 2 signed n (--rescale_features),
                               3 round(255 (n*0.5+0.5)) clamped to 0..255 (the uint8 an RGB read-back returns) */
-  int32_t reserved;
+  int32_t mode;            /* search engine of flyby_render; results are identical bit for bit:
+                              0 default (= 1 unless the FLYBY_MODE environment variable names another, for A/B runs),
+                              1 raster: triangle-centric scan conversion + exact resolve,
+                              2 bvh:    warp-cooperative float32 LBVH packet traversal + exact resolve,
+                              3 fused:  warp-cooperative stackless LBVH traversal, exact test at the leaves */
   double plane_scale;      /* planeScaleFactor, default 1.0 */
   double plane_spacing;    /* planeSpacing, default 1.0 */
   double z_scale;          /* depth multiplier (1/z_far when rescaling), default 1.0 */
@@ -91,7 +100,8 @@ typedef struct {
   int32_t reserved;
   int64_t n_rays, n_hits;
   int64_t nodes_visited, tris_tested; /* filled only by flyby_render with count_work=1 */
-  float ms_trace, ms_resolve;         /* the two kernels of ms_render: float32 trace, exact resolve */
+  float ms_trace, ms_resolve;         /* the two stages of ms_render (candidate search, exact resolve), summed
+                                         over the pixel slabs of the render */
 } flyby_stats;
 
 /* ---- lifetime ---------------------------------------------------------- */
@@ -111,6 +121,20 @@ FLYBY_API int flyby_synchronize(flyby_ctx* ctx);
 FLYBY_API int flyby_set_mesh(flyby_ctx* ctx, const float* verts, int64_t n_verts, const int32_t* tris,
                    int64_t n_tris, const flyby_norm_opts* opts);
 FLYBY_API int flyby_build(flyby_ctx* ctx);
+/* The source buffers of flyby_set_mesh / flyby_set_point_scalars / flyby_views_custom may be pinned host memory,
+ * in which case the copy is asynchronous: keep them valid and unmodified until flyby_build (which synchronises
+ * once, for the index validation) or flyby_synchronize has returned. */
+/* Per-point scalars that flyby_render writes behind the C feature channels: out_features becomes
+ * [views, res, res, C + n_scalars] -- `--point_features <name> --point_features_concat 1` of
+ * src/py/fly_by_features.py:334-402 in one pass, without the RGB id-map round trip (utils.py:604-684).
+ * feats float32 [V, n_scalars] (host or device; copied).  mode 0: the value at the hit cell's vertex 0, which is
+ * what ExtractPointFeaturesClass returns through GetPointIdColors (utils.py:604-621,644-662); mode 1: barycentric
+ * interpolation with the exact test's weights, as fly_by_features.cxx:766-793 interpolates its normals.
+ * Miss pixels get `zero` (--zero).  n_scalars = 0 removes them; flyby_set_mesh removes them too.  Call after
+ * flyby_set_mesh.  Only the orthographic render (flyby_render / flyby_render_async) writes them. */
+FLYBY_API int flyby_set_point_scalars(flyby_ctx* ctx, const float* feats, int n_scalars, int mode, float zero);
+/* cells reversed by the consistency pass (consistency = 1), 0 otherwise; flipped uint8 [T] optional */
+FLYBY_API int flyby_get_winding(flyby_ctx* ctx, int64_t* n_flipped, uint8_t* flipped);
 /* Read back what the build produced (parity checks): unit-surf points [V,3],
  * point normals [V,3], centre_scale[4] = centre xyz + scale.  Any may be NULL. */
 FLYBY_API int flyby_get_mesh(flyby_ctx* ctx, float* unit_verts, float* normals, double* centre_scale);
@@ -187,11 +211,20 @@ FLYBY_API int flyby_interpolate_features(flyby_ctx* ctx, int view_begin, int vie
 FLYBY_API int flyby_point_features(flyby_ctx* ctx, const int32_t* cell_ids, int64_t n_pix, const float* feats,
                          int n_feat, float zero, int mode, float* out);
 
+/* The decoded GetPointIdMapActor image (utils.py:604-637, predict_v3.py:34-41,63-67): point id of the hit
+ * cell's vertex 0 per pixel, -1 for a miss / out-of-range cell id.  int32 in, int32 out, [n_pix]. */
+FLYBY_API int flyby_point_ids(flyby_ctx* ctx, const int32_t* cell_ids, int64_t n_pix, int32_t* out_point_ids);
+
 /* ---- universal-labeling back-projection --------------------------------- */
 /* dental_model_seg.py:192-199, predict_v3.py:59-80, predict.py:154-169.
  * votes int32 [n_cells,K] is ACCUMULATED into (caller zeroes it). */
 FLYBY_API int flyby_backproject(flyby_ctx* ctx, const int32_t* cell_ids, const int32_t* labels,
                       int64_t n_pix, int n_classes, int32_t* votes);
+/* Per-POINT votes of predict_v3.py:59-69 and predict.py:121-157: every hit pixel votes for the vertex 0 of its
+ * cell (the point the RGB id map encodes).  votes int32 [V,K], accumulated into.  A miss never votes (the
+ * reference's predict_v3 loop lets id -1 index the last row). */
+FLYBY_API int flyby_backproject_points(flyby_ctx* ctx, const int32_t* cell_ids, const int32_t* labels,
+                             int64_t n_pix, int n_classes, int32_t* votes);
 /* Soft votes: probs float32 [n_pix,K] accumulated as round(p * 2^20) into
  * int64 votes_fx [n_cells,K] (integer atomics -> order independent). */
 FLYBY_API int flyby_backproject_soft(flyby_ctx* ctx, const int32_t* cell_ids, const float* probs,

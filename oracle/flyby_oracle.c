@@ -5,15 +5,24 @@
  * include, link or call this file.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs use it, as the checker.
  *
- * PARITY UNPINNED: the arithmetic of this path lives in VTK (vtk==9.2.2,
+ * PARITY: PARTLY PINNED.  Everything the reference computes in its own Python is
+ * pinned: tests/golden/ref_*.npz hold vectors produced by importing
+ * /root/reference/src/py unmodified (tests/golden/make_ref_golden.py, container-only
+ * vtk stand-in tests/refshim) and tests/test_ref_golden.py holds this file to them bit
+ * for bit -- O1 unit surface (ScaleSurf), O3 icosahedron viewpoints incl. the
+ * float-equality duplicates (LinearSubdivisionFilter + normalize_points), O4 spiral,
+ * O5 plane basis / segments (python twin predict.py:86-126), the point-id codec and
+ * feature lookup, O9 votes / argmax / cell->point, and post_process.py (postproc_oracle.c).
+ * PARITY UNPINNED for the arithmetic that lives inside VTK (vtk==9.2.2,
  * reference src/py/challenge-teeth/flyby.yml:93; C++ tool built on VTK-9.0.1,
  * src/app/README.md:22), which is not vendored under /root/reference and is
- * not installable here.  The reference ships no golden vectors or tests for
- * this path.  The VTK calls are therefore restated from VTK 9's published
- * algorithms (vtkTriangle::IntersectWithLine, vtkPlane::IntersectWithLine,
- * vtkTriangle::EvaluatePosition, vtkPlaneSource, vtkPolyDataNormals,
- * vtkPlatonicSolidSource, vtkCellLocator) and anchored on the reference's own
- * call sites, cited per function below (paths relative to /root/reference).
+ * not installable here: O2 vtkPolyDataNormals (incl. its consistency pass), the
+ * float32 storage of vtkPlaneSource, O6 vtkCellLocator / vtkTriangle::IntersectWithLine /
+ * vtkPlane::IntersectWithLine / vtkTriangle::EvaluatePosition, O7 shading on those
+ * weights, and the constants of vtkPlatonicSolidSource.  Those are restated from VTK 9's
+ * published algorithms and anchored on the reference's own call sites, cited per
+ * function below (paths relative to /root/reference); oracle/pin_vtk.py is their pin
+ * for a machine that has VTK.  The reference ships no golden vectors or tests of its own.
  *
  * Arithmetic: double on float32 inputs, exactly as VTK sees float vtkPoints.
  * Build with -ffp-contract=off so no FMA contraction changes a result.
@@ -156,6 +165,83 @@ ORC_API void orc_point_normals(const float* verts, int64_t V, const int32_t* tri
 }
 
 /* ------------------------------------------------------------------ */
+/* O2b consistency pass of vtkPolyDataNormals (ConsistencyOn, VTK's      */
+/*   default: src/py/utils.py:493-501, src/app/fly_by_features.cxx:472-478) */
+/* vtkPolyDataNormals::RequestData / TraverseAndOrder restated: cells are visited in */
+/* waves from every still unvisited cell in ascending id; for edge (p1,p2) of the     */
+/* current cell (its CURRENT point order) a not yet visited neighbour must contain    */
+/* ... p2, p1 ... in that cyclic order, else vtkPolyData::ReverseCell makes it        */
+/* (p2,p1,p0).  Deviation shared with the product: edges used by three or more cells  */
+/* are not crossed (NonManifoldTraversal off).  tris is edited in place; flipped[T]   */
+/* (optional) gets 1 for reversed cells.  Returns the number of reversed cells, -1 if */
+/* some component has no consistent orientation (an already visited neighbour         */
+/* disagrees).                                                                        */
+/* ------------------------------------------------------------------ */
+ORC_API int64_t orc_orient_cells(int32_t* tris, int64_t T, int64_t V, uint8_t* flipped) {
+  /* point -> cells links, ascending cell id (vtkCellLinks::BuildLinks) */
+  int64_t* start = (int64_t*)calloc((size_t)V + 2, sizeof(int64_t));
+  for (int64_t i = 0; i < 3 * T; i++) start[tris[i] + 1]++;
+  for (int64_t v = 0; v < V; v++) start[v + 1] += start[v];
+  int32_t* links = (int32_t*)malloc(sizeof(int32_t) * (size_t)(3 * T > 0 ? 3 * T : 1));
+  int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * (size_t)(V + 1));
+  memcpy(fill, start, sizeof(int64_t) * (size_t)(V + 1));
+  for (int64_t c = 0; c < T; c++)
+    for (int j = 0; j < 3; j++) {
+      int32_t v = tris[3 * c + j];
+      /* a cell that lists a point twice appears once in its links */
+      if ((j == 1 && v == tris[3 * c]) || (j == 2 && (v == tris[3 * c] || v == tris[3 * c + 1]))) continue;
+      links[fill[v]++] = (int32_t)c;
+    }
+  uint8_t* visited = (uint8_t*)calloc((size_t)(T > 0 ? T : 1), 1);
+  int32_t* wave = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T > 0 ? T : 1));
+  if (flipped) memset(flipped, 0, (size_t)T);
+  int64_t n_flip = 0;
+  int bad = 0;
+  for (int64_t seed = 0; seed < T; seed++) {
+    if (visited[seed]) continue;
+    int64_t head = 0, tail = 0;
+    wave[tail++] = (int32_t)seed;
+    visited[seed] = 1;
+    while (head < tail) {
+      const int32_t c = wave[head++];
+      for (int j = 0; j < 3; j++) {
+        const int32_t p1 = tris[3 * (int64_t)c + j], p2 = tris[3 * (int64_t)c + (j + 1) % 3];
+        if (p1 == p2) continue;
+        /* GetCellEdgeNeighbors: the other cells that use both points */
+        int32_t nb = -1;
+        int n_nb = 0;
+        for (int64_t q = start[p1]; q < fill[p1]; q++) {
+          const int32_t n = links[q];
+          if (n == c) continue;
+          const int32_t* t = tris + 3 * (int64_t)n;
+          if (t[0] == p2 || t[1] == p2 || t[2] == p2) { nb = n; n_nb++; }
+        }
+        if (n_nb != 1) continue;
+        const int32_t* t = tris + 3 * (int64_t)nb;
+        int l = t[0] == p2 ? 0 : (t[1] == p2 ? 1 : 2);
+        const int consistent = t[(l + 1) % 3] == p1;
+        if (visited[nb]) {
+          if (!consistent) bad = 1;
+          continue;
+        }
+        if (!consistent) {
+          int32_t* w = tris + 3 * (int64_t)nb;
+          const int32_t t0 = w[0];
+          w[0] = w[2];
+          w[2] = t0;
+          if (flipped) flipped[nb] = 1;
+          n_flip++;
+        }
+        visited[nb] = 1;
+        wave[tail++] = nb;
+      }
+    }
+  }
+  free(start); free(links); free(fill); free(visited); free(wave);
+  return bad ? -1 : n_flip;
+}
+
+/* ------------------------------------------------------------------ */
 /* O3  icosahedron-subdivision viewpoints                              */
 /*   src/py/utils.py:36-50 (CreateIcosahedron)                         */
 /*   src/py/LinearSubdivisionFilter.py:42-67 (lattice order, de-dup)   */
@@ -172,9 +258,11 @@ static const int ICO_FACES[20][3] = {
     {5, 10, 4}, {4, 10, 6}, {4, 6, 3},  {3, 6, 7},   {3, 7, 2},  {2, 7, 8},  {2, 8, 1},
     {1, 8, 9},  {9, 8, 11}, {9, 11, 10}, {10, 11, 6}, {6, 11, 7}, {7, 11, 8}};
 /* uniform solid scale applied by vtkPlatonicSolidSource before float storage
- * (recalled constant, medium confidence; irrelevant after normalize_points
- * except for the last float32 bit of a viewpoint) */
-#define ICO_SOLID_SCALE (1.0 / 0.58285)
+ * (recalled constant of vtkPlatonicSolidSource.cxx, not byte-verified; after normalize_points
+ * it only decides the last float32 bit of a viewpoint and which float-equality duplicates
+ * leak -- tests/refshim/vtk uses the same value, so the reference's own subdivision code
+ * run on it reproduces orc_icosahedron(dedupe = 1) bit for bit) */
+#define ICO_SOLID_SCALE (1.0 / 0.58778524999243)
 
 /* dedupe: 0 = exact integer lattice (canonical, 10 L^2 + 2 points),
  *         1 = float32 exact-equality emulation of

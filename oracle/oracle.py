@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs.  The product package
-(fly-by-cnn_b200/) never imports this module.  Parity unpinned: see the header
-of flyby_oracle.c.
+(fly-by-cnn_b200/) never imports this module.  Parity: pinned to the reference's own
+Python arithmetic through tests/golden/ref_*.npz, unpinned for what lives inside VTK --
+see the header of flyby_oracle.c.
 """
 import ctypes as C
 import os
@@ -76,6 +77,16 @@ def point_normals(verts, tris):
     out = np.empty_like(v)
     lib().orc_point_normals(_p(v), C.c_int64(len(v)), _p(t), C.c_int64(len(t)), _p(out))
     return out
+
+
+def orient_cells(tris, n_points):
+    """vtkPolyDataNormals' consistency pass: returns (tris reoriented, flipped uint8 [T], n_flipped or -1)."""
+    t = _i32(tris).copy()
+    flipped = np.zeros(len(t), dtype=np.uint8)
+    f = lib().orc_orient_cells
+    f.restype = C.c_int64
+    n = f(_p(t), C.c_int64(len(t)), C.c_int64(int(n_points)), _p(flipped))
+    return t, flipped, int(n)
 
 
 def icosahedron(L, radius, dedupe=0):

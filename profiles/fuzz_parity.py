@@ -58,7 +58,7 @@ def one_case(case):
     skip = bool(rng.integers(0, 2))
     if skip:
         P = (P / max(1e-6, np.abs(P).max()) * rng.choice([0.01, 0.5, 1.0, 30.0])).astype(np.float32)
-    ctx.set_mesh(P, F, skip_normalise=skip)
+    ctx.set_mesh(P, F, skip_normalise=skip, consistency="off")  # soups are not orientable surfaces: cells as given
     ctx.build()
     uv, nrm, _, _ = ctx.get_mesh()
     pre_ok = np.array_equal(nrm, orc.point_normals(uv, F), equal_nan=True)      # vtkPolyDataNormals restatement

@@ -22,7 +22,7 @@ def run(n_cases, seed, context=None):
     for case in range(n_cases):
         P, F = fz.mesh()
         P = (P / max(1e-6, np.abs(P).max())).astype(np.float32)
-        ctx.set_mesh(P, F, skip_normalise=True)
+        ctx.set_mesh(P, F, skip_normalise=True, consistency="off")
         ctx.build()
         uv, nrm, _, _ = ctx.get_mesh()
         V = len(P)

@@ -31,9 +31,10 @@ def test_free_functions_match_oracle(fbf, orc):
     assert np.array_equal(fbf.GetUnitSurf(surf, mean_arr=[1, 2, 3], scale_factor=0.05).points,
                           orc.unit_surf(P, translate=[1, 2, 3], scale_factor=0.05)[0])
     assert np.array_equal(fbf.ComputeNormals(unit).point_data["Normals"], orc.point_normals(U, F))
-    assert np.array_equal(fbf.CreateIcosahedron(2.75, 3).points, orc.icosahedron(3, 2.75))
+    assert np.array_equal(fbf.CreateIcosahedron(2.75, 3).points, orc.icosahedron(3, 2.75, dedupe=1))
+    assert np.array_equal(fbf.CreateIcosahedron(2.75, 3, dedupe=0).points, orc.icosahedron(3, 2.75))
     sp = fbf.CreateSpiral(4, 64, 4)
-    assert sp.GetNumberOfPoints() == 64 and np.allclose(sp.points, orc.spiral(64, 4, 4.0), atol=1e-6)
+    assert sp.GetNumberOfPoints() == 64 and np.array_equal(sp.points, orc.spiral(64, 4, 4.0))
 
 
 def test_cli_config1_small(fbf, orc, tmp_path):
@@ -51,6 +52,32 @@ def test_cli_config1_small(fbf, orc, tmp_path):
     N = orc.point_normals(U, F)
     ref, ids = orc.render(U, F, N, orc.icosahedron(2, 2.0), 2.0, 64, use_z=1, split_z=1, grid=True, grid_div=16)
     assert np.allclose(img, ref, rtol=1e-5, atol=1e-7) and (ids >= 0).mean() > 0.5
+
+
+def test_cli_cxx_tool_output_contract(fbf, orc, tmp_path):
+    """--flyByCompose / --planeSpacing / --planeScaleFactor: the C++ tool's output (fly_by_features.cxx:802-807,
+    1047-1110): itk::Image<RGBPixel<double>,3>, pixel = (n*0.5+0.5)*depth, spacing (planeSpacing, planeSpacing, 1)."""
+    import os
+    from flyby_b200 import nrrd
+    P, F = synth.bumpy_sphere(16, 3)
+    surf = _mesh_file(tmp_path, P, F)
+    U, _, _ = orc.unit_surf(P)
+    N = orc.point_normals(U, F)
+    views = orc.icosahedron(1, 3.0, dedupe=1)
+    ref, ids = orc.render(U, F, N, views, 3.0, 48, plane_scale=2.0, spacing=0.75, use_z=1, split_z=0, normal_encoding=0,
+                          zscale=1.0, grid=False)
+    out = str(tmp_path / "vol.nrrd")
+    base = "--surf %s --subdivision 1 --resolution 48 --radius 3 --planeSpacing 0.75 --planeScaleFactor 2 " % surf
+    fbf.main(fbf.build_parser().parse_args((base + "--flyByCompose 1 --out " + out).split()))
+    img, hdr = nrrd.read(out)
+    assert img.dtype == np.float64 and hdr["type"] == "double" and hdr["sizes"] == "3 48 48 12"
+    assert hdr["kinds"].split()[0] == "RGB-color" and "(0.75,0,0) (0,0.75,0) (0,0,1)" in hdr["space directions"]
+    assert np.array_equal(img, ref.astype(np.float64)) and (ids >= 0).any() and (ids < 0).any()
+    outdir = str(tmp_path / "per_view")
+    fbf.main(fbf.build_parser().parse_args((base + "--flyByCompose 0 --out " + outdir).split()))
+    assert sorted(os.listdir(outdir), key=lambda s: int(s.split(".")[0])) == ["%d.nrrd" % i for i in range(12)]
+    one, hdr = nrrd.read(os.path.join(outdir, "5.nrrd"))
+    assert one.dtype == np.float64 and hdr["sizes"] == "3 48 48" and np.array_equal(one, ref[5].astype(np.float64))
 
 
 def test_cli_spiral_point_features_and_per_view_files(fbf, orc, tmp_path):

@@ -71,8 +71,7 @@ def test_views_spiral(gpu_ctx, orc):
     for N, turns, R in [(64, 4, 4.0), (64, 4, 2.0), (17, 3, 1.5)]:
         assert gpu_ctx.views_spiral(N, turns, R) == N
         got, ref = gpu_ctx.get_views(), orc.spiral(N, turns, R)
-        # device sin/cos differ from libm by <= 1 ulp of double; after float32 storage at most 1 float ulp
-        assert np.all(np.abs(got - ref) <= np.spacing(np.abs(ref).astype(np.float32)) + 1e-30)
+        assert np.array_equal(got, ref)      # libm on the host, as the reference's math.sin / math.cos
         assert np.array_equal(got[0], np.array([0, 0, R], np.float32))
 
 
@@ -568,3 +567,187 @@ def test_randomised_parity(gpu_ctx, orc):
     fuzz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fuzz)
     assert fuzz.run(60, 11, context=gpu_ctx) == 0
+
+
+# ---------------------------------------------------------------- round 2: engines through the ABI, scalars, winding
+@pytest.mark.parametrize("mode", ["raster", "bvh", "fused"])
+def test_render_engines_selected_through_the_abi(gpu_ctx, orc, mode):
+    """flyby_render_opts.mode picks the search engine in-process; all three equal the oracle bit for bit
+    (reference: the ray loop of fly_by_features.cxx:742-807).  The fused engine also runs instrumented
+    (count_work) so that nodes_visited / tris_tested are exercised."""
+    P, F = synth.bumpy_sphere(30, 5)
+    gpu_ctx.views_icosahedron(2, 2.0)
+    for cfg in (dict(use_z=1, split_z=1), dict(use_z=1, split_z=0, plane_scale=2.0)):
+        r = _compare_render(gpu_ctx, orc, P, F, 2.0, 96, dict(cfg, mode=mode))
+        assert r["hits"] > 0 and r["t_bit_equal"] and r["feat_bit_equal"]
+    st = gpu_ctx.stats()
+    assert st["ms_trace"] > 0 and st["ms_render"] >= st["ms_trace"]
+    if mode != "raster":
+        gpu_ctx.set_count_work(True)
+        try:
+            opts = gpu_ctx.render_opts(mode=mode)
+            f1, i1 = gpu_ctx.render(64, opts)
+            st = gpu_ctx.stats()
+            assert st["nodes_visited"] > 0 and st["tris_tested"] >= st["n_hits"] > 0
+        finally:
+            gpu_ctx.set_count_work(False)
+        f0, i0 = gpu_ctx.render(64, gpu_ctx.render_opts(mode="raster"))
+        assert np.array_equal(i0, i1) and np.array_equal(f0, f1)
+
+
+def test_unknown_mode_is_rejected(gpu_ctx):
+    from flyby_b200 import FlyByError
+    P, F = synth.bumpy_sphere(6, 1)
+    _build(gpu_ctx, P, F)
+    gpu_ctx.views_icosahedron(1, 2.0)
+    with pytest.raises(FlyByError):
+        gpu_ctx.render(8, gpu_ctx.render_opts(mode=9))
+
+
+@pytest.mark.parametrize("mode", ["raster", "bvh", "fused"])
+@pytest.mark.parametrize("smode", ["vertex0", "barycentric"])
+def test_point_scalars_written_by_the_render(gpu_ctx, orc, mode, smode):
+    """--point_features ... --point_features_concat 1 (src/py/fly_by_features.py:334-402) in one pass: the S scalar
+    channels behind the C image channels equal the reference's id-map lookup (vertex 0; utils.py:604-684) /
+    the C++ tool's barycentric interpolation (fly_by_features.cxx:766-793), background = zero."""
+    rng = np.random.default_rng(8)
+    P, F = synth.dental_crown(24, 3)
+    uv, nrm, _, _ = _build(gpu_ctx, P, F)
+    views = gpu_ctx.views_icosahedron(1, 2.0) and gpu_ctx.get_views()
+    for S, cfg in ((1, dict(use_z=1, split_z=1)), (3, dict(use_z=1, split_z=0)), (5, dict(use_z=0, split_z=0, plane_scale=2.0))):
+        feats = rng.normal(size=(len(P), S)).astype(np.float32)
+        gpu_ctx.set_point_scalars(feats, mode=smode, zero=-3.5)
+        opts = gpu_ctx.render_opts(mode=mode, **cfg)
+        C = gpu_ctx.channels(opts)
+        out, ids = gpu_ctx.render(48, opts)
+        assert out.shape[-1] == C + S
+        fo, io = orc.render(uv, F, nrm, views, 2.0, 48, plane_scale=cfg.get("plane_scale", 1.0), use_z=cfg["use_z"],
+                            split_z=cfg["split_z"])
+        assert np.array_equal(ids, io) and np.array_equal(out[..., :C], fo)
+        if smode == "vertex0":
+            want = orc.point_features(io, F, feats, zero=-3.5)
+        else:
+            want = orc.interpolate_features(uv, F, views, 2.0, 48, io, feats, plane_scale=cfg.get("plane_scale", 1.0), zero=-3.5)
+        assert np.array_equal(out[..., C:], want)
+        assert (io < 0).any() and (io >= 0).any()
+    # view-range slabs and removal
+    part, _ = gpu_ctx.render(48, opts, view_begin=3, view_end=7)
+    assert np.array_equal(part, out[3:7])
+    gpu_ctx.set_point_scalars(None)
+    plain, _ = gpu_ctx.render(48, opts)
+    assert plain.shape[-1] == C and np.array_equal(plain, out[..., :C])
+
+
+def _scramble_winding(F, seed, frac=0.3):
+    rng = np.random.default_rng(seed)
+    G = F.copy()
+    flip = rng.random(len(G)) < frac
+    G[flip] = G[flip][:, ::-1]
+    return np.ascontiguousarray(G), flip
+
+
+def test_winding_consistency_pass(gpu_ctx, orc):
+    """vtkPolyDataNormals' consistency pass (utils.py:493-501, fly_by_features.cxx:472-478): a mesh with reversed
+    cells is refused by default, reoriented like the oracle's restatement of VTK's wave traversal with
+    consistency="fix" (every component follows its lowest cell id), used as given with "off"."""
+    from flyby_b200 import FlyByError, _cabi
+    P, F = synth.bumpy_sphere(14, 6)
+    # two components: a second, shifted copy whose FIRST cell is reversed (the whole copy must follow it)
+    P2 = np.concatenate([P, P + np.float32(3.0)]).astype(np.float32)
+    F2 = np.concatenate([F, F[:, ::-1] + len(P)]).astype(np.int32)
+    G, flip = _scramble_winding(F2, 4)
+    assert flip.any() and not flip.all()
+    gpu_ctx.set_mesh(P2, G)                                   # default: check
+    with pytest.raises(FlyByError) as e:
+        gpu_ctx.build()
+    assert e.value.status == _cabi.ERR_UNSUPPORTED and "consisten" in str(e.value)
+    want_tris, want_flip, n = orc.orient_cells(G, len(P2))
+    assert n > 0
+    gpu_ctx.set_mesh(P2, G, consistency="fix")
+    gpu_ctx.build()
+    n_gpu, got_flip = gpu_ctx.get_winding()
+    assert n_gpu == n and np.array_equal(got_flip, want_flip)
+    uv, nrm, _, _ = gpu_ctx.get_mesh()
+    U, _, _ = orc.unit_surf(P2)
+    assert np.array_equal(uv, U) and np.array_equal(nrm, orc.point_normals(U, want_tris))
+    gpu_ctx.views_icosahedron(1, 2.0)
+    views = gpu_ctx.get_views()
+    feats = np.random.default_rng(2).normal(size=(len(P2), 2)).astype(np.float32)
+    gpu_ctx.set_point_scalars(feats, mode="vertex0", zero=9.0)
+    opts = gpu_ctx.render_opts(plane_scale=2.0)
+    out, ids, t = gpu_ctx.render(64, opts, want_t=True)
+    fo, io, to = orc.render(U, want_tris, nrm, views, 2.0, 64, plane_scale=2.0, want_t=True)
+    assert np.array_equal(ids, io) and np.array_equal(t, to) and np.array_equal(out[..., :4], fo) and (io >= 0).any()
+    # "vertex 0" stays the caller's vertex 0 (the reference builds its point-id map from the original surface)
+    assert np.array_equal(out[..., 4:], orc.point_features(io, G, feats, zero=9.0))
+    assert np.array_equal(gpu_ctx.point_ids(ids), np.where(io >= 0, G[np.maximum(io, 0), 0], -1))
+    lab = (np.arange(len(G)) % 5).astype(np.int32)
+    assert np.array_equal(gpu_ctx.cells_to_points(lab, default=-1), orc.cells_to_points(lab, G, len(P2), default=-1))
+    gpu_ctx.set_point_scalars(None)
+    # a consistent mesh: nothing flips in any mode, and "fix" equals "check"
+    for mode in ("check", "fix", "off"):
+        gpu_ctx.set_mesh(P, F, consistency=mode)
+        gpu_ctx.build()
+        assert gpu_ctx.get_winding()[0] == 0
+    # off: the scrambled cells are used as given
+    gpu_ctx.set_mesh(P2, G, consistency="off")
+    gpu_ctx.build()
+    assert np.array_equal(gpu_ctx.get_mesh()[1], orc.point_normals(U, G))
+    # a Moebius band has no consistent orientation: refused in "fix" mode, like the oracle (-1)
+    n_seg = 24
+    a = np.linspace(0, 2 * np.pi, n_seg, endpoint=False)
+    ring = []
+    for s in (-0.3, 0.3):
+        ring.append(np.stack([(1 + s * np.cos(a / 2)) * np.cos(a), (1 + s * np.cos(a / 2)) * np.sin(a), s * np.sin(a / 2)], 1))
+    Pm = np.concatenate(ring).astype(np.float32)
+    Fm = []
+    for i in range(n_seg):
+        j = (i + 1) % n_seg
+        lo_i, hi_i = i, n_seg + i
+        lo_j, hi_j = (j, n_seg + j) if j else (n_seg, 0)      # the half twist swaps the rims at the seam
+        Fm += [[lo_i, lo_j, hi_i], [lo_j, hi_j, hi_i]]
+    Fm = np.asarray(Fm, np.int32)
+    assert orc.orient_cells(Fm, len(Pm))[2] == -1
+    gpu_ctx.set_mesh(Pm, Fm, consistency="fix")
+    with pytest.raises(FlyByError) as e:
+        gpu_ctx.build()
+    assert e.value.status == _cabi.ERR_UNSUPPORTED
+
+
+def test_entry_points_validate_indices_without_a_build(gpu_ctx):
+    """cells_to_points / point_features / point_ids / backproject_points read the triangles after
+    flyby_set_mesh alone -- out-of-range indices must be refused there too, and ids beyond T are misses."""
+    from flyby_b200 import FlyByError
+    V = np.zeros((3, 3), np.float32)
+    bad = np.array([[0, 1, 2], [7, 1, 2]], np.int32)
+    ids = np.array([0, 1, -1, 5], np.int32)
+    for call in (lambda: gpu_ctx.cells_to_points(np.zeros(2, np.int32)),
+                 lambda: gpu_ctx.point_features(ids, np.zeros((3, 1), np.float32)),
+                 lambda: gpu_ctx.point_ids(ids),
+                 lambda: gpu_ctx.backproject_points(ids, np.zeros(4, np.int32), 2)):
+        gpu_ctx.set_mesh(V, bad)
+        with pytest.raises(FlyByError):
+            call()
+    good = np.array([[0, 1, 2], [2, 1, 0]], np.int32)
+    gpu_ctx.set_mesh(V, good)
+    assert np.array_equal(gpu_ctx.point_ids(ids), np.array([0, 2, -1, -1], np.int32))
+    # mode 1 (decoded point ids) never reads the triangles: usable even with bad cells
+    gpu_ctx.set_mesh(V, bad)
+    f = np.arange(3, dtype=np.float32).reshape(3, 1)
+    assert np.array_equal(gpu_ctx.point_features(np.array([2, 0, 9, -1], np.int32), f, zero=-1.0, mode=1).reshape(-1),
+                          np.array([2, 0, -1, -1], np.float32))
+
+
+def test_interpolate_ignores_foreign_cell_ids(gpu_ctx, orc):
+    """a cell id >= T (ids from another mesh) is a miss, never a gather."""
+    P, F = synth.bumpy_sphere(8, 1)
+    _build(gpu_ctx, P, F)
+    gpu_ctx.views_icosahedron(1, 2.0)
+    opts = gpu_ctx.render_opts()
+    _, ids = gpu_ctx.render(16, opts)
+    feats = np.ones((len(P), 2), np.float32)
+    want = gpu_ctx.interpolate_features(16, opts, ids, feats, zero=-1.0)
+    spoiled = ids.copy()
+    spoiled[0, :4] = len(F) + np.arange(4 * 16).reshape(4, 16) * 1000 + 1
+    got = gpu_ctx.interpolate_features(16, opts, spoiled, feats, zero=-1.0)
+    assert np.all(got[0, :4] == -1.0) and np.array_equal(got[0, 4:], want[0, 4:]) and np.array_equal(got[1:], want[1:])

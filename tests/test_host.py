@@ -326,3 +326,30 @@ def test_no_stream_waits_for_an_event_recorded_on_itself():
                     assert r.group(2) != stream, "%s:%d waits on %s for an event recorded on it" % (path, i + 1, stream)
                     break
     assert pairs >= 4  # unit surface, sort, front buffer, chunked copy-out
+
+
+def test_nrrd_every_written_type_reads_back_and_crlf_headers(tmp_path):
+    """read() must know every type spelling write() emits (int64 -> 'long long'), and CRLF headers."""
+    from flyby_b200 import nrrd
+    rng = np.random.default_rng(0)
+    for dt in nrrd._NAMES:
+        a = (rng.random((3, 4, 5, 2)) * 100).astype(dt)
+        path = str(tmp_path / ("t_%s.nrrd" % np.dtype(dt).name))
+        nrrd.write(path, a)
+        b, hdr = nrrd.read(path)
+        assert b.dtype == np.dtype(dt) and np.array_equal(a, b), dt
+    for name in ("long", "unsigned long long", "uint16", "uint32", "int64_t"):
+        assert name in nrrd._TYPES or name == "long"
+    a = rng.random((2, 3, 1)).astype(np.float32)
+    nrrd.write(str(tmp_path / "lf.nrrd"), a, compress=False)
+    raw = open(str(tmp_path / "lf.nrrd"), "rb").read()
+    end = raw.find(b"\n\n")
+    open(str(tmp_path / "crlf.nrrd"), "wb").write(raw[:end].replace(b"\n", b"\r\n") + b"\r\n\r\n" + raw[end + 2:])
+    b, hdr = nrrd.read(str(tmp_path / "crlf.nrrd"))
+    assert np.array_equal(a, b) and hdr["encoding"] == "raw"
+    # the C++ tool's image type: RGB pixels of doubles with a spacing (fly_by_features.cxx:1047-1068)
+    img = nrrd.Image(rng.random((4, 6, 6, 3)), spacing=[0.5, 0.5, 1.0], kind="RGB-color")
+    nrrd.write(str(tmp_path / "rgb.nrrd"), img)
+    b, hdr = nrrd.read(str(tmp_path / "rgb.nrrd"))
+    assert b.dtype == np.float64 and hdr["type"] == "double" and hdr["kinds"].split()[0] == "RGB-color"
+    assert hdr["sizes"] == "3 6 6 4" and "(0.5,0,0) (0,0.5,0) (0,0,1)" in hdr["space directions"]

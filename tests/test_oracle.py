@@ -27,12 +27,14 @@ def test_icosahedron_counts_and_order(orc):
 
 
 def test_icosahedron_float_dedupe_leaks_duplicates(orc):
-    """Hazard H1: the reference de-duplicates by float equality and leaks duplicate viewpoints
-    (its readme documents 268 ids for subdivision 5, ideal 252): the emulation shows the same effect."""
+    """Hazard H1: the reference de-duplicates by float equality and leaks duplicate viewpoints.  The counts are what
+    the reference's own LinearSubdivisionFilter produces under tests/refshim (tests/golden/ref_views.npz): 94 at
+    subdivision 3, none leaked at 1, 2, 4, 5, 10.  (Its readme quotes 268 / 1026 ids for subdivisions 5 / 10, which
+    neither solid-scale assumption nor an octree-leaf model of the point locator reproduces: DESIGN.md section 2.)"""
     assert len(orc.icosahedron(2, 2.0, dedupe=1)) == 42
     assert len(orc.icosahedron(4, 2.0, dedupe=1)) == 162
-    assert len(orc.icosahedron(3, 2.0, dedupe=1)) > 92
-    assert len(orc.icosahedron(5, 2.0, dedupe=1)) > 252
+    assert len(orc.icosahedron(3, 2.0, dedupe=1)) == 94
+    assert len(orc.icosahedron(5, 2.0, dedupe=1)) == 252
 
 
 def test_spiral(orc):
