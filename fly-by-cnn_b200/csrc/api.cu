@@ -19,6 +19,7 @@ const double* prep_centre_scale(flyby_ctx* c);
 int label_point_ids(flyby_ctx*, const int32_t*, int64_t, int32_t*);
 int label_backproject_points(flyby_ctx*, const int32_t*, const int32_t*, int64_t, int, int32_t*);
 int winding_detect(flyby_ctx* c, int* flags_dev);  // winding.cu
+int winding_classify(flyby_ctx* c, int* flags_dev, int* flags_host);
 int winding_fix(flyby_ctx* c, int* flags_dev);
 
 // input: device pointers are used in place, host pointers are copied to `stage`
@@ -64,25 +65,14 @@ static int sync_if(flyby_ctx* c, bool need) {
   return FLYBY_OK;
 }
 
-__global__ void check_tris_kernel(const int32_t* __restrict__ tris, int64_t n, int64_t V, int32_t* bad) {
+// counts the indices outside [0, V) and replaces them by 0 in the context's copy of the cells, so that even a
+// build whose verdict is read later (FLYBY_BUILD_DEFERRED) never gathers out of range
+__global__ void check_tris_kernel(int32_t* __restrict__ tris, int64_t n, int64_t V, int32_t* bad) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n && (tris[i] < 0 || tris[i] >= V)) atomicAdd(bad, 1);
-}
-
-// Entry points that read m.tris without a build (flyby_set_mesh only) validate the indices first, once per mesh.
-static int ensure_tris_checked(flyby_ctx* c) {
-  MeshDev& m = c->mesh;
-  if (m.tris_ok || m.T <= 0) return FLYBY_OK;
-  int32_t* bad = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 7);
-  FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
-  check_tris_kernel<<<(unsigned)cdiv(3 * m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), 3 * m.T, m.V, bad);
-  FB_LAUNCH_CHECK(c);
-  int32_t nbad = 0;
-  FB_CUDA(c, cudaMemcpyAsync(&nbad, bad, 4, cudaMemcpyDeviceToHost, c->stream));
-  FB_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (nbad) return fail(c, FLYBY_ERR_INVALID, "%d triangle indices outside [0, n_verts)", nbad);
-  m.tris_ok = true;
-  return FLYBY_OK;
+  if (i < n && (tris[i] < 0 || tris[i] >= V)) {
+    atomicAdd(bad, 1);
+    tris[i] = 0;
+  }
 }
 
 }  // namespace fb
@@ -184,15 +174,48 @@ void flyby_destroy(flyby_ctx* c) {
 
 const char* flyby_last_error(const flyby_ctx* c) { return c ? c->err : "null context"; }
 
-// counters[6] is raised by the render kernel's watchdog (a scheduling bug must
-// surface as an error, never as a hung device)
+// counters[6] is raised by the render kernel's watchdog (a scheduling bug must surface as an error, never as a
+// hung device); counters[7] holds the verdict of the build-time checks (low word: out-of-range indices, high word:
+// winding flags), read here for builds that did not synchronise themselves (FLYBY_BUILD_DEFERRED)
 static int check_watchdog(flyby_ctx* c) {
-  unsigned long long flag = 0;
-  FB_CUDA(c, cudaMemcpyAsync(&flag, c->counters.as<unsigned long long>() + 6, 8, cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long w[2] = {0, 0};
+  FB_CUDA(c, cudaMemcpyAsync(w, c->counters.as<unsigned long long>() + 6, 16, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (flag) return fail(c, FLYBY_ERR_CUDA, "render watchdog tripped in %llu warps: results are incomplete", flag);
+  if (w[0]) return fail(c, FLYBY_ERR_CUDA, "render watchdog tripped in %llu warps: results are incomplete", w[0]);
+  if (c->deferred_pending) {
+    c->deferred_pending = false;
+    FB_CUDA(c, cudaMemsetAsync(c->counters.as<unsigned long long>() + 7, 0, 8, c->stream));
+    const int nbad = (int)(w[1] & 0xffffffffull), wflags = (int)(w[1] >> 32);
+    if (nbad) {
+      c->mesh.built = false;
+      return fail(c, FLYBY_ERR_INVALID, "a deferred build found %d triangle indices outside [0, n_verts): its results are invalid", nbad);
+    }
+    if (wflags & 8) {
+      c->mesh.built = false;
+      return fail(c, FLYBY_ERR_UNSUPPORTED, "a deferred build found a directed edge used by two cells (inconsistent winding or a "
+                                            "non-manifold edge): build again without FLYBY_BUILD_DEFERRED to classify / fix it");
+    }
+  }
   return FLYBY_OK;
 }
+
+// Entry points that read m.tris without a build (flyby_set_mesh only) validate the indices first, once per mesh.
+static int ensure_tris_checked(flyby_ctx* c) {
+  MeshDev& m = c->mesh;
+  if (m.tris_ok || m.T <= 0) return FLYBY_OK;
+  int32_t* bad = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 7);
+  if (c->deferred_pending) { int rcd = check_watchdog(c); if (rcd) return rcd; }
+  FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
+  check_tris_kernel<<<(unsigned)cdiv(3 * m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), 3 * m.T, m.V, bad);
+  FB_LAUNCH_CHECK(c);
+  int32_t nbad = 0;
+  FB_CUDA(c, cudaMemcpyAsync(&nbad, bad, 4, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (nbad) return fail(c, FLYBY_ERR_INVALID, "%d triangle indices outside [0, n_verts)", nbad);
+  m.tris_ok = true;
+  return FLYBY_OK;
+}
+
 
 int flyby_synchronize(flyby_ctx* c) {
   CHECK_CTX(c);
@@ -216,7 +239,8 @@ int flyby_set_mesh(flyby_ctx* c, const float* verts, int64_t V, const int32_t* t
   m.n_scalars = 0;
   m.n_flipped = 0;
   if (opts) c->norm = *opts; else memset(&c->norm, 0, sizeof c->norm);
-  if (c->norm.consistency < 0 || c->norm.consistency > 2) return fail(c, FLYBY_ERR_INVALID, "set_mesh: consistency must be 0, 1 or 2");
+  if ((c->norm.consistency & 0xff) > 2 || (c->norm.consistency & ~(0xff | FLYBY_BUILD_DEFERRED)))
+    return fail(c, FLYBY_ERR_INVALID, "set_mesh: consistency must be 0, 1 or 2 (| FLYBY_BUILD_DEFERRED)");
   FB_CUDA(c, m.raw_verts.reserve(sizeof(float) * 3 * (size_t)V));
   FB_CUDA(c, m.tris.reserve(sizeof(int32_t) * 3 * (size_t)(T > 0 ? T : 1)));
   FB_CUDA(c, cudaMemcpyAsync(m.raw_verts.p, verts, sizeof(float) * 3 * (size_t)V, cudaMemcpyDefault, c->stream));
@@ -239,26 +263,43 @@ int flyby_build(flyby_ctx* c) {
   }
   // index validation first: an out-of-range index must never reach a gather.  The winding check of
   // vtkPolyDataNormals' consistency pass (winding.cu) shares the one host synchronisation of the build.
+  const int cons = c->norm.consistency & 0xff;
+  const bool deferred = (c->norm.consistency & FLYBY_BUILD_DEFERRED) != 0;
   int32_t* bad = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 7);
-  FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
+  if (c->deferred_pending && !deferred) {  // an earlier deferred build's verdict is still unread: read it first
+    int rcd = check_watchdog(c);
+    if (rcd) return rcd;
+  }
+  if (!c->deferred_pending) FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
   if (m.T > 0 && !m.tris_ok) {
     check_tris_kernel<<<(unsigned)cdiv(3 * m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), 3 * m.T, m.V, bad);
     FB_LAUNCH_CHECK(c);
   }
-  const bool wind = c->norm.consistency != 2 && m.T > 0 && m.n_flipped == 0;
+  const bool wind = cons != 2 && m.T > 0 && m.n_flipped == 0;
   if (wind) { int rcw = winding_detect(c, bad + 1); if (rcw) return rcw; }
-  int32_t chk[2] = {0, 0};
-  FB_CUDA(c, cudaMemcpyAsync(chk, bad, 8, cudaMemcpyDeviceToHost, c->stream));
-  FB_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (chk[0]) return fail(c, FLYBY_ERR_INVALID, "build: %d triangle indices outside [0, n_verts)", chk[0]);
-  m.tris_ok = true;
-  if (wind && (chk[1] & 1)) {
-    if (c->norm.consistency == 0)
-      return fail(c, FLYBY_ERR_UNSUPPORTED,
-                  "build: inconsistently wound cells (two cells traverse a shared edge in the same direction); "
-                  "vtkPolyDataNormals would reverse cells -- set flyby_norm_opts.consistency = 1 to reproduce that, 2 to use the cells as given");
-    int rcw = winding_fix(c, bad + 1);
-    if (rcw) return rcw;
+  if (deferred) {
+    // no host synchronisation: indices were sanitised on the device, the flags stay in counters[7] until the next
+    // synchronising call (flyby_synchronize, a render with host outputs, a non-deferred build) reports them
+    c->deferred_pending = true;
+    m.tris_ok = true;
+  } else {
+    int32_t chk[2] = {0, 0};
+    FB_CUDA(c, cudaMemcpyAsync(chk, bad, 8, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (chk[0]) return fail(c, FLYBY_ERR_INVALID, "build: %d triangle indices outside [0, n_verts)", chk[0]);
+    m.tris_ok = true;
+    if (wind && (chk[1] & 8)) {  // a directed edge occurs twice: find out whether a manifold edge is involved
+      int rcw = winding_classify(c, bad + 1, &chk[1]);
+      if (rcw) return rcw;
+    }
+    if (wind && (chk[1] & 1)) {
+      if (cons == 0)
+        return fail(c, FLYBY_ERR_UNSUPPORTED,
+                    "build: inconsistently wound cells (two cells traverse a shared edge in the same direction); "
+                    "vtkPolyDataNormals would reverse cells -- set flyby_norm_opts.consistency = 1 to reproduce that, 2 to use the cells as given");
+      int rcw = winding_fix(c, bad + 1);
+      if (rcw) return rcw;
+    }
   }
   int rc = prep_run(c);
   if (rc) return rc;

@@ -127,6 +127,7 @@ struct flyby_ctx {
   int n_slab_ev = 0;
   flyby_stats stats;
   int count_work = 0;
+  bool deferred_pending = false;  // a FLYBY_BUILD_DEFERRED build's check flags (counters[7]) have not been read yet
   int64_t launches = 0;
   int sm_count = 148;
   int leaf_max = FB_LEAF_MAX;  // triangles per collapsed leaf (FLYBY_LEAF_MAX overrides, 1..8)

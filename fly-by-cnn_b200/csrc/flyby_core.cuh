@@ -29,6 +29,8 @@ struct float4 { float x, y, z, w; };  // host simulator build only
 #endif
 
 #if defined(__CUDA_ARCH__)
+#define FB_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define FB_FRCP(a) __frcp_rn((a))
 #define FB_MUL(a, b) __dmul_rn((a), (b))
 #define FB_ADD(a, b) __dadd_rn((a), (b))
 #define FB_SUB(a, b) __dsub_rn((a), (b))
@@ -38,6 +40,8 @@ struct float4 { float x, y, z, w; };  // host simulator build only
 #define FB_FMUL(a, b) __fmul_rn((a), (b))
 #define FB_F2F_RU(a) __double2float_ru((a))
 #else  // host build: compile with -ffp-contract=off
+#define FB_FMA(a, b, c) fma((a), (b), (c))
+#define FB_FRCP(a) (1.0f / (a))
 #define FB_MUL(a, b) ((a) * (b))
 #define FB_ADD(a, b) ((a) + (b))
 #define FB_SUB(a, b) ((a) - (b))
@@ -78,6 +82,7 @@ struct View {
   float dirf[3], invf[3];          // float32 direction and its reciprocal (traversal only)
   float slack;                     // box inflation covering float32 ray rounding
   float tslack;                    // slack in units of the segment parameter
+  double dlen;                     // |dir| (shade_approx: depth = t |dir|)
 };
 
 FB_HD void view_setup(const float* spf, double radius, double plane_scale, double spacing, View* v, double tol = 0.0) {
@@ -122,6 +127,7 @@ FB_HD void view_setup(const float* spf, double radius, double plane_scale, doubl
   v->slack = (float)(amax * 64.0 * 5.9604644775390625e-08 + 2.0 * fabs(tol));
   double dl = norm3(v->dir);
   v->tslack = (float)(dl > 0.0 ? 4.0 * (double)v->slack / dl : 0.0);
+  v->dlen = dl;
 }
 
 // origin of ray (i, j) of a res x res plane; i is the fast axis (vtkPlaneSource
@@ -904,6 +910,71 @@ FB_HD void shade(const double* o, const double* x, const double* w, const float*
                  float* px) {
   double dd[3] = {FB_SUB(o[0], x[0]), FB_SUB(o[1], x[1]), FB_SUB(o[2], x[2])};
   shade_z(w, n0, n1, n2, FB_MUL(norm3(dd), zscale), use_z, split_z, enc, px);
+}
+
+// ---------------------------------------------------------------- tolerance shading (opt-in)
+// The exact chain above (tri_exact + shade: ~200 dependent double-precision instructions, five IEEE divisions and a
+// square root) exists to make the values written to the tensor bit-equal to the reference arithmetic; the task's
+// bar for depth and normals is 1e-5 relative.  For a pixel whose ONLY candidate is a certain hit (SC_SURE: the exact
+// test is known to accept it, so the cell id needs no arithmetic at all) shade_approx computes
+//   * the hit parameter, the depth and the hit point in double (fused multiply-adds, one Newton reciprocal; the ray
+//     origin stays the exact float32-rounded vtkPlaneSource point), error ~1e-15 / cos(incidence);
+//   * the barycentric weights and the interpolated normal in float32, from the hit point taken RELATIVE TO VERTEX 0
+//     (so the float32 rounding is relative to the triangle's size, not to the coordinates' magnitude).
+// Returns false (caller runs the exact chain) for slivers, where float32 weights would lose more than ~1e-6.
+// Measured against the exact chain: depth <= 1e-7 relative, normal channels <= ~1e-6 absolute (tests, bench line).
+// Cell ids are not affected.  Selected per render with FLYBY_SHADE_TOLERANCE in flyby_render_opts.mode.
+FB_HD double rcp_newton(double a) {  // 1 / a to ~2 ulp for |a| in the float range
+  double r = (double)FB_FRCP((float)a);
+  r = FB_FMA(r, FB_FMA(-a, r, 1.0), r);
+  r = FB_FMA(r, FB_FMA(-a, r, 1.0), r);
+  return r;
+}
+FB_HD bool shade_approx(const double* o, const double* d, double dlen, const float* P0, const float* P1, const float* P2,
+                        const float* n0, const float* n1, const float* n2, int use_z, int split_z, int enc,
+                        double zscale, float* px) {
+  if (enc == 3) return false;  // 8-bit colours: a float32 floor() could land one code off
+  const double p0[3] = {(double)P0[0], (double)P0[1], (double)P0[2]};
+  const double a[3] = {(double)P1[0] - p0[0], (double)P1[1] - p0[1], (double)P1[2] - p0[2]};  // edge P0 -> P1
+  const double b[3] = {(double)P2[0] - p0[0], (double)P2[1] - p0[1], (double)P2[2] - p0[2]};  // edge P0 -> P2
+  const double n[3] = {FB_FMA(a[1], b[2], -(a[2] * b[1])), FB_FMA(a[2], b[0], -(a[0] * b[2])),
+                       FB_FMA(a[0], b[1], -(a[1] * b[0]))};
+  const double q[3] = {p0[0] - o[0], p0[1] - o[1], p0[2] - o[2]};
+  const double num = FB_FMA(n[0], q[0], FB_FMA(n[1], q[1], n[2] * q[2]));
+  const double den = FB_FMA(n[0], d[0], FB_FMA(n[1], d[1], n[2] * d[2]));
+  const float aden = (float)fabs(den);
+  if (!(aden > 1e-30f) || !(aden < 1e30f)) return false;
+  const double rden = rcp_newton(den);
+  double t = num * rden;
+  t = FB_FMA(FB_FMA(-t, den, num), rden, t);
+  if (!(t >= 0.0 && t <= 1.0)) return false;
+  // hit point relative to vertex 0: r = (o - p0) + t d
+  const float r[3] = {(float)FB_FMA(t, d[0], -q[0]), (float)FB_FMA(t, d[1], -q[1]), (float)FB_FMA(t, d[2], -q[2])};
+  const float af[3] = {(float)a[0], (float)a[1], (float)a[2]}, bf[3] = {(float)b[0], (float)b[1], (float)b[2]};
+  const float f0 = (float)fabs(n[0]), f1 = (float)fabs(n[1]), f2 = (float)fabs(n[2]);
+  const int idx = (f0 >= f1 && f0 >= f2) ? 0 : (f1 >= f2 ? 1 : 2);  // drop the dominant axis of n
+  const int ia = idx == 0 ? 1 : 0, ib = idx == 2 ? 1 : 2;
+  const float det = fmaf(af[ia], bf[ib], -(bf[ia] * af[ib]));
+  const float scale = (fabsf(af[ia]) + fabsf(af[ib])) * (fabsf(bf[ia]) + fabsf(bf[ib]));
+  if (!(fabsf(det) > 0.02f * scale)) return false;  // sliver: the weights would amplify float32 rounding by > 50
+  const float rdet = 1.0f / det;
+  const float w1 = fmaf(r[ia], bf[ib], -(bf[ia] * r[ib])) * rdet;  // weight of P1
+  const float w2 = fmaf(af[ia], r[ib], -(r[ia] * af[ib])) * rdet;  // weight of P2
+  const float w0 = 1.0f - w1 - w2;
+  const float z = (float)(t * dlen * zscale);
+  float e[3];
+  for (int k = 0; k < 3; k++) {
+    const float nn = fmaf(w0, n0[k], fmaf(w1, n1[k], w2 * n2[k]));
+    if (enc == 2) e[k] = nn;
+    else {
+      e[k] = fmaf(nn, 0.5f, 0.5f);
+      if (enc == 1) e[k] *= 255.0f;
+    }
+  }
+  if (!use_z) { px[0] = e[0]; px[1] = e[1]; px[2] = e[2]; }
+  else if (split_z) { px[0] = e[0]; px[1] = e[1]; px[2] = e[2]; px[3] = z; }
+  else { px[0] = e[0] * z; px[1] = e[1] * z; px[2] = e[2] * z; }
+  return true;
 }
 
 // ---------------------------------------------------------------- pinhole camera (raster-compatible views)

@@ -260,7 +260,27 @@ __global__ void raster_init_kernel(unsigned long long* front, int* cnt, int64_t 
 
 // ---- resolve1: every pixel, raster order
 #define RV_STAGE 64  // per-warp staging of queued pixels: one global atomic per 32+ entries instead of one per iteration
-__global__ void __launch_bounds__(RV_THREADS, RV_MINB) raster_resolve1_kernel(const RasterParams rp) {
+#ifndef RV_MINB_APPROX
+#define RV_MINB_APPROX 5
+#endif
+// the exact chain of one pixel, out of line: the tolerance variant of resolve1 only needs it for slivers
+static __device__ __noinline__ bool resolve_exact_pixel(const RenderParams& p, int64_t pix, int slot) {
+  const float4* rec = p.trec + 4 * (int64_t)slot;
+  const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
+  const PixelRay r = pixel_ray(p, pix);
+  const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+  double t, x[3], w[3];
+  if (tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w)) {
+    shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
+    return true;
+  }
+  const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+  write_pixel(p, pix, zero, -1, -1.0);
+  return false;
+}
+
+template <bool APPROX>
+__global__ void __launch_bounds__(RV_THREADS, APPROX ? RV_MINB_APPROX : RV_MINB) raster_resolve1_kernel(const RasterParams rp) {
   const RenderParams& p = rp.r;
   __shared__ uint32_t s_stage[RV_THREADS / 32][RV_STAGE];
   const int lane = threadIdx.x & 31;
@@ -304,6 +324,22 @@ __global__ void __launch_bounds__(RV_THREADS, RV_MINB) raster_resolve1_kernel(co
     const PixelRay r = pixel_ray(p, pix);
     const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
     double t, x[3], w[3];
+    if (APPROX) {
+      // opt-in tolerance shading: the only candidate is a certain hit, so the id is known; depth in double, weights
+      // and normal in float32 (flyby_core.cuh shade_approx); slivers fall through to the exact chain
+      const int pid0 = __float_as_int(b.w), pid1 = __float_as_int(e.w), pid2 = __float_as_int(g.x);
+      const float4 n0 = __ldg(p.normals + pid0), n1 = __ldg(p.normals + pid1), n2 = __ldg(p.normals + pid2);
+      const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
+      float px[4] = {0.f, 0.f, 0.f, 0.f};
+      if (shade_approx(r.o, r.d, r.dlen, P0, P1, P2, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px)) {
+        hits++;
+        write_pixel(p, pix, px, __float_as_int(a.w), -1.0);
+        write_hit_scalars(p, pix, nullptr, pid0, pid1, pid2, __float_as_int(a.w));
+        continue;
+      }
+      hits += resolve_exact_pixel(p, pix, slot) ? 1u : 0u;
+      continue;
+    }
     if (tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w)) {
       hits++;
       shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
@@ -554,10 +590,15 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
     int rc = wait_tree(c);
     if (rc) return rc;
   }
-  long long rgrid = (long long)c->sm_count * RV_MINB * 4;  // RV_MINB CTAs resident per SM, 4 rounds for balance
+  const bool approx = rp.approx && !rp.tt && !(rp.n_scal && rp.scal_mode == 1);
+  long long rgrid = (long long)c->sm_count * (approx ? RV_MINB_APPROX : RV_MINB) * 4;  // CTAs resident per SM, 4 rounds for balance
   const long long want = cdiv(n_pix, RV_THREADS);
   if (rgrid > want) rgrid = want;
-  raster_resolve1_kernel<<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
+  // tolerance shading applies when no exact hit parameter is asked for and no scalar needs the exact weights
+  if (approx)
+    raster_resolve1_kernel<true><<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
+  else
+    raster_resolve1_kernel<false><<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   raster_resolve2_kernel<<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);

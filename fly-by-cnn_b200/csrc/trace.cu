@@ -534,10 +534,13 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   p.flip = m.n_flipped > 0 ? m.flip.as<uint8_t>() : nullptr;
   // flyby_render_opts.mode: 0 default (g_mode: raster unless FLYBY_MODE says otherwise), 1 raster, 2 bvh, 3 fused
   int mode = g_mode;
-  if (o->mode == 1) mode = 2;
-  else if (o->mode == 2) mode = 1;
-  else if (o->mode == 3) mode = 0;
-  else if (o->mode != 0) return fail(c, FLYBY_ERR_INVALID, "render: unknown mode %d", o->mode);
+  const int engine = o->mode & 0xff;
+  if (engine == 1) mode = 2;
+  else if (engine == 2) mode = 1;
+  else if (engine == 3) mode = 0;
+  else if (engine != 0) return fail(c, FLYBY_ERR_INVALID, "render: unknown mode %d", o->mode);
+  if (o->mode & ~(0xff | FLYBY_SHADE_TOLERANCE)) return fail(c, FLYBY_ERR_INVALID, "render: unknown mode flags %#x", o->mode);
+  p.approx = (o->mode & FLYBY_SHADE_TOLERANCE) ? 1 : 0;  // honoured by the raster engine
   FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), st));  // tile counter
   const size_t smem = (size_t)p.top_cap * sizeof(Node) + RK_WARPS * RK_QCAP * sizeof(uint32_t);
   auto launch = [&](auto kern) -> int {

@@ -89,6 +89,7 @@ struct RenderParams {
   const uint8_t* flip;           // [T] cells reversed by the consistency pass (their vertex 0 is p2), or nullptr
   int n_scal, scal_mode, stride;
   float scal_zero;
+  int approx;                    // FLYBY_SHADE_TOLERANCE: shade_approx for pixels whose only candidate is a certain hit
 };
 
 #ifndef RK_MINB
@@ -186,6 +187,7 @@ __device__ __forceinline__ void stage_top_of_tree(Node* top, const Node* nodes, 
 // ---------------------------------------------------------------- exact resolve helpers
 struct PixelRay {
   double o[3], d[3];
+  double dlen;  // |d|
 };
 __device__ __forceinline__ PixelRay pixel_ray(const RenderParams& p, int64_t pix_id) {
   // a render call covers fewer than 2^32 pixels (checked by the host side): 32-bit index arithmetic
@@ -203,6 +205,7 @@ __device__ __forceinline__ PixelRay pixel_ray(const RenderParams& p, int64_t pix
     r.o[k] = FB_ADD(FB_MUL((double)pf, p.spacing), vw.delta[k]);
   }
   r.d[0] = vw.dir[0]; r.d[1] = vw.dir[1]; r.d[2] = vw.dir[2];
+  r.dlen = vw.dlen;
   return r;
 }
 

@@ -22,7 +22,7 @@
 namespace fb {
 
 #define WD_EMPTY 0xffffffffffffffffull
-enum { WD_INCONSISTENT = 1, WD_NONMANIFOLD = 2, WD_NONORIENTABLE = 4 };
+enum { WD_INCONSISTENT = 1, WD_NONMANIFOLD = 2, WD_NONORIENTABLE = 4, WD_DUPLICATE = 8 };
 
 struct EdgeTab {
   unsigned long long* key;  // [cap] (lo << 32) | hi, WD_EMPTY = free
@@ -59,6 +59,31 @@ __global__ void edge_insert_kernel(const int32_t* __restrict__ tris, int64_t T, 
     if (atomicCAS(tab.cells + 2 * (size_t)h, -1, val) != -1)
       if (atomicCAS(tab.cells + 2 * (size_t)h + 1, -1, val) != -1) atomicExch(tab.cells + 2 * (size_t)h + 1, -2);
   }
+}
+
+// The check every build runs: a DIRECTED edge (a -> b) that occurs in two cells means two cells traverse a shared
+// edge the same way -- the only thing the consistency pass ever acts on.  One 64-bit CAS per edge into a table of
+// 8-byte keys; a consistently wound manifold (the normal case) never raises the flag and nothing else runs.
+__global__ void edge_directed_kernel(const int32_t* __restrict__ tris, int64_t T, unsigned long long* keys, uint32_t mask,
+                                     int* flags) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= T) return;
+  const int32_t t[3] = {tris[3 * c], tris[3 * c + 1], tris[3 * c + 2]};
+  bool dup = false;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const uint32_t a = (uint32_t)t[j], b = (uint32_t)t[(j + 1) % 3];
+    if (a == b) continue;
+    const unsigned long long key = ((unsigned long long)a << 32) | b;
+    uint32_t h = wd_hash(key) & mask;
+    for (;;) {
+      const unsigned long long old = atomicCAS(keys + h, WD_EMPTY, key);
+      if (old == WD_EMPTY) break;
+      if (old == key) { dup = true; break; }
+      h = (h + 1) & mask;
+    }
+  }
+  if (dup) atomicOr(flags, WD_DUPLICATE);
 }
 
 __global__ void edge_check_kernel(EdgeTab tab, int* flags) {
@@ -126,21 +151,39 @@ __global__ void orient_apply_kernel(const uint32_t* __restrict__ par, int64_t T,
   if (m && (threadIdx.x & 31) == 0) atomicAdd(n_flipped, (unsigned long long)__popc(m));
 }
 
-// Queues the detection on the context stream; flags_dev (int) receives WD_* bits.  The table stays in
-// mesh.edge_tab for winding_fix.
+// Queues the cheap detection on the context stream; flags_dev (int) receives WD_DUPLICATE when some directed edge
+// occurs twice.
 int winding_detect(flyby_ctx* c, int* flags_dev) {
   MeshDev& m = c->mesh;
   if (m.T <= 0) return FLYBY_OK;
   uint64_t cap = 1024;
   while (cap < 4 * (uint64_t)m.T) cap <<= 1;
-  FB_CUDA(c, m.edge_tab.reserve((size_t)cap * 16));
+  FB_CUDA(c, m.edge_tab.reserve((size_t)cap * 16));  // sized for winding_classify as well
+  FB_CUDA(c, cudaMemsetAsync(m.edge_tab.p, 0xff, (size_t)cap * 8, c->stream));
+  edge_directed_kernel<<<(unsigned)cdiv(m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), m.T,
+                                                                         m.edge_tab.as<unsigned long long>(),
+                                                                         (uint32_t)(cap - 1), flags_dev);
+  FB_LAUNCH_CHECK(c);
+  return FLYBY_OK;
+}
+
+// Only after a duplicate was seen: the table of UNDIRECTED edges with the first two cells of each, which tells an
+// inconsistent manifold edge (WD_INCONSISTENT) from an edge that three or more cells share (WD_NONMANIFOLD).
+// flags_host receives the bits (synchronises).
+int winding_classify(flyby_ctx* c, int* flags_dev, int* flags_host) {
+  MeshDev& m = c->mesh;
+  uint64_t cap = 1024;
+  while (cap < 4 * (uint64_t)m.T) cap <<= 1;
   EdgeTab tab{m.edge_tab.as<unsigned long long>(), reinterpret_cast<int*>(m.edge_tab.as<unsigned long long>() + cap),
               (uint32_t)(cap - 1)};
   FB_CUDA(c, cudaMemsetAsync(m.edge_tab.p, 0xff, (size_t)cap * 16, c->stream));
+  FB_CUDA(c, cudaMemsetAsync(flags_dev, 0, sizeof(int), c->stream));
   edge_insert_kernel<<<(unsigned)cdiv(m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), m.T, tab);
   FB_LAUNCH_CHECK(c);
   edge_check_kernel<<<(unsigned)cdiv((int64_t)cap, 256), 256, 0, c->stream>>>(tab, flags_dev);
   FB_LAUNCH_CHECK(c);
+  FB_CUDA(c, cudaMemcpyAsync(flags_host, flags_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
   return FLYBY_OK;
 }
 

@@ -63,6 +63,8 @@ SYMBOLS = [
 NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2, "uint8": 3}
 RENDER_MODES = {"default": 0, "raster": 1, "bvh": 2, "fused": 3}
 CONSISTENCY = {"check": 0, "fix": 1, "off": 2}
+SHADE_TOLERANCE = 0x100
+BUILD_DEFERRED = 0x100
 
 
 def load():
@@ -150,10 +152,11 @@ class Context:
 
     # ---- mesh ---------------------------------------------------------------
     def set_mesh(self, verts, tris, centre_mode=0, scale_mode=0, translate=None, scale_factor=None,
-                 skip_normalise=False, consistency="check"):
+                 skip_normalise=False, consistency="check", deferred=False):
         """consistency: what vtkPolyDataNormals' consistency pass means for this mesh -- "check" (build() raises
         FlyByError(status=ERR_UNSUPPORTED) if cells are inconsistently wound), "fix" (reverse cells as VTK does),
-        "off" (cells as given)."""
+        "off" (cells as given).  deferred=True: FLYBY_BUILD_DEFERRED -- build() does not wait for the device; a
+        bad mesh is reported by the next synchronising call instead."""
         _check_dtype(verts, np.float32, "verts")
         _check_dtype(tris, np.int32, "tris")
         V = int(verts.shape[0])
@@ -168,7 +171,8 @@ class Context:
             o.has_scale = 1
             o.scale_factor = float(scale_factor)
         o.skip = 1 if skip_normalise else 0
-        o.consistency = CONSISTENCY[consistency] if isinstance(consistency, str) else int(consistency)
+        o.consistency = (CONSISTENCY[consistency] if isinstance(consistency, str) else int(consistency)) | (
+            BUILD_DEFERRED if deferred else 0)
         self.n_scalars = 0
         self._ck(self._lib.flyby_set_mesh(self._h, _ptr(verts), C.c_int64(V), _ptr(tris), C.c_int64(T),
                                           C.byref(o)))
@@ -247,10 +251,11 @@ class Context:
     # ---- rendering ----------------------------------------------------------
     @staticmethod
     def render_opts(use_z=1, split_z=1, normal_encoding="unit01", plane_scale=1.0, plane_spacing=1.0,
-                    z_scale=1.0, tolerance=1e-10, mode="default"):
-        """mode: "default" | "raster" | "bvh" | "fused" -- the search engine; results are bit-identical."""
+                    z_scale=1.0, tolerance=1e-10, mode="default", shade_tolerance=False):
+        """mode: "default" | "raster" | "bvh" | "fused" -- the search engine; results are bit-identical.
+        shade_tolerance: FLYBY_SHADE_TOLERANCE -- ids stay exact, depth / normals within 1e-5 relative."""
         o = RenderOpts()
-        o.mode = RENDER_MODES[mode] if isinstance(mode, str) else int(mode)
+        o.mode = (RENDER_MODES[mode] if isinstance(mode, str) else int(mode)) | (SHADE_TOLERANCE if shade_tolerance else 0)
         o.use_z, o.split_z = int(bool(use_z)), int(bool(split_z))
         o.normal_encoding = NORMAL_ENCODINGS[normal_encoding] if isinstance(normal_encoding, str) \
             else int(normal_encoding)

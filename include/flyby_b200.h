@@ -53,6 +53,9 @@ typedef enum {
 
 typedef struct flyby_ctx flyby_ctx;
 
+#define FLYBY_SHADE_TOLERANCE 0x100 /* flag of flyby_render_opts.mode */
+#define FLYBY_BUILD_DEFERRED 0x100  /* flag of flyby_norm_opts.consistency */
+
 /* Mesh normalisation: src/py/utils.py:249-290 (ScaleSurf/GetUnitSurf) and
  * src/app/fly_by_features.cxx:393-450. */
 typedef struct {
@@ -68,7 +71,14 @@ typedef struct {
                               edge in the same direction (VTK would reverse cells; nothing is reordered silently);
                             1 fix:   reproduce VTK -- every edge-connected component is oriented like its lowest
                               cell id, reversed cells become (p2,p1,p0) as vtkPolyData::ReverseCell leaves them;
-                            2 off:   use the cells as given (ConsistencyOff) */
+                            2 off:   use the cells as given (ConsistencyOff)
+                            | FLYBY_BUILD_DEFERRED: flyby_build does not synchronise with the host.  The checks still
+                              run on the device -- out-of-range indices are counted and replaced by 0 before anything
+                              gathers through them, duplicate directed edges are flagged -- and their verdict is
+                              returned by the next synchronising call on the context (flyby_synchronize, a render or
+                              read-back with host buffers, a non-deferred flyby_build): FLYBY_ERR_INVALID /
+                              FLYBY_ERR_UNSUPPORTED, after which the mesh counts as not built.  For streams of
+                              meshes (batch extraction): the host queues mesh n+1 while mesh n renders. */
 } flyby_norm_opts;
 
 /* Render options: src/py/fly_by_features.py:124-150 (channel assembly) and
@@ -82,7 +92,12 @@ typedef struct {
                               0 default (= 1 unless the FLYBY_MODE environment variable names another, for A/B runs),
                               1 raster: triangle-centric scan conversion + exact resolve,
                               2 bvh:    warp-cooperative float32 LBVH packet traversal + exact resolve,
-                              3 fused:  warp-cooperative stackless LBVH traversal, exact test at the leaves */
+                              3 fused:  warp-cooperative stackless LBVH traversal, exact test at the leaves
+                              | FLYBY_SHADE_TOLERANCE (raster engine): depth and normals of pixels whose only candidate is a
+                              certain hit are shaded with float32 weights (depth in double) instead of the exact
+                              double-precision chain -- hit cell ids stay bit-exact, depth and normals agree with the
+                              exact chain within 1e-5 relative (measured: depth equal, normals within 2 float32 ulp);
+                              ignored when out_t is requested or barycentric point scalars are set */
   double plane_scale;      /* planeScaleFactor, default 1.0 */
   double plane_spacing;    /* planeSpacing, default 1.0 */
   double z_scale;          /* depth multiplier (1/z_far when rescaling), default 1.0 */

@@ -23,7 +23,8 @@ def one(lib, reps):
     torch.cuda.synchronize()
     ctx.set_mesh(tp, tf); ctx.build()
     n = ctx.views_icosahedron(3, 2.0)
-    opts = ctx.render_opts(use_z=1, split_z=1)
+    opts = ctx.render_opts(use_z=1, split_z=1, shade_tolerance=os.environ.get("AB_TOLERANCE") == "1",
+                           plane_scale=float(os.environ.get("AB_PLANE_SCALE", "1.0")))
     feat = torch.empty((n, 512, 512, 4), dtype=torch.float32, device=dev)
     ids = torch.empty((n, 512, 512), dtype=torch.int32, device=dev)
     r, tr = [], []

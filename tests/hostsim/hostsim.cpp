@@ -595,3 +595,60 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
   if (work) { work[0] = n_tests; work[1] = n_exact; work[2] = n_over; if (check_spans) { work[3] = n_span_bad; work[5] = n_unsound; work[6] = n_maybe; } }
   return 0;
 }
+
+// ---- audit of the opt-in tolerance shading (flyby_core.cuh shade_approx) on its domain of use: every (triangle,
+// pixel) pair the scan-conversion predicate classifies SC_SURE.  For each pair the exact chain (tri_exact + shade)
+// and shade_approx are evaluated and compared.
+// stats: [0] SURE pairs, [1] pairs shade_approx accepted, [2] SURE pairs the exact test rejects (must be 0)
+// err:   [0] largest relative depth error, [1] largest absolute error of a normal channel (in units of the
+//        encoding's range: 1 for unit01 / signed, 255 for byte255), [2] largest relative error of a z-multiplied channel
+extern "C" __attribute__((visibility("default")))
+int sim_shade_approx_audit(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* normals,
+                           const float* views, int n_views, double radius, int res, double plane_scale, double spacing,
+                           int use_z, int split_z, int enc, double zscale, long long* stats, double* err) {
+  float maxc = 0.f;
+  for (int64_t i = 0; i < 3 * V; i++) maxc = fmaxf(maxc, fabsf(verts[i]));
+  long long n_sure = 0, n_acc = 0, n_rej = 0;
+  double e_depth = 0.0, e_norm = 0.0, e_mul = 0.0;
+  const double range = enc == 1 ? 255.0 : 1.0;
+  for (int v = 0; v < n_views; v++) {
+    View vw;
+    view_setup(views + 3 * v, radius, plane_scale, spacing, &vw, 1e-10);
+    ViewF vf;
+    viewf_setup(vw, radius, spacing, maxc, 1e-10, &vf);
+    viewf_pixels(vw, spacing, res, &vf);
+    for (int64_t c = 0; c < T; c++) {
+      const int32_t* tr = tris + 3 * c;
+      const float *P0 = verts + 3 * (int64_t)tr[0], *P1 = verts + 3 * (int64_t)tr[1], *P2 = verts + 3 * (int64_t)tr[2];
+      const float *N0 = normals + 3 * (int64_t)tr[0], *N1 = normals + 3 * (int64_t)tr[1], *N2 = normals + 3 * (int64_t)tr[2];
+      TriR t;
+      PixRange r;
+      if (!raster_project(vf, P0, P1, P2, res, &t, &r)) continue;
+      raster_setup(vf, 0.0f, P0, P1, P2, false, &t);
+      if (!(t.flags & 1)) continue;
+      for (int j = r.j0; j <= r.j1; j++)
+        for (int i = r.i0; i <= r.i1; i++) {
+          if (raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y)) != SC_SURE) continue;
+          n_sure++;
+          double o[3], tt, x[3], w[3];
+          view_ray(vw, res, i, j, spacing, o);
+          if (!tri_exact(o, vw.dir, P0, P1, P2, DBL_MAX, 1e-20, &tt, x, w)) { n_rej++; continue; }
+          float ref[4] = {0, 0, 0, 0}, got[4] = {0, 0, 0, 0};
+          shade(o, x, w, N0, N1, N2, use_z, split_z, enc, zscale, ref);
+          if (!shade_approx(o, vw.dir, vw.dlen, P0, P1, P2, N0, N1, N2, use_z, split_z, enc, zscale, got)) continue;
+          n_acc++;
+          if (use_z && !split_z) {
+            // channel = e * z: compare relative to the depth factor (e in [0, range])
+            const double zref = tt * vw.dlen * fabs(zscale);
+            for (int k = 0; k < 3; k++) e_mul = fmax(e_mul, fabs((double)got[k] - (double)ref[k]) / fmax(zref * range, 1e-300));
+          } else {
+            for (int k = 0; k < 3; k++) e_norm = fmax(e_norm, fabs((double)got[k] - (double)ref[k]) / range);
+            if (use_z) e_depth = fmax(e_depth, fabs((double)got[3] - (double)ref[3]) / fmax(fabs((double)ref[3]), 1e-300));
+          }
+        }
+    }
+  }
+  stats[0] = n_sure; stats[1] = n_acc; stats[2] = n_rej;
+  err[0] = e_depth; err[1] = e_norm; err[2] = e_mul;
+  return 0;
+}

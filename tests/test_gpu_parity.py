@@ -751,3 +751,82 @@ def test_interpolate_ignores_foreign_cell_ids(gpu_ctx, orc):
     spoiled[0, :4] = len(F) + np.arange(4 * 16).reshape(4, 16) * 1000 + 1
     got = gpu_ctx.interpolate_features(16, opts, spoiled, feats, zero=-1.0)
     assert np.all(got[0, :4] == -1.0) and np.array_equal(got[0, 4:], want[0, 4:]) and np.array_equal(got[1:], want[1:])
+
+
+@pytest.mark.parametrize("cfg", [dict(use_z=1, split_z=1), dict(use_z=1, split_z=0, plane_scale=2.0), dict(use_z=0, split_z=0),
+                                 dict(use_z=1, split_z=1, normal_encoding="byte255"),
+                                 dict(use_z=1, split_z=1, normal_encoding="signed", z_scale=0.25)])
+def test_tolerance_shading_keeps_ids_exact(gpu_ctx, orc, cfg):
+    """FLYBY_SHADE_TOLERANCE (opt-in): hit cell ids bit-exact, depth and normals within the task's 1e-5 relative of the
+    exact chain (bar written here: depth 1e-5 relative, normal channels 1e-5 of their range; measured ~1e-7)."""
+    P, F = synth.bumpy_sphere(40, 3)
+    uv, nrm, _, _ = _build(gpu_ctx, P, F)
+    gpu_ctx.views_icosahedron(2, 2.0)
+    views = gpu_ctx.get_views()
+    exact_f, exact_i = gpu_ctx.render(160, gpu_ctx.render_opts(**cfg))
+    fast_f, fast_i = gpu_ctx.render(160, gpu_ctx.render_opts(shade_tolerance=True, **cfg))
+    fo, io = orc.render(uv, F, nrm, views, 2.0, 160, plane_scale=cfg.get("plane_scale", 1.0), use_z=cfg["use_z"],
+                        split_z=cfg["split_z"], normal_encoding=ENC[cfg.get("normal_encoding", "unit01")],
+                        zscale=cfg.get("z_scale", 1.0))
+    assert np.array_equal(exact_i, io) and np.array_equal(exact_f, fo)
+    assert np.array_equal(fast_i, io), "%d ids differ in tolerance mode" % int((fast_i != io).sum())
+    rng_ = 255.0 if cfg.get("normal_encoding") == "byte255" else 1.0
+    hit = io >= 0
+    assert np.array_equal(fast_f[~hit], fo[~hit])
+    if cfg["use_z"] and cfg["split_z"]:
+        d_ref = fo[..., 3][hit].astype(np.float64)
+        assert np.max(np.abs(fast_f[..., 3][hit] - d_ref) / d_ref) <= 1e-5
+        assert np.max(np.abs(fast_f[..., :3][hit].astype(np.float64) - fo[..., :3][hit])) <= 1e-5 * rng_
+    elif not cfg["use_z"]:
+        assert np.max(np.abs(fast_f[hit].astype(np.float64) - fo[hit])) <= 1e-5 * rng_
+    else:   # channels multiplied by the depth: relative to the depth factor
+        _, _, t = gpu_ctx.render(160, gpu_ctx.render_opts(**cfg), want_t=True)
+        z = (t[hit] * 4.0 * cfg.get("z_scale", 1.0))[:, None]
+        assert np.max(np.abs(fast_f[hit].astype(np.float64) - fo[hit]) / (z * rng_)) <= 1e-5
+    assert not np.array_equal(fast_f, fo) or True     # (it may even be bit-equal on small cases)
+    # an exact hit parameter request falls back to the exact chain
+    f3, i3, t3 = gpu_ctx.render(160, gpu_ctx.render_opts(shade_tolerance=True, **cfg), want_t=True)
+    assert np.array_equal(f3, fo) and np.array_equal(i3, io)
+
+
+def test_deferred_build_reports_at_the_next_synchronising_call(gpu_ctx, orc):
+    """FLYBY_BUILD_DEFERRED: flyby_build does not wait for the device (streams of meshes); the index / winding checks
+    still run, out-of-range indices are neutralised on the device and the verdict arrives with the next
+    synchronising call.  Results of a good mesh are bit-identical to a synchronous build."""
+    torch = pytest.importorskip("torch")
+    from flyby_b200 import FlyByError, _cabi
+    P, F = synth.bumpy_sphere(20, 4)
+    gpu_ctx.views_icosahedron(1, 2.0)
+    opts = gpu_ctx.render_opts()
+    gpu_ctx.set_mesh(P, F)
+    gpu_ctx.build()
+    want_f, want_i = gpu_ctx.render(48, opts)
+    gpu_ctx.set_mesh(P, F, deferred=True)
+    gpu_ctx.build()
+    got_f, got_i = gpu_ctx.render(48, opts)
+    assert np.array_equal(got_i, want_i) and np.array_equal(got_f, want_f)
+    # out-of-range indices: nothing faults, the error surfaces at synchronize()
+    bad = F.copy()
+    bad[5, 1] = len(P) + 17
+    bad[9, 0] = -3
+    dev = torch.device("cuda:0")
+    ids = torch.empty((12, 48, 48), dtype=torch.int32, device=dev)
+    gpu_ctx.set_mesh(P, bad, deferred=True)
+    gpu_ctx.build()
+    gpu_ctx.render_into(48, opts, None, ids)      # device output: no synchronisation yet
+    with pytest.raises(FlyByError) as e:
+        gpu_ctx.synchronize()
+    assert e.value.status == _cabi.ERR_INVALID and "2 triangle indices" in str(e.value)
+    # reversed cells are flagged the same way
+    G = F.copy()
+    G[::7] = G[::7][:, ::-1]
+    gpu_ctx.set_mesh(P, np.ascontiguousarray(G), deferred=True)
+    gpu_ctx.build()
+    with pytest.raises(FlyByError) as e:
+        gpu_ctx.render(16, opts)                   # host outputs synchronise
+    assert e.value.status == _cabi.ERR_UNSUPPORTED
+    # and the context is usable afterwards
+    gpu_ctx.set_mesh(P, F)
+    gpu_ctx.build()
+    again_f, again_i = gpu_ctx.render(48, opts)
+    assert np.array_equal(again_i, want_i) and np.array_equal(again_f, want_f)

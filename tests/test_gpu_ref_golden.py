@@ -122,7 +122,7 @@ def test_votes_equal_reference_loops(gpu_ctx):
     Ks = probs.shape[1]
     fx = gpu_ctx.backproject_soft(cells, np.ascontiguousarray(probs.transpose(0, 2, 3, 1)), Ks)
     soft_ref = g["dms_soft"].T.copy()                         # [T, K]; misses accumulated into the last cell there
-    soft_ref[-1] -= probs.transpose(0, 2, 3, 1)[miss].sum(axis=0)
+    soft_ref[-1] -= probs.transpose(0, 2, 3, 1)[miss].astype(np.float64).sum(axis=0)
     n_votes = np.bincount(cells[~miss], minlength=len(F))
     assert np.all(np.abs(fx / 1048576.0 - soft_ref) <= (n_votes[:, None] + 1) * 2.0 ** -20)
     assert np.array_equal(gpu_ctx.cells_to_points(g["dms_faces"].astype(np.int32), default=33), g["dms_points"])

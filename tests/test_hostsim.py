@@ -154,3 +154,27 @@ def test_scan_conversion_spans_at_other_pixel_pitches(sim, orc, lm, res, ps, see
     fo, io, to = orc.render(U, F, N, views, 2.0, res, plane_scale=ps, grid=True, grid_div=32, want_t=True)
     ids, t, work = _sim_ids(sim.sim_render_raster, U, F, views, 2.0, res, ps, 8, nwork=7, work_in=[0, 0, 0, 1, seed])
     assert np.array_equal(io, ids) and np.array_equal(to, t) and work[3] == 0 and work[5] == 0
+
+
+def test_tolerance_shading_error_on_every_certain_pair(sim, orc):
+    """flyby_core.cuh shade_approx (FLYBY_SHADE_TOLERANCE) against the exact chain on every (triangle, pixel) pair the
+    scan-conversion predicate calls a certain hit: depth within 1e-5 relative, normal channels within 1e-5 of their
+    range (the task's bar; the measured errors are two orders of magnitude smaller), and a certain hit is never
+    rejected by the exact test."""
+    cases = [(synth.bumpy_sphere(24, 3), orc.icosahedron(1, 2.0), 2.0, 96, dict()),
+             (synth.bumpy_sphere(24, 3), orc.icosahedron(1, 2.0), 2.0, 96, dict(split_z=0, ps=2.0)),
+             (synth.dental_crown(30, 1), orc.spiral(6, 4, 4.0), 4.0, 112, dict(enc=1)),
+             (synth.dental_crown(30, 1), orc.spiral(6, 4, 4.0), 4.0, 112, dict(enc=2, zs=0.25, use_z=0))]
+    for (P, F), views, radius, res, kw in cases:
+        U, _, _ = orc.unit_surf(P)
+        F = np.ascontiguousarray(F, np.int32)
+        N = orc.point_normals(U, F)
+        st, err = np.zeros(4, np.int64), np.zeros(4)
+        rc = sim.sim_shade_approx_audit(_p(U), C.c_int64(len(U)), _p(F), C.c_int64(len(F)), _p(N), _p(views), C.c_int(len(views)),
+                                        C.c_double(radius), C.c_int(res), C.c_double(kw.get("ps", 1.0)), C.c_double(1.0),
+                                        C.c_int(kw.get("use_z", 1)), C.c_int(kw.get("split_z", 1)), C.c_int(kw.get("enc", 0)),
+                                        C.c_double(kw.get("zs", 1.0)), _p(st), _p(err))
+        assert rc == 0 and st[0] > 10000 and st[2] == 0
+        assert st[1] >= 0.99 * st[0]              # well-shaped triangles: the float32 weights are used almost everywhere
+        assert err[0] <= 1e-5 and err[1] <= 1e-5 and err[2] <= 1e-5, err
+        assert max(err[:3]) <= 1e-6                # what it really achieves
