@@ -135,6 +135,20 @@ def run_reference(args):
     emit(line)
 
 
+def _hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _max_over_ranks(torch, dist, world, dev, vals):
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
 def _host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -216,18 +230,25 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     T, V = len(meshes[0][1]), len(meshes[0][0])
 
-    def step_resident(k):
+    # FLYBY_BUILD_DEFERRED: the build's index / winding checks run on the device as always, but the host does not
+    # wait for their verdict -- it arrives with the next synchronising call (ctx.synchronize() below raises on a bad
+    # mesh).  The host thus queues mesh n+1 while mesh n renders; `sync_build` times the same loop with the
+    # synchronising build for comparison.
+    def step_resident(k, deferred=True):
         P, F = dev_meshes[k % MESH_POOL]
-        ctx.set_mesh(P, F)
+        ctx.set_mesh(P, F, deferred=deferred)
         ctx.build()
         ctx.render_into(RES, opts, feat, ids)
+
+    def step_resident_sync(k):
+        step_resident(k, deferred=False)
 
     # The e2e product is what the reference's entry point returns / writes with --out: the views x res x res x C
     # feature tensor (fly_by_features.py:63-154).  The hit-cell-id map is a second, optional output (needed only by
     # the labeling back-projection); the run that also copies it out is reported beside the headline.
     def step_e2e(k, with_ids=False):
         P, F = pin_meshes[k % MESH_POOL]
-        ctx.set_mesh(P.numpy(), F.numpy())
+        ctx.set_mesh(P.numpy(), F.numpy(), deferred=True)
         ctx.build()
         # D2H inside, returns after the copy
         ctx.render_into(RES, opts, feat_host.numpy(), ids_host.numpy() if with_ids else None)
@@ -238,7 +259,7 @@ def run_ours(args):
     def step_e2e_stream(k):
         """the same through flyby_render_async: returns when queued; this mesh's copy-out overlaps the next mesh"""
         P, F = pin_meshes[k % MESH_POOL]
-        ctx.set_mesh(P.numpy(), F.numpy())
+        ctx.set_mesh(P.numpy(), F.numpy(), deferred=True)
         ctx.build()
         ctx.render_into(RES, opts, feat_hosts[k % 2].numpy(), None, wait=False)
 
@@ -292,6 +313,8 @@ def run_ours(args):
     ms_step, ms_render, ms_trace = timed(step_resident, args.steps, args.warmup, collect_render=True)
     launches = ctx.launch_count() - l0
     st = ctx.stats()
+    ctx.synchronize()  # (reads the deferred builds' verdict: raises if a mesh was bad)
+    ms_step_sync, _, _ = timed(step_resident_sync, max(4, min(args.steps, 10)), 3)
     ms_e2e, _, _ = timed(step_e2e, max(2, min(args.steps, 8)), 3)
     ms_e2e_ids, _, _ = timed(step_e2e_ids, max(2, min(args.steps, 8)), 2)
     ms_e2e_stream = timed_stream(max(4, args.steps), 3)  # K meshes as a whole: fill and drain of the pipeline included
@@ -310,7 +333,7 @@ def run_ours(args):
         P, F = dev_meshes[k % MESH_POOL]
         with torch.cuda.stream(s_):
             flush.zero_()
-        c_.set_mesh(P, F)
+        c_.set_mesh(P, F, deferred=True)
         c_.build()
         c_.render_into(RES, opts, f_, i_)
 
@@ -329,6 +352,8 @@ def run_ours(args):
     e1.synchronize()
     ms_two = e0.elapsed_time(e1) / k_two
     launches_two = ctx.launch_count() + ctx2.launch_count() - l0
+    ctx.synchronize()   # deferred builds: a bad mesh would raise here
+    ctx2.synchronize()
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -360,17 +385,57 @@ def run_ours(args):
     if not verified:
         raise SystemExit("bench.py: the pipelined loop's outputs differ from a serial context's -- numbers withheld")
 
-    t = torch.tensor([ms_step, ms_e2e, ms_e2e_stream, ms_two, ms_e2e_ids], dtype=torch.float64, device=dev)
+    # ---- records beside the headline (bench_extra.py): plane scale 2.0, tolerance shading, the node's D2H ceiling,
+    # BASELINE configs[4] sharded by viewpoint and configs[3] with the NCCL vote all-reduce.  Not part of `value`.
+    import bench_extra as bx
+    extras = {}
+    if not args.no_extras:
+        P0, F0 = dev_meshes[0]
+        ms_r1, ms_t1, st1 = bx.render_variant(torch, ctx, stream, flush, (P0, F0), RES, opts, feat, ids)
+        feat_exact, ids_exact = feat.clone(), ids.clone()
+        opts_tol = ctx.render_opts(use_z=1, split_z=1, plane_scale=PLANE_SCALE, shade_tolerance=True)
+        ms_rt, ms_tt, _ = bx.render_variant(torch, ctx, stream, flush, (P0, F0), RES, opts_tol, feat, ids)
+        tol = bx.tolerance_errors(torch, feat_exact, ids_exact, feat, ids)
+        del feat_exact, ids_exact
+        opts2 = ctx.render_opts(use_z=1, split_z=1, plane_scale=2.0)
+        ms_r2, ms_t2, st2 = bx.render_variant(torch, ctx, stream, flush, (P0, F0), RES, opts2, feat, ids)
+        vals = _max_over_ranks(torch, dist, world, dev, [ms_r1, ms_t1, ms_rt, ms_tt, ms_r2, ms_t2])
+        alg1 = algorithmic_bytes(n_rays, C, T, V)
+        extras["plane_scale_2"] = {
+            "render_ms": vals[4], "candidate_search_ms": vals[5], "exact_resolve_ms": vals[4] - vals[5],
+            "render_mrays_per_s": n_rays / (vals[4] * 1e-3) / 1e6, "views_per_s_render_only": n_views / (vals[4] * 1e-3),
+            "hit_fraction": st2["n_hits"] / max(1, st2["n_rays"]),
+            "roofline_frac": alg1 / (vals[4] * 1e-3) / 1e9 / _hbm_peak()[0],
+            "beside": {"plane_scale": 1.0, "render_ms": vals[0], "hit_fraction": st1["n_hits"] / max(1, st1["n_rays"])},
+            "note": "planeScaleFactor 2.0 shows the whole unit surface (SURVEY 8d O5); 1.0 is the reference default the "
+                    "headline uses (the unit surface puts the bounding-box corner on the unit sphere, so the mesh is ~1.15 wide: a 1 x 1 "
+                    "window is 91 % covered, a 2 x 2 window 27 %)"}
+        extras["tolerance_mode"] = dict(tol, render_ms=vals[2], candidate_search_ms=vals[3],
+                                        exact_resolve_ms=vals[2] - vals[3], exact_render_ms=vals[0],
+                                        views_per_s_render_only=n_views / (vals[2] * 1e-3),
+                                        note="FLYBY_SHADE_TOLERANCE (opt-in; the headline uses the exact chain)")
+        d2h_bytes = n_rays * 4 * C
+        slow, total = bx.copy_ceiling(torch, dist, world, dev, d2h_bytes, feat_hosts[0])
+        extras["copy_ceiling"] = {"d2h_gb_s_slowest_rank": slow, "d2h_gb_s_all_ranks": total, "bytes": d2h_bytes,
+                                  "views_per_s": world * n_views / (d2h_bytes / (slow * 1e9)),
+                                  "how": "every rank: one plain cudaMemcpyAsync of the e2e payload into its pinned buffer, all "
+                                         "ranks at the same time, best of 6"}
+        del feat, ids
+        torch.cuda.empty_cache()
+        extras["by_view"] = bx.by_view(torch, dist, _cabi, synth, fdist, world, rank, local, dev, stream, barrier)
+        try:
+            extras["votes_allreduce"] = bx.votes_allreduce(torch, dist, _cabi, synth, fdist, world, rank, local, dev, stream,
+                                                           barrier)
+        except (_cabi.FlyByError, ImportError) as ex:  # NCCL or torchvision missing on this box
+            extras["votes_allreduce"] = {"unavailable": str(ex)[:200]}
+
+    t = torch.tensor([ms_step, ms_e2e, ms_e2e_stream, ms_two, ms_e2e_ids, ms_step_sync], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step_max, ms_e2e_max, ms_e2e_stream_max, ms_two_max, ms_e2e_ids_max = (float(x) for x in t)
+    ms_step_max, ms_e2e_max, ms_e2e_stream_max, ms_two_max, ms_e2e_ids_max, ms_step_sync_max = (float(x) for x in t)
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        peak, peak_src = _hbm_peak()
         alg = algorithmic_bytes(n_rays, C, T, V)
         # the render is a short pipeline of kernels (candidate search: raster_kernel; exact decision:
         # raster_resolve1/2, spill_*); the roofline is taken over the pipeline, CUDA events on its stream
@@ -397,6 +462,10 @@ def run_ours(args):
                 "pipelining": "two contexts (two streams) per GPU alternate meshes: the build of mesh n+1 overlaps the "
                               "render of mesh n; K meshes timed as a whole, max over ranks",
                 "single_context_ms_per_step": ms_step_max,
+                "single_context_sync_build_ms_per_step": ms_step_sync_max,
+                "build_checks": "FLYBY_BUILD_DEFERRED in the timed loops: the index / winding checks run on the device in "
+                                "every step, their verdict is read by the synchronising call after the loop; "
+                                "single_context_sync_build_ms_per_step is the same loop with the synchronising build",
                 "single_context_note": "one context, every step timed on its own between device synchronisations "
                                        "(render_ms, build_ms and the roofline come from this loop)",
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -409,8 +478,10 @@ def run_ours(args):
                         "mode": ("flyby_render_async" if ms_e2e_stream_max < ms_e2e_max else "blocking flyby_render")
                                 + " per mesh: pinned H2D of the mesh, build, render in view chunks, chunked D2H of the "
                                   "feature tensor (what fly_by_features.py --out holds) into pinned host memory; "
-                                  "PCIe-bound (profiles/pcie_bw.py: 57 GB/s pinned D2H on this box)",
+                                  "PCIe-bound: copy_ceiling_frac = this value / what N concurrent plain pinned D2H copies of the "
+                                  "same payload reach on this node (copy_ceiling)",
                         "host_buffers_numa_node": numa.node,
+                        "copy_ceiling_frac": (e2e_views / extras["copy_ceiling"]["views_per_s"]) if "copy_ceiling" in extras else None,
                         "blocking_ms_per_step": ms_e2e_max,
                         "streamed_ms_per_step": ms_e2e_stream_max,
                         "streamed_note": "flyby_render_async (copy-out of mesh n overlaps upload/build/render of mesh "
@@ -423,6 +494,7 @@ def run_ours(args):
                 "outputs_verified": "ids and features of the last two pipelined steps are bit-equal to a serial "
                                     "context's (no side stream, synchronised after every call)",
                 "gpu_launches": launches_two, "gpu_launches_single_context_loop": launches,
+                **extras,
                 "clocks": sampler.summary()}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -454,6 +526,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", dest="no_extras", action="store_true",
+                    help="skip the records beside the headline (plane scale 2, tolerance mode, configs[3] / [4])")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
