@@ -156,7 +156,9 @@ def _host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline_sample():
+def cpu_baseline_sample(gpu_sample=None):
+    """Times the oracle port on a bounded sample; the rays it casts for that are also the parity sample of the
+    bench line: gpu_sample = (features, ids) of views 1..4 of mesh seed 0 as the CUDA path rendered them."""
     from oracle import oracle as orc
     from flyby_b200 import synth
     orc.set_threads(_host_threads())
@@ -165,18 +167,29 @@ def cpu_baseline_sample():
     N = orc.point_normals(U, F)
     views = orc.icosahedron(SUBDIVISION, RADIUS)
     out = {}
+    parity = None
     for name, div, nv in (("vtk_buckets", 0, 4), ("tuned_grid64", 64, 8)):
         orc.render(U, F, N, views[:1], RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=div)
         t0 = time.perf_counter()
-        orc.render(U, F, N, views[1:1 + nv], RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=div)
+        fo, io = orc.render(U, F, N, views[1:1 + nv], RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=div)
         out[name] = nv / (time.perf_counter() - t0)
+        if name == "vtk_buckets" and gpu_sample is not None:
+            gf, gi = gpu_sample
+            hit = io >= 0
+            parity = {"rays": int(io.size), "hits": int(hit.sum()), "id_mismatches": int((gi != io).sum()),
+                      "grazing_edge_disagreements": int(((gi != io) & (gi >= 0) & hit).sum()),
+                      "features_bit_equal": bool(np.array_equal(gf, fo)),
+                      "max_rel_err_depth": float(np.max(np.abs(gf[..., 3][hit] - fo[..., 3][hit]) / fo[..., 3][hit])) if hit.any() else 0.0,
+                      "max_abs_err_normals": float(np.max(np.abs(gf[..., :3] - fo[..., :3]))),
+                      "sample": "views 1..4 of the first bench mesh at res 512 (the rays the CPU baseline is timed on), "
+                                "CUDA path vs oracle; tie-break smallest t, then lowest cell id"}
     cores = orc.num_threads()
     orc.set_threads(1)  # the reference's own loop is serial: one view, one thread
     t0 = time.perf_counter()
     orc.render(U, F, N, views[1:2], RADIUS, RES, plane_scale=PLANE_SCALE, grid=True, grid_div=0)
     single = 1.0 / (time.perf_counter() - t0)
     orc.set_threads(cores)
-    return {"value": out["vtk_buckets"], "unit": "views/s", "cores": cores, "kind": "port",
+    return {"value": out["vtk_buckets"], "unit": "views/s", "cores": cores, "kind": "port", "parity_sample": parity,
             "single_thread_views_per_s": single,
             "sample": "4 views at res 512 of the bench mesh, oracle port of vtkCellLocator (VTK default bucket "
                       "rule) + VTK triangle test, OpenMP over rays, ray loop only",
@@ -449,7 +462,14 @@ def run_ours(args):
         # both move every step's mesh H2D and its feature tensor D2H inside the timed region
         ms_e2e_best = min(ms_e2e_max, ms_e2e_stream_max)
         e2e_views = world * n_views / (ms_e2e_best * 1e-3)
-        cpu = cpu_baseline_sample() if world == 1 else None
+        cpu = None
+        if world == 1:
+            c4 = _cabi.Context(local, stream=stream.cuda_stream)
+            c4.set_mesh(*dev_meshes[0])
+            c4.build()
+            c4.views_icosahedron(SUBDIVISION, RADIUS)
+            cpu = cpu_baseline_sample(c4.render(RES, opts, view_begin=1, view_end=5))
+            c4.close()
         line = {"metric": METRIC, "value": views_per_s, "unit": "views/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_two_max, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64 (hit decision, depth, normals) over f32 traversal",
@@ -497,6 +517,7 @@ def run_ours(args):
                 **extras,
                 "clocks": sampler.summary()}
         if cpu is not None:
+            line["parity_sample"] = cpu.pop("parity_sample")
             line["cpu_baseline"] = cpu
         emit(line)
     ctx.close()

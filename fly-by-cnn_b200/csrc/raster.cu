@@ -261,24 +261,29 @@ __global__ void raster_init_kernel(unsigned long long* front, int* cnt, int64_t 
 // ---- resolve1: every pixel, raster order
 #define RV_STAGE 64  // per-warp staging of queued pixels: one global atomic per 32+ entries instead of one per iteration
 #ifndef RV_MINB_APPROX
-#define RV_MINB_APPROX 5
+#define RV_MINB_APPROX 8  // 64 registers: 0.60 ms against 0.64 (6) and 0.78 (10) on the bench workload (profiles/r02_ab_series.txt)
 #endif
-// the exact chain of one pixel, out of line: the tolerance variant of resolve1 only needs it for slivers
-static __device__ __noinline__ bool resolve_exact_pixel(const RenderParams& p, int64_t pix, int slot) {
-  const float4* rec = p.trec + 4 * (int64_t)slot;
-  const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
-  const PixelRay r = pixel_ray(p, pix);
-  const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-  double t, x[3], w[3];
-  if (tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w)) {
-    shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
-    return true;
+// per-warp staging of queued pixels, flushed with one global atomic per 32+ entries
+__device__ __forceinline__ void stage_pixels(const RasterParams& rp, uint32_t* stage, int& n_stage, bool mine, uint32_t pix,
+                                             int lane) {
+  const unsigned mq = __ballot_sync(0xffffffffu, mine);
+  if (!mq) return;
+  if (mine) stage[n_stage + __popc(mq & ((1u << lane) - 1u))] = pix;
+  n_stage += __popc(mq);
+  __syncwarp();
+  if (n_stage > RV_STAGE - 32) {
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(rp.n_queue, (unsigned int)n_stage);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int k = lane; k < n_stage; k += 32) rp.queue[base + k] = stage[k];
+    n_stage = 0;
+    __syncwarp();
   }
-  const float zero[4] = {0.f, 0.f, 0.f, 0.f};
-  write_pixel(p, pix, zero, -1, -1.0);
-  return false;
 }
 
+// APPROX (FLYBY_SHADE_TOLERANCE): a pixel whose only candidate is a certain hit is shaded by shade_approx; the exact
+// chain is not part of this variant at all (fewer registers, more resident warps) -- a pixel it declines (sliver
+// triangle) joins the queue of resolve2, which runs the exact chain on the front candidate.
 template <bool APPROX>
 __global__ void __launch_bounds__(RV_THREADS, APPROX ? RV_MINB_APPROX : RV_MINB) raster_resolve1_kernel(const RasterParams rp) {
   const RenderParams& p = rp.r;
@@ -298,55 +303,43 @@ __global__ void __launch_bounds__(RV_THREADS, APPROX ? RV_MINB_APPROX : RV_MINB)
       f = __ldcs(rp.front + pix);
       nc = __ldcs(rp.cnt + pix);
     }
-    const unsigned mq = __ballot_sync(0xffffffffu, nc > 0);
-    if (mq) {  // pixels that have more than the front candidate go to resolve2
-      if (nc > 0) stage[n_stage + __popc(mq & ((1u << lane) - 1u))] = (uint32_t)pix;
-      n_stage += __popc(mq);
-      __syncwarp();
-      if (n_stage > RV_STAGE - 32) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(rp.n_queue, (unsigned int)n_stage);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int k = lane; k < n_stage; k += 32) rp.queue[base + k] = stage[k];
-        n_stage = 0;
-        __syncwarp();
+    if (!APPROX) stage_pixels(rp, stage, n_stage, nc > 0, (uint32_t)pix, lane);  // more than the front candidate: resolve2
+    bool declined = false;
+    if (valid && nc == 0) {
+      if (f == ~0ull) {
+        const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+        write_pixel(p, pix, zero, -1, -1.0);
+      } else {
+        const int slot = FB_FRONT_SLOT(f);
+        const float4* rec = p.trec + 4 * (int64_t)slot;
+        const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
+        const PixelRay r = pixel_ray(p, pix);
+        const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+        const int pid0 = __float_as_int(b.w), pid1 = __float_as_int(e.w), pid2 = __float_as_int(g.x), cell = __float_as_int(a.w);
+        if (APPROX) {
+          const float4 n0 = __ldg(p.normals + pid0), n1 = __ldg(p.normals + pid1), n2 = __ldg(p.normals + pid2);
+          const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
+          float px[4] = {0.f, 0.f, 0.f, 0.f};
+          if (shade_approx(r.o, r.d, r.dlen, P0, P1, P2, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px)) {
+            hits++;
+            write_pixel(p, pix, px, cell, -1.0);
+            write_hit_scalars(p, pix, nullptr, pid0, pid1, pid2, cell);
+          } else {
+            declined = true;
+          }
+        } else {
+          double t, x[3], w[3];
+          if (tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w)) {
+            hits++;
+            shade_and_write(p, pix, r, t, w, pid0, pid1, pid2, cell);
+          } else {
+            const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+            write_pixel(p, pix, zero, -1, -1.0);
+          }
+        }
       }
     }
-    if (!valid || nc > 0) continue;
-    if (f == ~0ull) {
-      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
-      write_pixel(p, pix, zero, -1, -1.0);
-      continue;
-    }
-    const int slot = FB_FRONT_SLOT(f);
-    const float4* rec = p.trec + 4 * (int64_t)slot;
-    const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
-    const PixelRay r = pixel_ray(p, pix);
-    const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
-    double t, x[3], w[3];
-    if (APPROX) {
-      // opt-in tolerance shading: the only candidate is a certain hit, so the id is known; depth in double, weights
-      // and normal in float32 (flyby_core.cuh shade_approx); slivers fall through to the exact chain
-      const int pid0 = __float_as_int(b.w), pid1 = __float_as_int(e.w), pid2 = __float_as_int(g.x);
-      const float4 n0 = __ldg(p.normals + pid0), n1 = __ldg(p.normals + pid1), n2 = __ldg(p.normals + pid2);
-      const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
-      float px[4] = {0.f, 0.f, 0.f, 0.f};
-      if (shade_approx(r.o, r.d, r.dlen, P0, P1, P2, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px)) {
-        hits++;
-        write_pixel(p, pix, px, __float_as_int(a.w), -1.0);
-        write_hit_scalars(p, pix, nullptr, pid0, pid1, pid2, __float_as_int(a.w));
-        continue;
-      }
-      hits += resolve_exact_pixel(p, pix, slot) ? 1u : 0u;
-      continue;
-    }
-    if (tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w)) {
-      hits++;
-      shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
-    } else {
-      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
-      write_pixel(p, pix, zero, -1, -1.0);
-    }
+    if (APPROX) stage_pixels(rp, stage, n_stage, nc > 0 || declined, (uint32_t)pix, lane);
   }
   __syncwarp();
   if (n_stage) {
@@ -357,6 +350,29 @@ __global__ void __launch_bounds__(RV_THREADS, APPROX ? RV_MINB_APPROX : RV_MINB)
   }
   for (int o2 = 16; o2 > 0; o2 >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o2);
   if (lane == 0 && hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
+}
+
+// Shading of a decided pixel outside resolve1.  In tolerance mode (rp.r.approx) the winner is shaded by shade_approx
+// here as well, so that every hit pixel is the same function of (pixel, winning triangle) whichever kernel finishes
+// it -- which pixels carry extra candidates depends on the order the atomics of raster_kernel land in.
+static __device__ __noinline__ void shade_decided(const RenderParams& p, int64_t pix, const PixelRay& r, double t,
+                                                   double w0, double w1, double w2, int slot, int cell) {
+  const float4* rec = p.trec + 4 * (int64_t)slot;
+  const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
+  const int pid0 = __float_as_int(b.w), pid1 = __float_as_int(e.w), pid2 = __float_as_int(g.x);
+  if (p.approx) {
+    const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
+    const float4 n0 = __ldg(p.normals + pid0), n1 = __ldg(p.normals + pid1), n2 = __ldg(p.normals + pid2);
+    const float N0[3] = {n0.x, n0.y, n0.z}, N1[3] = {n1.x, n1.y, n1.z}, N2[3] = {n2.x, n2.y, n2.z};
+    float px[4] = {0.f, 0.f, 0.f, 0.f};
+    if (shade_approx(r.o, r.d, r.dlen, P0, P1, P2, N0, N1, N2, p.use_z, p.split_z, p.enc, p.zscale, px)) {
+      write_pixel(p, pix, px, cell, -1.0);
+      write_hit_scalars(p, pix, nullptr, pid0, pid1, pid2, cell);
+      return;
+    }
+  }
+  const double w[3] = {w0, w1, w2};
+  shade_and_write(p, pix, r, t, w, pid0, pid1, pid2, cell);
 }
 
 // ---- resolve2: queued pixels (near edges, silhouettes, layered geometry)
@@ -378,7 +394,7 @@ __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve2_kernel(const Ra
     if (nc > 4) c1 = __ldcs(reinterpret_cast<const int4*>(rp.extra2) + pix);
     const PixelRay r = pixel_ray(p, pix);
     double best_t = DBL_MAX, bw[3] = {0.0, 0.0, 0.0};
-    int best_slot = -1, best_cell = 0x7fffffff, bp0 = 0, bp1 = 0, bp2 = 0;
+    int best_slot = -1, best_cell = 0x7fffffff;
     for (int i = (f == ~0ull ? 0 : -1); i < nc; i++) {
       const int4 cc = i < 4 ? c0 : c1;
       const int j = i & 3;
@@ -392,7 +408,6 @@ __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve2_kernel(const Ra
         if (tt < best_t || (tt == best_t && c < best_cell)) {
           best_t = tt; best_slot = slot; best_cell = c;
           bw[0] = w[0]; bw[1] = w[1]; bw[2] = w[2];
-          bp0 = __float_as_int(b.w); bp1 = __float_as_int(e.w); bp2 = __float_as_int(g.x);
         }
       }
     }
@@ -410,7 +425,7 @@ __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve2_kernel(const Ra
     }
     if (best_slot >= 0) {
       hits++;
-      shade_and_write(p, pix, r, best_t, bw, bp0, bp1, bp2, best_cell);
+      shade_decided(p, pix, r, best_t, bw[0], bw[1], bw[2], best_slot, best_cell);
     } else {
       const float zero[4] = {0.f, 0.f, 0.f, 0.f};
       write_pixel(p, pix, zero, -1, -1.0);
@@ -481,7 +496,7 @@ __global__ void __launch_bounds__(RV_THREADS) spill_shade_kernel(const RasterPar
     double t, x[3], w[3];
     tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w);  // hit by construction; recomputed for the weights
     hits++;
-    shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
+    shade_decided(p, pix, r, t, w[0], w[1], w[2], slot, __float_as_int(a.w));
   }
   if (hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
   if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.counters + 4, (unsigned long long)n);  // pixels finished from the spill list
@@ -503,9 +518,7 @@ __global__ void __launch_bounds__(64) raster_resolve3_kernel(const RasterParams 
     const ExactHit h = resolve_overflow(p, p.view_begin + v, r.o[0], r.o[1], r.o[2], vf->enabled ? vf : nullptr, qx, qy);
     if (h.slot >= 0) {
       hits++;
-      const int4 vid = p.tvid[h.slot];
-      const double w[3] = {h.w0, h.w1, h.w2};
-      shade_and_write(p, pix, r, h.t, w, vid.x, vid.y, vid.z, h.cell);
+      shade_decided(p, pix, r, h.t, h.w0, h.w1, h.w2, h.slot, h.cell);
     } else {
       const float zero[4] = {0.f, 0.f, 0.f, 0.f};
       write_pixel(p, pix, zero, -1, -1.0);
@@ -520,6 +533,9 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   const int64_t n_pix = (int64_t)rp.n_views * rp.res * rp.res;
   RasterParams p;
   p.r = rp;
+  // tolerance shading applies when no exact hit parameter is asked for and no scalar needs the exact weights
+  const bool approx = rp.approx && !rp.tt && !(rp.n_scal && rp.scal_mode == 1);
+  p.r.approx = approx ? 1 : 0;
   p.n_pix = n_pix;
   p.T = (int)c->mesh.T;
   FB_CUDA(c, c->cand.reserve(sizeof(int4) * (size_t)n_pix));
@@ -590,11 +606,9 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
     int rc = wait_tree(c);
     if (rc) return rc;
   }
-  const bool approx = rp.approx && !rp.tt && !(rp.n_scal && rp.scal_mode == 1);
   long long rgrid = (long long)c->sm_count * (approx ? RV_MINB_APPROX : RV_MINB) * 4;  // CTAs resident per SM, 4 rounds for balance
   const long long want = cdiv(n_pix, RV_THREADS);
   if (rgrid > want) rgrid = want;
-  // tolerance shading applies when no exact hit parameter is asked for and no scalar needs the exact weights
   if (approx)
     raster_resolve1_kernel<true><<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
   else

@@ -177,6 +177,8 @@ int trace_interpolate(flyby_ctx* c, int vb, int ve, int res, const flyby_render_
   p.tc = c->tc_table.as<double>();
   p.views = c->views.as<View>();
   p.view_begin = vb; p.n_views = ve - vb; p.res = res;
+  p.div_view = make_fastdiv((uint32_t)res * (uint32_t)res);
+  p.div_res = make_fastdiv((uint32_t)res);
   p.spacing = o->plane_spacing;
   p.tol2 = o->tolerance * o->tolerance;
   interpolate_kernel<<<(unsigned)cdiv(n_pix, 128), 128, 0, c->stream>>>(p, m.verts.as<float>(), m.tris.as<int32_t>(),
@@ -517,6 +519,8 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   p.views = c->views.as<View>();
   p.ubox = prep_unit_box(c);
   p.view_begin = vb; p.n_views = nv; p.res = res;
+  p.div_view = make_fastdiv((uint32_t)res * (uint32_t)res);  // (res <= 16384: res * res < 2^32)
+  p.div_res = make_fastdiv((uint32_t)res);
   p.use_z = o->use_z; p.split_z = o->split_z; p.enc = o->normal_encoding; p.channels = channels;
   p.zscale = o->z_scale; p.spacing = o->plane_spacing;
   p.tol2 = o->tolerance * o->tolerance;

@@ -61,6 +61,27 @@ struct WorkCount {
   __device__ __forceinline__ void tri() { tris++; }
 };
 
+// ---------------------------------------------------------------- division by a launch-invariant divisor
+// n / d for 32-bit n with a multiply-high and two shifts (Granlund & Montgomery): pixel_ray splits a pixel id into
+// (view, row, column) once per pixel, which as two hardware-less 32-bit divisions cost ~40 instructions
+struct FastDiv {
+  uint32_t mul, sh1, sh2;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{0u, 0u, 0u};
+  if (d <= 1) return f;  // q = n
+  uint32_t l = 0;
+  while ((1ull << l) < d) l++;
+  f.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1ull);
+  f.sh1 = 1;
+  f.sh2 = l - 1;
+  return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.mul, n);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
 // ---------------------------------------------------------------- render
 struct RenderParams {
   const Node* nodes;
@@ -90,6 +111,7 @@ struct RenderParams {
   int n_scal, scal_mode, stride;
   float scal_zero;
   int approx;                    // FLYBY_SHADE_TOLERANCE: shade_approx for pixels whose only candidate is a certain hit
+  FastDiv div_view, div_res;     // by res * res and by res
 };
 
 #ifndef RK_MINB
@@ -192,12 +214,12 @@ struct PixelRay {
 __device__ __forceinline__ PixelRay pixel_ray(const RenderParams& p, int64_t pix_id) {
   // a render call covers fewer than 2^32 pixels (checked by the host side): 32-bit index arithmetic
   const uint32_t per_view = (uint32_t)p.res * (uint32_t)p.res;
-  const uint32_t v = (uint32_t)pix_id / per_view;
+  const uint32_t v = fastdiv((uint32_t)pix_id, p.div_view);
   const uint32_t pix = (uint32_t)pix_id - v * per_view;
   const View& vw = p.views[p.view_begin + (int)v];
   PixelRay r;
   // view_ray() with the two divisions i / (res - 1) taken from the table (bit-identical values)
-  const uint32_t pj = pix / (uint32_t)p.res, pi = pix - pj * (uint32_t)p.res;
+  const uint32_t pj = fastdiv(pix, p.div_res), pi = pix - pj * (uint32_t)p.res;
   const double tc0 = p.tc[pi], tc1 = p.tc[pj];
 #pragma unroll
   for (int k = 0; k < 3; k++) {

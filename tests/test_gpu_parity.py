@@ -783,7 +783,13 @@ def test_tolerance_shading_keeps_ids_exact(gpu_ctx, orc, cfg):
         _, _, t = gpu_ctx.render(160, gpu_ctx.render_opts(**cfg), want_t=True)
         z = (t[hit] * 4.0 * cfg.get("z_scale", 1.0))[:, None]
         assert np.max(np.abs(fast_f[hit].astype(np.float64) - fo[hit]) / (z * rng_)) <= 1e-5
-    assert not np.array_equal(fast_f, fo) or True     # (it may even be bit-equal on small cases)
+    # reproducible: every hit pixel is the same function of (pixel, winning triangle) whichever kernel finishes it,
+    # so repeated renders and view-range slabs give identical bits although the atomics land in another order
+    for _ in range(3):
+        again_f, again_i = gpu_ctx.render(160, gpu_ctx.render_opts(shade_tolerance=True, **cfg))
+        assert np.array_equal(again_f, fast_f) and np.array_equal(again_i, fast_i)
+    part_f, _ = gpu_ctx.render(160, gpu_ctx.render_opts(shade_tolerance=True, **cfg), view_begin=5, view_end=9)
+    assert np.array_equal(part_f, fast_f[5:9])
     # an exact hit parameter request falls back to the exact chain
     f3, i3, t3 = gpu_ctx.render(160, gpu_ctx.render_opts(shade_tolerance=True, **cfg), want_t=True)
     assert np.array_equal(f3, fo) and np.array_equal(i3, io)
