@@ -952,14 +952,17 @@ FB_HD bool shade_approx(const double* o, const double* d, double dlen, const flo
   const float r[3] = {(float)FB_FMA(t, d[0], -q[0]), (float)FB_FMA(t, d[1], -q[1]), (float)FB_FMA(t, d[2], -q[2])};
   const float af[3] = {(float)a[0], (float)a[1], (float)a[2]}, bf[3] = {(float)b[0], (float)b[1], (float)b[2]};
   const float f0 = (float)fabs(n[0]), f1 = (float)fabs(n[1]), f2 = (float)fabs(n[2]);
-  const int idx = (f0 >= f1 && f0 >= f2) ? 0 : (f1 >= f2 ? 1 : 2);  // drop the dominant axis of n
-  const int ia = idx == 0 ? 1 : 0, ib = idx == 2 ? 1 : 2;
-  const float det = fmaf(af[ia], bf[ib], -(bf[ia] * af[ib]));
-  const float scale = (fabsf(af[ia]) + fabsf(af[ib])) * (fabsf(bf[ia]) + fabsf(bf[ib]));
+  // drop the dominant axis of n; the two kept components are selected without indexed arrays
+  const bool d0 = f0 >= f1 && f0 >= f2, d2 = !d0 && f2 > f1;  // dominant axis 0 / 2 (else 1)
+  const float aa = d0 ? af[1] : af[0], ab = d2 ? af[1] : af[2];
+  const float ba = d0 ? bf[1] : bf[0], bb = d2 ? bf[1] : bf[2];
+  const float ra = d0 ? r[1] : r[0], rb = d2 ? r[1] : r[2];
+  const float det = fmaf(aa, bb, -(ba * ab));
+  const float scale = (fabsf(aa) + fabsf(ab)) * (fabsf(ba) + fabsf(bb));
   if (!(fabsf(det) > 0.02f * scale)) return false;  // sliver: the weights would amplify float32 rounding by > 50
   const float rdet = 1.0f / det;
-  const float w1 = fmaf(r[ia], bf[ib], -(bf[ia] * r[ib])) * rdet;  // weight of P1
-  const float w2 = fmaf(af[ia], r[ib], -(r[ia] * af[ib])) * rdet;  // weight of P2
+  const float w1 = fmaf(ra, bb, -(ba * rb)) * rdet;  // weight of P1
+  const float w2 = fmaf(aa, rb, -(ra * ab)) * rdet;  // weight of P2
   const float w0 = 1.0f - w1 - w2;
   const float z = (float)(t * dlen * zscale);
   float e[3];

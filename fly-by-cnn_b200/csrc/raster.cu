@@ -425,7 +425,13 @@ __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve2_kernel(const Ra
     }
     if (best_slot >= 0) {
       hits++;
-      shade_decided(p, pix, r, best_t, bw[0], bw[1], bw[2], best_slot, best_cell);
+      if (p.approx) {
+        shade_decided(p, pix, r, best_t, bw[0], bw[1], bw[2], best_slot, best_cell);
+      } else {  // the exact chain's weights are at hand: shade in line
+        const float4* rec = p.trec + 4 * (int64_t)best_slot;
+        shade_and_write(p, pix, r, best_t, bw, __float_as_int(__ldg(rec + 1).w), __float_as_int(__ldg(rec + 2).w),
+                        __float_as_int(__ldg(rec + 3).x), best_cell);
+      }
     } else {
       const float zero[4] = {0.f, 0.f, 0.f, 0.f};
       write_pixel(p, pix, zero, -1, -1.0);
@@ -496,7 +502,8 @@ __global__ void __launch_bounds__(RV_THREADS) spill_shade_kernel(const RasterPar
     double t, x[3], w[3];
     tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w);  // hit by construction; recomputed for the weights
     hits++;
-    shade_decided(p, pix, r, t, w[0], w[1], w[2], slot, __float_as_int(a.w));
+    if (p.approx) shade_decided(p, pix, r, t, w[0], w[1], w[2], slot, __float_as_int(a.w));
+    else shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
   }
   if (hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
   if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.counters + 4, (unsigned long long)n);  // pixels finished from the spill list

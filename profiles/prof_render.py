@@ -19,7 +19,8 @@ ctx.set_mesh(tp, tf)
 ctx.build()
 n = ctx.views_icosahedron(level, 2.0)
 n = min(n, views)
-opts = ctx.render_opts(use_z=1, split_z=1)
+opts = ctx.render_opts(use_z=1, split_z=1, shade_tolerance=os.environ.get("PROF_TOLERANCE") == "1",
+                       plane_scale=float(os.environ.get("PROF_PLANE_SCALE", "1.0")))
 feat = torch.empty((n, res, res, 4), dtype=torch.float32, device=dev)
 ids = torch.empty((n, res, res), dtype=torch.int32, device=dev)
 for it in range(2):
