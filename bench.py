@@ -350,24 +350,55 @@ def run_ours(args):
         c_.build()
         c_.render_into(RES, opts, f_, i_)
 
-    for k in range(max(4, args.warmup)):
-        step_two(k)
-    barrier()
+    def timed_pipelined(step_fn, warm):
+        """exactly K steps as a whole: CUDA events on the two streams between barriers; returns (ms per step, launches)"""
+        for k in range(warm):
+            step_fn(k)
+        barrier()
+        l0_ = ctx.launch_count() + ctx2.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        stream2.wait_event(e0)
+        for k in range(args.steps):
+            step_fn(k)
+        stream.wait_stream(stream2)
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        n_launch = ctx.launch_count() + ctx2.launch_count() - l0_
+        ctx.synchronize()   # deferred builds: a bad mesh would raise here
+        ctx2.synchronize()
+        barrier()
+        return ms, n_launch
+
     k_two = args.steps
-    l0 = ctx.launch_count() + ctx2.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    stream2.wait_event(e0)
-    for k in range(k_two):
-        step_two(k)
-    stream.wait_stream(stream2)
-    e1.record(stream)
-    e1.synchronize()
-    ms_two = e0.elapsed_time(e1) / k_two
-    launches_two = ctx.launch_count() + ctx2.launch_count() - l0
-    ctx.synchronize()   # deferred builds: a bad mesh would raise here
-    ctx2.synchronize()
-    barrier()
+    ms_two_calls, launches_calls = timed_pipelined(step_two, max(4, args.warmup))
+
+    # The same loop with every step replayed as a CUDA graph (flyby_capture_begin / _end / flyby_graph_launch): one
+    # launch per mesh instead of ~50, the side-stream work as parallel branches of the graph.  One graph per
+    # (context, pool mesh): a graph re-reads the device buffers its captured flyby_set_mesh named.
+    graphs = {}
+    for ci, (c_, s_, f_, i_) in enumerate(pair):
+        for m in range(MESH_POOL):
+            P, F = dev_meshes[m]
+            c_.set_mesh(P, F, deferred=True)   # warm-up of this very step: buffers get their size
+            c_.build()
+            c_.render_into(RES, opts, f_, i_)
+            c_.synchronize()
+            with c_.capture() as cap:
+                c_.set_mesh(P, F, deferred=True)
+                c_.build()
+                c_.render_into(RES, opts, f_, i_)
+            graphs[(ci, m)] = cap.graph
+
+    def step_two_graph(k):
+        c_, s_, f_, i_ = pair[k % 2]
+        with torch.cuda.stream(s_):
+            flush.zero_()
+        c_.graph_launch(graphs[(k % 2, k % MESH_POOL)])
+
+    ms_two_graph, launches_graph = timed_pipelined(step_two_graph, max(4, args.warmup))
+    ms_two, launches_two = ms_two_graph, launches_graph
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -394,6 +425,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         verified = verified and bool(torch.equal(ids3, i_)) and bool(torch.equal(feat3.view(torch.int32), f_.view(torch.int32)))
     ctx3.close()
+    for (ci, m), g in graphs.items():
+        pair[ci][0].graph_destroy(g)
     ctx2.close()
     if not verified:
         raise SystemExit("bench.py: the pipelined loop's outputs differ from a serial context's -- numbers withheld")
@@ -442,10 +475,10 @@ def run_ours(args):
         except (_cabi.FlyByError, ImportError) as ex:  # NCCL or torchvision missing on this box
             extras["votes_allreduce"] = {"unavailable": str(ex)[:200]}
 
-    t = torch.tensor([ms_step, ms_e2e, ms_e2e_stream, ms_two, ms_e2e_ids, ms_step_sync], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, ms_e2e, ms_e2e_stream, ms_two, ms_e2e_ids, ms_step_sync, ms_two_calls], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step_max, ms_e2e_max, ms_e2e_stream_max, ms_two_max, ms_e2e_ids_max, ms_step_sync_max = (float(x) for x in t)
+    ms_step_max, ms_e2e_max, ms_e2e_stream_max, ms_two_max, ms_e2e_ids_max, ms_step_sync_max, ms_two_calls_max = (float(x) for x in t)
 
     if rank == 0:
         peak, peak_src = _hbm_peak()
@@ -480,7 +513,10 @@ def run_ours(args):
                 "build_ms": {k: st[k] for k in ("ms_normalise", "ms_normals", "ms_sort", "ms_tree")},
                 "hit_fraction": st["n_hits"] / max(1, st["n_rays"]),
                 "pipelining": "two contexts (two streams) per GPU alternate meshes: the build of mesh n+1 overlaps the "
-                              "render of mesh n; K meshes timed as a whole, max over ranks",
+                              "render of mesh n; every step is one CUDA-graph replay of set_mesh + build + render "
+                              "(flyby_graph_launch); K meshes timed as a whole, max over ranks",
+                "ms_per_step_without_graph": ms_two_calls_max,
+                "gpu_launches_without_graph": launches_calls,
                 "single_context_ms_per_step": ms_step_max,
                 "single_context_sync_build_ms_per_step": ms_step_sync_max,
                 "build_checks": "FLYBY_BUILD_DEFERRED in the timed loops: the index / winding checks run on the device in "

@@ -61,6 +61,7 @@ struct StageOut {
 };
 
 static int sync_if(flyby_ctx* c, bool need) {
+  if (need && c->capturing) return fail(c, FLYBY_ERR_INVALID, "a captured step cannot use host buffers");
   if (need) FB_CUDA(c, cudaStreamSynchronize(c->stream));
   return FLYBY_OK;
 }
@@ -265,12 +266,13 @@ int flyby_build(flyby_ctx* c) {
   // vtkPolyDataNormals' consistency pass (winding.cu) shares the one host synchronisation of the build.
   const int cons = c->norm.consistency & 0xff;
   const bool deferred = (c->norm.consistency & FLYBY_BUILD_DEFERRED) != 0;
+  if (c->capturing && !deferred) return fail(c, FLYBY_ERR_INVALID, "build: a captured step needs FLYBY_BUILD_DEFERRED (no host synchronisation)");
   int32_t* bad = reinterpret_cast<int32_t*>(c->counters.as<unsigned long long>() + 7);
   if (c->deferred_pending && !deferred) {  // an earlier deferred build's verdict is still unread: read it first
     int rcd = check_watchdog(c);
     if (rcd) return rcd;
   }
-  if (!c->deferred_pending) FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
+  if (!c->deferred_pending && !c->capturing) FB_CUDA(c, cudaMemsetAsync(bad, 0, 8, c->stream));
   if (m.T > 0 && !m.tris_ok) {
     check_tris_kernel<<<(unsigned)cdiv(3 * m.T, 256), 256, 0, c->stream>>>(m.tris.as<int32_t>(), 3 * m.T, m.V, bad);
     FB_LAUNCH_CHECK(c);
@@ -281,6 +283,7 @@ int flyby_build(flyby_ctx* c) {
     // no host synchronisation: indices were sanitised on the device, the flags stay in counters[7] until the next
     // synchronising call (flyby_synchronize, a render with host outputs, a non-deferred build) reports them
     c->deferred_pending = true;
+    if (c->capturing) c->cap_has_build = true;
     m.tris_ok = true;
   } else {
     int32_t chk[2] = {0, 0};
@@ -427,6 +430,7 @@ int flyby_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if ((rc = st.begin(c, c->stage_t, out_t, n_pix))) return rc;
   const bool any_host = sf.host || si.host || st.host;
   if (!any_host) return trace_render(c, vb, ve, res, o, sf.dev, si.dev, st.dev);
+  if (c->capturing) return fail(c, FLYBY_ERR_INVALID, "render: a captured step needs device outputs");
 
   // Host outputs: render in view chunks and copy every finished chunk back on the copy
   // stream while the next chunk renders (PCIe D2H overlaps the traversal).
@@ -838,6 +842,103 @@ int flyby_votes_allreduce(flyby_ctx* c, int32_t* votes, int64_t n, int root) {
   CHECK_CTX(c);
   if (!is_device_ptr(votes)) return fail(c, FLYBY_ERR_INVALID, "votes_allreduce: votes must be device memory");
   return nccl_votes_allreduce(c, votes, n, root);
+}
+
+// ---- CUDA-graph replay of a step (streams of equally shaped meshes)
+struct flyby_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+  bool has_build = false;  // the step contains a deferred build: every replay leaves a verdict to be read
+};
+
+int flyby_capture_begin(flyby_ctx* c) {
+  CHECK_CTX(c);
+  if (c->capturing) return fail(c, FLYBY_ERR_INVALID, "capture_begin: already capturing");
+  // what the step may lean on must not come from outside the capture: join the side stream's pending work now
+  { int rc = wait_tree(c); if (rc) return rc; }
+  c->tree_pending = false;
+  if (c->ev_front && c->ev_front_live) FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_front, 0));
+  // the check flags of deferred builds are sticky inside a graph (a replay must not clear what an earlier replay
+  // found): start from clean flags unless an unread verdict is pending
+  if (!c->deferred_pending)
+    FB_CUDA(c, cudaMemsetAsync(c->counters.as<unsigned long long>() + 7, 0, 8, c->stream));
+  FB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+  c->capturing = true;
+  c->cap_forked = c->cap_front_forked = c->cap_has_build = false;
+  c->cap_launches0 = c->launches;
+  capture_flag() = true;
+  int rc = raster_capture_prologue(c);
+  if (rc) {
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(c->stream, &g);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    c->capturing = false;
+    capture_flag() = false;
+  }
+  return rc;
+}
+
+int flyby_capture_end(flyby_ctx* c, flyby_graph** out) {
+  CHECK_CTX(c);
+  if (!out) return FLYBY_ERR_INVALID;
+  *out = nullptr;
+  if (!c->capturing) return fail(c, FLYBY_ERR_INVALID, "capture_end: not capturing");
+  cudaError_t e = cudaSuccess;
+  if (c->side_stream && c->cap_forked) {  // join whatever the side stream still does for this step
+    e = cudaEventRecord(c->ev_tree, c->side_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_tree, 0);
+  }
+  cudaGraph_t g = nullptr;
+  cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+  c->capturing = false;
+  capture_flag() = false;
+  c->tree_pending = false;   // replays are ordered on the context stream as a whole
+  c->front_clean = 0;        // a replayed render leaves the front buffer used
+  c->ev_front_live = false;  // (its last record belongs to the graph)
+  if (e == cudaSuccess) e = e2;
+  if (e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return fail(c, FLYBY_ERR_CUDA, "capture_end: %s (a call inside the capture allocated, synchronised or used host buffers?)",
+                cudaGetErrorString(e));
+  }
+  flyby_graph* fg = new (std::nothrow) flyby_graph();
+  if (!fg) { cudaGraphDestroy(g); return FLYBY_ERR_INVALID; }
+  fg->graph = g;
+  fg->launches = c->launches - c->cap_launches0;
+  fg->has_build = c->cap_has_build;
+  c->launches = c->cap_launches0;  // captured, not launched
+  e = cudaGraphInstantiate(&fg->exec, g, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(g);
+    delete fg;
+    return fail(c, FLYBY_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  }
+  *out = fg;
+  return FLYBY_OK;
+}
+
+int flyby_graph_launch(flyby_ctx* c, flyby_graph* g) {
+  CHECK_CTX(c);
+  if (!g || !g->exec) return fail(c, FLYBY_ERR_INVALID, "graph_launch: no graph");
+  if (c->capturing) return fail(c, FLYBY_ERR_INVALID, "graph_launch: the context is capturing");
+  { int rc = wait_tree(c); if (rc) return rc; }
+  c->tree_pending = false;
+  if (c->ev_front && c->ev_front_live) FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_front, 0));  // side-stream init of the last render
+  c->front_clean = 0;
+  FB_CUDA(c, cudaGraphLaunch(g->exec, c->stream));
+  c->launches += g->launches;
+  if (g->has_build) c->deferred_pending = true;
+  return FLYBY_OK;
+}
+
+void flyby_graph_destroy(flyby_graph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
 }
 
 int flyby_get_stats(flyby_ctx* c, flyby_stats* out) {

@@ -11,12 +11,20 @@
 
 namespace fb {
 
+// set while a context of this thread captures its stream into a CUDA graph (flyby_capture_begin): allocations are
+// not allowed then, the buffers must have their size from an identical warm-up step
+inline bool& capture_flag() {
+  static thread_local bool f = false;
+  return f;
+}
+
 // grow-only device allocation
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    if (capture_flag()) return cudaErrorStreamCaptureUnsupported;  // run the same step once before capturing it
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -127,7 +135,12 @@ struct flyby_ctx {
   int n_slab_ev = 0;
   flyby_stats stats;
   int count_work = 0;
-  bool deferred_pending = false;  // a FLYBY_BUILD_DEFERRED build's check flags (counters[7]) have not been read yet
+  bool deferred_pending = false;
+  // CUDA-graph capture of a step (flyby_capture_begin / _end): no timing events, no allocations, no host syncs
+  bool capturing = false, cap_forked = false, cap_front_forked = false, cap_has_build = false;
+  bool ev_front_live = false;  // ev_front was last recorded outside a capture (only then may it be waited for outside one)
+  int64_t cap_launches0 = 0;
+  int64_t last_front_pix = 0;  // pixels of the front buffer the last scan-conversion render used  // a FLYBY_BUILD_DEFERRED build's check flags (counters[7]) have not been read yet
   int64_t launches = 0;
   int sm_count = 148;
   int leaf_max = FB_LEAF_MAX;  // triangles per collapsed leaf (FLYBY_LEAF_MAX overrides, 1..8)
@@ -177,9 +190,22 @@ inline bool is_device_ptr(const void* p) {
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// timing events of flyby_get_stats: skipped inside a captured step
+#define FB_STAT_EVENT(ctx, ev, st)                      \
+  do {                                                  \
+    if (!(ctx)->capturing) FB_CUDA((ctx), cudaEventRecord((ev), (st))); \
+  } while (0)
+// the side stream waits for an event of the main stream (a fork, when capturing)
+#define FB_SIDE_WAIT(ctx, ev)                                                  \
+  do {                                                                         \
+    FB_CUDA((ctx), cudaStreamWaitEvent((ctx)->side_stream, (ev), 0));          \
+    if ((ctx)->capturing) (ctx)->cap_forked = true;                            \
+  } while (0)
+
 // stage boundaries of one pixel slab of a render: which = 0 start of the candidate search, 1 start of the exact
 // resolve, 2 end (advances to the next slab).  flyby_get_stats sums the two intervals over the slabs.
 inline int slab_mark(flyby_ctx* c, int which) {
+  if (c->capturing) return FLYBY_OK;  // stats are not part of a captured step
   const int k = c->n_slab_ev;
   if (k < flyby_ctx::kMaxSlabEv) {
     cudaEvent_t& e = c->slab_ev[3 * k + which];
@@ -212,6 +238,7 @@ int pp_erode(flyby_ctx* c, int32_t* labels, int32_t label, int has_ignore, int32
              int has_target, int32_t target);
 int pp_dilate(flyby_ctx* c, int32_t* labels, int32_t label, int64_t iterations, int over_target, int32_t target);
 int pp_relabel(flyby_ctx* c, int32_t* labels, int32_t label, int32_t relabel);
+int raster_capture_prologue(flyby_ctx* c);                                      // raster.cu
 int views_icosahedron(flyby_ctx* c, int L, double radius, int dedupe);          // views.cu
 int views_spiral(flyby_ctx* c, int n, double turns, double radius);             // views.cu
 

@@ -458,7 +458,7 @@ int lbvh_run(flyby_ctx* c) {
     t = v0; v0 = v1; v1 = t;
   }
   // after an odd number of passes the sorted data sits in the alternate buffers: k0 / v0 point at it
-  FB_CUDA(c, cudaEventRecord(c->ev[3], st));
+  FB_STAT_EVENT(c, c->ev[3], st);
 
   reorder_kernel<<<gT, 256, 0, st>>>(m.verts.as<float>(), m.tris.as<int32_t>(), T, v0,
                                      m.tv0.as<float4>(), m.tv1.as<float4>(), m.tv2.as<float4>(),
@@ -471,7 +471,7 @@ int lbvh_run(flyby_ctx* c) {
     FB_LAUNCH_CHECK(c);
     m.n_nodes = 1;
     m.n_top_dev = m.remap.as<int32_t>();
-    FB_CUDA(c, cudaEventRecord(c->ev[4], st));
+    FB_STAT_EVENT(c, c->ev[4], st);
     return FLYBY_OK;
   }
   const int n = (int)T, ni = n - 1;
@@ -480,7 +480,7 @@ int lbvh_run(flyby_ctx* c) {
   cudaStream_t ss = c->side_stream ? c->side_stream : st;
   if (ss != st) {
     FB_CUDA(c, cudaEventRecord(c->ev_sorted, st));
-    FB_CUDA(c, cudaStreamWaitEvent(ss, c->ev_sorted, 0));
+    FB_SIDE_WAIT(c, c->ev_sorted);
   }
   int32_t* leaf_parent = reinterpret_cast<int32_t*>(v1);  // the sort's spare index buffer is free again
   karras_kernel<<<(unsigned)cdiv(ni, 256), 256, 0, ss>>>(k0, n, m.knode.as<int4>(), leaf_parent, m.krange.as<int2>());
@@ -515,7 +515,7 @@ int lbvh_run(flyby_ctx* c) {
       m.remap.as<int32_t>(),
       nontop_scan, m.topflag.as<int32_t>(), n_top_dev, m.nodes.as<Node>());
   FB_LAUNCH_CHECK(c);
-  FB_CUDA(c, cudaEventRecord(c->ev[4], ss));
+  FB_STAT_EVENT(c, c->ev[4], ss);
   m.n_nodes = ni;
   m.n_top_dev = n_top_dev;
   return FLYBY_OK;

@@ -268,7 +268,7 @@ int prep_run(flyby_ctx* c) {
   Reduce* red = m.reduce.as<Reduce>();
   const int skip = c->norm.skip;
 
-  FB_CUDA(c, cudaEventRecord(c->ev[0], st));
+  FB_STAT_EVENT(c, c->ev[0], st);
   reduce_init_kernel<<<1, 32, 0, st>>>(red);
   FB_LAUNCH_CHECK(c);
   int blocks = (int)(cdiv(V, 256) < 1184 ? cdiv(V, 256) : 1184);
@@ -298,13 +298,13 @@ int prep_run(flyby_ctx* c) {
   FB_LAUNCH_CHECK(c);
   unit_box_kernel<<<1, 32, 0, st>>>(red, skip);
   FB_LAUNCH_CHECK(c);
-  FB_CUDA(c, cudaEventRecord(c->ev[1], st));
+  FB_STAT_EVENT(c, c->ev[1], st);
 
   // point normals: not needed before the shading, so they go to the side stream (see ctx.h)
   cudaStream_t ss = c->side_stream ? c->side_stream : st;
   if (ss != st) {
     FB_CUDA(c, cudaEventRecord(c->ev_unit, st));  // the unit surface is complete on the main stream ...
-    FB_CUDA(c, cudaStreamWaitEvent(ss, c->ev_unit, 0));  // ... before the side stream reads it
+    FB_SIDE_WAIT(c, c->ev_unit);  // ... before the side stream reads it
   }
   FB_CUDA(c, cudaMemsetAsync(m.adj_start.p, 0, sizeof(uint32_t) * (size_t)(V + 1), ss));
   FB_CUDA(c, cudaMemsetAsync(m.adj_cur.p, 0, sizeof(uint32_t) * (size_t)(V + 1), ss));
@@ -323,7 +323,7 @@ int prep_run(flyby_ctx* c) {
   point_normal_kernel<<<(unsigned)cdiv(V, 128), 128, 0, ss>>>(
       V, m.adj_start.as<uint32_t>(), m.adj.as<int32_t>(), m.face_n.as<float>(), m.normals.as<float4>());
   FB_LAUNCH_CHECK(c);
-  FB_CUDA(c, cudaEventRecord(c->ev[2], ss));
+  FB_STAT_EVENT(c, c->ev[2], ss);
   return FLYBY_OK;
 }
 

@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(RV_THREADS, APPROX ? RV_MINB_APPROX : RV_MINB)
 // Shading of a decided pixel outside resolve1.  In tolerance mode (rp.r.approx) the winner is shaded by shade_approx
 // here as well, so that every hit pixel is the same function of (pixel, winning triangle) whichever kernel finishes
 // it -- which pixels carry extra candidates depends on the order the atomics of raster_kernel land in.
-static __device__ __noinline__ void shade_decided(const RenderParams& p, int64_t pix, const PixelRay& r, double t,
+static __device__ __forceinline__ void shade_decided(const RenderParams& p, int64_t pix, const PixelRay& r, double t,
                                                    double w0, double w1, double w2, int slot, int cell) {
   const float4* rec = p.trec + 4 * (int64_t)slot;
   const float4 a = __ldg(rec), b = __ldg(rec + 1), e = __ldg(rec + 2), g = __ldg(rec + 3);
@@ -376,6 +376,7 @@ static __device__ __noinline__ void shade_decided(const RenderParams& p, int64_t
 }
 
 // ---- resolve2: queued pixels (near edges, silhouettes, layered geometry)
+template <bool APPROX>
 __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve2_kernel(const RasterParams rp) {
   const RenderParams& p = rp.r;
   const unsigned int n = *rp.n_queue;
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(RV_THREADS, 4) raster_resolve2_kernel(const Ra
     }
     if (best_slot >= 0) {
       hits++;
-      if (p.approx) {
+      if (APPROX) {
         shade_decided(p, pix, r, best_t, bw[0], bw[1], bw[2], best_slot, best_cell);
       } else {  // the exact chain's weights are at hand: shade in line
         const float4* rec = p.trec + 4 * (int64_t)best_slot;
@@ -481,6 +482,7 @@ __global__ void __launch_bounds__(RV_THREADS) spill_cell_kernel(const RasterPara
   }
 }
 
+template <bool APPROX>
 __global__ void __launch_bounds__(RV_THREADS) spill_shade_kernel(const RasterParams rp) {
   const RenderParams& p = rp.r;
   const unsigned int n = rp.n_spill[1];
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(RV_THREADS) spill_shade_kernel(const RasterPar
     double t, x[3], w[3];
     tri_exact(r.o, r.d, P0, P1, P2, DBL_MAX, p.tol2, &t, x, w);  // hit by construction; recomputed for the weights
     hits++;
-    if (p.approx) shade_decided(p, pix, r, t, w[0], w[1], w[2], slot, __float_as_int(a.w));
+    if (APPROX) shade_decided(p, pix, r, t, w[0], w[1], w[2], slot, __float_as_int(a.w));
     else shade_and_write(p, pix, r, t, w, __float_as_int(b.w), __float_as_int(e.w), __float_as_int(g.x), __float_as_int(a.w));
   }
   if (hits) atomicAdd(p.counters + 3, (unsigned long long)hits);
@@ -511,6 +513,7 @@ __global__ void __launch_bounds__(RV_THREADS) spill_shade_kernel(const RasterPar
 
 // ---- resolve3: the few pixels with more candidates than the lists hold: one thread each re-traces
 // its ray through the LBVH (screening test first, exact test on what is left)
+template <bool APPROX>
 __global__ void __launch_bounds__(64) raster_resolve3_kernel(const RasterParams rp) {
   const RenderParams& p = rp.r;
   const unsigned int n = rp.n_queue[1];
@@ -525,7 +528,13 @@ __global__ void __launch_bounds__(64) raster_resolve3_kernel(const RasterParams 
     const ExactHit h = resolve_overflow(p, p.view_begin + v, r.o[0], r.o[1], r.o[2], vf->enabled ? vf : nullptr, qx, qy);
     if (h.slot >= 0) {
       hits++;
-      shade_decided(p, pix, r, h.t, h.w0, h.w1, h.w2, h.slot, h.cell);
+      if (APPROX) {
+        shade_decided(p, pix, r, h.t, h.w0, h.w1, h.w2, h.slot, h.cell);
+      } else {
+        const int4 vid = p.tvid[h.slot];
+        const double w[3] = {h.w0, h.w1, h.w2};
+        shade_and_write(p, pix, r, h.t, w, vid.x, vid.y, vid.z, h.cell);
+      }
     } else {
       const float zero[4] = {0.f, 0.f, 0.f, 0.f};
       write_pixel(p, pix, zero, -1, -1.0);
@@ -597,7 +606,8 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   // is waited for in any case: the buffer must not be written while that kernel runs), the rest is set here
   const int64_t clean = c->front_clean;
   c->front_clean = 0;  // dirty from here on
-  if (c->ev_front) FB_CUDA(c, cudaStreamWaitEvent(st, c->ev_front, 0));  // (no-op before the first record)
+  // (no-op before the first record; inside a captured step only the prologue's record may be waited for)
+  if (c->ev_front && (c->capturing ? c->cap_front_forked : c->ev_front_live)) FB_CUDA(c, cudaStreamWaitEvent(st, c->ev_front, 0));
   if (n_pix > clean) {
     raster_init_kernel<<<(unsigned)cdiv(n_pix - clean, 256), 256, 0, st>>>(p.front + clean, p.cnt + clean, n_pix - clean);
     FB_LAUNCH_CHECK(c);
@@ -621,19 +631,23 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
   else
     raster_resolve1_kernel<false><<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
-  raster_resolve2_kernel<<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
+  if (approx) raster_resolve2_kernel<true><<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
+  else raster_resolve2_kernel<false><<<(unsigned)rgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   const unsigned sgrid = (unsigned)c->sm_count * 4;
   spill_t_kernel<<<sgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   spill_cell_kernel<<<sgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
-  spill_shade_kernel<<<sgrid, RV_THREADS, 0, st>>>(p);
+  if (approx) spill_shade_kernel<true><<<sgrid, RV_THREADS, 0, st>>>(p);
+  else spill_shade_kernel<false><<<sgrid, RV_THREADS, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
-  raster_resolve3_kernel<<<(unsigned)c->sm_count, 64, 0, st>>>(p);
+  if (approx) raster_resolve3_kernel<true><<<(unsigned)c->sm_count, 64, 0, st>>>(p);
+  else raster_resolve3_kernel<false><<<(unsigned)c->sm_count, 64, 0, st>>>(p);
   FB_LAUNCH_CHECK(c);
   { int rc = slab_mark(c, 2); if (rc) return rc; }
-  if (c->side_stream && c->ev_front) {
+  c->last_front_pix = n_pix;
+  if (c->side_stream && c->ev_front && !c->capturing) {
     // the next render's initialisation, off the critical path: the side stream runs it beside the upload / unit
     // surface / sort of the next mesh (or right away, when the next render follows at once)
     FB_CUDA(c, cudaEventRecord(c->ev_front_free, st));
@@ -642,8 +656,35 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
     raster_init_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, c->side_stream>>>(p.front, p.cnt, n_pix);
     FB_LAUNCH_CHECK(c);
     FB_CUDA(c, cudaEventRecord(c->ev_front, c->side_stream));
+    c->ev_front_live = true;
     c->front_clean = n_init;
   }
+  return FLYBY_OK;
+}
+
+// A captured step cannot lean on what happened before it: the front / count words its render will use are
+// initialised at its start, on the side stream (a fork of the captured graph) beside upload / unit surface / sort,
+// and the render joins it through ev_front as usual.  The post-render initialisation is left out while capturing.
+int raster_capture_prologue(flyby_ctx* c) {
+  c->front_clean = 0;
+  const int64_t n = c->last_front_pix;
+  if (n <= 0 || c->raster_tmp.cap < 12 * (size_t)n) return FLYBY_OK;  // the render initialises on its own stream
+  const size_t cap_pix = c->raster_tmp.cap / 12;
+  unsigned long long* front = c->raster_tmp.as<unsigned long long>();
+  int* cnt = reinterpret_cast<int*>(front + cap_pix);
+  cudaStream_t s = c->stream;
+  if (c->side_stream && c->ev_front) {
+    FB_CUDA(c, cudaEventRecord(c->ev_front_free, c->stream));
+    FB_SIDE_WAIT(c, c->ev_front_free);
+    s = c->side_stream;
+  }
+  raster_init_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(front, cnt, n);
+  FB_LAUNCH_CHECK(c);
+  if (s != c->stream) {
+    FB_CUDA(c, cudaEventRecord(c->ev_front, s));
+    c->cap_front_forked = true;
+  }
+  c->front_clean = n;
   return FLYBY_OK;
 }
 

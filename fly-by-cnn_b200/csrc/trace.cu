@@ -484,7 +484,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   const int channels = (o->use_z && o->split_z) ? 4 : 3;
   if (first_chunk) {
     c->n_slab_ev = 0;
-    FB_CUDA(c, cudaEventRecord(c->ev[5], st));
+    FB_STAT_EVENT(c, c->ev[5], st);
     FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 7 * sizeof(unsigned long long), st));
     FB_CUDA(c, cudaMemsetAsync(c->counters.as<unsigned long long>() + 8, 0, 8 * sizeof(unsigned long long), st));
     c->stats.n_rays = 0;
@@ -493,7 +493,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   if (m.T == 0) {
     fill_miss_kernel<<<(unsigned)cdiv(n_pix, 256), 256, 0, st>>>(feat, ids, tt, n_pix, channels, m.n_scalars, m.scalar_zero);
     FB_LAUNCH_CHECK(c);
-    if (last_chunk) FB_CUDA(c, cudaEventRecord(c->ev[6], st));
+    if (last_chunk) FB_STAT_EVENT(c, c->ev[6], st);
     return FLYBY_OK;
   }
   static bool env_read = false;
@@ -598,7 +598,7 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
     if (!rc) rc = slab_mark(c, 2);
   }
   if (rc) return rc;
-  if (last_chunk) FB_CUDA(c, cudaEventRecord(c->ev[6], st));
+  if (last_chunk) FB_STAT_EVENT(c, c->ev[6], st);
   return FLYBY_OK;
 }
 

@@ -57,7 +57,7 @@ SYMBOLS = [
     "flyby_launch_count", "flyby_labels_remove_islands", "flyby_labels_connectivity", "flyby_labels_erode",
     "flyby_labels_dilate", "flyby_labels_relabel", "flyby_interpolate_features", "flyby_render_perspective",
     "flyby_render_async", "flyby_set_point_scalars", "flyby_get_winding", "flyby_point_ids",
-    "flyby_backproject_points",
+    "flyby_backproject_points", "flyby_capture_begin", "flyby_capture_end", "flyby_graph_launch", "flyby_graph_destroy",
 ]
 
 NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2, "uint8": 3}
@@ -113,6 +113,23 @@ def _check_dtype(x, np_dtype, name):
         ok = str(x.dtype).replace("torch.", "") == np.dtype(np_dtype).name
     if not ok:
         raise FlyByError("%s must have dtype %s, got %s" % (name, np.dtype(np_dtype).name, x.dtype))
+
+
+class _Capture:
+    def __init__(self, ctx):
+        self.ctx, self.graph = ctx, None
+
+    def __enter__(self):
+        self.ctx._ck(self.ctx._lib.flyby_capture_begin(self.ctx._h))
+        return self
+
+    def __exit__(self, et, ev, tb):
+        g = C.c_void_p()
+        rc = self.ctx._lib.flyby_capture_end(self.ctx._h, C.byref(g))
+        if et is None:
+            self.ctx._ck(rc)
+            self.graph = g
+        return False
 
 
 class Context:
@@ -458,6 +475,20 @@ class Context:
     def votes_allreduce(self, votes, root=-1):
         n = int(np.prod(votes.shape))
         self._ck(self._lib.flyby_votes_allreduce(self._h, _ptr(votes), C.c_int64(n), C.c_int(root)))
+
+    # ---- CUDA-graph replay of a step ------------------------------------------
+    def capture(self):
+        """Context manager: the set_mesh(deferred=True) / build / render_into(device tensors) calls inside are recorded
+        into a CUDA graph instead of run; `.graph` is then launched with graph_launch().  Run the identical step once
+        before capturing it."""
+        return _Capture(self)
+
+    def graph_launch(self, graph):
+        self._ck(self._lib.flyby_graph_launch(self._h, graph))
+
+    def graph_destroy(self, graph):
+        self._lib.flyby_graph_destroy.restype = None
+        self._lib.flyby_graph_destroy(graph)
 
     # ---- measurement --------------------------------------------------------
     def stats(self):

@@ -292,6 +292,21 @@ FLYBY_API int flyby_nccl_unique_id(flyby_ctx* ctx, uint8_t id_out[128]);
 FLYBY_API int flyby_nccl_init(flyby_ctx* ctx, const uint8_t id[128], int rank, int world);
 FLYBY_API int flyby_votes_allreduce(flyby_ctx* ctx, int32_t* votes, int64_t n, int root /* -1 = all */);
 
+/* ---- replay of a step as a CUDA graph ------------------------------------ */
+/* Batch extraction (BASELINE configs[2]: 1000 equally shaped meshes) repeats one step -- flyby_set_mesh from the
+ * same device buffers, flyby_build, flyby_render into the same device outputs -- some sixty kernel launches of a few
+ * microseconds each.  Between flyby_capture_begin and flyby_capture_end those calls are recorded instead of run (the
+ * side-stream work becomes parallel branches of the graph); flyby_graph_launch replays the whole step with ONE launch
+ * on the context stream, re-reading the source buffers the captured flyby_set_mesh named.  Rules: run the identical
+ * step once before capturing it (buffers must have their size: nothing may allocate while capturing); device buffers
+ * only; the mesh must be set with FLYBY_BUILD_DEFERRED (no host synchronisation -- a bad mesh is reported by the next
+ * synchronising call, as always); flyby_get_stats timings do not cover replays. */
+typedef struct flyby_graph flyby_graph;
+FLYBY_API int flyby_capture_begin(flyby_ctx* ctx);
+FLYBY_API int flyby_capture_end(flyby_ctx* ctx, flyby_graph** out);
+FLYBY_API int flyby_graph_launch(flyby_ctx* ctx, flyby_graph* graph);
+FLYBY_API void flyby_graph_destroy(flyby_graph* graph);
+
 /* ---- measurement -------------------------------------------------------- */
 FLYBY_API int flyby_get_stats(flyby_ctx* ctx, flyby_stats* out);
 /* 1: the next flyby_render also counts nodes visited / triangles tested. */

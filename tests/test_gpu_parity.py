@@ -836,3 +836,74 @@ def test_deferred_build_reports_at_the_next_synchronising_call(gpu_ctx, orc):
     gpu_ctx.build()
     again_f, again_i = gpu_ctx.render(48, opts)
     assert np.array_equal(again_i, want_i) and np.array_equal(again_f, want_f)
+
+
+def test_graph_replay_of_a_step(gpu_ctx, orc):
+    """flyby_capture_begin / _end / flyby_graph_launch: set_mesh + build + render of a fixed-shape mesh recorded once and
+    replayed with one launch; a replay re-reads the device buffers the captured set_mesh named, so new vertex data in the
+    same buffers gives that mesh's result -- bit-equal to the ordinary calls, and a bad mesh is still reported."""
+    torch = pytest.importorskip("torch")
+    from flyby_b200 import FlyByError, _cabi
+    dev = torch.device("cuda:0")
+    ctx = _cabi.Context(0)
+    try:
+        meshes = [synth.bumpy_sphere(24, s) for s in (1, 2, 3)]
+        n = ctx.views_icosahedron(2, 2.0)
+        opts = ctx.render_opts()
+        res = 96
+        want = []
+        for P, F in meshes:
+            ctx.set_mesh(P, F)
+            ctx.build()
+            want.append(ctx.render(res, opts))
+        tp = torch.from_numpy(meshes[0][0]).to(dev)
+        tf = torch.from_numpy(meshes[0][1]).to(dev)
+        feat = torch.empty((n, res, res, 4), dtype=torch.float32, device=dev)
+        ids = torch.empty((n, res, res), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+
+        def step():
+            ctx.set_mesh(tp, tf, deferred=True)
+            ctx.build()
+            ctx.render_into(res, opts, feat, ids)
+
+        step()                      # warm-up: every buffer gets its size
+        ctx.synchronize()
+        l0 = ctx.launch_count()
+        with ctx.capture() as cap:
+            step()
+        assert ctx.launch_count() == l0          # recorded, not launched
+        for k in (1, 2, 0, 1):
+            tp.copy_(torch.from_numpy(meshes[k][0]))
+            torch.cuda.synchronize()
+            feat.zero_(); ids.zero_()
+            torch.cuda.synchronize()
+            before = ctx.launch_count()
+            ctx.graph_launch(cap.graph)
+            ctx.synchronize()
+            assert ctx.launch_count() - before > 20  # the replay accounts for the kernels it ran
+            assert np.array_equal(ids.cpu().numpy(), want[k][1]) and np.array_equal(feat.cpu().numpy(), want[k][0]), k
+        # ordinary calls still work after replays (front buffer, tree events)
+        ctx.set_mesh(*meshes[2])
+        ctx.build()
+        f, i = ctx.render(res, opts)
+        assert np.array_equal(i, want[2][1]) and np.array_equal(f, want[2][0])
+        # a replay over corrupted cells reports at the next synchronising call
+        ctx.graph_launch(cap.graph)
+        ctx.synchronize()
+        bad = meshes[0][1].copy()
+        bad[3, 2] = 10 ** 6
+        tf.copy_(torch.from_numpy(bad))
+        torch.cuda.synchronize()
+        ctx.graph_launch(cap.graph)
+        with pytest.raises(FlyByError) as e:
+            ctx.synchronize()
+        assert e.value.status == _cabi.ERR_INVALID
+        ctx.graph_destroy(cap.graph)
+        # what a captured step must not do
+        with pytest.raises(FlyByError):
+            with ctx.capture():
+                ctx.set_mesh(tp, tf)           # not deferred
+                ctx.build()
+    finally:
+        ctx.close()
