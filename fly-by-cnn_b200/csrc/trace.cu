@@ -567,7 +567,13 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
     // the per-pixel scratch of the scan conversion (~58 B / pixel) is sized for at most 2^26 pixels at a time:
     // long view lists are rendered in slabs of whole views, each straight into its part of the outputs
     const int64_t per_view = (int64_t)res * res;
-    int slab = (int)(((int64_t)1 << 26) / per_view);
+    static int64_t slab_pix = 0;
+    if (!slab_pix) {
+      const char* e = getenv("FLYBY_SLAB_PIXELS");  // A/B hook
+      slab_pix = e ? atoll(e) : ((int64_t)1 << 26);
+      if (slab_pix < 1) slab_pix = (int64_t)1 << 26;
+    }
+    int slab = (int)(slab_pix / per_view);
     if (slab < 1) slab = 1;
     if (slab > 65535) slab = 65535;  // gridDim.y of raster_kernel
     rc = FLYBY_OK;
