@@ -311,19 +311,21 @@ def test_no_stream_waits_for_an_event_recorded_on_itself():
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fly-by-cnn_b200", "csrc")
     rec = re.compile(r"cudaEventRecord\(\s*([^,]+?)\s*,\s*([^)]+?)\s*\)")
     wait = re.compile(r"cudaStreamWaitEvent\(\s*([^,]+?)\s*,\s*([^,]+?)\s*,")
+    side_wait = re.compile(r"FB_SIDE_WAIT\(\s*c\s*,\s*([^)]+?)\s*\)")  # ctx.h: the side stream waits (a fork, when capturing)
     pairs = 0
     for path in glob.glob(os.path.join(root, "*.cu")):
         lines = open(path).read().splitlines()
         for i, ln in enumerate(lines):
-            m = wait.search(ln)
-            if not m:
+            m, ms = wait.search(ln), side_wait.search(ln)
+            if not m and not ms:
                 continue
-            stream, event = m.group(1), m.group(2)
+            stream, event = (m.group(1), m.group(2)) if m else ("c->side_stream", ms.group(1))
             for back in lines[max(0, i - 3):i][::-1]:
                 r = rec.search(back)
                 if r and r.group(1) == event:
                     pairs += 1
-                    assert r.group(2) != stream, "%s:%d waits on %s for an event recorded on it" % (path, i + 1, stream)
+                    assert r.group(2) != stream and not (ms and r.group(2) == "ss"), \
+                        "%s:%d waits on %s for an event recorded on it" % (path, i + 1, stream)
                     break
     assert pairs >= 4  # unit surface, sort, front buffer, chunked copy-out
 
