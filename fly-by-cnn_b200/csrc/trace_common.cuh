@@ -124,7 +124,7 @@ struct RenderParams {
 __device__ __forceinline__ void write_pixel(const RenderParams& p, int64_t pix, const float* px, int cell,
                                             double t) {
   if (p.feat) {
-    if (p.stride == 4) {
+    if (p.channels == 4 && p.n_scal == 0) {  // (3 image channels + 1 scalar also make a stride of 4: not this path)
       __stcs(reinterpret_cast<float4*>(p.feat) + pix, make_float4(px[0], px[1], px[2], px[3]));
     } else {
       float* o = p.feat + pix * p.stride;

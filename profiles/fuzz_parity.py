@@ -82,11 +82,31 @@ def one_case(case):
     sp = float(rng.choice([0.5, 1.0, 1.0, 1.3]))
     tol = float(rng.choice([1e-10, 1e-10, 1e-8, 1e-5]))
     cfg = dict(use_z=int(rng.integers(0, 2)), split_z=int(rng.integers(0, 2)))
-    opts = ctx.render_opts(plane_scale=ps, plane_spacing=sp, tolerance=tol, **cfg)
+    mode = str(rng.choice(["raster", "bvh", "fused"]))     # the engine, through the ABI (flyby_render_opts.mode)
+    opts = ctx.render_opts(plane_scale=ps, plane_spacing=sp, tolerance=tol, mode=mode, **cfg)
+    # per-point scalars written by the render, in half of the cases (vertex 0 / barycentric)
+    S = int(rng.choice([0, 0, 1, 3]))
+    smode = str(rng.choice(["vertex0", "barycentric"]))
+    scal = rng.normal(size=(len(P), S)).astype(np.float32) if S else None
+    ctx.set_point_scalars(scal, mode=smode, zero=-1.5)
     feat, ids, t = ctx.render(res, opts, want_t=True)
     orc.set_tolerance(tol)
     fo, io, to = orc.render(uv, F, nrm, views, radius, res, plane_scale=ps, spacing=sp, grid=False, want_t=True, **cfg)
-    ok = pre_ok and np.array_equal(ids, io) and np.array_equal(t, to) and np.array_equal(feat, fo, equal_nan=True)
+    Cn = fo.shape[-1]
+    ok = pre_ok and np.array_equal(ids, io) and np.array_equal(t, to) and np.array_equal(feat[..., :Cn], fo, equal_nan=True)
+    if S:
+        want = orc.point_features(io, F, scal, zero=-1.5) if smode == "vertex0" else \
+            orc.interpolate_features(uv, F, views, radius, res, io, scal, plane_scale=ps, spacing=sp, zero=-1.5)
+        ok = ok and np.array_equal(feat[..., Cn:], want, equal_nan=True)
+    ctx.set_point_scalars(None)
+    # opt-in tolerance shading: ids bit-exact, values within the bar (finite meshes only; slivers fall back to exact)
+    if mode == "raster" and np.isfinite(uv).all():
+        tf, ti = ctx.render(res, ctx.render_opts(plane_scale=ps, plane_spacing=sp, tolerance=tol, shade_tolerance=True, **cfg))
+        hit = io >= 0
+        ok = ok and np.array_equal(ti, io) and np.array_equal(tf[~hit], fo[~hit])
+        if hit.any():
+            scale = np.maximum(np.abs(fo[hit]).max(), 1.0)
+            ok = ok and bool(np.all(np.abs(tf[hit].astype(np.float64) - fo[hit]) <= 1e-5 * scale))
     # arbitrary segments through the same mesh (flyby_cast): the per-ray LBVH traversal with the same tolerance
     nseg = 2000
     a = rng.uniform(-1.5, 1.5, (nseg, 3)) * ext
@@ -99,7 +119,7 @@ def one_case(case):
     hit_c = oi >= 0
     ok = ok and np.array_equal(ci, oi) and np.array_equal(ct, ot) and np.array_equal(cw[hit_c], ow[hit_c])
     if not ok:
-        print("MISMATCH case", case, "T", len(F), "skip", skip, "R", radius, "res", res, "ps", ps, "sp", sp, "tol", tol,
+        print("MISMATCH case", case, "mode", mode, "S", S, smode, "T", len(F), "skip", skip, "R", radius, "res", res, "ps", ps, "sp", sp, "tol", tol,
               "ids", int((ids != io).sum()), "t", int((t != to).sum()))
     return ok
 

@@ -614,7 +614,8 @@ def test_point_scalars_written_by_the_render(gpu_ctx, orc, mode, smode):
     P, F = synth.dental_crown(24, 3)
     uv, nrm, _, _ = _build(gpu_ctx, P, F)
     views = gpu_ctx.views_icosahedron(1, 2.0) and gpu_ctx.get_views()
-    for S, cfg in ((1, dict(use_z=1, split_z=1)), (3, dict(use_z=1, split_z=0)), (5, dict(use_z=0, split_z=0, plane_scale=2.0))):
+    for S, cfg in ((1, dict(use_z=1, split_z=1)), (3, dict(use_z=1, split_z=0)), (5, dict(use_z=0, split_z=0, plane_scale=2.0)),
+                   (1, dict(use_z=1, split_z=0))):   # 3 + 1: a pixel stride of 4 that is NOT four image channels
         feats = rng.normal(size=(len(P), S)).astype(np.float32)
         gpu_ctx.set_point_scalars(feats, mode=smode, zero=-3.5)
         opts = gpu_ctx.render_opts(mode=mode, **cfg)
