@@ -397,6 +397,34 @@ def run_ours(args):
             flush.zero_()
         c_.graph_launch(graphs[(k % 2, k % MESH_POOL)])
 
+    # the same pipelined graph loop with FLYBY_SHADE_TOLERANCE (opt-in contract: ids exact, depth / normals within
+    # 1e-5 relative), reported beside the headline as tolerance_mode.views_per_s
+    opts_tol_two = ctx.render_opts(use_z=1, split_z=1, plane_scale=PLANE_SCALE, shade_tolerance=True)
+    graphs_tol = {}
+    if not args.no_extras:
+        for ci, (c_, s_, f_, i_) in enumerate(pair):
+            for m in range(MESH_POOL):
+                P, F = dev_meshes[m]
+                c_.set_mesh(P, F, deferred=True)
+                c_.build()
+                c_.render_into(RES, opts_tol_two, f_, i_)
+                c_.synchronize()
+                with c_.capture() as cap:
+                    c_.set_mesh(P, F, deferred=True)
+                    c_.build()
+                    c_.render_into(RES, opts_tol_two, f_, i_)
+                graphs_tol[(ci, m)] = cap.graph
+
+        def step_two_graph_tol(k):
+            c_, s_, f_, i_ = pair[k % 2]
+            with torch.cuda.stream(s_):
+                flush.zero_()
+            c_.graph_launch(graphs_tol[(k % 2, k % MESH_POOL)])
+
+        ms_two_tol, _ = timed_pipelined(step_two_graph_tol, max(4, args.warmup))
+    else:
+        ms_two_tol = 0.0
+
     ms_two_graph, launches_graph = timed_pipelined(step_two_graph, max(4, args.warmup))
     ms_two, launches_two = ms_two_graph, launches_graph
     sampler.stop_flag = True
@@ -425,7 +453,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         verified = verified and bool(torch.equal(ids3, i_)) and bool(torch.equal(feat3.view(torch.int32), f_.view(torch.int32)))
     ctx3.close()
-    for (ci, m), g in graphs.items():
+    for (ci, m), g in list(graphs.items()) + list(graphs_tol.items()):
         pair[ci][0].graph_destroy(g)
     ctx2.close()
     if not verified:
@@ -445,7 +473,7 @@ def run_ours(args):
         del feat_exact, ids_exact
         opts2 = ctx.render_opts(use_z=1, split_z=1, plane_scale=2.0)
         ms_r2, ms_t2, st2 = bx.render_variant(torch, ctx, stream, flush, (P0, F0), RES, opts2, feat, ids)
-        vals = _max_over_ranks(torch, dist, world, dev, [ms_r1, ms_t1, ms_rt, ms_tt, ms_r2, ms_t2])
+        vals = _max_over_ranks(torch, dist, world, dev, [ms_r1, ms_t1, ms_rt, ms_tt, ms_r2, ms_t2, ms_two_tol])
         alg1 = algorithmic_bytes(n_rays, C, T, V)
         extras["plane_scale_2"] = {
             "render_ms": vals[4], "candidate_search_ms": vals[5], "exact_resolve_ms": vals[4] - vals[5],
@@ -459,6 +487,7 @@ def run_ours(args):
         extras["tolerance_mode"] = dict(tol, render_ms=vals[2], candidate_search_ms=vals[3],
                                         exact_resolve_ms=vals[2] - vals[3], exact_render_ms=vals[0],
                                         views_per_s_render_only=n_views / (vals[2] * 1e-3),
+                                        ms_per_step=vals[6], views_per_s=world * n_views / (vals[6] * 1e-3),
                                         note="FLYBY_SHADE_TOLERANCE (opt-in; the headline uses the exact chain)")
         d2h_bytes = n_rays * 4 * C
         slow, total = bx.copy_ceiling(torch, dist, world, dev, d2h_bytes, feat_hosts[0])

@@ -908,3 +908,23 @@ def test_graph_replay_of_a_step(gpu_ctx, orc):
                 ctx.build()
     finally:
         ctx.close()
+
+
+def test_winding_fix_on_a_large_mesh(gpu_ctx, orc):
+    """The union-find with parity of the consistency pass on 180 000 cells with a third of them reversed, against the
+    oracle's literal wave traversal; and the cheap detection leaves a consistent mesh of that size alone."""
+    P, F = synth.bumpy_sphere(95, 8)
+    G, flip = _scramble_winding(F, 17, frac=0.33)
+    want_tris, want_flip, n = orc.orient_cells(G, len(P))
+    assert n > 50000
+    gpu_ctx.set_mesh(P, G, consistency="fix")
+    gpu_ctx.build()
+    n_gpu, got_flip = gpu_ctx.get_winding()
+    assert n_gpu == n and np.array_equal(got_flip, want_flip)
+    U, _, _ = orc.unit_surf(P)
+    assert np.array_equal(gpu_ctx.get_mesh()[1], orc.point_normals(U, want_tris))
+    # cell 0 is never reversed (VTK's seed); if cell 0 itself was scrambled the whole component follows it
+    assert got_flip[0] == 0
+    gpu_ctx.set_mesh(P, F, consistency="fix")
+    gpu_ctx.build()
+    assert gpu_ctx.get_winding()[0] == 0
