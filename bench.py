@@ -41,7 +41,7 @@ SUBDIVISION = 3     # 92 views
 RES = 512
 RADIUS = 2.0
 PLANE_SCALE = 1.0   # reference default planeScaleFactor (fly_by_features.xml:76)
-MESH_POOL = 4       # distinct meshes per rank, cycled
+MESH_POOL = 4       # distinct meshes, cycled; every rank cycles through the SAME four shapes, starting at its own offset
 METRIC = "views/s at res 512 (fly-by feature extraction; Mrays/s = views/s * 0.262144)"
 
 
@@ -51,7 +51,7 @@ def workload_config(n_views):
                         "one step = one mesh (unit-surf + normals + LBVH build + %d rays + tensor write)"
                         % (n_views, n_views * RES * RES),
             "triangles": 20 * LM * LM, "views": n_views, "resolution": RES, "channels": 4,
-            "sharding": "by mesh, no collective",
+            "sharding": "by mesh, no collective; every rank's share is the same four mesh shapes (seeds 0..3) in rotated order",
             "l2": "explicit 256 MiB L2 flush before every step, on the step's stream (inside the timed region of the "
                   "pipelined loop; outside the per-step events of the single-context loop)"}
 
@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,temperature.gpu")
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
@@ -89,8 +89,14 @@ class ClockSampler(threading.Thread):
         mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
-                "samples": len(self.rows)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+               "samples": len(self.rows)}
+        try:
+            out["power_w_max"] = max(float(r[6]) for r in self.rows if len(r) > 6)
+            out["temp_c_max"] = max(float(r[7]) for r in self.rows if len(r) > 7)
+        except ValueError:
+            pass
+        return out
 
 
 def run_reference(args):
@@ -222,7 +228,12 @@ def run_ours(args):
     C = 4
     n_rays = n_views * RES * RES
 
-    meshes = [synth.bumpy_sphere(LM, seed=rank * MESH_POOL + k) for k in range(MESH_POOL)]
+    # Render time depends on the shape (seeds 12..15 take 5 % longer than 0..3), and the job's time is the MAX over
+    # ranks: with four private meshes per rank the scaling curve measured which rank drew the hardest four, not the
+    # system.  Every rank now processes the same four shapes in rotated order (K steps = K / 4 passes over the pool),
+    # so the shares have identical composition, as a 125-mesh share of BASELINE configs[2] has on average.
+    pool = [synth.bumpy_sphere(LM, seed=k) for k in range(MESH_POOL)]
+    meshes = [pool[(k + rank) % MESH_POOL] for k in range(MESH_POOL)]
     dev_meshes = [(torch.from_numpy(P).to(dev), torch.from_numpy(F).to(dev)) for P, F in meshes]
     torch.cuda.synchronize()  # uploads ran on torch's default stream; the contexts work on their own streams
     # pinned host buffers are allocated (first-touched) on the NUMA node the GPU hangs off: with several ranks the
@@ -508,6 +519,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step_max, ms_e2e_max, ms_e2e_stream_max, ms_two_max, ms_e2e_ids_max, ms_step_sync_max, ms_two_calls_max = (float(x) for x in t)
+    # per-rank view of the headline loop: the job's ms_per_step is the MAX over ranks, i.e. the slowest GPU of the node
+    per_rank = [{"rank": rank, "gpu": local, "ms_per_step": ms_two, "render_ms": ms_render, **sampler.summary()}]
+    if world > 1:
+        box = [None] * world
+        dist.all_gather_object(box, per_rank[0])
+        per_rank = box
 
     if rank == 0:
         peak, peak_src = _hbm_peak()
@@ -545,6 +562,7 @@ def run_ours(args):
                               "render of mesh n; every step is one CUDA-graph replay of set_mesh + build + render "
                               "(flyby_graph_launch); K meshes timed as a whole, max over ranks",
                 "ms_per_step_without_graph": ms_two_calls_max,
+                "per_rank": per_rank,
                 "gpu_launches_without_graph": launches_calls,
                 "single_context_ms_per_step": ms_step_max,
                 "single_context_sync_build_ms_per_step": ms_step_sync_max,
