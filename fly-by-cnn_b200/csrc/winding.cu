@@ -4,10 +4,11 @@
 // VTK walks the cells in waves from the lowest unvisited cell id; a neighbour across an edge (p1,p2) of the
 // current cell must traverse that edge as (p2,p1), otherwise vtkPolyData::ReverseCell turns it into
 // (p2,p1,p0).  On a consistently wound mesh the pass changes nothing -- the case of every mesh the reference
-// ships models for -- so the default here only DETECTS: one hash table of undirected edges (key = the two
-// point ids, value = the first two cells that use the edge with the direction each traverses it), filled with
-// integer atomics, then one scan of the table.  Edge used by exactly two cells in the same direction ->
-// "inconsistent".  With flyby_norm_opts.consistency = 1 the pass is reproduced: union-find with parity over the
+// ships models for -- so every build only DETECTS, with one kernel: a hash set of DIRECTED edges (one 64-bit CAS per
+// edge); a directed edge that occurs twice means two cells traverse a shared edge the same way, the only thing the
+// pass ever acts on.  Only then is the table of undirected edges built (key = the two point ids, value = the first
+// two cells that use the edge with the direction each traverses it), which tells an inconsistent manifold edge from
+// an edge that three or more cells share.  With flyby_norm_opts.consistency = 1 the pass is reproduced: union-find with parity over the
 // manifold edges (root = lowest cell id of the component = VTK's seed, parity = reversed relative to the seed),
 // cells with parity 1 are reversed in place and remembered in mesh.flip so that "vertex 0 of a cell" keeps
 // meaning the caller's vertex 0 (the reference's point-id map is built from the ORIGINAL surface,
@@ -16,7 +17,7 @@
 // Deviation: edges shared by three or more cells are not crossed (VTK's NonManifoldTraversal would
 // cross them in an order that depends on its wave sequence); they are reported, never reoriented.
 //
-// Integer / byte work, HBM-bound: 36 B read per cell, 3 CAS + 3 CAS per cell into a table of 16 B entries.
+// Integer / byte work, L2-atomic-bound: 12 B read per cell, 3 CAS per cell into a table of 8-byte keys (24 B per cell).
 #include "ctx.h"
 
 namespace fb {
