@@ -663,7 +663,10 @@ FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* 
   // pixel range (0.01 pixel per side and the rounding of the index arithmetic, < 0.02 pixel in all)
   const float R1 = ((t->x1 - t->x0) + (t->y1 - t->y0) + 0.04f * (fabsf(V.qdx) + fabsf(V.qdy))) * 1.000001f;
   const float l0 = fabsf(t->e0x) + fabsf(t->e0y), l1 = fabsf(t->e1x) + fabsf(t->e1y), l2 = fabsf(t->e2x) + fabsf(t->e2y);
-  const float k2 = 2.0f * V.e_p, kd = k2 + V.d0, kr = 2.384185791015625e-07f;
+  // kr = 2^-20: 2^-22 bounds the rounding of raster_pixel's own products and differences; the linear form below
+  // (raster_linear_*) adds < 2^-22 l_k R1 of its own; the sum is doubled like every other margin.  Against k2 R1 the
+  // term is ~0.5 % for the triangles of a 100k-2M surface.
+  const float k2 = 2.0f * V.e_p, kd = k2 + V.d0, kr = 9.5367431640625e-07f;
   t->g0 = fmaf(k2, R1, fmaf(kd, l0, kr * l0 * R1)) * 1.000001f;
   t->g1 = fmaf(k2, R1, fmaf(kd, l1, kr * l1 * R1)) * 1.000001f;
   t->g2 = fmaf(k2, R1, fmaf(kd, l2, kr * l2 * R1)) * 1.000001f;
@@ -726,6 +729,63 @@ FB_HD void raster_span(const ViewF& V, const TriR& t, float qy, int i0, int i1, 
   const float fh = fminf((float)i1, floorf(((t.x0 - V.q0x) + (xh + t.sigma)) * ix + 0.01f));
   *lo = (int)fl;
   *hi = fh >= fl ? (int)fh : (int)fl - 1;
+}
+
+// ---- linear form of raster_pixel: the three edge functions are affine in the pixel index, so the per-pixel work is
+// two fused multiply-adds per edge instead of the differences and products of raster_pixel:
+//     E_k(i0 + di, j0 + dj) = C_k + A_k di + B_k dj,   A_k = -e_ky qdx,  B_k = e_kx qdy,
+// C_k = E_k at the corner pixel (i0, j0) of the triangle's pixel range, evaluated exactly as raster_pixel evaluates it
+// there.  What the linear form adds to raster_pixel's error at a pixel of the range (|di qdx| + |dj qdy| <= R1):
+//   rounding of A_k, B_k (one product each):  2^-24 (|e_ky| |di qdx| + |e_kx| |dj qdy|)  <=  2^-24 l_k R1
+//   the two fmaf roundings:                   2 * 2^-24 max|E_k|                          <=  2^-23 l_k R1 (1 + 2^-20)
+// i.e. < 2^-22 l_k R1, which raster_setup's kr carries.  The position the form evaluates at is (float corner) +
+// (di qdx, dj qdy) in exact arithmetic: one fmaf rounding away from the lattice q0 + i qd -- the same distance
+// raster_pixel's fmaf(i, qd, q0) has, and what e_q (viewf_setup) budgets for.  The twice-area is the corner pixel's
+// (any pixel's value is within G of the true one, which is all the orientation / strip argument uses); its sign is
+// folded into the coefficients.  Decisions: exactly those of raster_pixel with E_k replaced -- MISS / SURE / MAYBE
+// keep their meaning, audited pixel by pixel against the exact test by tests/hostsim.
+struct TriL {
+  float A0, A1, A2, B0, B1, B2, C0, C1, C2;  // sign-folded (orientation +1) unless strip
+  float g0, g1, g2;
+  float lim;   // strip: |area2| + G
+  int flags;   // 1 strip test (nearly edge-on), 2 SURE-eligible
+};
+
+FB_HD void raster_linear_setup(const ViewF& V, const TriR& t, int i0, int j0, TriL* L) {
+  const float qx = fmaf((float)i0, V.qdx, V.q0x), qy = fmaf((float)j0, V.qdy, V.q0y);
+  const float r0x = qx - t.ax, r0y = qy - t.ay, r1x = qx - t.bx, r1y = qy - t.by, r2x = qx - t.cx, r2y = qy - t.cy;
+  const float p0a = t.e0x * r0y, p0b = t.e0y * r0x, p1a = t.e1x * r1y, p1b = t.e1y * r1x, p2a = t.e2x * r2y, p2b = t.e2y * r2x;
+  const float E0 = p0a - p0b, E1 = p1a - p1b, E2 = p2a - p2b;
+  const float area2 = (E0 + E1) + E2;
+  const bool strip = fabsf(area2) <= 2.0f * t.G;
+  const float s = (strip || area2 > 0.f) ? 1.0f : -1.0f;
+  L->A0 = -s * (t.e0y * V.qdx); L->A1 = -s * (t.e1y * V.qdx); L->A2 = -s * (t.e2y * V.qdx);
+  L->B0 = s * (t.e0x * V.qdy); L->B1 = s * (t.e1x * V.qdy); L->B2 = s * (t.e2x * V.qdy);
+  L->C0 = s * E0; L->C1 = s * E1; L->C2 = s * E2;
+  L->g0 = t.g0; L->g1 = t.g1; L->g2 = t.g2;
+  L->lim = fabsf(area2) + t.G;
+  L->flags = (strip ? 1 : 0) | (t.flags & 2);
+}
+
+// (di, dj) = pixel offsets from the corner as floats (exact: small integers).  The two variants are the two branches
+// of raster_pixel; raster_kernel picks the first for a whole warp when none of its triangles is edge-on.
+FB_HD int raster_linear_pixel_plain(const TriL& L, float di, float dj) {
+  const float E0 = fmaf(L.A0, di, fmaf(L.B0, dj, L.C0));
+  const float E1 = fmaf(L.A1, di, fmaf(L.B1, dj, L.C1));
+  const float E2 = fmaf(L.A2, di, fmaf(L.B2, dj, L.C2));
+  if (E0 < -L.g0 || E1 < -L.g1 || E2 < -L.g2) return SC_MISS;
+  if (!(E0 > L.g0 && E1 > L.g1 && E2 > L.g2)) return SC_MAYBE;
+  return (L.flags & 2) ? SC_SURE : SC_MAYBE;
+}
+FB_HD int raster_linear_pixel_strip(const TriL& L, float di, float dj) {
+  const float E0 = fmaf(L.A0, di, fmaf(L.B0, dj, L.C0));
+  const float E1 = fmaf(L.A1, di, fmaf(L.B1, dj, L.C1));
+  const float E2 = fmaf(L.A2, di, fmaf(L.B2, dj, L.C2));
+  if (fabsf(E0) > L.lim + L.g0 || fabsf(E1) > L.lim + L.g1 || fabsf(E2) > L.lim + L.g2) return SC_MISS;
+  return SC_MAYBE;
+}
+FB_HD int raster_linear_pixel(const TriL& L, float di, float dj) {
+  return (L.flags & 1) ? raster_linear_pixel_strip(L, di, dj) : raster_linear_pixel_plain(L, di, dj);
 }
 
 // ---- front-buffer key of the single-pass scan conversion (raster.cu):

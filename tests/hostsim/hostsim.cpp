@@ -488,6 +488,10 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
   for (int64_t i = 0; i < 3 * V; i++) maxc = fmaxf(maxc, fabsf(verts[i]));
   long long n_tests = 0, n_exact = 0, n_over = 0, n_span_bad = 0, n_unsound = 0, n_maybe = 0;
   const bool check_spans = work && work[3] == 1;
+  // in: work[5] selects the per-pixel predicate: 0 as raster.cu (linear form for boxes up to RT_BIG pixels, raster_pixel
+  // for the larger ones, which raster_big_kernel walks), 1 the linear form for every box (raster_kernel's inline
+  // fallback when the big-triangle queue is full), 2 raster_pixel with row spans (the round-1 kernel)
+  const long long pred_mode = work ? work[5] : 0;
   const long long order_seed = work ? work[4] : 0;  // in: work[4] != 0 shuffles the arrival order of the triangles  // in: work[3] = 1 asks for the span audit; out: work[3] = violations
   SimCount cnt;
   SimFetch f{b.nodes.data()};
@@ -519,18 +523,22 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
       PixRange r;
       if (!raster_project(vf, P0, P1, P2, res, &t, &r)) continue;
       const long long npx = (long long)(r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
-      raster_setup(vf, 0.0f, P0, P1, P2, npx > 12, &t);
+      raster_setup(vf, 0.0f, P0, P1, P2, pred_mode == 2 && npx > 12, &t);
       if (!(t.flags & 1)) continue;
       const uint64_t key = front_key(t.zlo, t.zhi, (int)slot);
       const uint32_t zlo_ord = ford_bits(t.zlo);
-      const bool use_spans = npx <= 96 && (t.flags & 4);  // RT_BIG of raster.cu
+      const bool use_spans = pred_mode == 2 && npx <= 96 && (t.flags & 4);  // RT_BIG of raster.cu
+      const bool linear = pred_mode == 1 || (pred_mode == 0 && npx <= 96);
+      TriL L;
+      raster_linear_setup(vf, t, r.i0, r.j0, &L);
       for (int j = r.j0; j <= r.j1; j++) {
         int lo = r.i0, hi = r.i1;
         if (use_spans) raster_span(vf, t, fmaf((float)j, vf.qdy, vf.q0y), r.i0, r.i1, &lo, &hi);
         if (check_spans)
           for (int i = r.i0; i <= r.i1; i++) {
             // every pixel the span skips must be a certain miss
-            const int c2 = raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y));
+            const int c2 = linear ? raster_linear_pixel(L, (float)(i - r.i0), (float)(j - r.j0))
+                                  : raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y));
             if ((i < lo || i > hi) && c2 != SC_MISS) n_span_bad++;
             // soundness of the predicate itself: MISS => the exact test rejects, SURE => it accepts
             if (c2 != SC_MAYBE) {
@@ -546,7 +554,7 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
           }
         for (int i = lo; i <= hi; i++) {
           float qx = fmaf((float)i, vf.qdx, vf.q0x), qy = fmaf((float)j, vf.qdy, vf.q0y);
-          int cls = raster_pixel(t, qx, qy);
+          int cls = linear ? raster_linear_pixel(L, (float)(i - r.i0), (float)(j - r.j0)) : raster_pixel(t, qx, qy);
           n_tests++;
           if (cls == SC_MISS) continue;
           size_t pix = (size_t)j * res + i;
