@@ -591,19 +591,13 @@ FB_HD int screen_tri(const ViewF& V, float qx, float qy, float zo, const float* 
 // padded bounding box |r|_1 <= R1 = (box size)_1 + 2 m0, so
 //     g_k = k2 R1 + kd l_k + kr l_k R1   >=   the g_k screen_pixel would use at any such pixel.
 // Larger margins only turn decisions into SC_MAYBE, so the guarantees of screen_pixel carry over.
-// For a triangle whose orientation is reliable the pixels of a row that are not a certain miss form one
-// interval; raster_span bounds it (slope / intercept per edge, relative to the box corner so that the
-// rounding error stays proportional to the box size) and sigma covers the rounding of that bound.
 struct TriR {
   float ax, ay, bx, by, cx, cy;        // projected vertices
   float e0x, e0y, e1x, e1y, e2x, e2y;  // edges a->b, b->c, c->a
   float g0, g1, g2, G;                 // margins of the three edge functions and their sum
   float x0, x1, y0, y1;                // padded bounding box (lox - m0 ...)
   float zlo, zhi;                      // depth interval, widened by e_z
-  float m0s, m1s, m2s, b0s, b1s, b2s;  // span bound of edge k: x - x0 <=/>= b_k + m_k (qy - y0)
-  float sigma;                         // slack of the span bounds
-  int flags;                           // 1 depth range overlaps the segment, 2 SURE-eligible, 4 spans usable,
-                                       // 8/16/32: edge 0/1/2 bounds the span from above (else from below), 64/128/256: edge usable
+  int flags;                           // 1 depth range overlaps the segment, 2 SURE-eligible
 };
 
 // projection, padded box and pixel range; false when no pixel of the view can see the triangle's box
@@ -633,9 +627,8 @@ FB_HD bool raster_project(const ViewF& V, const float* P0, const float* P1, cons
   return true;
 }
 
-// the rest of the per-triangle work (depth range, flags, margins, span coefficients); zo = depth of the ray origins
-FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* P1, const float* P2, bool want_spans,
-                        TriR* t) {
+// the rest of the per-triangle work (depth range, flags, margins); zo = depth of the ray origins
+FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* P1, const float* P2, TriR* t) {
   const float az = V.rp - fmaf(P0[0], V.nf[0], fmaf(P0[1], V.nf[1], P0[2] * V.nf[2]));
   const float bz = V.rp - fmaf(P1[0], V.nf[0], fmaf(P1[1], V.nf[1], P1[2] * V.nf[2]));
   const float cz = V.rp - fmaf(P2[0], V.nf[0], fmaf(P2[1], V.nf[1], P2[2] * V.nf[2]));
@@ -671,31 +664,6 @@ FB_HD void raster_setup(const ViewF& V, float zo, const float* P0, const float* 
   t->g1 = fmaf(k2, R1, fmaf(kd, l1, kr * l1 * R1)) * 1.000001f;
   t->g2 = fmaf(k2, R1, fmaf(kd, l2, kr * l2 * R1)) * 1.000001f;
   t->G = (t->g0 + t->g1 + t->g2) * 1.000001f;
-  // spans: only when the sign of the area is beyond doubt (the per-pixel area differs from this one by < G)
-  t->m0s = t->m1s = t->m2s = t->b0s = t->b1s = t->b2s = 0.f;
-  t->sigma = fmaf(4.0e-5f, R1, 4.76837158203125e-07f * (fabsf(t->x0) + fabsf(t->x1) + fabsf(V.q0x) + R1));
-  if (want_spans && fabsf(area2) > 4.0f * t->G) {
-    flags |= 4;
-    const float s = area2 > 0.f ? 1.0f : -1.0f;
-    // not a certain miss w.r.t. edge k:  s E_k >= -g_k,  E_k = e_kx (qy - P_ky) - e_ky (qx - P_kx)
-    //   <=>  (s e_ky) (qx - P_kx) <= g_k + (s e_kx) (qy - P_ky)
-    // an edge within ~3 degrees of the row direction gives no usable bound
-    if (fabsf(t->e0y) >= 0.05f * l0) {
-      const float c = s * t->e0y, m = t->e0x / t->e0y;
-      t->m0s = m; t->b0s = (t->ax - t->x0) + t->g0 / c - m * (t->ay - t->y0);
-      flags |= 64 | (c > 0.f ? 8 : 0);
-    }
-    if (fabsf(t->e1y) >= 0.05f * l1) {
-      const float c = s * t->e1y, m = t->e1x / t->e1y;
-      t->m1s = m; t->b1s = (t->bx - t->x0) + t->g1 / c - m * (t->by - t->y0);
-      flags |= 128 | (c > 0.f ? 16 : 0);
-    }
-    if (fabsf(t->e2y) >= 0.05f * l2) {
-      const float c = s * t->e2y, m = t->e2x / t->e2y;
-      t->m2s = m; t->b2s = (t->cx - t->x0) + t->g2 / c - m * (t->cy - t->y0);
-      flags |= 256 | (c > 0.f ? 32 : 0);
-    }
-  }
   t->flags = flags;
 }
 
@@ -715,20 +683,6 @@ FB_HD int raster_pixel(const TriR& t, float qx, float qy) {
   if (v0 < -t.g0 || v1 < -t.g1 || v2 < -t.g2) return SC_MISS;
   if (!(v0 > t.g0 && v1 > t.g1 && v2 > t.g2)) return SC_MAYBE;
   return (t.flags & 2) ? SC_SURE : SC_MAYBE;
-}
-
-// pixels [lo, hi] of row qy outside of which raster_pixel is certain to answer SC_MISS (flags & 4 only)
-FB_HD void raster_span(const ViewF& V, const TriR& t, float qy, int i0, int i1, int* lo, int* hi) {
-  const float dy = qy - t.y0;
-  float xl = -1.0e30f, xh = 1.0e30f;
-  if (t.flags & 64) { const float x = fmaf(t.m0s, dy, t.b0s); if (t.flags & 8) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
-  if (t.flags & 128) { const float x = fmaf(t.m1s, dy, t.b1s); if (t.flags & 16) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
-  if (t.flags & 256) { const float x = fmaf(t.m2s, dy, t.b2s); if (t.flags & 32) xh = fminf(xh, x); else xl = fmaxf(xl, x); }
-  const float ix = V.iqx;
-  const float fl = fmaxf((float)i0, ceilf(((t.x0 - V.q0x) + (xl - t.sigma)) * ix - 0.01f));
-  const float fh = fminf((float)i1, floorf(((t.x0 - V.q0x) + (xh + t.sigma)) * ix + 0.01f));
-  *lo = (int)fl;
-  *hi = fh >= fl ? (int)fh : (int)fl - 1;
 }
 
 // ---- linear form of raster_pixel: the three edge functions are affine in the pixel index, so the per-pixel work is
@@ -773,9 +727,10 @@ FB_HD int raster_linear_pixel_plain(const TriL& L, float di, float dj) {
   const float E0 = fmaf(L.A0, di, fmaf(L.B0, dj, L.C0));
   const float E1 = fmaf(L.A1, di, fmaf(L.B1, dj, L.C1));
   const float E2 = fmaf(L.A2, di, fmaf(L.B2, dj, L.C2));
-  if (E0 < -L.g0 || E1 < -L.g1 || E2 < -L.g2) return SC_MISS;
-  if (!(E0 > L.g0 && E1 > L.g1 && E2 > L.g2)) return SC_MAYBE;
-  return (L.flags & 2) ? SC_SURE : SC_MAYBE;
+  // (no short-circuit: the device code is three comparisons per line into one predicate, no branches)
+  const bool miss = (E0 < -L.g0) | (E1 < -L.g1) | (E2 < -L.g2);
+  const bool inside = (E0 > L.g0) & (E1 > L.g1) & (E2 > L.g2) & ((L.flags & 2) != 0);
+  return miss ? SC_MISS : (inside ? SC_SURE : SC_MAYBE);
 }
 FB_HD int raster_linear_pixel_strip(const TriL& L, float di, float dj) {
   const float E0 = fmaf(L.A0, di, fmaf(L.B0, dj, L.C0));

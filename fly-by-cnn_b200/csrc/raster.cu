@@ -36,12 +36,6 @@ namespace fb {
 #define RT_BIG 96    // bounding boxes with more pixels than this go to raster_big_kernel (row bands over the whole grid)
 #define RT_EXTRA 8    // extra candidates kept per pixel (two int4)
 #define RT_BAND 4096  // pixels of a big triangle's box handled by one warp of raster_big_kernel
-#ifndef RT_SPAN_MIN
-#define RT_SPAN_MIN 12 // bounding boxes up to this many pixels are walked whole (the span set-up would cost more)
-#endif
-#ifndef RT_UNROLL
-#define RT_UNROLL 4    // pixels of a row in flight at a time
-#endif
 #define RV_THREADS 128
 #ifndef RV_MINB
 #define RV_MINB 5
@@ -146,10 +140,12 @@ template <bool STRIP>
 __device__ __forceinline__ void rt_window(const TriL& L, float di0, float dj, int nvalid, uint32_t ent0, uint32_t* q, int& qn, unsigned ltmask) {
 #pragma unroll
   for (int u = 0; u < RT_U; u++) {
-    int cls = SC_MISS;
-    if (u < nvalid) cls = STRIP ? raster_linear_pixel(L, di0 + (float)u, dj) : raster_linear_pixel_plain(L, di0 + (float)u, dj);
-    const unsigned m = __ballot_sync(0xffffffffu, cls != SC_MISS);
-    if (cls != SC_MISS) q[qn + __popc(m & ltmask)] = ent0 + ((uint32_t)u << 13) + (cls == SC_SURE ? 32u : 0u);
+    const int c = STRIP ? raster_linear_pixel(L, di0 + (float)u, dj) : raster_linear_pixel_plain(L, di0 + (float)u, dj);
+    const bool keep = (c != SC_MISS) & (u < nvalid);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    uint32_t* at = q + (qn + __popc(m & ltmask));  // computed by every lane so that the store is a single predicated instruction
+    const uint32_t ent = ent0 + ((uint32_t)u << 13) + (c == SC_SURE ? 32u : 0u);
+    if (keep) *at = ent;
     qn += __popc(m);
   }
 }
@@ -160,6 +156,8 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
   __shared__ int s_pre[RT_WARPS][32];
   __shared__ uint32_t s_q[RT_WARPS][RT_QCAP];
   const int view = blockIdx.y;  // local view index of this render call
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int slot = blockIdx.x * RT_THREADS + threadIdx.x;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.r.viewsf + p.r.view_begin + view);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s_vf);
@@ -169,8 +167,6 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
   const ViewF& V = s_vf;
   const int res = p.r.res;
   const uint32_t view_base = (uint32_t)view * (uint32_t)res * (uint32_t)res;  // a render call has < 2^32 pixels
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int slot = blockIdx.x * RT_THREADS + threadIdx.x;
   RtRec* rec = s_rec[wid];
   uint32_t* q = s_q[wid];
   const unsigned ltmask = (1u << lane) - 1u;
@@ -186,7 +182,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
       const float P0[3] = {a.x, a.y, a.z}, P1[3] = {b.x, b.y, b.z}, P2[3] = {e.x, e.y, e.z};
       if (raster_project(V, P0, P1, P2, res, &t, &r)) {  // triangles outside a close-up view end here
         npx = (r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
-        raster_setup(V, 0.0f, P0, P1, P2, false, &t);  // ray origins lie in the view plane: depth 0 (+- e_z)
+        raster_setup(V, 0.0f, P0, P1, P2, &t);  // ray origins lie in the view plane: depth 0 (+- e_z)
         if (!(t.flags & 1)) npx = 0;
       }
     }
@@ -286,7 +282,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
     TriR u;
     PixRange r;
     if (!raster_project(V, P0, P1, P2, res, &u, &r)) continue;
-    raster_setup(V, 0.0f, P0, P1, P2, false, &u);
+    raster_setup(V, 0.0f, P0, P1, P2, &u);
     const unsigned long long key = front_key(u.zlo, u.zhi, uslot);
     const unsigned int zlo_ord = ford_bits(u.zlo);
     const int w = r.i1 - r.i0 + 1;
@@ -329,7 +325,7 @@ __global__ void __launch_bounds__(128) raster_big_kernel(const RasterParams p) {
     TriR u;
     PixRange r;
     if (!raster_project(V, P0, P1, P2, res, &u, &r)) continue;
-    raster_setup(V, 0.0f, P0, P1, P2, false, &u);
+    raster_setup(V, 0.0f, P0, P1, P2, &u);
     const int jb = r.j0 + (int)(b - (unsigned int)ent.z) * rpb;
     if (jb > r.j1) continue;  // a band of an entry that lies behind the stored ones
     const int je = min(r.j1, jb + rpb - 1);

@@ -480,19 +480,19 @@ int sim_render_packet_screen(const float* verts, int64_t V, const int32_t* tris,
 extern "C" __attribute__((visibility("default")))
 int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_t T, const float* views,
                       int n_views, double radius, int res, double plane_scale, double spacing, int cand_cap,
-                      int32_t* out_ids, double* out_t, long long* work /* [7]: pixel tests, exact tests, overflow pixels, span audit, in: order seed, out: unsound decisions, MAYBE box pixels */) {
+                      int32_t* out_ids, double* out_t, long long* work /* [7]: pixel tests, exact tests, overflow pixels, in: 1 = audit every decision (out: 0), in: order seed, in: predicate / out: unsound decisions, MAYBE box pixels */) {
   SimBvh b;
   build(verts, V, tris, T, b);
   if (b.nodes.empty()) return 1;
   float maxc = 0.f;
   for (int64_t i = 0; i < 3 * V; i++) maxc = fmaxf(maxc, fabsf(verts[i]));
-  long long n_tests = 0, n_exact = 0, n_over = 0, n_span_bad = 0, n_unsound = 0, n_maybe = 0;
-  const bool check_spans = work && work[3] == 1;
+  long long n_tests = 0, n_exact = 0, n_over = 0, n_unsound = 0, n_maybe = 0;
+  const bool audit = work && work[3] == 1;  // every MISS / SURE decision of the predicate against the exact test
   // in: work[5] selects the per-pixel predicate: 0 as raster.cu (linear form for boxes up to RT_BIG pixels, raster_pixel
-  // for the larger ones, which raster_big_kernel walks), 1 the linear form for every box (raster_kernel's inline
-  // fallback when the big-triangle queue is full), 2 raster_pixel with row spans (the round-1 kernel)
+  // for the larger ones, which raster_big_kernel and raster_kernel's inline fallback walk), 1 the linear form for every
+  // box, 2 raster_pixel for every box
   const long long pred_mode = work ? work[5] : 0;
-  const long long order_seed = work ? work[4] : 0;  // in: work[4] != 0 shuffles the arrival order of the triangles  // in: work[3] = 1 asks for the span audit; out: work[3] = violations
+  const long long order_seed = work ? work[4] : 0;  // in: work[4] != 0 shuffles the arrival order of the triangles
   SimCount cnt;
   SimFetch f{b.nodes.data()};
   for (int v = 0; v < n_views; v++) {
@@ -523,23 +523,19 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
       PixRange r;
       if (!raster_project(vf, P0, P1, P2, res, &t, &r)) continue;
       const long long npx = (long long)(r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
-      raster_setup(vf, 0.0f, P0, P1, P2, pred_mode == 2 && npx > 12, &t);
+      raster_setup(vf, 0.0f, P0, P1, P2, &t);
       if (!(t.flags & 1)) continue;
       const uint64_t key = front_key(t.zlo, t.zhi, (int)slot);
       const uint32_t zlo_ord = ford_bits(t.zlo);
-      const bool use_spans = pred_mode == 2 && npx <= 96 && (t.flags & 4);  // RT_BIG of raster.cu
       const bool linear = pred_mode == 1 || (pred_mode == 0 && npx <= 96);
       TriL L;
       raster_linear_setup(vf, t, r.i0, r.j0, &L);
       for (int j = r.j0; j <= r.j1; j++) {
-        int lo = r.i0, hi = r.i1;
-        if (use_spans) raster_span(vf, t, fmaf((float)j, vf.qdy, vf.q0y), r.i0, r.i1, &lo, &hi);
-        if (check_spans)
+        const int lo = r.i0, hi = r.i1;
+        if (audit)
           for (int i = r.i0; i <= r.i1; i++) {
-            // every pixel the span skips must be a certain miss
             const int c2 = linear ? raster_linear_pixel(L, (float)(i - r.i0), (float)(j - r.j0))
                                   : raster_pixel(t, fmaf((float)i, vf.qdx, vf.q0x), fmaf((float)j, vf.qdy, vf.q0y));
-            if ((i < lo || i > hi) && c2 != SC_MISS) n_span_bad++;
             // soundness of the predicate itself: MISS => the exact test rejects, SURE => it accepts
             if (c2 != SC_MAYBE) {
               double o[3], tt, xx[3], ww[3];
@@ -600,7 +596,7 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
         out_ids[id] = h.cell; out_t[id] = h.slot >= 0 ? h.t : -1.0;
       }
   }
-  if (work) { work[0] = n_tests; work[1] = n_exact; work[2] = n_over; if (check_spans) { work[3] = n_span_bad; work[5] = n_unsound; work[6] = n_maybe; } }
+  if (work) { work[0] = n_tests; work[1] = n_exact; work[2] = n_over; if (audit) { work[3] = 0; work[5] = n_unsound; work[6] = n_maybe; } }
   return 0;
 }
 
@@ -632,7 +628,7 @@ int sim_shade_approx_audit(const float* verts, int64_t V, const int32_t* tris, i
       TriR t;
       PixRange r;
       if (!raster_project(vf, P0, P1, P2, res, &t, &r)) continue;
-      raster_setup(vf, 0.0f, P0, P1, P2, false, &t);
+      raster_setup(vf, 0.0f, P0, P1, P2, &t);
       if (!(t.flags & 1)) continue;
       for (int j = r.j0; j <= r.j1; j++)
         for (int i = r.i0; i <= r.i1; i++) {
