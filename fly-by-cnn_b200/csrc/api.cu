@@ -1,6 +1,8 @@
 // api.cu -- the C-ABI of include/flyby_b200.h: context lifetime, host/device
 // buffer staging and call ordering.  All compute is in the kernels of
 // prep.cu / lbvh.cu / views.cu / trace.cu / label.cu.
+#include <algorithm>
+#include <cstdint>
 #include <new>
 
 #include "ctx.h"
@@ -152,7 +154,8 @@ void flyby_destroy(flyby_ctx* c) {
                     &m.node_box, &m.knode, &m.krange, &m.remap, &m.topflag, &m.nodes, &m.tv0, &m.tv1, &m.tv2, &m.tvid, &m.trec,
                     &c->view_pts, &c->views, &c->viewsf, &c->tc_table, &c->cand, &c->cand2, &c->pix_lists, &c->raster_tmp, &c->stage_feat, &c->stage_ids, &c->stage_t, &c->stage_in0,
                     &m.flip, &m.edge_tab, &m.orient, &m.scalars, &c->stage_in1, &c->stage_out0, &c->stage_misc, &c->pp_tmp, &c->pp_tmp2, &c->raster_ovf, &c->raster_big, &c->counters,
-                    &c->async_feat[0], &c->async_feat[1], &c->async_ids[0], &c->async_ids[1], &c->async_t[0], &c->async_t[1]};
+                    &c->async_feat[0], &c->async_feat[1], &c->async_ids[0], &c->async_ids[1], &c->async_t[0], &c->async_t[1],
+                    &c->pk_feat, &c->pk_rgb[0], &c->pk_rgb[1], &c->pk_z[0], &c->pk_z[1]};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -518,6 +521,74 @@ int flyby_render_async(flyby_ctx* c, int vb, int ve, int res, const flyby_render
     if (dt) FB_CUDA(c, cudaMemcpyAsync(out_t + off, dt + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
   }
   FB_CUDA(c, cudaEventRecord(c->async_done[s], c->copy_stream));
+  return FLYBY_OK;
+}
+
+// ---- packed output (normal_encoding 3): uint8 colours + float32 depth, 7 bytes per pixel across PCIe instead of 16
+int flyby_render_packed(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, uint8_t* out_rgb, float* out_depth,
+                        int32_t* out_cell_ids) {
+  CHECK_CTX(c);
+  int rc = check_render_args(c, vb, ve, res, o, true);
+  if (rc) return rc;
+  if (!out_rgb) return fail(c, FLYBY_ERR_INVALID, "render_packed: null colour output");
+  if (o->normal_encoding != 3)
+    return fail(c, FLYBY_ERR_UNSUPPORTED, "render_packed: needs normal_encoding 3 (the 8-bit colours): other encodings are not integers");
+  if (o->use_z && !o->split_z)
+    return fail(c, FLYBY_ERR_UNSUPPORTED, "render_packed: use_z without split_z multiplies the colours by the depth: not 8-bit values");
+  if (c->mesh.n_scalars) return fail(c, FLYBY_ERR_UNSUPPORTED, "render_packed: point scalars are float channels: use flyby_render");
+  const int channels = (o->use_z && o->split_z) ? 4 : 3;
+  if (out_depth && channels != 4) return fail(c, FLYBY_ERR_INVALID, "render_packed: a depth output needs use_z and split_z");
+  const bool dev_out = is_device_ptr(out_rgb);
+  if ((out_depth && is_device_ptr(out_depth) != dev_out) || (out_cell_ids && is_device_ptr(out_cell_ids) != dev_out))
+    return fail(c, FLYBY_ERR_INVALID, "render_packed: outputs must be all host or all device memory");
+  const size_t per_view = (size_t)res * res;
+  const size_t n_pix = (size_t)(ve - vb) * per_view;
+  if ((rc = views_setup(c, o, res))) return rc;
+  const int nv = ve - vb;
+  int n_chunks = nv < 8 ? 1 : (nv + 11) / 12;
+  if (n_chunks > 16) n_chunks = 16;
+  int bounds[17];
+  size_t max_chunk = 0;
+  for (int k = 0; k <= n_chunks; k++) bounds[k] = vb + (int)((long long)nv * k / n_chunks);
+  for (int k = 0; k < n_chunks; k++) max_chunk = std::max(max_chunk, (size_t)(bounds[k + 1] - bounds[k]) * per_view);
+  FB_CUDA(c, c->pk_feat.reserve(max_chunk * channels * sizeof(float)));
+  float* df = c->pk_feat.as<float>();
+  uint8_t* drgb = out_rgb;
+  float* dz = out_depth;
+  int32_t* di = out_cell_ids;
+  int s = 0;
+  if (!dev_out) {
+    s = c->async_flip;
+    c->async_flip ^= 1;
+    for (int i = 0; i < 2; i++)
+      if (!c->async_done[i]) FB_CUDA(c, cudaEventCreateWithFlags(&c->async_done[i], cudaEventDisableTiming));
+    // growing a staging buffer frees the old one: drain the copies that may still read it first
+    if (c->pk_rgb[s].cap < n_pix * 3 || (out_depth && c->pk_z[s].cap < n_pix * sizeof(float)) ||
+        (out_cell_ids && c->async_ids[s].cap < n_pix * sizeof(int32_t)))
+      FB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    FB_CUDA(c, c->pk_rgb[s].reserve(n_pix * 3));
+    drgb = c->pk_rgb[s].as<uint8_t>();
+    if (out_depth) { FB_CUDA(c, c->pk_z[s].reserve(n_pix * sizeof(float))); dz = c->pk_z[s].as<float>(); }
+    if (out_cell_ids) { FB_CUDA(c, c->async_ids[s].reserve(n_pix * sizeof(int32_t))); di = c->async_ids[s].as<int32_t>(); }
+    FB_CUDA(c, cudaStreamWaitEvent(c->stream, c->async_done[s], 0));  // the set's previous copy-out (two calls ago)
+  }
+  for (int k = 0; k < n_chunks; k++) {
+    const size_t off = (size_t)(bounds[k] - vb) * per_view;
+    const size_t cnt = (size_t)(bounds[k + 1] - bounds[k]) * per_view;
+    rc = trace_render(c, bounds[k], bounds[k + 1], res, o, df, di ? di + off : nullptr, nullptr, k == 0, k == n_chunks - 1);
+    if (rc) return rc;
+    // vector path: whole groups of 4 pixels and word-aligned colour / depth rows of this chunk
+    const int vec = (cnt % 4 == 0 && off % 4 == 0 && ((uintptr_t)drgb % 4 == 0) && (!dz || (uintptr_t)dz % 16 == 0)) ? 1 : 0;
+    if ((rc = fb::pack_rgb8(c, df, channels, (int64_t)cnt, drgb + 3 * off, dz ? dz + off : nullptr, vec))) return rc;
+    if (!dev_out) {
+      FB_CUDA(c, cudaEventRecord(c->chunk_ev[k], c->stream));
+      FB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[k], 0));
+      FB_CUDA(c, cudaMemcpyAsync(out_rgb + 3 * off, drgb + 3 * off, cnt * 3, cudaMemcpyDeviceToHost, c->copy_stream));
+      if (dz) FB_CUDA(c, cudaMemcpyAsync(out_depth + off, dz + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+      if (di) FB_CUDA(c, cudaMemcpyAsync(out_cell_ids + off, di + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+  }
+  if (!dev_out) FB_CUDA(c, cudaEventRecord(c->async_done[s], c->copy_stream));
   return FLYBY_OK;
 }
 

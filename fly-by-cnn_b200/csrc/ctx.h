@@ -124,6 +124,7 @@ struct flyby_ctx {
   fb::DevBuf pp_tmp, pp_tmp2;  // label post-processing scratch (postproc.cu)
   // flyby_render_async: two sets of device staging so that the copy-out of call n overlaps the work of call n + 1
   fb::DevBuf async_feat[2], async_ids[2], async_t[2];
+  fb::DevBuf pk_feat, pk_rgb[2], pk_z[2];  // flyby_render_packed: float staging of one view chunk, packed staging sets
   cudaEvent_t async_done[2] = {nullptr, nullptr};  // recorded on copy_stream behind the copies of a set
   int async_flip = 0;
   fb::DevBuf counters;  // uint64 [8]: tile counter, work counters
@@ -225,6 +226,7 @@ int wait_tree(flyby_ctx* c);  // lbvh.cu: make the main stream wait for the side
 int views_setup(flyby_ctx* c, const flyby_render_opts* o, int res);                      // trace.cu
 int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,
                  int32_t* ids, double* tt, bool first_chunk = true, bool last_chunk = true);                                     // trace.cu
+int pack_rgb8(flyby_ctx* c, const float* feat, int channels, int64_t n_pix, uint8_t* rgb, float* depth, int vec);  // trace.cu
 int trace_render_perspective(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, double tan_half,
                              double z_near, double z_far, float* feat, int32_t* ids, double* depth);
 int trace_interpolate(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, const int32_t* cell_ids,

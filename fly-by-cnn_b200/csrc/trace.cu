@@ -472,6 +472,49 @@ int raster_render(flyby_ctx* c, const RenderParams& p);  // raster.cu: scan-conv
 static int g_mode = 2;  // what flyby_render_opts.mode 0 means; FLYBY_MODE (A/B runs): 2 raster, 1 bvh, 0 fused
 static int g_use_top = 1;  // FLYBY_NO_SMEM_TOP=1 disables the shared-memory top (A/B measurements)
 
+// ---- flyby_render_packed: float feature tensor of one view chunk -> uint8 colours + float32 depth
+// 4 pixels per thread when the chunk is a multiple of 4 pixels (12 colour bytes = three aligned words), else one
+template <int C>
+__global__ void __launch_bounds__(256) pack_rgb8_kernel(const float* __restrict__ feat, int64_t n_pix, uint8_t* __restrict__ rgb,
+                                                         float* __restrict__ depth, int vec) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (vec) {
+    if (4 * i >= n_pix) return;
+    uint32_t b[12];
+    float z[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float r, g, bl;
+      if (C == 4) {
+        const float4 f = __ldcs(reinterpret_cast<const float4*>(feat) + 4 * i + k);
+        r = f.x; g = f.y; bl = f.z; z[k] = f.w;
+      } else {
+        const float* f = feat + 3 * (4 * i + k);
+        r = __ldcs(f); g = __ldcs(f + 1); bl = __ldcs(f + 2); z[k] = 0.f;
+      }
+      b[3 * k] = (uint32_t)(int)r & 255u; b[3 * k + 1] = (uint32_t)(int)g & 255u; b[3 * k + 2] = (uint32_t)(int)bl & 255u;
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(rgb) + 3 * i;
+    __stcs(o, b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24));
+    __stcs(o + 1, b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+    __stcs(o + 2, b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24));
+    if (C == 4 && depth) __stcs(reinterpret_cast<float4*>(depth) + i, make_float4(z[0], z[1], z[2], z[3]));
+  } else {
+    if (i >= n_pix) return;
+    const float* f = feat + C * i;
+    rgb[3 * i] = (uint8_t)(int)f[0]; rgb[3 * i + 1] = (uint8_t)(int)f[1]; rgb[3 * i + 2] = (uint8_t)(int)f[2];
+    if (C == 4 && depth) depth[i] = f[3];
+  }
+}
+
+int pack_rgb8(flyby_ctx* c, const float* feat, int channels, int64_t n_pix, uint8_t* rgb, float* depth, int vec) {
+  const unsigned grid = (unsigned)((vec ? n_pix / 4 : n_pix) / 256 + 1);
+  if (channels == 4) pack_rgb8_kernel<4><<<grid, 256, 0, c->stream>>>(feat, n_pix, rgb, depth, vec);
+  else pack_rgb8_kernel<3><<<grid, 256, 0, c->stream>>>(feat, n_pix, rgb, nullptr, vec);
+  FB_LAUNCH_CHECK(c);
+  return FLYBY_OK;
+}
+
 // first_chunk / last_chunk: a render call may be split into view chunks (api.cu overlaps the
 // copy-back of one chunk with the render of the next); stats and events span all chunks.
 int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts* o, float* feat,

@@ -57,7 +57,7 @@ SYMBOLS = [
     "flyby_launch_count", "flyby_labels_remove_islands", "flyby_labels_connectivity", "flyby_labels_erode",
     "flyby_labels_dilate", "flyby_labels_relabel", "flyby_interpolate_features", "flyby_render_perspective",
     "flyby_render_async", "flyby_set_point_scalars", "flyby_get_winding", "flyby_point_ids",
-    "flyby_backproject_points", "flyby_capture_begin", "flyby_capture_end", "flyby_graph_launch", "flyby_graph_destroy",
+    "flyby_backproject_points", "flyby_render_packed", "flyby_capture_begin", "flyby_capture_end", "flyby_graph_launch", "flyby_graph_destroy",
 ]
 
 NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2, "uint8": 3}
@@ -306,6 +306,16 @@ class Context:
         fn = self._lib.flyby_render if wait else self._lib.flyby_render_async
         self._ck(fn(self._h, C.c_int(view_begin), C.c_int(ve), C.c_int(res), C.byref(opts),
                     _ptr(features), _ptr(cell_ids), _ptr(t)))
+
+    def render_packed_into(self, res, opts, rgb, depth=None, cell_ids=None, view_begin=0, view_end=None):
+        """flyby_render_packed: uint8 colours [n,res,res,3] + float32 depth [n,res,res] (normal_encoding "uint8").
+        Host buffers: streaming (complete after synchronize()); device tensors: in stream order."""
+        ve = self.num_views() if view_end is None else view_end
+        _check_dtype(rgb, np.uint8, "rgb")
+        _check_dtype(depth, np.float32, "depth")
+        _check_dtype(cell_ids, np.int32, "cell_ids")
+        self._ck(self._lib.flyby_render_packed(self._h, C.c_int(view_begin), C.c_int(ve), C.c_int(res), C.byref(opts),
+                                               _ptr(rgb), _ptr(depth), _ptr(cell_ids)))
 
     def render(self, res, opts, view_begin=0, view_end=None, want_t=False):
         """Render to new numpy arrays: (features [n,res,res,C], cell_ids [n,res,res][, t])."""

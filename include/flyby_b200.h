@@ -193,6 +193,15 @@ FLYBY_API int flyby_render(flyby_ctx* ctx, int view_begin, int view_end, int res
 FLYBY_API int flyby_render_async(flyby_ctx* ctx, int view_begin, int view_end, int res,
                        const flyby_render_opts* opts, float* out_features, int32_t* out_cell_ids,
                        double* out_t);
+/* Packed output for PCIe-bound consumers of the 8-bit contract (normal_encoding 3 -- the values
+ * FlyByGenerator.getFlyBy holds after its RGB read-back, src/py/fly_by_features.py:121-125, are uint8): the three
+ * colour channels travel as bytes and the depth as float32, 7 bytes per pixel instead of the 16 of the float tensor,
+ * losslessly.  out_rgb uint8 [n, res, res, 3]; out_depth float32 [n, res, res] or NULL (needs use_z && split_z);
+ * out_cell_ids optional.  Requires normal_encoding 3, no point scalars, and not (use_z && !split_z).  Host outputs:
+ * streaming like flyby_render_async (pinned buffers, complete after flyby_synchronize, alternate two sets); device
+ * outputs: in stream order. */
+FLYBY_API int flyby_render_packed(flyby_ctx* ctx, int view_begin, int view_end, int res,
+                        const flyby_render_opts* opts, uint8_t* out_rgb, float* out_depth, int32_t* out_cell_ids);
 /* Raster-compatible views: what FlyByGenerator.getFlyBy reads back from OpenGL
  * (src/py/fly_by_features.py:85-152), produced by the ray caster: a pinhole camera at the viewpoint looking
  * at the origin, view-up (0,0,-1) ((+-1,0,0) exactly at the poles, :93-98), view angle in degrees (vtkCamera

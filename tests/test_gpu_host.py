@@ -204,6 +204,59 @@ def test_render_async_streams_meshes(gpu_ctx):
     assert np.array_equal(f.numpy(), want[-1][0]) and np.array_equal(i.numpy(), want[-1][1])
 
 
+@pytest.mark.parametrize("res,split_z", [(96, 1), (33, 1), (64, 0)])
+def test_render_packed_equals_the_float_tensor(gpu_ctx, res, split_z):
+    """flyby_render_packed (uint8 colours + float32 depth, 7 B per pixel) holds exactly what flyby_render writes for
+    normal_encoding "uint8": streamed through pinned host buffers (two meshes, two staging sets), into device tensors,
+    at a resolution whose pixel count is not a multiple of 4 (scalar packing path), and without a depth channel."""
+    torch = pytest.importorskip("torch")
+    from flyby_b200 import synth, _cabi
+    gpu_ctx.views_icosahedron(2, 2.0)
+    use_z = 1 if split_z else 0
+    opts = gpu_ctx.render_opts(use_z=use_z, split_z=split_z, normal_encoding="uint8")
+    meshes = [synth.bumpy_sphere(16 + 6 * k, k) for k in range(3)]
+    n = gpu_ctx.num_views()
+    C = 4 if split_z else 3
+    bufs = [(torch.empty((n, res, res, 3), dtype=torch.uint8).pin_memory(), torch.empty((n, res, res), dtype=torch.float32).pin_memory(),
+             torch.empty((n, res, res), dtype=torch.int32).pin_memory()) for _ in range(2)]
+    want, got = [], []
+    for P, F in meshes:
+        gpu_ctx.set_mesh(P, F)
+        gpu_ctx.build()
+        want.append(gpu_ctx.render(res, opts))
+    for k, (P, F) in enumerate(meshes):
+        gpu_ctx.set_mesh(P, F)
+        gpu_ctx.build()
+        rgb, z, ids = bufs[k % 2]
+        gpu_ctx.render_packed_into(res, opts, rgb.numpy(), z.numpy() if split_z else None, ids.numpy())
+        gpu_ctx.synchronize()
+        got.append((rgb.numpy().copy(), z.numpy().copy(), ids.numpy().copy()))
+    for (feat, ids_w), (rgb, z, ids) in zip(want, got):
+        assert feat.shape[-1] == C and np.array_equal(ids_w, ids)
+        assert np.array_equal(feat[..., :3], rgb.astype(np.float32))  # the colours are integers 0..255
+        assert rgb.max() > 200 and (rgb[ids_w < 0] == 0).all()
+        if split_z:
+            assert np.array_equal(feat[..., 3].view(np.int32), z.view(np.int32))
+    # device outputs, in stream order; two back-to-back streamed calls without a synchronisation in between
+    dev = torch.device("cuda", 0)
+    rgb_d = torch.empty((n, res, res, 3), dtype=torch.uint8, device=dev)
+    z_d = torch.empty((n, res, res), dtype=torch.float32, device=dev) if split_z else None
+    torch.cuda.synchronize()
+    gpu_ctx.render_packed_into(res, opts, rgb_d, z_d, None)
+    gpu_ctx.render_packed_into(res, opts, bufs[0][0].numpy(), bufs[0][1].numpy() if split_z else None, None)
+    gpu_ctx.render_packed_into(res, opts, bufs[1][0].numpy(), bufs[1][1].numpy() if split_z else None, None)
+    gpu_ctx.synchronize()
+    assert np.array_equal(rgb_d.cpu().numpy(), got[-1][0]) and np.array_equal(bufs[0][0].numpy(), got[-1][0])
+    assert np.array_equal(bufs[1][0].numpy(), got[-1][0])
+    if split_z:
+        assert np.array_equal(z_d.cpu().numpy(), got[-1][1]) and np.array_equal(bufs[1][1].numpy(), got[-1][1])
+    # contracts the packed form cannot carry are refused
+    with pytest.raises(_cabi.FlyByError):
+        gpu_ctx.render_packed_into(res, gpu_ctx.render_opts(normal_encoding="unit01"), rgb_d, None, None)
+    with pytest.raises(_cabi.FlyByError):
+        gpu_ctx.render_packed_into(res, gpu_ctx.render_opts(use_z=1, split_z=0, normal_encoding="uint8"), rgb_d, None, None)
+
+
 def test_two_contexts_interleaved_on_one_gpu(gpu_ctx):
     """Independent contexts on their own streams may overlap on the device: results equal the sequential ones."""
     torch = pytest.importorskip("torch")
