@@ -545,8 +545,18 @@ int flyby_render_packed(flyby_ctx* c, int vb, int ve, int res, const flyby_rende
   const size_t n_pix = (size_t)(ve - vb) * per_view;
   if ((rc = views_setup(c, o, res))) return rc;
   const int nv = ve - vb;
-  int n_chunks = nv < 8 ? 1 : (nv + 11) / 12;
+  // Two chunks per call (more only to keep the float staging of a chunk under 256 MB): the copy-out of a call overlaps
+  // the next call anyway, and every additional cudaMemcpyAsync costs more than its earlier start gains -- streamed
+  // bench meshes: 3.15 / 3.04 / 3.14 / 3.48 / 3.80 ms per mesh with 1 / 2 / 4 / 8 / 16 chunks (the copy alone: 2.96)
+  int n_chunks = (int)((n_pix * channels * sizeof(float) + (256u << 20) - 1) / (256u << 20));
+  if (n_chunks < 2) n_chunks = 2;
   if (n_chunks > 16) n_chunks = 16;
+  if (n_chunks > nv) n_chunks = nv;
+  {
+    static int env_chunks = -1;  // FLYBY_PK_CHUNKS: A/B hook
+    if (env_chunks < 0) { const char* e = getenv("FLYBY_PK_CHUNKS"); env_chunks = e ? atoi(e) : 0; }
+    if (env_chunks > 0) n_chunks = env_chunks > 16 ? 16 : (env_chunks > nv ? nv : env_chunks);
+  }
   int bounds[17];
   size_t max_chunk = 0;
   for (int k = 0; k <= n_chunks; k++) bounds[k] = vb + (int)((long long)nv * k / n_chunks);
