@@ -29,7 +29,9 @@
 
 namespace fb {
 
+#ifndef RT_THREADS
 #define RT_THREADS 128
+#endif
 #ifndef RT_MINB
 #define RT_MINB 12
 #endif
