@@ -39,6 +39,12 @@ namespace fb {
 #define RT_EXTRA 8    // extra candidates kept per pixel (two int4)
 #define RT_BAND 4096  // pixels of a big triangle's box handled by one warp of raster_big_kernel
 #define RV_THREADS 128
+#ifndef RV_SHARE
+#define RV_SHARE 4         // FLYBY_SHARE_GPU: persistent CTAs of raster_resolve1_kernel per SM (exact / tolerance variant)
+#endif
+#ifndef RV_SHARE_APPROX
+#define RV_SHARE_APPROX 6
+#endif
 #ifndef RV_MINB
 #define RV_MINB 5
 #endif
@@ -722,6 +728,13 @@ int raster_render(flyby_ctx* c, const RenderParams& rp) {
     if (rc) return rc;
   }
   long long rgrid = (long long)c->sm_count * (approx ? RV_MINB_APPROX : RV_MINB) * 4;  // CTAs resident per SM, 4 rounds for balance
+  {  // FLYBY_SHARE_GPU: exactly this many persistent resolve1 CTAs per SM (4 x 96 registers x 128 threads leave room for
+     // three CTAs of another context's raster_kernel; 2 / 3 / 4 / 5 measured 1.77 / 1.79 / 1.50 / 1.66 ms per mesh for two
+     // alternating contexts).  FLYBY_RV_CTAS: A/B hook
+    static int env_rv = -1;
+    if (env_rv < 0) { const char* e = getenv("FLYBY_RV_CTAS"); env_rv = e ? atoi(e) : 0; }
+    if (env_rv > 0 || rp.share) rgrid = (long long)c->sm_count * (env_rv > 0 ? env_rv : (approx ? RV_SHARE_APPROX : RV_SHARE));
+  }
   const long long want = cdiv(n_pix, RV_THREADS);
   if (rgrid > want) rgrid = want;
   if (approx)

@@ -586,8 +586,9 @@ int trace_render(flyby_ctx* c, int vb, int ve, int res, const flyby_render_opts*
   else if (engine == 2) mode = 1;
   else if (engine == 3) mode = 0;
   else if (engine != 0) return fail(c, FLYBY_ERR_INVALID, "render: unknown mode %d", o->mode);
-  if (o->mode & ~(0xff | FLYBY_SHADE_TOLERANCE)) return fail(c, FLYBY_ERR_INVALID, "render: unknown mode flags %#x", o->mode);
+  if (o->mode & ~(0xff | FLYBY_SHADE_TOLERANCE | FLYBY_SHARE_GPU)) return fail(c, FLYBY_ERR_INVALID, "render: unknown mode flags %#x", o->mode);
   p.approx = (o->mode & FLYBY_SHADE_TOLERANCE) ? 1 : 0;  // honoured by the raster engine
+  p.share = (o->mode & FLYBY_SHARE_GPU) ? 1 : 0;
   FB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), st));  // tile counter
   const size_t smem = (size_t)p.top_cap * sizeof(Node) + RK_WARPS * RK_QCAP * sizeof(uint32_t);
   auto launch = [&](auto kern) -> int {

@@ -111,6 +111,7 @@ struct RenderParams {
   int n_scal, scal_mode, stride;
   float scal_zero;
   int approx;                    // FLYBY_SHADE_TOLERANCE: shade_approx for pixels whose only candidate is a certain hit
+  int share;                     // FLYBY_SHARE_GPU: the resolve kernels leave room for another context's candidate search
   FastDiv div_view, div_res;     // by res * res and by res
 };
 

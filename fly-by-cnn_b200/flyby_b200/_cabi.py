@@ -64,6 +64,7 @@ NORMAL_ENCODINGS = {"unit01": 0, "byte255": 1, "signed": 2, "uint8": 3}
 RENDER_MODES = {"default": 0, "raster": 1, "bvh": 2, "fused": 3}
 CONSISTENCY = {"check": 0, "fix": 1, "off": 2}
 SHADE_TOLERANCE = 0x100
+SHARE_GPU = 0x200
 BUILD_DEFERRED = 0x100
 
 
@@ -268,11 +269,13 @@ class Context:
     # ---- rendering ----------------------------------------------------------
     @staticmethod
     def render_opts(use_z=1, split_z=1, normal_encoding="unit01", plane_scale=1.0, plane_spacing=1.0,
-                    z_scale=1.0, tolerance=1e-10, mode="default", shade_tolerance=False):
+                    z_scale=1.0, tolerance=1e-10, mode="default", shade_tolerance=False, share_gpu=False):
         """mode: "default" | "raster" | "bvh" | "fused" -- the search engine; results are bit-identical.
-        shade_tolerance: FLYBY_SHADE_TOLERANCE -- ids stay exact, depth / normals within 1e-5 relative."""
+        shade_tolerance: FLYBY_SHADE_TOLERANCE -- ids stay exact, depth / normals within 1e-5 relative.
+        share_gpu: FLYBY_SHARE_GPU -- another context renders on this GPU at the same time (two contexts fed alternately)."""
         o = RenderOpts()
-        o.mode = (RENDER_MODES[mode] if isinstance(mode, str) else int(mode)) | (SHADE_TOLERANCE if shade_tolerance else 0)
+        o.mode = (RENDER_MODES[mode] if isinstance(mode, str) else int(mode)) | (SHADE_TOLERANCE if shade_tolerance else 0) \
+            | (SHARE_GPU if share_gpu else 0)
         o.use_z, o.split_z = int(bool(use_z)), int(bool(split_z))
         o.normal_encoding = NORMAL_ENCODINGS[normal_encoding] if isinstance(normal_encoding, str) \
             else int(normal_encoding)
