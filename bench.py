@@ -364,8 +364,8 @@ def run_ours(args):
     feat2, ids2 = torch.empty_like(feat), torch.empty_like(ids)
     pair = [(ctx, stream, feat, ids), (ctx2, stream2, feat2, ids2)]
 
-    # FLYBY_SHARE_GPU: the exact-resolve kernel of one context (bound by double-precision latency) keeps to four CTAs
-    # per SM, so that the other context's candidate search (bound by instruction issue) runs beside it, not behind it
+    # FLYBY_SHARE_GPU: the exact-resolve kernels of one context are four persistent CTAs per SM (dispatched at once, registers
+    # to spare), so that the other context's build and the start of its candidate search run beside them, not behind their last wave
     opts_share = ctx.render_opts(use_z=1, split_z=1, plane_scale=PLANE_SCALE, share_gpu=True)
 
     def step_two(k):
@@ -613,8 +613,8 @@ def run_ours(args):
                 "pipelining": "two contexts (two streams) per GPU alternate meshes, K meshes timed as a whole, max over ranks; "
                               "driven two ways, the faster is the headline: " +
                               ("[headline] " if not use_graph else "") + "host launches (~51 per mesh) with FLYBY_SHARE_GPU -- the "
-                              "exact-resolve kernel of one context keeps to 4 CTAs per SM and the candidate search of the other "
-                              "runs beside it; " + ("[headline] " if use_graph else "") + "one CUDA-graph replay of set_mesh + build "
+                              "exact-resolve kernels of one context are 4 persistent CTAs per SM and the build of the other "
+                              "context's next mesh runs beside them; " + ("[headline] " if use_graph else "") + "one CUDA-graph replay of set_mesh + build "
                               "+ render per mesh (flyby_graph_launch), where the two graphs overlap only in the build",
                 "headline_loop": "graph_replay" if use_graph else "host_launches_share_gpu",
                 "ms_per_step_graph_replay": ms_two_graph_max,

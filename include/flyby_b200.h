@@ -100,11 +100,11 @@ typedef struct {
                               exact chain within 1e-5 relative (measured: depth equal, normals within 2 float32 ulp);
                               ignored when out_t is requested or barycentric point scalars are set
                               | FLYBY_SHARE_GPU (raster engine): another context renders on the same GPU at the same time
-                              (two contexts fed alternately, batch extraction): the exact-resolve kernel keeps to four
-                              persistent CTAs per SM, so that the other context's candidate search -- bound by instruction
-                              issue where the resolve is bound by double-precision latency -- runs beside it instead of
-                              behind it.  Same results; a lone render is ~8 % slower with the flag, two alternating
-                              contexts ~10 % faster per mesh */
+                              (two contexts fed alternately, batch extraction): the exact-resolve kernels are launched as
+                              four persistent CTAs per SM -- dispatched at once, with registers to spare -- so that the
+                              other context's build and the start of its candidate search run beside them instead of
+                              behind their last wave.  Same results; a lone render is ~8 % slower with the flag, two
+                              alternating contexts ~10 % faster per mesh */
   double plane_scale;      /* planeScaleFactor, default 1.0 */
   double plane_spacing;    /* planeSpacing, default 1.0 */
   double z_scale;          /* depth multiplier (1/z_far when rescaling), default 1.0 */
