@@ -257,6 +257,22 @@ def test_render_packed_equals_the_float_tensor(gpu_ctx, res, split_z):
         gpu_ctx.render_packed_into(res, gpu_ctx.render_opts(use_z=1, split_z=0, normal_encoding="uint8"), rgb_d, None, None)
 
 
+def test_share_gpu_flag_changes_no_result(gpu_ctx):
+    """FLYBY_SHARE_GPU only changes how the resolve kernels are launched (four persistent CTAs per SM): same tensors,
+    exact and tolerance shading, also for a render of a single view (fewer pixels than the persistent grid has threads)."""
+    from flyby_b200 import synth
+    P, F = synth.dental_crown(40, 2)
+    gpu_ctx.set_mesh(P, F)
+    gpu_ctx.build()
+    gpu_ctx.views_icosahedron(1, 2.0)
+    for kw in (dict(), dict(shade_tolerance=True), dict(use_z=1, split_z=0, plane_scale=2.0)):
+        for res, ve in ((160, None), (24, 1)):
+            f0, i0 = gpu_ctx.render(res, gpu_ctx.render_opts(**kw), view_end=ve)
+            f1, i1 = gpu_ctx.render(res, gpu_ctx.render_opts(share_gpu=True, **kw), view_end=ve)
+            assert np.array_equal(i0, i1) and np.array_equal(f0.view(np.int32), f1.view(np.int32))
+            assert (i0 >= 0).any()
+
+
 def test_two_contexts_interleaved_on_one_gpu(gpu_ctx):
     """Independent contexts on their own streams may overlap on the device: results equal the sequential ones."""
     torch = pytest.importorskip("torch")
