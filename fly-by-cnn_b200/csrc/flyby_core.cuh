@@ -743,6 +743,18 @@ FB_HD int raster_linear_pixel(const TriL& L, float di, float dj) {
   return (L.flags & 1) ? raster_linear_pixel_strip(L, di, dj) : raster_linear_pixel_plain(L, di, dj);
 }
 
+// Work items of raster_kernel: a box of w x h pixels is cut into ipr = ceil(w / U) items per row; item k of the box is
+// row k / ipr.  The division is a multiply-shift by rt_magic(ipr) = floor(2^16 / ipr) + 1 (the float quotient is within
+// 0.004 of 2^16 / ipr, whose distance from the next integer below is >= 1 / ipr unless it is one itself):
+// (k * magic) >> 16 == k / ipr for every k < 2^9 and ipr <= 2^7 -- boxes have at most 96 pixels (tests/hostsim checks all).
+FB_HD uint32_t rt_magic(int ipr) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)(65536.0f * __frcp_rn((float)ipr)) + 1u;
+#else
+  return (uint32_t)(65536.0f * (1.0f / (float)ipr)) + 1u;  // (1 / x in float is correctly rounded, as __frcp_rn)
+#endif
+}
+
 // ---- front-buffer key of the single-pass scan conversion (raster.cu):
 //   [63:32] far depth bound zhi as an order-preserving integer   [31:27] thickness code   [26:0] slot
 // The thickness code c bounds the triangle's depth extent: zhi - zlo < 2^(c - 24) (c = 31: no bound), so that

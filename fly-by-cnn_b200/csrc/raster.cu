@@ -227,8 +227,7 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
         strip = L.flags & 1;
         const unsigned long long key = front_key(t.zlo, t.zhi, slot);
         RtRec* o = rec + __popc(alive & ltmask);
-        // floor(2^16 / ipr) + 1 (ipr <= RT_BIG; the reciprocal is good to 2^-22): (k magic) >> 16 == k / ipr for k < 2^9
-        const uint32_t magic = (uint32_t)(65536.0f * __frcp_rn((float)ipr)) + 1u;
+        const uint32_t magic = rt_magic(ipr);  // (k magic) >> 16 == k / ipr
         *reinterpret_cast<float4*>(&o->A0) = make_float4(L.A0, L.A1, L.A2, L.B0);
         *reinterpret_cast<float4*>(&o->B1) = make_float4(L.B1, L.B2, L.C0, L.C1);
         *reinterpret_cast<float4*>(&o->C2) = make_float4(L.C2, L.g0, L.g1, L.g2);

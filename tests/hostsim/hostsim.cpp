@@ -600,6 +600,18 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
   return 0;
 }
 
+// ---- raster_kernel's row / column arithmetic: (k * rt_magic(ipr)) >> 16 against k / ipr; returns the mismatches
+extern "C" __attribute__((visibility("default")))
+long long sim_rt_magic_check(int max_ipr, int max_k) {
+  long long bad = 0;
+  for (int ipr = 1; ipr <= max_ipr; ipr++) {
+    const uint32_t m = rt_magic(ipr);
+    for (int k = 0; k < max_k; k++)
+      if ((int)(((uint32_t)k * m) >> 16) != k / ipr) bad++;
+  }
+  return bad;
+}
+
 // ---- audit of the opt-in tolerance shading (flyby_core.cuh shade_approx) on its domain of use: every (triangle,
 // pixel) pair the scan-conversion predicate classifies SC_SURE.  For each pair the exact chain (tri_exact + shade)
 // and shade_approx are evaluated and compared.

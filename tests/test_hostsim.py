@@ -182,3 +182,10 @@ def test_tolerance_shading_error_on_every_certain_pair(sim, orc):
         assert st[1] >= 0.99 * st[0]              # well-shaped triangles: the float32 weights are used almost everywhere
         assert err[0] <= 1e-5 and err[1] <= 1e-5 and err[2] <= 1e-5, err
         assert max(err[:3]) <= 1e-6                # what it really achieves
+
+
+def test_raster_item_division_is_exact(sim):
+    """raster_kernel splits a work-item index into (row, item of the row) with a multiply-shift by rt_magic(items per
+    row): exact for every index and divisor a box of at most 96 pixels can produce (and well beyond)."""
+    sim.sim_rt_magic_check.restype = C.c_longlong
+    assert sim.sim_rt_magic_check(C.c_int(128), C.c_int(512)) == 0
