@@ -755,6 +755,30 @@ FB_HD uint32_t rt_magic(int ipr) {
 #endif
 }
 
+// The flat enumeration of raster_kernel, lane by lane (tests/hostsim replays a warp with loops and these functions).
+// Records (the warp's visible triangles, compacted) own consecutive runs of work items; S = first item of a record.
+//   rt_start_bit   what record `lane` contributes to the OR of the window [base, base + 32): the bit of its first item
+//   rt_owner       the record that owns item base + lane: records started before the window + starts at or below the lane
+//   rt_item        item k of a box of width w, U pixels per item: row and first column
+FB_HD uint32_t rt_start_bit(int S, int base) {
+  const uint32_t rel = (uint32_t)(S - base);
+  return rel < 32u ? 1u << rel : 0u;
+}
+FB_HD int rt_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+FB_HD int rt_owner(uint32_t starts, int started, int lane) {
+  return started + rt_popc(starts & (0xffffffffu >> (31 - lane))) - 1;
+}
+FB_HD void rt_item(int k, int w, uint32_t magic, int U, int* row, int* col0) {
+  *row = (int)(((uint32_t)k * magic) >> 16);
+  *col0 = (k - *row * ((w + U - 1) / U)) * U;
+}
+
 // ---- front-buffer key of the single-pass scan conversion (raster.cu):
 //   [63:32] far depth bound zhi as an order-preserving integer   [31:27] thickness code   [26:0] slot
 // The thickness code c bounds the triangle's depth extent: zhi - zlo < 2^(c - 24) (c = 31: no bound), so that

@@ -242,15 +242,13 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
       // ---- pixels
       const int n_rec = __popc(alive);
       const int S = lane < n_rec ? s_pre[wid][lane] : 0x7fffffff;  // first work item of record `lane`
-      const unsigned lemask = ltmask | (1u << lane);
       int started = 0;  // records that start before the current window
       int qn = 0;       // entries in the settle queue
       for (int base = 0; base < n_items; base += 32) {
-        const unsigned rel = (unsigned)(S - base);
-        const unsigned starts = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+        const unsigned starts = __reduce_or_sync(0xffffffffu, rt_start_bit(S, base));
         const int item = base + lane;
         const bool valid = item < n_items;
-        const int own = valid ? started + __popc(starts & lemask) - 1 : 0;
+        const int own = valid ? rt_owner(starts, started, lane) : 0;
         started += __popc(starts);
         const int k = item - __shfl_sync(0xffffffffu, S, own);
         const RtRec* o = rec + own;
@@ -262,8 +260,8 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
         L.C2 = f2.x; L.g0 = f2.y; L.g1 = f2.z; L.g2 = f2.w; L.lim = __uint_as_float(f3.x);
         L.flags = (int)(f3.z >> 16);
         const int w = (int)(f3.z & 0xffffu);
-        const int row = (int)(((uint32_t)k * f3.w) >> 16);
-        const int col0 = (k - row * ((w + RT_U - 1) / RT_U)) * RT_U;
+        int row, col0;
+        rt_item(k, w, f3.w, RT_U, &row, &col0);
         const int nvalid = valid ? w - col0 : 0;
         const uint32_t ent0 = (uint32_t)own | ((uint32_t)row << 6) | ((uint32_t)col0 << 13);
         if (any_strip) rt_window<true>(L, (float)col0, (float)row, nvalid, ent0, q, qn, ltmask);

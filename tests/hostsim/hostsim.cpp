@@ -612,6 +612,44 @@ long long sim_rt_magic_check(int max_ipr, int max_k) {
   return bad;
 }
 
+// ---- raster_kernel's flat enumeration, one warp replayed with loops: 32 boxes (w[l] x h[l] pixels, 0 = not visible),
+// U pixels per work item.  Emits (lane of the triangle, row, column) of every pixel the kernel would test, in the
+// kernel's order, into out[3 * n]; returns n (or -1 if a record index leaves the compacted list).
+extern "C" __attribute__((visibility("default")))
+long long sim_flat_enumeration(const int* w, const int* h, int U, int* out, long long cap) {
+  int rec_lane[32], rec_w[32], S[32];
+  uint32_t magic[32];
+  int n_rec = 0, total = 0;
+  for (int l = 0; l < 32; l++) {
+    if (w[l] <= 0 || h[l] <= 0) continue;
+    const int ipr = (w[l] + U - 1) / U;
+    rec_lane[n_rec] = l; rec_w[n_rec] = w[l]; S[n_rec] = total; magic[n_rec] = rt_magic(ipr);
+    total += ipr * h[l];
+    n_rec++;
+  }
+  long long n = 0;
+  int started = 0;
+  for (int base = 0; base < total; base += 32) {
+    uint32_t starts = 0;
+    for (int l = 0; l < 32; l++) starts |= rt_start_bit(l < n_rec ? S[l] : 0x7fffffff, base);  // REDUX.OR
+    for (int u = 0; u < U; u++)  // the kernel's loop order: pixel u of every lane's item, then u + 1
+      for (int lane = 0; lane < 32; lane++) {
+        const int item = base + lane;
+        if (item >= total) continue;
+        const int own = rt_owner(starts, started, lane);
+        if (own < 0 || own >= n_rec) return -1;
+        int row, col0;
+        rt_item(item - S[own], rec_w[own], magic[own], U, &row, &col0);
+        if (u < rec_w[own] - col0) {
+          if (n < cap) { out[3 * n] = rec_lane[own]; out[3 * n + 1] = row; out[3 * n + 2] = col0 + u; }
+          n++;
+        }
+      }
+    started += rt_popc(starts);
+  }
+  return n;
+}
+
 // ---- audit of the opt-in tolerance shading (flyby_core.cuh shade_approx) on its domain of use: every (triangle,
 // pixel) pair the scan-conversion predicate classifies SC_SURE.  For each pair the exact chain (tri_exact + shade)
 // and shade_approx are evaluated and compared.

@@ -189,3 +189,32 @@ def test_raster_item_division_is_exact(sim):
     row): exact for every index and divisor a box of at most 96 pixels can produce (and well beyond)."""
     sim.sim_rt_magic_check.restype = C.c_longlong
     assert sim.sim_rt_magic_check(C.c_int(128), C.c_int(512)) == 0
+
+
+@pytest.mark.parametrize("U", [1, 2, 4])
+def test_flat_enumeration_visits_every_box_pixel_once(sim, U):
+    """raster_kernel's flat enumeration (owner search by one OR per window of 32 work items, multiply-shift row /
+    column), replayed for one warp with the kernel's own index functions: every pixel of every visible box exactly
+    once, no others -- for random boxes up to 96 pixels, all-dead warps, a single box, and boxes of one pixel."""
+    sim.sim_flat_enumeration.restype = C.c_longlong
+    rng = np.random.default_rng(11 + U)
+    cases = []
+    for _ in range(300):
+        w = rng.integers(1, 97, 32)
+        h = np.array([rng.integers(1, 96 // wi + 1) for wi in w])
+        dead = rng.random(32) < rng.random()
+        cases.append((np.where(dead, 0, w), np.where(dead, 0, h)))
+    cases.append((np.zeros(32, int), np.zeros(32, int)))
+    one = np.zeros(32, int); one[17] = 96
+    cases.append((one, (one > 0).astype(int)))
+    cases.append((np.ones(32, int), np.ones(32, int)))
+    cases.append((np.full(32, 96), np.ones(32, int)))
+    cases.append((np.ones(32, int), np.full(32, 96)))
+    for w, h in cases:
+        w32, h32 = np.ascontiguousarray(w, np.int32), np.ascontiguousarray(h, np.int32)
+        want = sorted((l, r, c) for l in range(32) for r in range(h32[l]) for c in range(w32[l]))
+        out = np.zeros((len(want) + 8, 3), np.int32)
+        n = sim.sim_flat_enumeration(_p(w32), _p(h32), C.c_int(U), _p(out), C.c_longlong(len(out)))
+        assert n == len(want)
+        got = [tuple(x) for x in out[:n]]
+        assert sorted(got) == want and len(set(got)) == n
