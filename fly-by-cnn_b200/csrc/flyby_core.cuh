@@ -771,9 +771,8 @@ FB_HD int rt_popc(uint32_t x) {
   return __builtin_popcount(x);
 #endif
 }
-FB_HD int rt_owner(uint32_t starts, int started, int lane) {
-  return started + rt_popc(starts & (0xffffffffu >> (31 - lane))) - 1;
-}
+FB_HD uint32_t rt_lemask(int lane) { return 0xffffffffu >> (31 - lane); }  // bits 0..lane
+FB_HD int rt_owner(uint32_t starts, int started, uint32_t lemask) { return started + rt_popc(starts & lemask) - 1; }
 FB_HD void rt_item(int k, int w, uint32_t magic, int U, int* row, int* col0) {
   *row = (int)(((uint32_t)k * magic) >> 16);
   *col0 = (k - *row * ((w + U - 1) / U)) * U;

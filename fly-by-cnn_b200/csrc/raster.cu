@@ -242,13 +242,14 @@ __global__ void __launch_bounds__(RT_THREADS, RT_MINB) raster_kernel(const Raste
       // ---- pixels
       const int n_rec = __popc(alive);
       const int S = lane < n_rec ? s_pre[wid][lane] : 0x7fffffff;  // first work item of record `lane`
+      const unsigned lemask = rt_lemask(lane);
       int started = 0;  // records that start before the current window
       int qn = 0;       // entries in the settle queue
       for (int base = 0; base < n_items; base += 32) {
         const unsigned starts = __reduce_or_sync(0xffffffffu, rt_start_bit(S, base));
         const int item = base + lane;
         const bool valid = item < n_items;
-        const int own = valid ? rt_owner(starts, started, lane) : 0;
+        const int own = valid ? rt_owner(starts, started, lemask) : 0;
         started += __popc(starts);
         const int k = item - __shfl_sync(0xffffffffu, S, own);
         const RtRec* o = rec + own;

@@ -636,7 +636,7 @@ long long sim_flat_enumeration(const int* w, const int* h, int U, int* out, long
       for (int lane = 0; lane < 32; lane++) {
         const int item = base + lane;
         if (item >= total) continue;
-        const int own = rt_owner(starts, started, lane);
+        const int own = rt_owner(starts, started, rt_lemask(lane));
         if (own < 0 || own >= n_rec) return -1;
         int row, col0;
         rt_item(item - S[own], rec_w[own], magic[own], U, &row, &col0);
