@@ -492,6 +492,9 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
   // for the larger ones, which raster_big_kernel and raster_kernel's inline fallback walk), 1 the linear form for every
   // box, 2 raster_pixel for every box
   const long long pred_mode = work ? work[5] : 0;
+  // in: work[6] = margins of the predicate in percent of their value (0 = 100): the audit with thinner margins measures
+  // how much headroom the rounding analysis leaves (the results stay exact either way only while no decision is wrong)
+  const float margin_scale = work && work[6] > 0 ? (float)work[6] * 0.01f : 1.0f;
   const long long order_seed = work ? work[4] : 0;  // in: work[4] != 0 shuffles the arrival order of the triangles
   SimCount cnt;
   SimFetch f{b.nodes.data()};
@@ -525,6 +528,7 @@ int sim_render_raster(const float* verts, int64_t V, const int32_t* tris, int64_
       const long long npx = (long long)(r.i1 - r.i0 + 1) * (r.j1 - r.j0 + 1);
       raster_setup(vf, 0.0f, P0, P1, P2, &t);
       if (!(t.flags & 1)) continue;
+      t.g0 *= margin_scale; t.g1 *= margin_scale; t.g2 *= margin_scale; t.G *= margin_scale;
       const uint64_t key = front_key(t.zlo, t.zhi, (int)slot);
       const uint32_t zlo_ord = ford_bits(t.zlo);
       const bool linear = pred_mode == 1 || (pred_mode == 0 && npx <= 96);
