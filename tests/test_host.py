@@ -3,6 +3,7 @@ the id codec, rotations, and the reference's command-line option surface."""
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -355,3 +356,19 @@ def test_nrrd_every_written_type_reads_back_and_crlf_headers(tmp_path):
     b, hdr = nrrd.read(str(tmp_path / "rgb.nrrd"))
     assert b.dtype == np.float64 and hdr["type"] == "double" and hdr["kinds"].split()[0] == "RGB-color"
     assert hdr["sizes"] == "3 6 6 4" and "(0.5,0,0) (0,0.5,0) (0,0,1)" in hdr["space directions"]
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the driver's CPU arm: the oracle port of the reference's locator loop, no GPU needed)
+    prints one JSON line with the contract's keys, the same metric / unit / config as the CUDA arm, and no GPU work."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "views/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "workload" in d["config"] and d["n_gpus"] == 1 and d["steps"] == 1
