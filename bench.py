@@ -399,7 +399,14 @@ def run_ours(args):
         return ms, n_launch
 
     k_two = args.steps
+
+    def last_two_digests():
+        """int64 sums of the ids and of the feature bit patterns the last two steps of a pipelined loop left behind"""
+        return [(int(pair[k % 2][3].to(torch.int64).sum()), int(pair[k % 2][2].view(torch.int32).to(torch.int64).sum()))
+                for k in (k_two - 2, k_two - 1) if k >= 0]
+
     ms_two_calls, launches_calls = timed_pipelined(step_two, max(4, args.warmup))
+    dig_calls = last_two_digests()
 
     # The same loop with every step replayed as a CUDA graph (flyby_capture_begin / _end / flyby_graph_launch): one
     # launch per mesh instead of ~50, the side-stream work as parallel branches of the graph.  One graph per
@@ -467,6 +474,7 @@ def run_ours(args):
         ms_two_tol = 0.0
 
     ms_two_graph, launches_graph = timed_pipelined(step_two_graph, max(4, args.warmup))
+    dig_graph = last_two_digests()  # (these tensors are compared bit for bit with a serial context's below)
     # the headline is the faster of the two ways to drive the pipeline, decided on the max over ranks of each
     both = _max_over_ranks(torch, dist, world, dev, [ms_two_graph, ms_two_calls])
     use_graph = both[0] <= both[1]
@@ -482,7 +490,7 @@ def run_ours(args):
     del os.environ["FLYBY_NO_SIDE_TREE"]
     ctx3.views_icosahedron(SUBDIVISION, RADIUS)
     feat3, ids3 = torch.empty_like(feat), torch.empty_like(ids)
-    verified = True
+    verified = dig_calls == dig_graph  # the host-launched FLYBY_SHARE_GPU loop and the graph replays left the same tensors
     for k in (k_two - 2, k_two - 1):
         if k < 0:
             continue
@@ -653,7 +661,8 @@ def run_ours(args):
                                           "note": "blocking call that also copies out the int32 hit-cell-id map "
                                                   "(input of the labeling back-projection)"}},
                 "outputs_verified": "ids and features of the last two pipelined steps are bit-equal to a serial "
-                                    "context's (no side stream, synchronised after every call)",
+                                    "context's (no side stream, synchronised after every call); the host-launched FLYBY_SHARE_GPU "
+                                    "loop and the graph replays left tensors with equal digests",
                 "gpu_launches": launches_two, "gpu_launches_single_context_loop": launches,
                 **extras,
                 "clocks": sampler.summary()}
